@@ -1,0 +1,88 @@
+// Kernel-level test hooks (C ABI, device pointers in/out).  Used only by
+// tests/ to check panel_gemm against a plain fp32 matmul on the same GPU.
+#include <cstdio>
+#include <cstring>
+
+#include "gemm_host.cuh"
+
+using namespace nmfb;
+
+static int fail(char* err, int errlen, const std::string& msg) {
+  if (err && errlen > 0) {
+    std::snprintf(err, errlen, "%s", msg.c_str());
+  }
+  return 1;
+}
+
+extern "C" {
+
+struct nmfb_debug_mat {
+  const float* base;
+  long long inner, outer, pitch;
+  int mn_major;
+};
+
+// out0[z*split_stride + col*ldo + row] = sum_k X0[row,k] * Y0[col,k]  (per split z)
+// out1[col*ldo + row]                  = sum_k X1[row,k] * Y1[col,k]  (if X1.base != NULL)
+int nmfb_debug_gemm_store(const nmfb_debug_mat* X0, const nmfb_debug_mat* Y0, long long kdim0,
+                          const nmfb_debug_mat* X1, const nmfb_debug_mat* Y1, long long kdim1,
+                          int rows, int ncols, int splits, float* out0, float* out1, long long ldo,
+                          long long split_stride, int* splits_used, char* err, int errlen) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  GemmLaunch L;
+  GemmOperand x0{{X0->base, X0->inner, X0->outer, X0->pitch}, X0->mn_major != 0};
+  Mat2D y0{Y0->base, Y0->inner, Y0->outer, Y0->pitch};
+  GemmOperand x1{};
+  Mat2D y1{};
+  const bool two = X1 && X1->base;
+  if (two) {
+    x1 = GemmOperand{{X1->base, X1->inner, X1->outer, X1->pitch}, X1->mn_major != 0};
+    y1 = Mat2D{Y1->base, Y1->inner, Y1->outer, Y1->pitch};
+  }
+  std::string e = plan_gemm(&L, x0, y0, kdim0, two ? &x1 : nullptr, two ? &y1 : nullptr, kdim1, rows,
+                            ncols, splits, sms);
+  if (!e.empty()) return fail(err, errlen, e);
+  L.args.out0 = out0;
+  L.args.out1 = out1;
+  L.args.ldo = ldo;
+  L.args.split_stride = split_stride;
+  if (splits_used) *splits_used = static_cast<int>(L.grid.z);
+  e = launch_gemm(L, EPI_STORE, 0);
+  if (!e.empty()) return fail(err, errlen, e);
+  cudaError_t ce = cudaDeviceSynchronize();
+  if (ce != cudaSuccess) return fail(err, errlen, std::string("sync: ") + cudaGetErrorString(ce));
+  return 0;
+}
+
+// Fused H update: acc0 = X0*Y0^T (N), acc1 = X1*Y1^T (D); H updated in place.
+int nmfb_debug_gemm_hupdate(const nmfb_debug_mat* X0, const nmfb_debug_mat* Y0, long long kdim0,
+                            const nmfb_debug_mat* X1, const nmfb_debug_mat* Y1, long long kdim1,
+                            int rows, int ncols, float* Hm, float* Hr32, float* Hc32, long long ldh,
+                            long long ldc, float lambda, double* partials, char* err, int errlen) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  GemmLaunch L;
+  GemmOperand x0{{X0->base, X0->inner, X0->outer, X0->pitch}, X0->mn_major != 0};
+  Mat2D y0{Y0->base, Y0->inner, Y0->outer, Y0->pitch};
+  GemmOperand x1{{X1->base, X1->inner, X1->outer, X1->pitch}, X1->mn_major != 0};
+  Mat2D y1{Y1->base, Y1->inner, Y1->outer, Y1->pitch};
+  std::string e = plan_gemm(&L, x0, y0, kdim0, &x1, &y1, kdim1, rows, ncols, 1, sms);
+  if (!e.empty()) return fail(err, errlen, e);
+  L.args.Hm = Hm;
+  L.args.Hr32 = Hr32;
+  L.args.Hc32 = Hc32;
+  L.args.ldh = ldh;
+  L.args.ldc = ldc;
+  L.args.lambda = lambda;
+  L.args.partials = partials;
+  e = launch_gemm(L, EPI_HUPDATE, 0);
+  if (!e.empty()) return fail(err, errlen, e);
+  cudaError_t ce = cudaDeviceSynchronize();
+  if (ce != cudaSuccess) return fail(err, errlen, std::string("sync: ") + cudaGetErrorString(ce));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+#include "gemm_host.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+namespace nmfb {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn(std::string* err) {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  static std::string saved_err;
+  std::call_once(once, [&]() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) {
+      saved_err = std::string("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: ") +
+                  cudaGetErrorString(e);
+    } else {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  if (!fn && err) *err = saved_err;
+  return fn;
+}
+
+std::string make_tmap(CUtensorMap* out, const Mat2D& m, uint32_t box_inner, uint32_t box_outer,
+                      bool atom32b) {
+  std::string err;
+  EncodeTiledFn fn = get_encode_fn(&err);
+  if (!fn) return err;
+  if ((m.pitch * 4) % 16 != 0) return "tensor map: row pitch is not a multiple of 16 bytes";
+  if ((reinterpret_cast<uintptr_t>(m.base) & 15) != 0) return "tensor map: base not 16-byte aligned";
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(m.inner), static_cast<cuuint64_t>(m.outer)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(m.pitch) * 4};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(m.base), gdim, gstride,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) +
+           " (inner=" + std::to_string(m.inner) + " outer=" + std::to_string(m.outer) +
+           " pitch=" + std::to_string(m.pitch) + " box=" + std::to_string(box_inner) + "x" +
+           std::to_string(box_outer) + ")";
+  }
+  return "";
+}
+
+int choose_splits(int tiles, int nkb0, int num_sms, int* kb_per_split) {
+  int splits = std::max(1, num_sms / std::max(1, tiles));
+  splits = std::min(splits, std::max(1, nkb0));
+  int per = (nkb0 + splits - 1) / std::max(1, splits);
+  per = std::max(per, 1);
+  splits = std::max(1, (nkb0 + per - 1) / per);
+  *kb_per_split = per;
+  return splits;
+}
+
+std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const Mat2D& Y0, long long kdim0,
+                      const GemmOperand* X1, const Mat2D* Y1, long long kdim1, int rows, int ncols,
+                      int splits_hint, int num_sms) {
+  if (ncols <= 0 || ncols % 32 != 0) return "plan_gemm: ncols must be a positive multiple of 32";
+  std::memset(L, 0, sizeof(*L));
+  GemmArgs& a = L->args;
+  a.rows = rows;
+  a.ncols = ncols;
+  a.box_n = std::min(ncols, kMaxN);
+  a.nkb0 = static_cast<int>((kdim0 + kBlockK - 1) / kBlockK);
+  a.nkb1 = (X1 != nullptr) ? static_cast<int>((kdim1 + kBlockK - 1) / kBlockK) : 0;
+  a.xmn0 = X0.mn_major ? 1 : 0;
+  a.xmn1 = (X1 && X1->mn_major) ? 1 : 0;
+  const int tiles = (rows + kTileM - 1) / kTileM;
+  const int chunks = (ncols + kMaxN - 1) / kMaxN;
+  int splits = 1;
+  a.kb_per_split = std::max(a.nkb0, 1);
+  if (splits_hint != 1) {
+    if (splits_hint <= 0) {
+      splits = choose_splits(tiles * chunks, a.nkb0, num_sms, &a.kb_per_split);
+    } else {
+      int per = std::max(1, (a.nkb0 + splits_hint - 1) / splits_hint);
+      splits = std::max(1, (a.nkb0 + per - 1) / per);
+      a.kb_per_split = per;
+    }
+  }
+  L->grid = dim3(tiles, chunks, splits);
+
+  std::string e;
+  auto xmap = [&](CUtensorMap* tm, const GemmOperand& X) {
+    return X.mn_major ? make_tmap(tm, X.m, 32, 32, true) : make_tmap(tm, X.m, kBlockK, kTileM, false);
+  };
+  if (!(e = xmap(&L->tmX0, X0)).empty()) return "X0 " + e;
+  if (!(e = make_tmap(&L->tmY0, Y0, kBlockK, a.box_n, false)).empty()) return "Y0 " + e;
+  if (X1) {
+    if (!(e = xmap(&L->tmX1, *X1)).empty()) return "X1 " + e;
+    if (!(e = make_tmap(&L->tmY1, *Y1, kBlockK, a.box_n, false)).empty()) return "Y1 " + e;
+  } else {
+    L->tmX1 = L->tmX0;
+    L->tmY1 = L->tmY0;
+  }
+  return "";
+}
+
+std::string launch_gemm(const GemmLaunch& L, int epi, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&]() {
+    attr_err = cudaFuncSetAttribute(panel_gemm_kernel<EPI_STORE>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(panel_gemm_kernel<EPI_HUPDATE>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+  });
+  if (attr_err != cudaSuccess)
+    return std::string("cudaFuncSetAttribute(panel_gemm): ") + cudaGetErrorString(attr_err);
+  if (epi == EPI_STORE) {
+    panel_gemm_kernel<EPI_STORE><<<L.grid, kGemmThreads, kGemmSmemBytes, stream>>>(
+        L.tmX0, L.tmY0, L.tmX1, L.tmY1, L.args);
+  } else {
+    if (L.grid.z != 1) return "launch_gemm: fused H update requires splits == 1";
+    panel_gemm_kernel<EPI_HUPDATE><<<L.grid, kGemmThreads, kGemmSmemBytes, stream>>>(
+        L.tmX0, L.tmY0, L.tmX1, L.tmY1, L.args);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return std::string("panel_gemm launch: ") + cudaGetErrorString(e);
+  return "";
+}
+
+}  // namespace nmfb

@@ -1,0 +1,51 @@
+// Host-side helpers for panel_gemm: TMA tensor-map construction (through the
+// driver entry point, so the library does not link libcuda) and launching.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+
+#include "panel_gemm.cuh"
+
+namespace nmfb {
+
+// A 2-D fp32 matrix as TMA sees it: `inner` contiguous elements per row,
+// `outer` rows, `pitch` elements between rows (pitch*4 must be a multiple of 16).
+struct Mat2D {
+  const float* base;
+  long long inner;
+  long long outer;
+  long long pitch;
+};
+
+// Operand description for one phase of panel_gemm.
+struct GemmOperand {
+  Mat2D m;
+  bool mn_major;  // X only: output rows run along the contiguous dimension
+};
+
+// Returns an empty string on success, else an error message.
+// atom32b selects the 128B-swizzle-with-32B-atom mode that MN-major fp32 operands need.
+std::string make_tmap(CUtensorMap* out, const Mat2D& m, uint32_t box_inner, uint32_t box_outer,
+                      bool atom32b);
+
+// Number of phase-0 k-blocks each split handles so that tiles*chunks*splits ~ fills the GPU.
+int choose_splits(int tiles, int nkb0, int num_sms, int* kb_per_split);
+
+struct GemmLaunch {
+  CUtensorMap tmX0, tmY0, tmX1, tmY1;
+  GemmArgs args;
+  dim3 grid;
+};
+
+// Builds tensor maps + args for out = X0*Y0^T (+ second accumulator X1*Y1^T).
+//   rows  : valid rows of X (output rows);  ncols: output columns (multiple of 32)
+//   kdim0 : contraction length of phase 0;  kdim1: of phase 1 (0 = none)
+std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const Mat2D& Y0, long long kdim0,
+                      const GemmOperand* X1, const Mat2D* Y1, long long kdim1, int rows, int ncols,
+                      int splits_hint, int num_sms);
+
+std::string launch_gemm(const GemmLaunch& L, int epi, cudaStream_t stream);
+
+}  // namespace nmfb

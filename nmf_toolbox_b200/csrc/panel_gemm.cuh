@@ -1,0 +1,337 @@
+// panel_gemm: the one tensor-core kernel behind every large contraction of the
+// NMF multiplicative updates (SURVEY.md section 7, K2/K4 and the Gram GEMMs).
+//
+//   acc0[128 x bn] = sum over k-blocks of  X0[r0:r0+128, kb] * Y0[n0:n0+bn, kb]^T   (phase 0)
+//   acc1[128 x bn] = sum over k-blocks of  X1[r0:r0+128, kb] * Y1[n0:n0+bn, kb]^T   (phase 1)
+//
+// X is the "panel" operand (V, W or H seen so that its rows are the output
+// rows), Y the small factor (H, W or a K x K Gram matrix).  Operands arrive by
+// TMA (128-byte swizzle) through a 4-stage mbarrier ring and tcgen05.mma
+// kind::tf32 accumulates into TMEM.
+//
+// Two-level accumulation.  The tensor core truncates (does not round) when it
+// adds into the fp32 accumulator, which gives a systematic relative bias of
+// about 5e-8 per accumulation step (measured on B200: 1.1e-4 after the 2048
+// steps of a 16384-long contraction).  Phase 0 is therefore cut into chunks of
+// kChunkKb k-blocks (32 MMA steps) that ping-pong between the two 256-column
+// TMEM buffers; eight epilogue warps drain each finished chunk with tcgen05.ld
+// and add it, round-to-nearest, into fp32 registers while the next chunk is
+// already accumulating.  Phase 1 (short: the K x K Gram products) is one chunk.
+//
+// Epilogues: EPI_STORE writes the raw sums (optionally one slab per split-K
+// slice); EPI_HUPDATE applies the fused multiplicative H update
+//   H <- H .* (N ./ max(D + lambda, eps))                  (nmf.m:180-181,199)
+// so that neither N = W'V nor D = W'V_hat ever exists in HBM.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA
+// issuer, warps 2..9 = epilogue (TMEM lane quarter = warp & 3, column half =
+// (warp - 2) >> 2).
+#pragma once
+#include "ptx.cuh"
+
+namespace nmfb {
+
+constexpr int kTileM = 128;   // output rows per CTA = TMEM lanes
+constexpr int kBlockK = 32;   // fp32 elements per 128-byte swizzle row
+constexpr int kUmmaK = 8;     // tf32 MMA K
+constexpr int kStages = 4;
+constexpr int kMaxN = 256;    // widest accumulator (fp32 TMEM columns)
+constexpr int kChunkKb = 8;   // k-blocks accumulated in TMEM before promotion to registers
+constexpr int kStageBytesX = kTileM * 128;
+constexpr int kStageBytesY = kMaxN * 128;
+constexpr int kStageBytes = kStageBytesX + kStageBytesY;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;
+constexpr int kGemmSmemBytes = kStages * kStageBytes + 1024;
+constexpr uint32_t kTmemCols = 512;
+constexpr int kMaxGroups = kMaxN / 16 / 2;  // 16-column groups per epilogue thread
+
+// MATLAB's eps (2^-52) - the reference clamps denominators with the double
+// eps even for single data (nmf.m:168,199); representable in fp32.
+#define NMFB_EPS 2.220446049250313e-16f
+
+enum { EPI_STORE = 0, EPI_HUPDATE = 1 };
+
+struct GemmArgs {
+  int rows;          // valid output rows (rows of X)
+  int ncols;         // valid output columns (padded K of this problem, multiple of 32)
+  int box_n;         // rows of the Y TMA box = min(ncols, 256)
+  int nkb0;          // phase-0 k-blocks in total (over all splits)
+  int kb_per_split;  // phase-0 k-blocks per split (blockIdx.z)
+  int nkb1;          // phase-1 k-blocks (split 0 only); 0 = no second accumulator
+  int xmn0, xmn1;    // X operand of phase 0 / 1 is MN-major (rows contiguous) instead of K-major
+  // EPI_STORE: out[z * split_stride + col * ldo + row]
+  float* out0;
+  float* out1;
+  long long ldo;
+  long long split_stride;
+  // EPI_HUPDATE: H master (fp32) and its tf32-rounded operand copies
+  float* Hm;     // [ncols][ldh]  row = basis index k, contiguous along samples
+  float* Hr32;   // same layout, tf32-rounded
+  float* Hc32;   // [rows][ldc]   contiguous along k (optional, may be null)
+  long long ldh;
+  long long ldc;
+  float lambda;
+  double* partials;  // [tiles*chunks][2]: sum(N .* Hnew), sum(Hnew)
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmY0,
+                  const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmY1,
+                  const GemmArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kStages];
+  __shared__ uint64_t empty_bar[kStages];
+  __shared__ uint64_t tfull_bar[2];   // TMEM buffer holds a finished chunk
+  __shared__ uint64_t tempty_bar[2];  // TMEM buffer has been drained
+  __shared__ uint32_t tmem_slot;
+  __shared__ double red[kEpiWarps][2];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  const int r0 = blockIdx.x * kTileM;
+  const int n0 = blockIdx.y * kMaxN;
+  const int bn = min(a.ncols - n0, kMaxN);  // multiple of 32
+  const int split = blockIdx.z;
+  const int kb_begin = split * a.kb_per_split;
+  const int n0kb = max(0, min(a.nkb0, kb_begin + a.kb_per_split) - kb_begin);
+  const int n1kb = (split == 0) ? a.nkb1 : 0;
+  const int nchunk0 = (n0kb + kChunkKb - 1) / kChunkKb;
+  const int nchunks = nchunk0 + (n1kb > 0 ? 1 : 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], kEpiWarps);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tmX0);
+    prefetch_tmap(&tmY0);
+    if (a.nkb1 > 0) {
+      prefetch_tmap(&tmX1);
+      prefetch_tmap(&tmY1);
+    }
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------ TMA producer
+    const uint32_t tx_bytes = kStageBytesX + a.box_n * 128;
+    const int total = n0kb + n1kb;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < total; ++it) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+      const bool ph1 = it >= n0kb;
+      const int kb = ph1 ? (it - n0kb) : (kb_begin + it);
+      const CUtensorMap* mx = ph1 ? &tmX1 : &tmX0;
+      const CUtensorMap* my = ph1 ? &tmY1 : &tmY0;
+      const uint32_t xs = sbase + stage * kStageBytes;
+      const uint32_t ys = xs + kStageBytesX;
+      // X is streamed once (evict-first); Y is re-read by every CTA (evict-last).
+      if (ph1 ? a.xmn1 : a.xmn0) {
+        // rows are the contiguous dimension: four 32(rows) x 32(k) boxes
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          tma_load_2d(xs + q * 4096, mx, &full_bar[stage], r0 + q * 32, kb * kBlockK, kEvictFirst);
+      } else {
+        tma_load_2d(xs, mx, &full_bar[stage], kb * kBlockK, r0, kEvictFirst);
+      }
+      tma_load_2d(ys, my, &full_bar[stage], kb * kBlockK, n0, kEvictLast);
+      if (++stage == kStages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------ MMA issuer
+    const uint32_t idesc_k = make_idesc_tf32(kTileM, bn, 0, 0);
+    const uint32_t idesc_mn = make_idesc_tf32(kTileM, bn, 1, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int buf = ch & 1;
+      const int use = ch >> 1;
+      if (use > 0) {
+        mbar_wait(&tempty_bar[buf], (use - 1) & 1);
+        tc_fence_after();
+      }
+      const bool ph1 = ch >= nchunk0;
+      const int nkb = ph1 ? n1kb : min(kChunkKb, n0kb - ch * kChunkKb);
+      const bool mn = ph1 ? (a.xmn1 != 0) : (a.xmn0 != 0);
+      const uint32_t d = tmem_base + static_cast<uint32_t>(buf * kMaxN);
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t xs = sbase + stage * kStageBytes;
+        const uint32_t ys = xs + kStageBytesX;
+#pragma unroll
+        for (int s = 0; s < kBlockK / kUmmaK; ++s) {
+          const uint64_t adesc = mn ? make_desc_mnmajor_sw128_32b(xs + s * 1024, 4096, 512)
+                                    : make_desc_kmajor_sw128(xs + s * (kUmmaK * 4));
+          const uint64_t bdesc = make_desc_kmajor_sw128(ys + s * (kUmmaK * 4));
+          mma_tf32_ss(d, adesc, bdesc, mn ? idesc_mn : idesc_k, (i == 0 && s == 0) ? 0u : 1u);
+        }
+        tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      tc_commit(&tfull_bar[buf]);  // chunk complete
+    }
+  } else if (warp >= 2) {
+    // ------------------------------------------------ epilogue
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which half of the 16-column groups
+    const int row = r0 + q * 32 + lane;
+    const bool row_ok = row < a.rows;
+    const int ngroups = bn >> 4;
+    const int g_begin = half ? ((ngroups + 1) >> 1) : 0;
+    const int g_count = half ? (ngroups - g_begin) : ((ngroups + 1) >> 1);
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+    float sum[kMaxGroups * 16];
+#pragma unroll
+    for (int i = 0; i < kMaxGroups * 16; ++i) sum[i] = 0.f;
+
+    // promote finished phase-0 chunks from TMEM into registers
+    for (int ch = 0; ch < nchunk0; ++ch) {
+      const int buf = ch & 1;
+      mbar_wait(&tfull_bar[buf], (ch >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t0 = tlane + static_cast<uint32_t>(buf * kMaxN + g_begin * 16);
+#pragma unroll
+      for (int g = 0; g < kMaxGroups; ++g) {
+        if (g < g_count) {
+          float v[16];
+          tmem_ld16(t0 + g * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 16; ++t) sum[g * 16 + t] += v[t];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+    // second accumulator (if any) sits in the next buffer of the alternation
+    const bool have1 = n1kb > 0;
+    const uint32_t t1 =
+        tlane + static_cast<uint32_t>((nchunk0 & 1) * kMaxN + g_begin * 16);
+    if (have1) {
+      mbar_wait(&tfull_bar[nchunk0 & 1], (nchunk0 >> 1) & 1);
+      tc_fence_after();
+    }
+    const int col0 = n0 + g_begin * 16;
+
+    if constexpr (EPI == EPI_STORE) {
+#pragma unroll
+      for (int g = 0; g < kMaxGroups; ++g) {
+        if (g < g_count) {
+          if (row_ok) {
+            float* o = a.out0 + static_cast<long long>(split) * a.split_stride +
+                       static_cast<long long>(col0 + g * 16) * a.ldo + row;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) o[t * a.ldo] = sum[g * 16 + t];
+          }
+          if (a.nkb1 > 0 && split == 0) {
+            float v[16];
+            if (have1) {
+              tmem_ld16(t1 + g * 16, v);
+              tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int t = 0; t < 16; ++t) v[t] = 0.f;
+            }
+            if (row_ok) {
+              float* o = a.out1 + static_cast<long long>(col0 + g * 16) * a.ldo + row;
+#pragma unroll
+              for (int t = 0; t < 16; ++t) o[t * a.ldo] = v[t];
+            }
+          }
+        }
+      }
+    } else {
+      // fused multiplicative H update; thread = one sample (column of V / H)
+      float s_nh = 0.f, s_h = 0.f;
+#pragma unroll
+      for (int g = 0; g < kMaxGroups; ++g) {
+        if (g < g_count) {
+          float dv[16];
+          tmem_ld16(t1 + g * 16, dv);
+          tmem_ld_wait();
+          if (row_ok) {
+            const long long hoff = static_cast<long long>(col0 + g * 16) * a.ldh + row;
+            float h[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) h[t] = a.Hm[hoff + t * a.ldh];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const float nv = sum[g * 16 + t];
+              const float hn = h[t] * (nv / fmaxf(dv[t] + a.lambda, NMFB_EPS));
+              s_nh += nv * hn;
+              s_h += hn;
+              a.Hm[hoff + t * a.ldh] = hn;
+              h[t] = tf32_rn(hn);
+              a.Hr32[hoff + t * a.ldh] = h[t];
+            }
+            if (a.Hc32 != nullptr) {
+              float4* o = reinterpret_cast<float4*>(a.Hc32 + static_cast<long long>(row) * a.ldc +
+                                                    (col0 + g * 16));
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                o[t] = make_float4(h[4 * t], h[4 * t + 1], h[4 * t + 2], h[4 * t + 3]);
+            }
+          }
+        }
+      }
+      double d0 = row_ok ? static_cast<double>(s_nh) : 0.0;
+      double d1 = row_ok ? static_cast<double>(s_h) : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+      }
+      if (lane == 0) {
+        red[warp - 2][0] = d0;
+        red[warp - 2][1] = d1;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // epilogue warps only
+      if (warp == 2 && lane == 0) {
+        double p0 = 0.0, p1 = 0.0;
+        for (int w = 0; w < kEpiWarps; ++w) {
+          p0 += red[w][0];
+          p1 += red[w][1];
+        }
+        const long long p = (static_cast<long long>(blockIdx.x) * gridDim.y + blockIdx.y) * 2;
+        a.partials[p] = p0;
+        a.partials[p + 1] = p1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace nmfb

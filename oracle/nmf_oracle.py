@@ -1,0 +1,567 @@
+"""CPU ORACLE - TEST INFRASTRUCTURE ONLY.  Not part of the product.
+
+Literal, line-by-line NumPy float64 restatement of the reference's MATLAB hot
+path (colinvaz/nmf-toolbox): ``nmf.m``, ``cnmf.m``, ``nmfsc.m``, ``projfunc.m``
+and ``ReconstructFromDecomposition.m``.  It deliberately keeps the reference's
+exact operation sequence - the dense ``ones(n, m)`` products, the
+``diag(diag(...))`` terms, the per-frame loops, the redundant GEMMs - so that it
+is a readable statement of WHAT the reference computes, not a fast one.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import this module, and only as the checker or
+the timed CPU baseline.  The product (``nmf_toolbox_b200`` / ``libnmfb200.so``)
+never imports, links or executes anything under ``oracle/``.
+
+PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
+ and no MATLAB/Octave exists in this environment, so
+this restatement cannot be checked against outputs of the reference itself.
+It is pinned only by (i) invariants derivable from the reference code
+(tests/test_oracle.py), (ii) an independently written Gram/trace-form
+re-derivation (oracle/restructured.py) agreeing to 1e-12, and (iii) sklearn's
+``NMF(solver="mu")`` for the one textbook Lee-Seung update in scope
+(nmfsc.m:182,232).
+
+MATLAB semantics honoured: column-major shapes, ``eps`` = 2**-52, ``x.^0 == 1``,
+``max(a, b)`` ignoring NaN (``np.fmax``), ``real(sqrt(negative)) == 0``
+(projfunc.m:37), ``find(v <= 0)`` (projfunc.m:49), 1-based shifts.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+EPS = 2.0 ** -52  # MATLAB eps
+
+__all__ = [
+    "EPS",
+    "reconstruct_from_decomposition",
+    "projfunc",
+    "nmf",
+    "cnmf",
+    "nmfsc",
+]
+
+
+class ReferenceError_(ValueError):
+    """Stands in for a MATLAB ``error(...)`` raised by the reference."""
+
+
+def _diagdiag(M):
+    """MATLAB ``diag(diag(M))``."""
+    return np.diag(np.diag(M))
+
+
+def _as_list(x):
+    return list(x) if isinstance(x, (list, tuple)) else [x]
+
+
+# --------------------------------------------------------------------------
+# ReconstructFromDecomposition.m:23-39
+# --------------------------------------------------------------------------
+def reconstruct_from_decomposition(W, H):
+    """V_hat = W*H (matrix W) or sum_t W(:,:,t) * [zeros(K,t-1) H(:,1:n-t+1)] (3-D W).
+
+    Follows ReconstructFromDecomposition.m:23-39.  Lists play the role of cell
+    arrays: W cells are concatenated horizontally, H cells vertically
+    (``cell2mat`` of a 1xS / Sx1 cell, lines 23-28).
+    """
+    if isinstance(W, (list, tuple)):
+        W = np.concatenate(list(W), axis=1)  # RFD.m:24
+    if isinstance(H, (list, tuple)):
+        H = np.concatenate(list(H), axis=0)  # RFD.m:27
+    W = np.asarray(W, dtype=np.float64)
+    H = np.asarray(H, dtype=np.float64)
+    if W.ndim == 2:  # RFD.m:30-31
+        return W @ H
+    if W.ndim == 3:  # RFD.m:32-38
+        m, K, T = W.shape
+        n = H.shape[1]
+        V_hat = np.zeros((m, n))
+        for t in range(1, T + 1):
+            H_shifted = np.concatenate([np.zeros((K, t - 1)), H[:, : n - t + 1]], axis=1)
+            V_hat = V_hat + W[:, :, t - 1] @ H_shifted
+        return V_hat
+    raise ReferenceError_("W must be a matrix or a 3-D tensor")
+
+
+# --------------------------------------------------------------------------
+# projfunc.m:13-65
+# --------------------------------------------------------------------------
+def projfunc(s, k1, k2, nn=1):
+    """Hoyer's L1/L2 projection, projfunc.m:13-65.  Returns ``(v, usediters)``."""
+    s = np.asarray(s, dtype=np.float64).reshape(-1).copy()
+    N = s.size  # projfunc.m:13
+    isneg = None
+    if not nn:  # projfunc.m:16-19
+        isneg = s < 0
+        s = np.abs(s)
+    v = s + (k1 - s.sum()) / N  # projfunc.m:22
+    zerocoeff = np.zeros(0, dtype=np.int64)  # projfunc.m:25
+    j = 0
+    while True:
+        midpoint = np.ones(N) * k1 / (N - zerocoeff.size)  # projfunc.m:31
+        midpoint[zerocoeff] = 0  # projfunc.m:32
+        w = v - midpoint  # projfunc.m:33
+        a = np.sum(w ** 2)  # projfunc.m:34
+        b = 2 * (w @ v)  # projfunc.m:35
+        c = np.sum(v ** 2) - k2  # projfunc.m:36
+        disc = b * b - 4 * a * c
+        root = np.sqrt(disc) if disc >= 0 else 0.0  # real(sqrt(.)), projfunc.m:37
+        with np.errstate(divide="ignore", invalid="ignore"):
+            alphap = (-b + root) / (2 * a)
+        v = alphap * w + v  # projfunc.m:38
+        if np.all(v >= 0):  # projfunc.m:40-44
+            usediters = j + 1
+            break
+        j += 1  # projfunc.m:46
+        zerocoeff = np.nonzero(v <= 0)[0]  # projfunc.m:49
+        v[zerocoeff] = 0  # projfunc.m:50
+        tempsum = v.sum()  # projfunc.m:51
+        v = v + (k1 - tempsum) / (N - zerocoeff.size)  # projfunc.m:52
+        v[zerocoeff] = 0  # projfunc.m:53
+        if not np.all(np.isfinite(v)):
+            # MATLAB would loop forever on NaN (all(NaN>=0) is false); bail out instead.
+            raise ReferenceError_("projfunc diverged (non-finite values)")
+    if not nn:  # projfunc.m:58-60
+        v = (-2.0 * isneg + 1.0) * v
+    # projfunc.m:63-65: imaginary-part check is vacuous here (real arithmetic throughout).
+    return v, usediters
+
+
+# --------------------------------------------------------------------------
+# shared config defaulting (nmf.m:238-413, cnmf.m:271-449)
+# --------------------------------------------------------------------------
+def _per_source(value, num_sources, what, clamp_nonneg):
+    """nmf.m:312-401 - scalar or 1-element cell is broadcast, S-element cell is kept."""
+    if value is None or (isinstance(value, (list, tuple)) and len(value) == 0):
+        return [0 if clamp_nonneg else False] * num_sources
+    if isinstance(value, (list, tuple)) and len(value) > 1:
+        if len(value) != num_sources:
+            raise ReferenceError_(
+                f"Requested {num_sources} sources. Given {len(value)} {what}."
+            )
+        return [max(v, 0) if clamp_nonneg else v for v in value]
+    v = value[0] if isinstance(value, (list, tuple)) else value
+    if clamp_nonneg:
+        v = max(v, 0)
+    return [v] * num_sources
+
+
+def _validate(V, num_basis_elems, config, context_len=None, rng=None):
+    """Private ValidateParameters of nmf.m (238-413) / cnmf.m (271-449)."""
+    cfg = dict(config or {})
+    m, n = V.shape
+    S = len(num_basis_elems)
+    rng = rng or np.random.default_rng()
+    cfg.setdefault("divergence", "euclidean")  # nmf.m:250-252
+    is_ab = cfg["divergence"] in ("ab_divergence", "ab")
+    if "alpha" not in cfg or not is_ab:  # nmf.m:255-259
+        cfg["alpha"] = 1
+    if "beta" not in cfg or not is_ab:  # nmf.m:262-266
+        cfg["beta"] = 1
+
+    H_init = cfg.get("H_init")
+    if H_init is None or (isinstance(H_init, (list, tuple)) and len(H_init) == 0):  # nmf.m:269-278
+        is_H_cell = S != 1
+        H_init = [np.fmax(rng.random((num_basis_elems[s], n)), EPS) for s in range(S)]
+    elif isinstance(H_init, (list, tuple)):
+        if len(H_init) != S:  # nmf.m:279-280
+            raise ReferenceError_(
+                f"Requested {S} sources. Given {len(H_init)} initial encoding matrices."
+            )
+        is_H_cell = True
+        H_init = [np.array(h, dtype=np.float64) for h in H_init]
+    else:  # nmf.m:281-283
+        is_H_cell = False
+        H_init = [np.array(H_init, dtype=np.float64)]
+    cfg["H_init"] = H_init
+
+    W_init = cfg.get("W_init")
+    if W_init is None or (isinstance(W_init, (list, tuple)) and len(W_init) == 0):
+        is_W_cell = S != 1
+        W_init = []
+        for s in range(S):
+            if context_len is None:  # nmf.m:298-299
+                w = np.fmax(rng.random((m, num_basis_elems[s])), EPS)
+                w = w @ np.diag(1.0 / np.sqrt(np.sum(w ** 2, axis=0)))
+            else:  # cnmf.m:331-335
+                w = rng.random((m, num_basis_elems[s], context_len))
+                for k in range(num_basis_elems[s]):
+                    w_norm = np.linalg.norm(w[:, k, :], "fro") / context_len
+                    w[:, k, :] = w[:, k, :] / w_norm
+            W_init.append(w)
+    elif isinstance(W_init, (list, tuple)):
+        if len(W_init) != S:  # nmf.m:301-302
+            raise ReferenceError_(
+                f"Requested {S} sources. Given {len(W_init)} initial basis matrices."
+            )
+        is_W_cell = True
+        W_init = [np.array(w, dtype=np.float64) for w in W_init]
+    else:
+        is_W_cell = False
+        W_init = [np.array(W_init, dtype=np.float64)]
+    cfg["W_init"] = W_init
+
+    cfg["W_sparsity"] = _per_source(cfg.get("W_sparsity"), S, "sparsity levels", True)
+    cfg["H_sparsity"] = _per_source(cfg.get("H_sparsity"), S, "sparsity levels", True)
+    cfg["W_fixed"] = _per_source(cfg.get("W_fixed"), S, "update switches", False)
+    cfg["H_fixed"] = _per_source(cfg.get("H_fixed"), S, "update switches", False)
+    if "maxiter" not in cfg or cfg["maxiter"] is None or cfg["maxiter"] <= 0:  # nmf.m:404-406
+        cfg["maxiter"] = 100
+    if "tolerance" not in cfg or cfg["tolerance"] is None or cfg["tolerance"] <= 0:  # nmf.m:409-411
+        cfg["tolerance"] = 1e-3
+    return cfg, is_W_cell, is_H_cell
+
+
+def _cost(divergence, V, V_hat, alpha, beta):
+    """nmf.m:206-215 / cnmf.m:239-248 (no 'frobenius' case: cost stays 0, a reference quirk)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if divergence == "euclidean":
+            return 0.5 * np.sum(np.sum((V - V_hat) ** 2))
+        if divergence in ("kl_divergence", "kl"):
+            return np.sum(np.sum(V * np.log(V / V_hat) - V + V_hat))
+        if divergence in ("is_divergence", "is"):
+            return np.sum(np.sum(np.log(V_hat / V) + (V / V_hat) - 1))
+        if divergence in ("ab_divergence", "ab"):
+            return (-1.0 / (alpha * beta)) * np.sum(
+                np.sum(
+                    V ** alpha * V_hat ** beta
+                    - (alpha * V ** (alpha + beta) + beta * V_hat ** (alpha + beta) + beta)
+                    / (alpha + beta)
+                )
+            )
+    return 0.0
+
+
+# --------------------------------------------------------------------------
+# nmf.m:109-236
+# --------------------------------------------------------------------------
+def nmf(V, num_basis_elems, config=None, rng=None):
+    """``[W, H, cost] = nmf(V, num_basis_elems, config)`` - nmf.m:1, loop 143-225."""
+    V = np.asarray(V, dtype=np.float64)
+    m, n = V.shape  # nmf.m:113
+    num_basis_elems = _as_list(num_basis_elems)  # nmf.m:114-116
+    S = len(num_basis_elems)
+    cfg, is_W_cell, is_H_cell = _validate(V, num_basis_elems, config, None, rng)  # nmf.m:118
+    div = cfg["divergence"]
+    alpha, beta = cfg["alpha"], cfg["beta"]
+    if div in ("ab_divergence", "ab") and alpha == 0 and beta == 0:  # nmf.m:120-122
+        raise ReferenceError_("alpha = 0 and beta = 0 is not supported at this time.")
+    use_dual = alpha == 0  # nmf.m:124-128
+
+    W = [w.copy() for w in cfg["W_init"]]  # nmf.m:130
+    H = [h.copy() for h in cfg["H_init"]]  # nmf.m:131
+    for s in range(S):  # nmf.m:132-134
+        W[s] = W[s] @ np.diag(1.0 / np.sqrt(np.sum(W[s] ** 2, axis=0)))
+    W_all = np.concatenate(W, axis=1)  # nmf.m:136
+    H_all = np.concatenate(H, axis=0)  # nmf.m:137
+    V_hat = reconstruct_from_decomposition(W_all, H_all)  # nmf.m:139
+    maxiter = int(cfg["maxiter"])
+    cost = np.zeros(maxiter)  # nmf.m:141
+    ones_nm = np.ones((n, m))
+    ones_mn = np.ones((m, n))
+
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for it in range(1, maxiter + 1):  # nmf.m:143
+            for s in range(S):  # nmf.m:145
+                if not cfg["W_fixed"][s]:
+                    Ws, Hs = W[s], H[s]
+                    if div == "euclidean":  # nmf.m:149-150
+                        neg = V @ Hs.T + Ws @ _diagdiag(Hs @ V_hat.T @ Ws)
+                        pos = V_hat @ Hs.T + Ws @ _diagdiag(Hs @ V.T @ Ws)
+                    elif div in ("kl_divergence", "kl"):  # nmf.m:152-153
+                        neg = (V / V_hat) @ Hs.T + Ws @ _diagdiag(Hs @ ones_nm @ Ws)
+                        pos = ones_mn @ Hs.T + Ws @ _diagdiag(Hs @ (V.T / V_hat.T) @ Ws)
+                    elif div in ("is_divergence", "is"):  # nmf.m:155-156
+                        neg = (V / V_hat ** 2) @ Hs.T + Ws @ _diagdiag(Hs @ (ones_nm / V_hat.T) @ Ws)
+                        pos = (ones_mn / V_hat) @ Hs.T + Ws @ _diagdiag(Hs @ (V.T / V_hat.T ** 2) @ Ws)
+                    elif div in ("ab_divergence", "ab"):  # nmf.m:158-164
+                        if use_dual:
+                            neg = ((V ** (alpha - 1) * V_hat ** beta) @ Hs.T
+                                   + Ws @ _diagdiag(Hs @ V.T ** (alpha + beta - 1) @ Ws)) ** (1.0 / beta)
+                            pos = (V ** (alpha + beta - 1) @ Hs.T
+                                   + Ws @ _diagdiag(Hs @ (V ** (alpha - 1) * V_hat ** beta).T @ Ws)) ** (1.0 / beta)
+                        else:
+                            neg = ((V ** alpha * V_hat ** (beta - 1)) @ Hs.T
+                                   + Ws @ _diagdiag(Hs @ V_hat.T ** (alpha + beta - 1) @ Ws)) ** (1.0 / alpha)
+                            pos = (V_hat ** (alpha + beta - 1) @ Hs.T
+                                   + Ws @ _diagdiag(Hs @ (V ** alpha * V_hat ** (beta - 1)).T @ Ws)) ** (1.0 / alpha)
+                    else:  # nmf.m:165-166
+                        raise ReferenceError_(
+                            "No update equations defined for cost function with divergence type " + str(div)
+                        )
+                    Ws = Ws * (neg / np.fmax(pos + cfg["W_sparsity"][s], EPS))  # nmf.m:168
+                    Ws = Ws @ np.diag(1.0 / np.sqrt(np.sum(Ws ** 2, axis=0)))  # nmf.m:169
+                    W[s] = Ws
+            W_all = np.concatenate(W, axis=1)  # nmf.m:172
+            V_hat = reconstruct_from_decomposition(W_all, H_all)  # nmf.m:173
+
+            for s in range(S):  # nmf.m:176
+                if not cfg["H_fixed"][s]:
+                    Ws, Hs = W[s], H[s]
+                    if div == "euclidean":  # nmf.m:180-181
+                        neg = Ws.T @ V
+                        pos = Ws.T @ V_hat
+                    elif div in ("kl_divergence", "kl"):  # nmf.m:183-184
+                        neg = Ws.T @ (V / V_hat)
+                        pos = Ws.T @ ones_mn
+                    elif div in ("is_divergence", "is"):  # nmf.m:186-187
+                        neg = Ws.T @ (V / V_hat ** 2)
+                        pos = Ws.T @ (ones_mn / V_hat)
+                    elif div in ("ab_divergence", "ab"):  # nmf.m:189-195
+                        if use_dual:
+                            neg = (Ws.T @ (V ** (alpha - 1) * V_hat ** beta)) ** (1.0 / beta)
+                            pos = (Ws.T @ V ** (alpha + beta - 1)) ** (1.0 / beta)
+                        else:
+                            neg = (Ws.T @ (V ** alpha * V_hat ** (beta - 1))) ** (1.0 / alpha)
+                            pos = (Ws.T @ V_hat ** (alpha + beta - 1)) ** (1.0 / alpha)
+                    else:  # nmf.m:196-197
+                        raise ReferenceError_(
+                            "No update equations defined for cost function with divergence type " + str(div)
+                        )
+                    H[s] = Hs * (neg / np.fmax(pos + cfg["H_sparsity"][s], EPS))  # nmf.m:199
+            H_all = np.concatenate(H, axis=0)  # nmf.m:202
+            V_hat = reconstruct_from_decomposition(W_all, H_all)  # nmf.m:203
+
+            c = _cost(div, V, V_hat, alpha, beta)  # nmf.m:206-215
+            for s in range(S):  # nmf.m:216-218
+                c = c + cfg["W_sparsity"][s] * np.sum(np.abs(W[s])) + cfg["H_sparsity"][s] * np.sum(np.abs(H[s]))
+            cost[it - 1] = c
+            # nmf.m:221-224
+            if it > 1 and cost[it - 1] < cost[it - 2] and cost[it - 2] - cost[it - 1] < cfg["tolerance"]:
+                cost = cost[:it]
+                break
+
+    W_out = W if is_W_cell else W[0]  # nmf.m:228-230
+    H_out = H if is_H_cell else H[0]  # nmf.m:232-234
+    return W_out, H_out, cost
+
+
+# --------------------------------------------------------------------------
+# cnmf.m:122-269
+# --------------------------------------------------------------------------
+def cnmf(V, num_basis_elems, context_len, config=None, rng=None):
+    """``[W, H, cost] = cnmf(V, num_basis_elems, context_len, config)`` - cnmf.m:1, loop 175-258."""
+    V = np.asarray(V, dtype=np.float64)
+    m, n = V.shape  # cnmf.m:126
+    num_basis_elems = _as_list(num_basis_elems)
+    S = len(num_basis_elems)
+    T = int(context_len)
+    cfg, is_W_cell, is_H_cell = _validate(V, num_basis_elems, config, T, rng)  # cnmf.m:131
+    div = cfg["divergence"]
+    alpha, beta = cfg["alpha"], cfg["beta"]
+    if div in ("ab_divergence", "ab") and alpha == 0 and beta == 0:  # cnmf.m:133-135
+        raise ReferenceError_("alpha = 0 and beta = 0 is not supported at this time.")
+    if div in ("euclidean", "frobenius"):  # cnmf.m:137-147
+        alpha, beta = 1, 1
+    elif div in ("kl_divergence", "kl"):
+        alpha, beta = 1, 0
+    elif div in ("is_divergence", "is"):
+        alpha, beta = 1, -1
+    use_dual = alpha == 0  # cnmf.m:149-153
+    is_kl = div in ("kl_divergence", "kl")
+
+    W = [w.copy() for w in cfg["W_init"]]  # cnmf.m:155
+    H = [h.copy() for h in cfg["H_init"]]  # cnmf.m:156
+    for s in range(S):  # cnmf.m:157-166
+        for k in range(num_basis_elems[s]):
+            w_norm = np.linalg.norm(W[s][:, k, :], "fro") / T
+            W[s][:, k, :] = W[s][:, k, :] / w_norm
+            H[s][k, :] = w_norm * H[s][k, :]
+    W_all = np.concatenate(W, axis=1)  # cnmf.m:168
+    H_all = np.concatenate(H, axis=0)  # cnmf.m:169
+    V_hat = reconstruct_from_decomposition(W_all, H_all)  # cnmf.m:171
+    maxiter = int(cfg["maxiter"])
+    cost = np.zeros(maxiter)  # cnmf.m:173
+
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for it in range(1, maxiter + 1):  # cnmf.m:175
+            for s in range(S):  # cnmf.m:177
+                if not cfg["W_fixed"][s]:
+                    Ks = num_basis_elems[s]
+                    for t in range(1, T + 1):  # cnmf.m:180 / 187
+                        H_shifted = np.concatenate([np.zeros((Ks, t - 1)), H[s][:, : n - t + 1]], axis=1)
+                        Wt = W[s][:, :, t - 1]
+                        if use_dual:  # cnmf.m:182-184
+                            g_neg = ((V ** (alpha - 1) * V_hat ** beta) @ H_shifted.T
+                                     + Wt @ _diagdiag(H_shifted @ V.T ** (alpha + beta - 1) @ Wt)) ** (1.0 / beta)
+                            g_pos = (V ** (alpha + beta - 1) @ H_shifted.T
+                                     + Wt @ _diagdiag(H_shifted @ (V ** (alpha - 1) * V_hat ** beta).T @ Wt)) ** (1.0 / beta)
+                        else:  # cnmf.m:191-193
+                            g_neg = ((V ** alpha * V_hat ** (beta - 1)) @ H_shifted.T
+                                     + Wt @ _diagdiag(H_shifted @ V_hat.T ** (alpha + beta - 1) @ Wt)) ** (1.0 / alpha)
+                            g_pos = (V_hat ** (alpha + beta - 1) @ H_shifted.T
+                                     + Wt @ _diagdiag(H_shifted @ (V ** alpha * V_hat ** (beta - 1)).T @ Wt)) ** (1.0 / alpha)
+                        W[s][:, :, t - 1] = Wt * (g_neg / np.fmax(g_pos + cfg["W_sparsity"][s], EPS))
+                    for k in range(Ks):  # cnmf.m:196-199
+                        w_norm = np.linalg.norm(W[s][:, k, :], "fro") / T
+                        W[s][:, k, :] = W[s][:, k, :] / w_norm
+            W_all = np.concatenate(W, axis=1)  # cnmf.m:202
+            H_all = np.concatenate(H, axis=0)  # cnmf.m:203
+            V_hat = reconstruct_from_decomposition(W_all, H_all)  # cnmf.m:204
+
+            for s in range(S):  # cnmf.m:207
+                if not cfg["H_fixed"][s]:
+                    Ks = num_basis_elems[s]
+                    if use_dual:  # cnmf.m:210-211
+                        V_neg = V ** (alpha - 1) * V_hat ** beta
+                        V_pos = V ** (alpha + beta - 1)
+                    else:  # cnmf.m:213-214
+                        V_neg = V ** alpha * V_hat ** (beta - 1)
+                        V_pos = V_hat ** (alpha + beta - 1)
+                    g_neg = np.zeros((Ks, n))  # cnmf.m:216
+                    g_pos = np.zeros((Ks, n))  # cnmf.m:217
+                    for t in range(1, T + 1):  # cnmf.m:218
+                        V_neg_shifted = np.concatenate([V_neg[:, t - 1:], np.zeros((m, t - 1))], axis=1)
+                        if is_kl:  # cnmf.m:220-221
+                            V_pos_shifted = V_pos
+                        else:  # cnmf.m:223
+                            V_pos_shifted = np.concatenate([V_pos[:, t - 1:], np.zeros((m, t - 1))], axis=1)
+                        g_neg = g_neg + W[s][:, :, t - 1].T @ V_neg_shifted  # cnmf.m:225
+                        g_pos = g_pos + W[s][:, :, t - 1].T @ V_pos_shifted  # cnmf.m:226
+                    p = (1.0 / beta) if use_dual else (1.0 / alpha)  # cnmf.m:228-232
+                    H[s] = H[s] * (g_neg ** p / np.fmax(g_pos ** p + cfg["H_sparsity"][s], EPS))
+            H_all = np.concatenate(H, axis=0)  # cnmf.m:235
+            V_hat = reconstruct_from_decomposition(W_all, H_all)  # cnmf.m:236
+
+            c = _cost(div, V, V_hat, alpha, beta)  # cnmf.m:239-248 ('frobenius' -> 0)
+            for s in range(S):  # cnmf.m:249-251
+                c = c + cfg["W_sparsity"][s] * np.sum(np.abs(W[s])) + cfg["H_sparsity"][s] * np.sum(np.abs(H[s]))
+            cost[it - 1] = c
+            # cnmf.m:254-257
+            if it > 1 and cost[it - 1] < cost[it - 2] and cost[it - 2] - cost[it - 1] < cfg["tolerance"]:
+                cost = cost[:it]
+                break
+
+    W_out = W if is_W_cell else W[0]
+    H_out = H if is_H_cell else H[0]
+    return W_out, H_out, cost
+
+
+# --------------------------------------------------------------------------
+# nmfsc.m:57-245
+# --------------------------------------------------------------------------
+def nmfsc(V, num_basis_elems, config=None, rng=None, info=None):
+    """``[W, H, cost] = nmfsc(V, num_basis_elems, config)`` - nmfsc.m:1, loop 141-245.
+
+    ``info`` (optional dict) receives bookkeeping that the reference does not
+    return (number of step halvings per iteration) - used by tests only.
+    """
+    V = np.asarray(V, dtype=np.float64)
+    if V.min() < 0:  # nmfsc.m:57-59
+        raise ReferenceError_("Negative values in data!")
+    V = V / V.max()  # nmfsc.m:62
+    m, n = V.shape  # nmfsc.m:65
+    K = int(num_basis_elems)
+    cfg = dict(config or {})
+    rng = rng or np.random.default_rng()
+    if cfg.get("W_init") is None:  # nmfsc.m:73-75
+        cfg["W_init"] = rng.random((m, K))
+    if cfg.get("H_init") is None:  # nmfsc.m:78-81
+        h = rng.random((K, n))
+        cfg["H_init"] = np.diag(1.0 / np.sqrt(np.sum(h ** 2, axis=1))) @ h
+    W = np.array(cfg["W_init"], dtype=np.float64)  # nmfsc.m:83
+    H = np.array(cfg["H_init"], dtype=np.float64)  # nmfsc.m:84
+
+    L1a = L1s = None
+    if cfg.get("W_sparsity") is None:  # nmfsc.m:87-88
+        cfg["W_sparsity"] = 0
+    elif cfg["W_sparsity"] > 0:  # nmfsc.m:89-97
+        if cfg["W_sparsity"] > 1:
+            cfg["W_sparsity"] = 1
+        L1a = np.sqrt(m) - (np.sqrt(m) - 1) * cfg["W_sparsity"]
+        for k in range(K):
+            W[:, k] = projfunc(W[:, k], L1a, 1, 1)[0]
+    if cfg.get("H_sparsity") is None:  # nmfsc.m:100-101
+        cfg["H_sparsity"] = 0
+    elif cfg["H_sparsity"] > 0:  # nmfsc.m:102-110
+        if cfg["H_sparsity"] > 1:
+            cfg["H_sparsity"] = 1
+        L1s = np.sqrt(n) - (np.sqrt(n) - 1) * cfg["H_sparsity"]
+        for k in range(K):
+            H[k, :] = projfunc(H[k, :], L1s, 1, 1)[0]
+    W_fixed = bool(cfg.get("W_fixed") or False)  # nmfsc.m:113-115
+    H_fixed = bool(cfg.get("H_fixed") or False)  # nmfsc.m:118-120
+    maxiter = cfg.get("maxiter")
+    if maxiter is None or maxiter <= 0:  # nmfsc.m:123-125
+        maxiter = 100
+    maxiter = int(maxiter)
+    tolerance = cfg.get("tolerance")
+    if tolerance is None or tolerance <= 0:  # nmfsc.m:128-130
+        tolerance = 1e-3
+
+    stepsizeW = 1.0  # nmfsc.m:133
+    stepsizeH = 1.0  # nmfsc.m:134
+    cost = np.zeros(maxiter + 1)  # nmfsc.m:137
+    V_hat = reconstruct_from_decomposition(W, H)  # nmfsc.m:138
+    cost[0] = 0.5 * np.sum(np.sum((V - V_hat) ** 2))  # nmfsc.m:139
+    halvings_H, halvings_W = [], []
+
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for it in range(1, maxiter + 1):  # nmfsc.m:141
+            if not H_fixed:  # nmfsc.m:143
+                neg = W.T @ V  # nmfsc.m:144
+                pos = W.T @ V_hat  # nmfsc.m:145
+                if cfg["H_sparsity"] > 0:  # nmfsc.m:146
+                    dH = pos - neg  # nmfsc.m:148
+                    begobj = cost[it - 1]  # nmfsc.m:149
+                    nh = 0
+                    while True:  # nmfsc.m:152
+                        Hnew = H - stepsizeH * dH  # nmfsc.m:154
+                        for k in range(K):  # nmfsc.m:155-157
+                            Hnew[k, :] = projfunc(Hnew[k, :], L1s, 1, 1)[0]
+                        V_hat = reconstruct_from_decomposition(W, Hnew)  # nmfsc.m:160
+                        newobj = 0.5 * np.sum(np.sum((V - V_hat) ** 2))  # nmfsc.m:161
+                        if newobj <= begobj:  # nmfsc.m:164-166
+                            break
+                        stepsizeH = stepsizeH / 2  # nmfsc.m:169
+                        nh += 1
+                        if stepsizeH < 1e-200:  # nmfsc.m:170-174
+                            cost = cost[:it]
+                            if info is not None:
+                                info.update(halvings_H=halvings_H, halvings_W=halvings_W, converged_early=True)
+                            return W, H, cost
+                    halvings_H.append(nh)
+                    stepsizeH = 1.2 * stepsizeH  # nmfsc.m:178
+                    H = Hnew  # nmfsc.m:179
+                else:  # nmfsc.m:181-188
+                    H = H * (neg / np.fmax(pos, EPS))
+                    norms = np.sqrt(np.sum(H ** 2, axis=1))
+                    H = np.diag(1.0 / norms) @ H
+                    W = W @ np.diag(norms)
+            if not W_fixed:  # nmfsc.m:192
+                V_hat = reconstruct_from_decomposition(W, H)  # nmfsc.m:193
+                neg = V @ H.T  # nmfsc.m:194
+                pos = V_hat @ H.T  # nmfsc.m:195
+                if cfg["W_sparsity"] > 0:  # nmfsc.m:196
+                    begobj = 0.5 * np.sum(np.sum((V - V_hat) ** 2))  # nmfsc.m:197
+                    dW = pos - neg  # nmfsc.m:200
+                    nh = 0
+                    while True:  # nmfsc.m:203
+                        Wnew = W - stepsizeW * dW  # nmfsc.m:205
+                        for k in range(K):  # nmfsc.m:206-208
+                            Wnew[:, k] = projfunc(Wnew[:, k], L1a, 1, 1)[0]
+                        V_hat = reconstruct_from_decomposition(Wnew, H)  # nmfsc.m:211
+                        newobj = 0.5 * np.sum(np.sum((V - V_hat) ** 2))  # nmfsc.m:212
+                        if newobj <= begobj:  # nmfsc.m:215-217
+                            break
+                        stepsizeW = stepsizeW / 2  # nmfsc.m:220
+                        nh += 1
+                        if stepsizeW < 1e-200:  # nmfsc.m:221-225
+                            cost = cost[:it]
+                            if info is not None:
+                                info.update(halvings_H=halvings_H, halvings_W=halvings_W, converged_early=True)
+                            return W, H, cost
+                    halvings_W.append(nh)
+                    stepsizeW = 1.2 * stepsizeW  # nmfsc.m:228
+                    W = Wnew  # nmfsc.m:229
+                else:  # nmfsc.m:232
+                    W = W * (neg / np.fmax(pos, EPS))
+            V_hat = reconstruct_from_decomposition(W, H)  # nmfsc.m:237
+            cost[it] = 0.5 * np.sum(np.sum((V - V_hat) ** 2))  # nmfsc.m:238
+            # nmfsc.m:241-244
+            if it > 1 and cost[it] < cost[it - 1] and cost[it - 1] - cost[it] < tolerance:
+                cost = cost[: it + 1]
+                break
+    if info is not None:
+        info.update(halvings_H=halvings_H, halvings_W=halvings_W, converged_early=False)
+    return W, H, cost
