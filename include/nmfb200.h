@@ -1,0 +1,147 @@
+/* nmfb200.h - C ABI of libnmfb200.so, the B200-native engine behind the
+ * multiplicative-update hot path of colinvaz/nmf-toolbox.
+ *
+ * The reference is pure MATLAB and has no FFI of its own; its boundary for this
+ * path is the MATLAB function-call level.  Every entry point below names the
+ * reference interface it replaces (file:line relative to the toolbox root):
+ *
+ *   nmfb_nmf          [W,H,cost] = nmf(V, num_basis_elems, config)              nmf.m:1
+ *   nmfb_cnmf         [W,H,cost] = cnmf(V, num_basis_elems, context_len, config) cnmf.m:1
+ *   nmfb_nmfsc        [W,H,cost] = nmfsc(V, num_basis_elems, config)            nmfsc.m:1
+ *   nmfb_reconstruct  V_hat = ReconstructFromDecomposition(W, H)     ReconstructFromDecomposition.m:1
+ *   nmfb_projfunc     [v,usediters] = projfunc(s, k1, k2, nn)                   projfunc.m:1
+ *
+ * Conventions
+ *   - All host matrices are column-major float32, exactly as MATLAB `single`
+ *     arrays are laid out: V is m x n, W is m x K (cnmf: m x K x T), H is K x n.
+ *   - Host buffers belong to the caller and are never retained; device buffers
+ *     for V, W, H and all scratch belong to the handle.
+ *   - Calls are synchronous at the boundary: outputs are valid on return.
+ *   - A handle is bound to one CUDA device and is not thread-safe (MATLAB calls
+ *     from a single interpreter thread).
+ *   - Every function returns NMFB_OK (0) or a non-zero nmfb_status; the message
+ *     of the last failure is available from nmfb_last_error().  MATLAB error()
+ *     sites of the reference map to NMFB_ERR_* codes (listed per function).
+ *   - There is no CPU fallback: without a CUDA device nmfb_create fails.
+ *
+ * Multi-GPU (one process per GPU): each rank creates a handle, joins a
+ * communicator (nmfb_comm_*), uploads its COLUMN SHARD of V and of H_init and
+ * passes the full W_init; W is returned replicated, H as the rank's shard, the
+ * cost trace is global.  One packed all-reduce per iteration carries the m x K
+ * numerator partial, the K x K Gram matrix and the scalar sums.
+ */
+#ifndef NMFB200_H_
+#define NMFB200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nmfb_handle nmfb_handle;
+
+typedef enum nmfb_status {
+  NMFB_OK = 0,
+  NMFB_ERR_INVALID_ARGUMENT = 1,   /* null pointers, non-positive sizes, ...                    */
+  NMFB_ERR_CUDA = 2,               /* a CUDA / NCCL call failed; see nmfb_last_error            */
+  NMFB_ERR_UNSUPPORTED = 3,        /* feature of the reference outside the accelerated path     */
+  NMFB_ERR_DIVERGENCE = 4,         /* nmf.m:165-166,196-197 "No update equations defined ..."   */
+  NMFB_ERR_AB_ZERO = 5,            /* nmf.m:120-122, cnmf.m:133-135 "alpha = 0 and beta = 0 ..." */
+  NMFB_ERR_NEGATIVE_DATA = 6,      /* nmfsc.m:57-59 "Negative values in data!"                  */
+  NMFB_ERR_NO_DATA = 7,            /* V has not been set on this handle                         */
+  NMFB_ERR_PROJFUNC = 8            /* projfunc produced non-finite values (MATLAB would spin)   */
+} nmfb_status;
+
+typedef enum nmfb_divergence {
+  NMFB_DIV_EUCLIDEAN = 0,  /* 'euclidean'                      nmf.m:148, cnmf.m:138 */
+  NMFB_DIV_KL = 1,         /* 'kl_divergence' | 'kl'           nmf.m:151             */
+  NMFB_DIV_FROBENIUS = 2,  /* 'frobenius': cnmf.m only (cnmf.m:138); same updates as
+                              euclidean but the reference's cost switch has no such
+                              case, so cost = sparsity terms only (cnmf.m:239-251).
+                              nmf.m rejects it (NMFB_ERR_DIVERGENCE).                */
+  NMFB_DIV_IS = 3,         /* recognised, NMFB_ERR_UNSUPPORTED (nmf.m:154-156)        */
+  NMFB_DIV_AB = 4          /* recognised, NMFB_ERR_UNSUPPORTED (nmf.m:157-164)        */
+} nmfb_divergence;
+
+typedef enum nmfb_cost_mode {
+  NMFB_COST_AUTO = 0,   /* Euclidean: Gram/trace identity (no extra pass over V); KL: fused */
+  NMFB_COST_DIRECT = 1  /* Euclidean: explicit 0.5*sum((V - W*H).^2) each iteration        */
+} nmfb_cost_mode;
+
+/* Mirror of the reference's `config` struct (nmf.m:17-65, cnmf.m:28-75,
+ * nmfsc.m:11-32).  Zero-initialise, then set what you need:
+ *   W_init/H_init NULL  -> uniform random (seeded by `seed`), as rand() in
+ *                          nmf.m:277,298 / cnmf.m:331 / nmfsc.m:74,79
+ *   maxiter   <= 0      -> 100    (nmf.m:404-406)
+ *   tolerance <= 0      -> 1e-3   (nmf.m:409-411)
+ *   *_sparsity < 0      -> 0      (nmf.m:321-333); nmfsc clamps to <= 1 (nmfsc.m:90,103) */
+typedef struct nmfb_config {
+  int divergence;        /* nmfb_divergence (ignored by nmfb_nmfsc)                     */
+  double alpha, beta;    /* only consulted for NMFB_DIV_AB (-> NMFB_ERR_AB_ZERO check)  */
+  const float* W_init;   /* m x K (x T) column-major, or NULL                           */
+  const float* H_init;   /* K x n_local column-major, or NULL                           */
+  double W_sparsity;     /* lambda_W (nmf/cnmf) or Hoyer sparseness of W columns (nmfsc) */
+  double H_sparsity;     /* lambda_H (nmf/cnmf) or Hoyer sparseness of H rows (nmfsc)    */
+  int W_fixed, H_fixed;  /* nmf.m:51-60                                                 */
+  int maxiter;
+  double tolerance;
+  unsigned long long seed; /* only used when an init pointer is NULL                    */
+  int cost_mode;         /* nmfb_cost_mode                                              */
+} nmfb_config;
+
+/* ---- handle ------------------------------------------------------------- */
+int nmfb_create(nmfb_handle** out, int device);
+void nmfb_destroy(nmfb_handle* h);
+const char* nmfb_last_error(const nmfb_handle* h); /* h may be NULL: last create error */
+
+/* Upload V (m x n column-major float32, host memory; pinned or pageable). */
+int nmfb_set_V(nmfb_handle* h, const float* V_host, int m, int n);
+/* Adopt a V that already lives on the handle's device (column-major, leading
+ * dimension ld >= m, ld % 4 == 0, 16-byte aligned).  Not copied, not modified;
+ * must stay alive until the next nmfb_set_V* or nmfb_destroy. */
+int nmfb_set_V_device(nmfb_handle* h, const float* V_dev, int m, int n, long long ld);
+
+/* ---- the reference's functions ------------------------------------------ */
+/* W_out: m*K floats, H_out: K*n floats, cost_out: >= maxiter doubles (after
+ * defaulting).  *n_cost = number of executed iterations = length of the
+ * reference's trimmed cost vector (nmf.m:222).  Outputs may be NULL. */
+int nmfb_nmf(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, float* H_out,
+             double* cost_out, int* n_cost);
+/* W_out: m*K*T floats (m x K x T column-major). */
+int nmfb_cnmf(nmfb_handle* h, int K, int T, const nmfb_config* cfg, float* W_out, float* H_out,
+              double* cost_out, int* n_cost);
+/* cost_out: >= maxiter+1 doubles; cost_out[0] is the initial cost (nmfsc.m:137-139).
+ * W_out, H_out factor V/max(V) (nmfsc.m:62). */
+int nmfb_nmfsc(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, float* H_out,
+               double* cost_out, int* n_cost);
+/* V_hat (m x n, host) = W*H, or sum_t W(:,:,t) * shift(H, t-1) when T > 1.
+ * Independent of any V set on the handle. */
+int nmfb_reconstruct(nmfb_handle* h, const float* W, const float* H, int m, int K, int T, int n,
+                     float* Vhat_out);
+/* Hoyer projection of `count` vectors of length N stored back to back
+ * (projfunc.m:13-55); iters_out (may be NULL) receives usediters per vector. */
+int nmfb_projfunc(nmfb_handle* h, const float* s, int N, int count, double k1, double k2, int nn,
+                  float* v_out, int* iters_out);
+
+/* ---- stepping interface (what nmfb_nmf does internally; used by bench.py to
+ *      time exactly K iterations with V, W, H resident) ---------------------- */
+int nmfb_nmf_begin(nmfb_handle* h, int K, const nmfb_config* cfg);
+/* Enqueue `iters` more iterations on the handle's stream (asynchronous). */
+int nmfb_nmf_step(nmfb_handle* h, int iters);
+/* Wait for the queued iterations; returns how many have been executed so far
+ * and the device time (CUDA events on the handle's stream) they took in total. */
+int nmfb_nmf_sync(nmfb_handle* h, int* iters_done, double* device_ms);
+int nmfb_nmf_end(nmfb_handle* h, float* W_out, float* H_out, double* cost_out, int* n_cost);
+/* Number of kernel launches issued by the handle since creation. */
+long long nmfb_launch_count(const nmfb_handle* h);
+
+/* ---- multi-GPU ---------------------------------------------------------- */
+#define NMFB_UNIQUE_ID_BYTES 128
+int nmfb_comm_unique_id(char id_out[NMFB_UNIQUE_ID_BYTES]);
+int nmfb_comm_init(nmfb_handle* h, const char id[NMFB_UNIQUE_ID_BYTES], int rank, int nranks);
+
+const char* nmfb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMFB200_H_ */

@@ -1,0 +1,216 @@
+// C ABI: handle lifetime, V upload, ReconstructFromDecomposition, projfunc.
+// (nmf / cnmf / nmfsc live in their *_driver.cu files.)
+#include <algorithm>
+#include <cstring>
+#include <string>
+
+#include "comm.cuh"
+#include "engine.cuh"
+#include "ew_kernels.cuh"
+
+using namespace nmfb;
+
+static std::string g_create_error;
+
+void nmf_session_release(nmfb_handle* h);  // nmf_driver.cu
+
+extern "C" const char* nmfb_version(void) { return "nmfb200 0.1 (sm_100a)"; }
+
+extern "C" const char* nmfb_last_error(const nmfb_handle* h) {
+  return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" long long nmfb_launch_count(const nmfb_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int nmfb_create(nmfb_handle** out, int device) {
+  if (!out) return NMFB_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                     "); libnmfb200 has no CPU fallback";
+    return NMFB_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    g_create_error = "device index out of range";
+    return NMFB_ERR_INVALID_ARGUMENT;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    return NMFB_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                     std::to_string(prop.minor) + "; libnmfb200 contains sm_100a code only";
+    return NMFB_ERR_CUDA;
+  }
+  e = cudaSetDevice(device);
+  nmfb_handle* h = new nmfb_handle();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("handle creation failed: ") + cudaGetErrorString(e);
+    delete h;
+    return NMFB_ERR_CUDA;
+  }
+  *out = h;
+  return NMFB_OK;
+}
+
+extern "C" void nmfb_destroy(nmfb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  nmf_session_release(h);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm) comm_destroy(h->comm);
+  if (h->Vown) cudaFree(h->Vown);
+  if (h->Vwork) cudaFree(h->Vwork);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+static void drop_V(nmfb_handle* h) {
+  if (h->Vown) cudaFree(h->Vown);
+  h->Vown = nullptr;
+  h->Vraw = nullptr;
+}
+
+extern "C" int nmfb_set_V(nmfb_handle* h, const float* V_host, int m, int n) {
+  if (!h) return NMFB_ERR_INVALID_ARGUMENT;
+  if (!V_host || m <= 0 || n <= 0) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "set_V: bad arguments");
+  cudaSetDevice(h->device);
+  nmf_session_release(h);
+  drop_V(h);
+  const long long ld = round_up(m, 4);
+  const size_t bytes = static_cast<size_t>(n) * ld * sizeof(float);
+  NMFB_CUDA(h, cudaMalloc(&h->Vown, bytes));
+  if (ld != m) NMFB_CUDA(h, cudaMemsetAsync(h->Vown, 0, bytes, h->stream));
+  h->Vraw = h->Vown;
+  h->m = m;
+  h->n = n;
+  h->ldv = ld;
+  NMFB_TRY(upload_colmajor(h, V_host, m, n, h->Vown, ld));
+  NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NMFB_OK;
+}
+
+extern "C" int nmfb_set_V_device(nmfb_handle* h, const float* V_dev, int m, int n, long long ld) {
+  if (!h) return NMFB_ERR_INVALID_ARGUMENT;
+  if (!V_dev || m <= 0 || n <= 0 || ld < m || ld % 4 != 0 ||
+      (reinterpret_cast<uintptr_t>(V_dev) & 15) != 0)
+    return h->fail(NMFB_ERR_INVALID_ARGUMENT,
+                   "set_V_device: need ld >= m, ld %% 4 == 0 and a 16-byte aligned pointer");
+  cudaSetDevice(h->device);
+  nmf_session_release(h);
+  drop_V(h);
+  h->Vraw = V_dev;
+  h->m = m;
+  h->n = n;
+  h->ldv = ld;
+  return NMFB_OK;
+}
+
+// ------------------------------------------------------------------ ReconstructFromDecomposition
+namespace apidetail {
+// hi = tf32(x), lo = tf32(x - hi): x ~ hi + lo to ~2^-22 relative.
+__global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi,
+                                  float* __restrict__ lo, long long count) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float x = src[i];
+    const float h = tf32_rn(x);
+    hi[i] = h;
+    lo[i] = tf32_rn(x - h);
+  }
+}
+// unrounded shifted stack (RFD.m:37)
+__global__ void hstack_raw_kernel(const float* __restrict__ H, float* __restrict__ Hs, int K, int T, int n,
+                                  long long ld) {
+  const int c = blockIdx.y;
+  const int k = c % K, t = c / K;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+    Hs[c * ld + j] = (j >= t) ? H[k * ld + (j - t)] : 0.f;
+}
+}  // namespace apidetail
+using namespace apidetail;
+
+// V_hat = W*H (RFD.m:31) or sum_t W(:,:,t)*[zeros(K,t-1) H(:,1:n-t+1)] (RFD.m:33-38).
+// The tensor cores multiply tf32 numbers; to return V_hat at fp32 accuracy each
+// factor is split into a tf32 head and tail and the contraction is run over the
+// stacked operands [W_hi W_lo W_hi] * [H_hi; H_hi; H_lo].
+extern "C" int nmfb_reconstruct(nmfb_handle* h, const float* W, const float* H, int m, int K, int T,
+                                int n, float* Vhat_out) {
+  if (!h) return NMFB_ERR_INVALID_ARGUMENT;
+  if (!W || !H || !Vhat_out || m <= 0 || K <= 0 || T <= 0 || n <= 0)
+    return h->fail(NMFB_ERR_INVALID_ARGUMENT, "reconstruct: bad arguments");
+  cudaSetDevice(h->device);
+  Arena ar;
+  const int KT = K * T, KTp = round_up(KT, 32);
+  const long long ldw = round_up(m, 4), ldh = round_up(n, 4);
+  float *Wc, *Hm, *Hs, *Xs, *Ys, *out;
+  NMFB_TRY(ar.alloc(h, &Wc, static_cast<size_t>(KTp) * ldw));
+  NMFB_TRY(ar.alloc(h, &Hm, static_cast<size_t>(K) * ldh));
+  NMFB_TRY(ar.alloc(h, &Hs, static_cast<size_t>(KTp) * ldh));
+  NMFB_TRY(ar.alloc(h, &Xs, static_cast<size_t>(3) * KTp * ldw));
+  NMFB_TRY(ar.alloc(h, &Ys, static_cast<size_t>(3) * KTp * ldh));
+  NMFB_TRY(ar.alloc(h, &out, static_cast<size_t>(n) * ldw));
+  NMFB_TRY(upload_colmajor(h, W, m, KT, Wc, ldw));
+  NMFB_TRY(upload_H(h, &ar, H, K, n, Hm, ldh));
+  hstack_raw_kernel<<<vec_grid(n, KT), 256, 0, h->stream>>>(Hm, Hs, K, T, n, ldh);
+  NMFB_TRY(check_launch(h, "hstack_raw"));
+  const long long cw = static_cast<long long>(KTp) * ldw, ch = static_cast<long long>(KTp) * ldh;
+  split_tf32_kernel<<<1024, 256, 0, h->stream>>>(Wc, Xs, Xs + cw, cw);
+  NMFB_TRY(check_launch(h, "split_tf32(W)"));
+  NMFB_CUDA(h, cudaMemcpyAsync(Xs + 2 * cw, Xs, cw * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  split_tf32_kernel<<<1024, 256, 0, h->stream>>>(Hs, Ys, Ys + 2 * ch, ch);
+  NMFB_TRY(check_launch(h, "split_tf32(H)"));
+  NMFB_CUDA(h, cudaMemcpyAsync(Ys + ch, Ys, ch * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  GemmOp op;
+  MatRef X{Xs, m, 3 * KTp, ldw, true};
+  MatRef Y{Ys, n, 3 * KTp, ldh, true};
+  NMFB_TRY(plan_fused(h, &op, EPI_RECON, X, Y, 3 * KTp, nullptr, nullptr, 0, m, round_up(n, 32), n,
+                      nullptr));
+  op.L.args.Qout = out;
+  op.L.args.ldv = ldw;
+  NMFB_TRY(run_gemm(h, op));
+  NMFB_TRY(download_colmajor(h, out, ldw, m, n, Vhat_out));
+  return NMFB_OK;
+}
+
+// ------------------------------------------------------------------ projfunc
+extern "C" int nmfb_projfunc(nmfb_handle* h, const float* s, int N, int count, double k1, double k2,
+                             int nn, float* v_out, int* iters_out) {
+  if (!h) return NMFB_ERR_INVALID_ARGUMENT;
+  if (!s || !v_out || N <= 0 || count <= 0)
+    return h->fail(NMFB_ERR_INVALID_ARGUMENT, "projfunc: bad arguments");
+  if (N > kProjThreads * 32 * kProjMaskWords)
+    return h->fail(NMFB_ERR_UNSUPPORTED, "projfunc: vectors longer than %d are not supported",
+                   kProjThreads * 32 * kProjMaskWords);
+  cudaSetDevice(h->device);
+  Arena ar;
+  float* X;
+  int *it, *fail;
+  const size_t total = static_cast<size_t>(N) * count;
+  NMFB_TRY(ar.alloc(h, &X, total));
+  NMFB_TRY(ar.alloc(h, &it, count));
+  NMFB_TRY(ar.alloc(h, &fail, 1));
+  NMFB_CUDA(h, cudaMemcpyAsync(X, s, total * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  projfunc_kernel<<<count, kProjThreads, 0, h->stream>>>(X, N, N, k1, k2, nn, it, fail);
+  NMFB_TRY(check_launch(h, "projfunc"));
+  int failed = 0;
+  NMFB_CUDA(h, cudaMemcpyAsync(v_out, X, total * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  NMFB_CUDA(h, cudaMemcpyAsync(&failed, fail, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (iters_out)
+    NMFB_CUDA(h, cudaMemcpyAsync(iters_out, it, count * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (failed) return h->fail(NMFB_ERR_PROJFUNC, "projfunc diverged (non-finite values)");
+  return NMFB_OK;
+}

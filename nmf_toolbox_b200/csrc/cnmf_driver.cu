@@ -1,0 +1,5 @@
+#include "engine.cuh"
+extern "C" int nmfb_cnmf(nmfb_handle* h, int K, int T, const nmfb_config* cfg, float* W_out, float* H_out,
+                         double* cost_out, int* n_cost) {
+  return h ? h->fail(NMFB_ERR_UNSUPPORTED, "cnmf: not built yet") : NMFB_ERR_INVALID_ARGUMENT;
+}

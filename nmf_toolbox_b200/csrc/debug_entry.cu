@@ -33,13 +33,13 @@ int nmfb_debug_gemm_store(const nmfb_debug_mat* X0, const nmfb_debug_mat* Y0, lo
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   GemmLaunch L;
   GemmOperand x0{{X0->base, X0->inner, X0->outer, X0->pitch}, X0->mn_major != 0};
-  Mat2D y0{Y0->base, Y0->inner, Y0->outer, Y0->pitch};
+  GemmOperand y0{{Y0->base, Y0->inner, Y0->outer, Y0->pitch}, Y0->mn_major != 0};
   GemmOperand x1{};
-  Mat2D y1{};
+  GemmOperand y1{};
   const bool two = X1 && X1->base;
   if (two) {
     x1 = GemmOperand{{X1->base, X1->inner, X1->outer, X1->pitch}, X1->mn_major != 0};
-    y1 = Mat2D{Y1->base, Y1->inner, Y1->outer, Y1->pitch};
+    y1 = GemmOperand{{Y1->base, Y1->inner, Y1->outer, Y1->pitch}, Y1->mn_major != 0};
   }
   std::string e = plan_gemm(&L, x0, y0, kdim0, two ? &x1 : nullptr, two ? &y1 : nullptr, kdim1, rows,
                             ncols, splits, sms);
@@ -66,9 +66,9 @@ int nmfb_debug_gemm_hupdate(const nmfb_debug_mat* X0, const nmfb_debug_mat* Y0, 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   GemmLaunch L;
   GemmOperand x0{{X0->base, X0->inner, X0->outer, X0->pitch}, X0->mn_major != 0};
-  Mat2D y0{Y0->base, Y0->inner, Y0->outer, Y0->pitch};
+  GemmOperand y0{{Y0->base, Y0->inner, Y0->outer, Y0->pitch}, Y0->mn_major != 0};
   GemmOperand x1{{X1->base, X1->inner, X1->outer, X1->pitch}, X1->mn_major != 0};
-  Mat2D y1{Y1->base, Y1->inner, Y1->outer, Y1->pitch};
+  GemmOperand y1{{Y1->base, Y1->inner, Y1->outer, Y1->pitch}, Y1->mn_major != 0};
   std::string e = plan_gemm(&L, x0, y0, kdim0, &x1, &y1, kdim1, rows, ncols, 1, sms);
   if (!e.empty()) return fail(err, errlen, e);
   L.args.Hm = Hm;
@@ -77,7 +77,7 @@ int nmfb_debug_gemm_hupdate(const nmfb_debug_mat* X0, const nmfb_debug_mat* Y0, 
   L.args.ldh = ldh;
   L.args.ldc = ldc;
   L.args.lambda = lambda;
-  L.args.partials = partials;
+  L.args.scal = partials;
   e = launch_gemm(L, EPI_HUPDATE, 0);
   if (!e.empty()) return fail(err, errlen, e);
   cudaError_t ce = cudaDeviceSynchronize();

@@ -1,0 +1,216 @@
+// Engine helpers: planned GEMMs, Gram matrices, V preparation, host<->device
+// transfers in the reference's (MATLAB, column-major) layouts.
+#include "engine.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "ew_kernels.cuh"
+
+namespace nmfb {
+
+int check_launch(nmfb_handle* h, const char* what) {
+  ++h->launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return h->fail(NMFB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  return NMFB_OK;
+}
+
+dim3 vec_grid(int len, int nvec, int threads) {
+  int bx = (len + threads * 4 - 1) / (threads * 4);
+  bx = std::max(1, std::min(bx, 64));
+  return dim3(bx, nvec, 1);
+}
+
+static int plan_common(nmfb_handle* h, GemmOp* op, const MatRef& X0, const MatRef& Y0,
+                       long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1,
+                       int rows, int ncols, int splits_hint) {
+  GemmOperand x0 = operand(X0), y0 = operand(Y0), x1{}, y1{};
+  if (X1) {
+    x1 = operand(*X1);
+    y1 = operand(*Y1);
+  }
+  std::string e = plan_gemm(&op->L, x0, y0, kdim0, X1 ? &x1 : nullptr, X1 ? &y1 : nullptr, kdim1,
+                            rows, ncols, splits_hint, h->num_sms);
+  if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "plan_gemm: %s", e.c_str());
+  op->splits = static_cast<int>(op->L.grid.z);
+  op->planned = true;
+  return NMFB_OK;
+}
+
+int plan_store(nmfb_handle* h, Arena* ar, GemmOp* op, const MatRef& X0, const MatRef& Y0,
+               long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1, int rows,
+               int ncols, float* out0, float* out1, long long ldo, bool allow_split,
+               const int* stop) {
+  op->epi = EPI_STORE;
+  NMFB_TRY(plan_common(h, op, X0, Y0, kdim0, X1, Y1, kdim1, rows, ncols, allow_split ? 0 : 1));
+  GemmArgs& a = op->L.args;
+  a.stop = stop;
+  a.out1 = out1;
+  a.ldo = ldo;
+  op->final0 = out0;
+  op->count = static_cast<long long>(ncols) * ldo;
+  if (op->splits > 1) {
+    NMFB_TRY(ar->alloc(h, &op->parts, static_cast<size_t>(op->splits) * op->count));
+    a.out0 = op->parts;
+    a.split_stride = op->count;
+  } else {
+    a.out0 = out0;
+    a.split_stride = 0;
+  }
+  return NMFB_OK;
+}
+
+int plan_fused(nmfb_handle* h, GemmOp* op, int epi, const MatRef& X0, const MatRef& Y0,
+               long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1, int rows,
+               int ncols, int ncols_valid, const int* stop) {
+  op->epi = epi;
+  NMFB_TRY(plan_common(h, op, X0, Y0, kdim0, X1, Y1, kdim1, rows, ncols, 1));
+  op->L.args.stop = stop;
+  op->L.args.ncols_valid = ncols_valid;
+  return NMFB_OK;
+}
+
+int run_gemm(nmfb_handle* h, const GemmOp& op) {
+  if (!op.planned) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "internal: GEMM not planned");
+  std::string e = launch_gemm(op.L, op.epi, h->stream);
+  ++h->launches;
+  if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "%s", e.c_str());
+  if (op.epi == EPI_STORE && op.splits > 1) {
+    const int threads = 256;
+    const int blocks = static_cast<int>(std::min<long long>((op.count + threads - 1) / threads, 4096));
+    split_reduce_kernel<<<blocks, threads, 0, h->stream>>>(op.parts, op.splits, op.count, op.final0,
+                                                           op.count, op.L.args.stop);
+    NMFB_TRY(check_launch(h, "split_reduce"));
+  }
+  return NMFB_OK;
+}
+
+int plan_gram(nmfb_handle* h, Arena* ar, GramOp* op, const float* Mt, int nvec, int len,
+              long long ld, const int* stop) {
+  op->nvec = nvec;
+  NMFB_TRY(ar->alloc(h, &op->g32, static_cast<size_t>(nvec) * nvec));
+  NMFB_TRY(ar->alloc(h, &op->gtf, static_cast<size_t>(nvec) * nvec));
+  MatRef M{Mt, len, nvec, ld, false};
+  op->g.epi = EPI_STORE;
+  NMFB_TRY(plan_common(h, &op->g, M, M, len, nullptr, nullptr, 0, nvec, nvec, 0));
+  GemmArgs& a = op->g.L.args;
+  a.stop = stop;
+  a.ldo = nvec;
+  op->g.count = static_cast<long long>(nvec) * nvec;
+  NMFB_TRY(ar->alloc(h, &op->g.parts, static_cast<size_t>(op->g.splits) * op->g.count));
+  a.out0 = op->g.parts;
+  a.split_stride = op->g.count;
+  return NMFB_OK;
+}
+
+int run_gram(nmfb_handle* h, const GramOp& op, const int* stop) {
+  std::string e = launch_gemm(op.g.L, EPI_STORE, h->stream);
+  ++h->launches;
+  if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "%s", e.c_str());
+  const int count = op.nvec * op.nvec;
+  gram_reduce_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(op.g.parts, op.g.splits, count,
+                                                                 op.g32, op.gtf, count, stop);
+  return check_launch(h, "gram_reduce");
+}
+
+// ---------------------------------------------------------------- V
+int compute_v_stats(nmfb_handle* h, bool want_log, VStats* out, double** dev_stats_out,
+                    unsigned int** dev_max_out, Arena* ar) {
+  double* st = nullptr;
+  unsigned int* su = nullptr;
+  NMFB_TRY(ar->alloc(h, &st, 4));
+  NMFB_TRY(ar->alloc(h, &su, 2));
+  const int blocks = std::min(h->n, h->num_sms * 8);
+  v_stats_kernel<<<blocks, 256, 0, h->stream>>>(h->Vraw, h->m, h->n, h->ldv, st, su, want_log ? 1 : 0);
+  NMFB_TRY(check_launch(h, "v_stats"));
+  double hs[4];
+  unsigned int hu[2];
+  NMFB_CUDA(h, cudaMemcpyAsync(hs, st, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
+  NMFB_CUDA(h, cudaMemcpyAsync(hu, su, sizeof(hu), cudaMemcpyDeviceToHost, h->stream));
+  NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  out->sumsq = hs[0];
+  out->sum = hs[1];
+  out->sumlog = hs[2];
+  std::memcpy(&out->vmax, &hu[0], 4);
+  out->any_negative = hu[1] != 0;
+  if (dev_stats_out) *dev_stats_out = st;
+  if (dev_max_out) *dev_max_out = su;
+  return NMFB_OK;
+}
+
+int prepare_v_work(nmfb_handle* h, bool divide_by_max, bool round, double* sumsq_dev,
+                   const unsigned int* maxbits_dev) {
+  const size_t bytes = static_cast<size_t>(h->n) * h->ldv * sizeof(float);
+  if (h->Vwork == nullptr || h->Vwork_bytes < bytes) {
+    if (h->Vwork) cudaFree(h->Vwork);
+    h->Vwork = nullptr;
+    NMFB_CUDA(h, cudaMalloc(&h->Vwork, bytes));
+    h->Vwork_bytes = bytes;
+  }
+  const int blocks = std::min(h->n, h->num_sms * 8);
+  v_prepare_kernel<<<blocks, 256, 0, h->stream>>>(h->Vraw, h->Vwork, h->m, h->n, h->ldv, h->ldv,
+                                                  divide_by_max ? maxbits_dev : nullptr,
+                                                  round ? 1 : 0, sumsq_dev);
+  return check_launch(h, "v_prepare");
+}
+
+// ---------------------------------------------------------------- transfers
+int upload_colmajor(nmfb_handle* h, const float* host, int rows, int cols, float* dev, long long ld) {
+  NMFB_CUDA(h, cudaMemcpy2DAsync(dev, ld * sizeof(float), host, static_cast<size_t>(rows) * sizeof(float),
+                                 static_cast<size_t>(rows) * sizeof(float), cols,
+                                 cudaMemcpyHostToDevice, h->stream));
+  return NMFB_OK;
+}
+int download_colmajor(nmfb_handle* h, const float* dev, long long ld, int rows, int cols, float* host) {
+  NMFB_CUDA(h, cudaMemcpy2DAsync(host, static_cast<size_t>(rows) * sizeof(float), dev,
+                                 ld * sizeof(float), static_cast<size_t>(rows) * sizeof(float), cols,
+                                 cudaMemcpyDeviceToHost, h->stream));
+  NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NMFB_OK;
+}
+
+int upload_H(nmfb_handle* h, Arena* ar, const float* host, int K, int n, float* Hm, long long ldh) {
+  float* tmp = nullptr;  // [n][K] as the host has it
+  NMFB_TRY(ar->alloc(h, &tmp, static_cast<size_t>(n) * K));
+  NMFB_CUDA(h, cudaMemcpyAsync(tmp, host, static_cast<size_t>(n) * K * sizeof(float),
+                               cudaMemcpyHostToDevice, h->stream));
+  dim3 grid((n + 31) / 32, (K + 31) / 32);
+  transpose_kernel<<<grid, dim3(32, 8), 0, h->stream>>>(tmp, K, Hm, ldh, K, n);
+  return check_launch(h, "transpose(H in)");
+}
+int download_H(nmfb_handle* h, const float* Hm, long long ldh, int K, int n, float* host) {
+  float* tmp = nullptr;
+  NMFB_CUDA(h, cudaMalloc(&tmp, static_cast<size_t>(n) * K * sizeof(float)));
+  dim3 grid((K + 31) / 32, (n + 31) / 32);
+  // dst[r = j][c = k] = src[c = k][r = j]
+  transpose_kernel<<<grid, dim3(32, 8), 0, h->stream>>>(Hm, ldh, tmp, K, n, K);
+  int rc = check_launch(h, "transpose(H out)");
+  if (rc == NMFB_OK) {
+    cudaError_t e = cudaMemcpyAsync(host, tmp, static_cast<size_t>(n) * K * sizeof(float),
+                                    cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = h->fail(NMFB_ERR_CUDA, "download H: %s", cudaGetErrorString(e));
+  }
+  cudaFree(tmp);
+  return rc;
+}
+
+// splitmix64 -> uniform (0,1); stands in for MATLAB's rand (nmf.m:277,298).
+void fill_uniform(std::vector<float>& v, unsigned long long seed, bool clamp_eps) {
+  unsigned long long s = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+  for (float& x : v) {
+    s += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    float u = static_cast<float>((z >> 40) + 1) * (1.0f / 16777218.0f);
+    if (clamp_eps) u = std::max(u, 2.220446049250313e-16f);
+    x = u;
+  }
+}
+
+}  // namespace nmfb

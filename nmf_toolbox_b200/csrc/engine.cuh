@@ -1,0 +1,159 @@
+// Host-side engine shared by the algorithm drivers: the handle, device memory,
+// planned GEMM operations and the small-kernel launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/nmfb200.h"
+#include "gemm_host.cuh"
+
+namespace nmfb {
+
+struct Comm;  // nccl communicator wrapper (comm.cu)
+
+inline int round_up(int x, int q) { return (x + q - 1) / q * q; }
+inline long long round_up_ll(long long x, long long q) { return (x + q - 1) / q * q; }
+
+}  // namespace nmfb
+
+struct NmfSession;  // nmf_driver.cu
+
+struct nmfb_handle {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  long long launches = 0;
+
+  // V as given (uploaded copy or adopted device pointer)
+  const float* Vraw = nullptr;
+  float* Vown = nullptr;
+  int m = 0, n = 0;
+  long long ldv = 0;
+  // working copy (tf32-rounded / rescaled), allocated on demand, same shape as Vraw
+  float* Vwork = nullptr;
+  size_t Vwork_bytes = 0;
+
+  nmfb::Comm* comm = nullptr;
+  NmfSession* sess = nullptr;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+namespace nmfb {
+
+#define NMFB_CUDA(h, call)                                                                    \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return (h)->fail(NMFB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                       __FILE__, __LINE__);                                                   \
+  } while (0)
+
+#define NMFB_TRY(expr)          \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != NMFB_OK) return rc__; \
+  } while (0)
+
+// Device allocations that live as long as one algorithm call / session.
+struct Arena {
+  std::vector<void*> ptrs;
+  ~Arena() { release(); }
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+  }
+  template <class T>
+  int alloc(nmfb_handle* h, T** out, size_t count) {
+    void* p = nullptr;
+    const size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
+    NMFB_CUDA(h, cudaMalloc(&p, bytes ? bytes : 256));
+    ptrs.push_back(p);
+    NMFB_CUDA(h, cudaMemsetAsync(p, 0, bytes ? bytes : 256, h->stream));
+    *out = static_cast<T*>(p);
+    return NMFB_OK;
+  }
+};
+
+// One planned panel_gemm (tensor maps are built once; buffers never move).
+struct GemmOp {
+  GemmLaunch L;
+  int epi = EPI_STORE;
+  int splits = 1;
+  float* parts = nullptr;   // split-K slabs (EPI_STORE, splits > 1)
+  float* final0 = nullptr;  // where the reduced phase-0 result goes
+  long long count = 0;      // elements per slab
+  bool planned = false;
+};
+
+struct MatRef {
+  const float* base;
+  long long inner, outer, pitch;
+  bool mn;
+};
+inline GemmOperand operand(const MatRef& r) {
+  return GemmOperand{{r.base, r.inner, r.outer, r.pitch}, r.mn};
+}
+
+// out0 = X0 * Y0' (+ out1 = X1 * Y1').  With allow_split the contraction of
+// phase 0 may be cut over several CTAs (EPI_STORE only); the slabs are summed
+// into out0 by run_gemm.
+int plan_store(nmfb_handle* h, Arena* ar, GemmOp* op, const MatRef& X0, const MatRef& Y0,
+               long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1, int rows,
+               int ncols, float* out0, float* out1, long long ldo, bool allow_split,
+               const int* stop);
+int plan_fused(nmfb_handle* h, GemmOp* op, int epi, const MatRef& X0, const MatRef& Y0,
+               long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1, int rows,
+               int ncols, int ncols_valid, const int* stop);
+int run_gemm(nmfb_handle* h, const GemmOp& op);
+
+// Gram matrix G = M M' of a factor stored as nvec contiguous vectors of length len
+// (nvec multiple of 32): fp32 result + tf32-rounded copy.
+struct GramOp {
+  GemmOp g;
+  float* g32 = nullptr;
+  float* gtf = nullptr;
+  int nvec = 0;
+};
+int plan_gram(nmfb_handle* h, Arena* ar, GramOp* op, const float* Mt, int nvec, int len,
+              long long ld, const int* stop);
+int run_gram(nmfb_handle* h, const GramOp& op, const int* stop);
+
+dim3 vec_grid(int len, int nvec, int threads = 256);
+
+// V preparation
+struct VStats {
+  double sumsq = 0, sum = 0, sumlog = 0;
+  float vmax = 0;
+  bool any_negative = false;
+};
+int compute_v_stats(nmfb_handle* h, bool want_log, VStats* out, double** dev_stats_out,
+                    unsigned int** dev_max_out, Arena* ar);
+// Vwork = tf32(V / max) ; returns sum of squares of the working copy through *sumsq_dev (device).
+int prepare_v_work(nmfb_handle* h, bool divide_by_max, bool round, double* sumsq_dev,
+                   const unsigned int* maxbits_dev);
+
+int upload_colmajor(nmfb_handle* h, const float* host, int rows, int cols, float* dev, long long ld);
+int download_colmajor(nmfb_handle* h, const float* dev, long long ld, int rows, int cols, float* host);
+// H: host K x n column-major  <->  device row-major [Kp][ldh]
+int upload_H(nmfb_handle* h, Arena* ar, const float* host, int K, int n, float* Hm, long long ldh);
+int download_H(nmfb_handle* h, const float* Hm, long long ldh, int K, int n, float* host);
+void fill_uniform(std::vector<float>& v, unsigned long long seed, bool clamp_eps);
+
+int check_launch(nmfb_handle* h, const char* what);
+
+}  // namespace nmfb

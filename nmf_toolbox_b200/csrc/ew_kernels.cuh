@@ -1,0 +1,528 @@
+// Vectorised-HBM / warp-shuffle kernels around the tensor-core contractions:
+// data preparation, the element-wise halves of the multiplicative updates, the
+// column / row reductions they need, the cost and stop test, the convolutive
+// shift-and-fold, and Hoyer's projection.  Reductions accumulate in fp64.
+//
+// Device layouts (all fp32):
+//   V   [n][ldv]    column-major m x n (as MATLAB supplies it), ldv % 4 == 0
+//   W   [Kp][ldw]   column-major m x K;   column k is contiguous
+//   H   [Kp][ldh]   ROW-major K x n;      row k is contiguous
+// so "vector c of a factor" (a column of W or a row of H) is always contiguous.
+// Kp = K rounded up to 32; padding vectors are all-zero and stay zero.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "ptx.cuh"
+
+namespace nmfb {
+
+#ifndef NMFB_EPS
+#define NMFB_EPS 2.220446049250313e-16f
+#endif
+
+#define NMFB_STOP_GUARD(stop) \
+  if ((stop) != nullptr && *(stop) != 0) return
+
+// ---------------------------------------------------------------- reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// Block-wide sum of NV doubles per thread; result valid in thread 0.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* sh /* [32*NV] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();  // protect sh from a previous use
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sh[warp * NV + i] = v[i];
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double x = lane < nw ? sh[lane * NV + i] : 0.0;
+      v[i] = warp_sum(x);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- V preparation
+// stats[0] += sum v^2, [1] += sum v, [2] += sum v*log(v); stats_u[0] = max bits, stats_u[1] = any negative
+__global__ void v_stats_kernel(const float* __restrict__ V, int m, int n, long long ldv,
+                               double* stats, unsigned int* stats_u, int want_log) {
+  __shared__ double sh[32 * 3];
+  double acc[3] = {0.0, 0.0, 0.0};
+  float mx = 0.f;
+  bool neg = false;
+  for (int j = blockIdx.x; j < n; j += gridDim.x) {
+    const float* col = V + static_cast<long long>(j) * ldv;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      const float v = col[i];
+      acc[0] += static_cast<double>(v) * v;
+      acc[1] += v;
+      if (want_log) acc[2] += static_cast<double>(v * logf(v));
+      mx = fmaxf(mx, v);
+      neg |= v < 0.f;
+    }
+  }
+  block_sum<3>(acc, sh);
+  if (threadIdx.x == 0) {
+    atomicAdd(stats + 0, acc[0]);
+    atomicAdd(stats + 1, acc[1]);
+    atomicAdd(stats + 2, acc[2]);
+  }
+  const unsigned int mb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(mx, 0.f)));
+  const bool anyneg = __any_sync(0xffffffffu, neg);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(stats_u, mb);
+    if (anyneg) atomicOr(stats_u + 1, 1u);
+  }
+}
+
+// Vt = tf32_rn(V / div) (div = 1: plain rounding); sumsq += sum Vt^2.
+__global__ void v_prepare_kernel(const float* __restrict__ V, float* __restrict__ Vt, int m, int n,
+                                 long long ldv_in, long long ldv_out, const unsigned int* maxbits,
+                                 int do_round, double* sumsq) {
+  __shared__ double sh[32];
+  const float div = maxbits ? __uint_as_float(*maxbits) : 1.f;
+  double acc[1] = {0.0};
+  for (int j = blockIdx.x; j < n; j += gridDim.x) {
+    const float* col = V + static_cast<long long>(j) * ldv_in;
+    float* out = Vt + static_cast<long long>(j) * ldv_out;
+    for (int i = threadIdx.x; i < ldv_out; i += blockDim.x) {
+      float v = 0.f;
+      if (i < m) {
+        v = col[i];
+        if (maxbits) v = v / div;
+        if (do_round) v = tf32_rn(v);
+      }
+      out[i] = v;
+      acc[0] += static_cast<double>(v) * v;
+    }
+  }
+  block_sum<1>(acc, sh);
+  if (threadIdx.x == 0 && sumsq) atomicAdd(sumsq, acc[0]);
+}
+
+// ---------------------------------------------------------------- generic helpers
+// dst[r][c] (ld_dst) = src[c][r] (ld_src) for r < rows, c < cols; rows beyond / cols beyond untouched.
+__global__ void transpose_kernel(const float* __restrict__ src, long long ld_src,
+                                 float* __restrict__ dst, long long ld_dst, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+    const int c = c0 + y, r = r0 + threadIdx.x;  // read src[c][r], r contiguous
+    tile[y][threadIdx.x] = (c < cols && r < rows) ? src[static_cast<long long>(c) * ld_src + r] : 0.f;
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+    const int r = r0 + y, c = c0 + threadIdx.x;  // write dst[r][c], c contiguous
+    if (r < rows && c < cols) dst[static_cast<long long>(r) * ld_dst + c] = tile[threadIdx.x][y];
+  }
+}
+
+// dst = tf32_rn(src) over nvec vectors of length len
+__global__ void round_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int nvec,
+                                  int len, long long ld, const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  for (int c = blockIdx.y; c < nvec; c += gridDim.y)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x)
+      dst[c * ld + i] = tf32_rn(src[c * ld + i]);
+}
+
+// out_sum[c] += sum_i M[c][i];  out_sq[c] += sum_i M[c][i]^2   (either may be null)
+__global__ void vec_sums_kernel(const float* __restrict__ M, int nvec, int len, long long ld,
+                                double* out_sum, double* out_sq, const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  __shared__ double sh[64];
+  const int c = blockIdx.y;
+  const float* v = M + static_cast<long long>(c) * ld;
+  double acc[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
+    const float x = v[i];
+    acc[0] += x;
+    acc[1] += static_cast<double>(x) * x;
+  }
+  block_sum<2>(acc, sh);
+  if (threadIdx.x == 0) {
+    if (out_sum) atomicAdd(out_sum + c, acc[0]);
+    if (out_sq) atomicAdd(out_sq + c, acc[1]);
+  }
+}
+
+// Sum split-K slabs of a Kp x Kp Gram matrix; write fp32 and tf32-rounded copies.
+__global__ void gram_reduce_kernel(const float* __restrict__ parts, int splits, long long slab,
+                                   float* __restrict__ g32, float* __restrict__ gtf, int count,
+                                   const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += parts[z * slab + i];
+  g32[i] = s;
+  gtf[i] = tf32_rn(s);
+}
+// Same for a general matrix with split-K slabs (fp32 result only).
+__global__ void split_reduce_kernel(const float* __restrict__ parts, int splits, long long slab,
+                                    float* __restrict__ out, long long count, const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += parts[z * slab + i];
+    out[i] = s;
+  }
+}
+
+// ---------------------------------------------------------------- W update
+// ab[c] += <W_c, A_c>, ab[Kp + c] += <W_c, B_c>      (the diag(diag(.)) terms, nmf.m:149-153)
+__global__ void w_dots_kernel(const float* __restrict__ W, const float* __restrict__ A,
+                              const float* __restrict__ B, int m, long long ld, int Kp, double* ab,
+                              const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  __shared__ double sh[64];
+  const int c = blockIdx.y;
+  const long long off = static_cast<long long>(c) * ld;
+  double acc[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const float w = W[off + i];
+    acc[0] += static_cast<double>(w) * A[off + i];
+    if (B) acc[1] += static_cast<double>(w) * B[off + i];
+  }
+  block_sum<2>(acc, sh);
+  if (threadIdx.x == 0) {
+    atomicAdd(ab + c, acc[0]);
+    if (B) atomicAdd(ab + Kp + c, acc[1]);
+  }
+}
+
+// Per-column coefficients of the generic W step
+//   W' = W .* (A + W*p_c) ./ max(Bterm + W*q_c + lambda, eps)
+// Euclidean (nmf.m:149-150): p = <W_c,B_c>, q = <W_c,A_c>, Bterm = B
+// KL        (nmf.m:152-153): p = hs_c*ws_c, q = <W_c,R_c>, Bterm = hs_c
+enum { WSTEP_EUCLID = 0, WSTEP_KL = 1, WSTEP_PLAIN = 2 };
+__global__ void w_coef_kernel(int mode, int Kp, const double* ab, const double* hs, const double* ws,
+                              float* p, float* q, float* bvec, const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Kp) return;
+  if (mode == WSTEP_EUCLID) {
+    p[c] = static_cast<float>(ab[Kp + c]);
+    q[c] = static_cast<float>(ab[c]);
+    bvec[c] = 0.f;
+  } else if (mode == WSTEP_KL) {
+    p[c] = static_cast<float>(hs[c] * ws[c]);
+    q[c] = static_cast<float>(ab[c]);
+    bvec[c] = static_cast<float>(hs[c]);
+  } else {
+    p[c] = 0.f;
+    q[c] = 0.f;
+    bvec[c] = 0.f;
+  }
+}
+
+// In place on W; norm2[c] += sum W'^2.  B may be null (then Bterm = bvec[c]).
+__global__ void w_update_kernel(float* __restrict__ W, const float* __restrict__ A,
+                                const float* __restrict__ B, int m, long long ld,
+                                const float* __restrict__ p, const float* __restrict__ q,
+                                const float* __restrict__ bvec, float lambda, double* norm2,
+                                const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  __shared__ double sh[32];
+  const int c = blockIdx.y;
+  const long long off = static_cast<long long>(c) * ld;
+  const float pc = p[c], qc = q[c], bc = bvec[c];
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const float w = W[off + i];
+    const float neg = A[off + i] + w * pc;
+    const float pos = (B ? B[off + i] : bc) + w * qc;
+    const float wn = w * (neg / fmaxf(pos + lambda, NMFB_EPS));
+    W[off + i] = wn;
+    acc[0] += static_cast<double>(wn) * wn;
+  }
+  block_sum<1>(acc, sh);
+  if (threadIdx.x == 0 && norm2) atomicAdd(norm2 + c, acc[0]);
+}
+
+// Column normalisation + tf32 copy + column sums.
+//   T == 0: no scaling (copy / round only)
+//   T == 1 (nmf.m:133,169):    W_c *= 1/sqrt(norm2[c])
+//   T >= 1, cnmf (cnmf.m:160-162,196-199): W(:,k,:) /= sqrt(sum_t norm2[k + K*t]) / T
+// hscale (optional, cnmf.m:163): receives the per-basis norm so H can be compensated at init.
+__global__ void w_normalize_kernel(float* __restrict__ W, float* __restrict__ Wt, int m, long long ld,
+                                   int K, int T, int cnmf_style, const double* norm2, double* wsum,
+                                   float* hscale, const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  __shared__ double sh[32];
+  const int c = blockIdx.y;  // < K*max(T,1)
+  const long long off = static_cast<long long>(c) * ld;
+  float mul = 1.f, div = 1.f;
+  if (T >= 1) {
+    if (cnmf_style) {
+      double s = 0.0;
+      const int k = c % K;
+      for (int t = 0; t < T; ++t) s += norm2[k + K * t];
+      div = static_cast<float>(sqrt(s) / T);
+      if (hscale && c < K && blockIdx.x == 0 && threadIdx.x == 0) hscale[c] = div;
+    } else {
+      mul = static_cast<float>(1.0 / sqrt(norm2[c]));
+    }
+  }
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    float w = W[off + i];
+    if (T >= 1) w = cnmf_style ? (w / div) : (w * mul);
+    W[off + i] = w;
+    Wt[off + i] = tf32_rn(w);
+    acc[0] += w;
+  }
+  block_sum<1>(acc, sh);
+  if (threadIdx.x == 0 && wsum) atomicAdd(wsum + c, acc[0]);
+}
+
+// H(k,:) *= scale[k] (cnmf.m:163), in place, + tf32 copy
+__global__ void row_scale_kernel(float* __restrict__ H, float* __restrict__ Ht, int len, long long ld,
+                                 const float* scale, int invert) {
+  const int c = blockIdx.y;
+  const float s = invert ? 1.f / scale[c] : scale[c];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
+    const float h = H[c * ld + i] * s;
+    H[c * ld + i] = h;
+    if (Ht) Ht[c * ld + i] = tf32_rn(h);
+  }
+}
+
+// ---------------------------------------------------------------- cost + stop test
+struct CostArgs {
+  int mode;             // 0 Euclid trace, 1 Euclid direct (scal[0] = sum (V-Vhat)^2), 2 KL, 3 sparsity terms only
+  int iter;             // 0-based index into cost[]
+  int Kp;
+  const float* GW;      // Kp x Kp fp32 Gram matrices (trace mode)
+  const float* GH;
+  double vsq;           // sum V^2                 (Euclid)
+  const double* vstats; // [1] sum V, [2] sum V log V (KL)
+  double* scal;         // accumulators filled by the H-update / cost epilogues; reset here
+  const double* wsum;   // per-column sums of W (Kp_w entries)
+  int n_wsum;
+  double lambda_w, lambda_h;
+  double tolerance;
+  double* cost;
+  int* stop;            // [0] stop flag, [1] number of valid cost entries
+  double scale;         // multi-GPU: scal/GH are already all-reduced; nothing to do here
+};
+__global__ void cost_kernel(CostArgs a) {
+  if (a.stop[0] != 0) return;
+  __shared__ double sh[64];
+  double acc[2] = {0.0, 0.0};
+  if (a.mode == 0) {
+    for (int i = threadIdx.x; i < a.Kp * a.Kp; i += blockDim.x)
+      acc[0] += static_cast<double>(a.GW[i]) * a.GH[i];
+  }
+  for (int i = threadIdx.x; i < a.n_wsum; i += blockDim.x) acc[1] += a.wsum[i];
+  block_sum<2>(acc, sh);
+  if (threadIdx.x != 0) return;
+  double c = 0.0;
+  if (a.mode == 0) {
+    c = 0.5 * (a.vsq - 2.0 * a.scal[0] + acc[0]);
+  } else if (a.mode == 1) {
+    c = 0.5 * a.scal[2];
+  } else if (a.mode == 2) {
+    c = a.vstats[2] - a.scal[2] - a.vstats[1] + a.scal[3];
+  }
+  c += a.lambda_w * acc[1] + a.lambda_h * a.scal[1];
+  a.cost[a.iter] = c;
+  a.stop[1] = a.iter + 1;
+  if (a.iter > 0) {
+    const double prev = a.cost[a.iter - 1];
+    if (c < prev && prev - c < a.tolerance) a.stop[0] = 1;  // nmf.m:221-224
+  }
+  a.scal[0] = a.scal[1] = a.scal[2] = a.scal[3] = 0.0;
+}
+
+// ---------------------------------------------------------------- convolutive helpers
+// Hs[k + K*t][j] = tf32(H[k][j - t]) for j >= t, else 0   (cnmf.m:188, RFD.m:37)
+__global__ void hstack_kernel(const float* __restrict__ H, float* __restrict__ Hs, int K, int T, int n,
+                              long long ld, const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  const int c = blockIdx.y;  // 0 .. K*T-1
+  const int k = c % K, t = c / K;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+    Hs[c * ld + j] = (j >= t) ? tf32_rn(H[k * ld + (j - t)]) : 0.f;
+}
+
+// neg[k][j] = sum_t P[k+K*t][j+t], pos likewise from D (cnmf.m:218-227, euclidean);
+// H <- H .* neg ./ max(pos + lambda, eps) (cnmf.m:231); scal[0] += <neg, tf32(Hnew)>, scal[1] += sum Hnew
+__global__ void fold_update_kernel(const float* __restrict__ P, const float* __restrict__ D,
+                                   float* __restrict__ H, int K, int T, int n, long long ld,
+                                   float lambda, int freeze, double* scal, const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  __shared__ double sh[64];
+  const int k = blockIdx.y;
+  double acc[2] = {0.0, 0.0};
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    float neg = 0.f, pos = 0.f;
+    for (int t = 0; t < T; ++t) {
+      if (j + t < n) {
+        const long long o = static_cast<long long>(k + K * t) * ld + j + t;
+        neg += P[o];
+        pos += D[o];
+      }
+    }
+    float h = H[k * ld + j];
+    if (!freeze) {
+      h = h * (neg / fmaxf(pos + lambda, NMFB_EPS));
+      H[k * ld + j] = h;
+    }
+    acc[0] += static_cast<double>(neg) * tf32_rn(h);
+    acc[1] += h;
+  }
+  block_sum<2>(acc, sh);
+  if (threadIdx.x == 0) {
+    atomicAdd(scal + 0, acc[0]);
+    atomicAdd(scal + 1, acc[1]);
+  }
+}
+
+// ---------------------------------------------------------------- nmfsc helpers
+// Xnew = X - step * (Dp - Dn)   (nmfsc.m:148,154 / 200,205)
+__global__ void grad_step_kernel(const float* __restrict__ X, const float* __restrict__ Dp,
+                                 const float* __restrict__ Dn, float* __restrict__ Xnew, int nvec,
+                                 int len, long long ld, const double* step) {
+  const float s = static_cast<float>(*step);
+  const int c = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
+    const long long o = static_cast<long long>(c) * ld + i;
+    Xnew[o] = X[o] - s * (Dp[o] - Dn[o]);
+  }
+}
+// plain multiplicative step X <- X .* N ./ max(D, eps)   (nmfsc.m:182,232)
+__global__ void mu_step_kernel(float* __restrict__ X, const float* __restrict__ N,
+                               const float* __restrict__ D, int len, long long ld) {
+  const int c = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
+    const long long o = static_cast<long long>(c) * ld + i;
+    X[o] = X[o] * (N[o] / fmaxf(D[o], NMFB_EPS));
+  }
+}
+// nmfsc.m:185-187: H rows -> unit L2, W columns scaled by the norms.  sq[c] = sum H_c^2.
+__global__ void renorm_pair_kernel(float* __restrict__ H, int n, long long ldh, float* __restrict__ W,
+                                   int m, long long ldw, const double* sq) {
+  const int c = blockIdx.y;
+  const float nrm = static_cast<float>(sqrt(sq[c]));
+  const float inv = 1.f / nrm;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    H[c * ldh + i] = inv * H[c * ldh + i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+    W[c * ldw + i] = W[c * ldw + i] * nrm;
+}
+
+// Hoyer's projection (projfunc.m:13-55, k2 and nn as given), one CTA per vector,
+// vector kept in global memory (L1/L2 resident), zero-set kept as per-thread bit masks.
+constexpr int kProjThreads = 512;
+constexpr int kProjMaskWords = 8;  // supports len <= 512 * 32 * 8 = 131072
+__global__ void __launch_bounds__(kProjThreads)
+projfunc_kernel(float* __restrict__ X, int len, long long ld, double k1, double k2, int nn,
+                int* iters_out, int* fail_flag) {
+  __shared__ double sh[32 * 3];
+  __shared__ double bc[4];
+  float* v = X + static_cast<long long>(blockIdx.x) * ld;
+  const int tid = threadIdx.x;
+  uint32_t zmask[kProjMaskWords];
+  uint32_t negmask[kProjMaskWords];  // signs when nn == 0
+#pragma unroll
+  for (int w = 0; w < kProjMaskWords; ++w) zmask[w] = negmask[w] = 0u;
+
+  // projfunc.m:16-22: v = s + (k1 - sum(s)) / N
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int e = tid, q = 0; e < len; e += kProjThreads, ++q) {
+    float s = v[e];
+    if (!nn && s < 0.f) {
+      negmask[q >> 5] |= 1u << (q & 31);
+      s = -s;
+      v[e] = s;
+    }
+    acc[0] += s;
+  }
+  block_sum<3>(acc, sh);
+  if (tid == 0) bc[0] = (k1 - acc[0]) / len;
+  __syncthreads();
+  double shift = bc[0];  // pending additive constant on all non-zeroed entries
+  int nz = 0;
+  int iters = 0;
+  for (int pass = 0; pass < 100000; ++pass) {
+    // sweep 1: apply pending shift, then a, b, c of projfunc.m:31-36
+    const double mid = k1 / (len - nz);
+    acc[0] = acc[1] = acc[2] = 0.0;
+    for (int e = tid, q = 0; e < len; e += kProjThreads, ++q) {
+      const bool z = (zmask[q >> 5] >> (q & 31)) & 1u;
+      float x = 0.f;
+      if (!z) {
+        x = static_cast<float>(static_cast<double>(v[e]) + shift);
+        v[e] = x;
+      }
+      const double w = z ? 0.0 : static_cast<double>(x) - mid;
+      acc[0] += w * w;
+      acc[1] += w * x;
+      acc[2] += static_cast<double>(x) * x;
+    }
+    block_sum<3>(acc, sh);
+    if (tid == 0) {
+      const double a = acc[0], b = 2.0 * acc[1], c = acc[2] - k2;
+      const double disc = b * b - 4.0 * a * c;
+      bc[0] = (-b + (disc > 0.0 ? sqrt(disc) : 0.0)) / (2.0 * a);  // real(sqrt(.)), projfunc.m:37
+    }
+    __syncthreads();
+    const double alphap = bc[0];
+    // sweep 2: v = alphap*w + v (projfunc.m:38); all(v >= 0)?; zero negatives, tempsum (49-51)
+    acc[0] = acc[1] = acc[2] = 0.0;  // [0] any negative, [1] zero count, [2] tempsum
+    for (int e = tid, q = 0; e < len; e += kProjThreads, ++q) {
+      const bool z = (zmask[q >> 5] >> (q & 31)) & 1u;
+      if (z) {
+        acc[1] += 1.0;
+        continue;
+      }
+      const float x0 = v[e];
+      const float x = static_cast<float>(alphap * (static_cast<double>(x0) - mid) + x0);
+      if (!(x >= 0.f)) acc[0] += 1.0;  // also catches NaN
+      if (x <= 0.f) {
+        zmask[q >> 5] |= 1u << (q & 31);
+        acc[1] += 1.0;
+        v[e] = x;  // finalised below only if the loop continues
+      } else {
+        v[e] = x;
+        acc[2] += x;
+      }
+    }
+    block_sum<3>(acc, sh);
+    if (tid == 0) {
+      bc[1] = acc[0];
+      bc[2] = acc[1];
+      bc[3] = acc[2];
+    }
+    __syncthreads();
+    iters = pass + 1;
+    if (bc[1] == 0.0) break;  // projfunc.m:40-44 (entries equal to 0 stay as they are)
+    nz = static_cast<int>(bc[2]);
+    if (!(bc[3] == bc[3]) || nz >= len) {  // NaN or everything zeroed: MATLAB would never return
+      if (tid == 0 && fail_flag) *fail_flag = 1;
+      break;
+    }
+    // projfunc.m:50-53: zero the set, spread (k1 - tempsum) over the rest (applied lazily in sweep 1)
+    for (int e = tid, q = 0; e < len; e += kProjThreads, ++q)
+      if ((zmask[q >> 5] >> (q & 31)) & 1u) v[e] = 0.f;
+    shift = (k1 - bc[3]) / (len - nz);
+    __syncthreads();
+  }
+  if (!nn) {  // projfunc.m:58-60
+    for (int e = tid, q = 0; e < len; e += kProjThreads, ++q)
+      if ((negmask[q >> 5] >> (q & 31)) & 1u) v[e] = -v[e];
+  }
+  if (tid == 0 && iters_out) iters_out[blockIdx.x] = iters;
+}
+
+}  // namespace nmfb

@@ -64,9 +64,9 @@ int choose_splits(int tiles, int nkb0, int num_sms, int* kb_per_split) {
   return splits;
 }
 
-std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const Mat2D& Y0, long long kdim0,
-                      const GemmOperand* X1, const Mat2D* Y1, long long kdim1, int rows, int ncols,
-                      int splits_hint, int num_sms) {
+std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const GemmOperand& Y0, long long kdim0,
+                      const GemmOperand* X1, const GemmOperand* Y1, long long kdim1, int rows,
+                      int ncols, int splits_hint, int num_sms) {
   if (ncols <= 0 || ncols % 32 != 0) return "plan_gemm: ncols must be a positive multiple of 32";
   std::memset(L, 0, sizeof(*L));
   GemmArgs& a = L->args;
@@ -77,6 +77,9 @@ std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const Mat2D& Y0, lon
   a.nkb1 = (X1 != nullptr) ? static_cast<int>((kdim1 + kBlockK - 1) / kBlockK) : 0;
   a.xmn0 = X0.mn_major ? 1 : 0;
   a.xmn1 = (X1 && X1->mn_major) ? 1 : 0;
+  a.ymn0 = Y0.mn_major ? 1 : 0;
+  a.ymn1 = (Y1 && Y1->mn_major) ? 1 : 0;
+  a.ncols_valid = ncols;
   const int tiles = (rows + kTileM - 1) / kTileM;
   const int chunks = (ncols + kMaxN - 1) / kMaxN;
   int splits = 1;
@@ -97,10 +100,14 @@ std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const Mat2D& Y0, lon
     return X.mn_major ? make_tmap(tm, X.m, 32, 32, true) : make_tmap(tm, X.m, kBlockK, kTileM, false);
   };
   if (!(e = xmap(&L->tmX0, X0)).empty()) return "X0 " + e;
-  if (!(e = make_tmap(&L->tmY0, Y0, kBlockK, a.box_n, false)).empty()) return "Y0 " + e;
+  auto ymap = [&](CUtensorMap* tm, const GemmOperand& Y) {
+    return Y.mn_major ? make_tmap(tm, Y.m, 32, 32, true)
+                      : make_tmap(tm, Y.m, kBlockK, a.box_n, false);
+  };
+  if (!(e = ymap(&L->tmY0, Y0)).empty()) return "Y0 " + e;
   if (X1) {
     if (!(e = xmap(&L->tmX1, *X1)).empty()) return "X1 " + e;
-    if (!(e = make_tmap(&L->tmY1, *Y1, kBlockK, a.box_n, false)).empty()) return "Y1 " + e;
+    if (!(e = ymap(&L->tmY1, *Y1)).empty()) return "Y1 " + e;
   } else {
     L->tmX1 = L->tmX0;
     L->tmY1 = L->tmY0;
@@ -108,25 +115,38 @@ std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const Mat2D& Y0, lon
   return "";
 }
 
+template <int EPI>
+static cudaError_t set_smem_attr() {
+  return cudaFuncSetAttribute(panel_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              kGemmSmemBytes);
+}
+
+template <int EPI>
+static void launch_one(const GemmLaunch& L, cudaStream_t stream) {
+  panel_gemm_kernel<EPI><<<L.grid, kGemmThreads, kGemmSmemBytes, stream>>>(L.tmX0, L.tmY0, L.tmX1,
+                                                                          L.tmY1, L.args);
+}
+
 std::string launch_gemm(const GemmLaunch& L, int epi, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&]() {
-    attr_err = cudaFuncSetAttribute(panel_gemm_kernel<EPI_STORE>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(panel_gemm_kernel<EPI_HUPDATE>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+    cudaError_t e[5] = {set_smem_attr<EPI_STORE>(), set_smem_attr<EPI_HUPDATE>(),
+                        set_smem_attr<EPI_RECON>(), set_smem_attr<EPI_RESID>(),
+                        set_smem_attr<EPI_KLQ>()};
+    for (cudaError_t x : e)
+      if (x != cudaSuccess) attr_err = x;
   });
   if (attr_err != cudaSuccess)
     return std::string("cudaFuncSetAttribute(panel_gemm): ") + cudaGetErrorString(attr_err);
-  if (epi == EPI_STORE) {
-    panel_gemm_kernel<EPI_STORE><<<L.grid, kGemmThreads, kGemmSmemBytes, stream>>>(
-        L.tmX0, L.tmY0, L.tmX1, L.tmY1, L.args);
-  } else {
-    if (L.grid.z != 1) return "launch_gemm: fused H update requires splits == 1";
-    panel_gemm_kernel<EPI_HUPDATE><<<L.grid, kGemmThreads, kGemmSmemBytes, stream>>>(
-        L.tmX0, L.tmY0, L.tmX1, L.tmY1, L.args);
+  if (epi != EPI_STORE && L.grid.z != 1) return "launch_gemm: fused epilogues require splits == 1";
+  switch (epi) {
+    case EPI_STORE: launch_one<EPI_STORE>(L, stream); break;
+    case EPI_HUPDATE: launch_one<EPI_HUPDATE>(L, stream); break;
+    case EPI_RECON: launch_one<EPI_RECON>(L, stream); break;
+    case EPI_RESID: launch_one<EPI_RESID>(L, stream); break;
+    case EPI_KLQ: launch_one<EPI_KLQ>(L, stream); break;
+    default: return "launch_gemm: unknown epilogue";
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return std::string("panel_gemm launch: ") + cudaGetErrorString(e);

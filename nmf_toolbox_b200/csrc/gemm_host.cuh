@@ -22,7 +22,7 @@ struct Mat2D {
 // Operand description for one phase of panel_gemm.
 struct GemmOperand {
   Mat2D m;
-  bool mn_major;  // X only: output rows run along the contiguous dimension
+  bool mn_major;  // the operand's rows (output rows for X, output columns for Y) are contiguous
 };
 
 // Returns an empty string on success, else an error message.
@@ -42,9 +42,9 @@ struct GemmLaunch {
 // Builds tensor maps + args for out = X0*Y0^T (+ second accumulator X1*Y1^T).
 //   rows  : valid rows of X (output rows);  ncols: output columns (multiple of 32)
 //   kdim0 : contraction length of phase 0;  kdim1: of phase 1 (0 = none)
-std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const Mat2D& Y0, long long kdim0,
-                      const GemmOperand* X1, const Mat2D* Y1, long long kdim1, int rows, int ncols,
-                      int splits_hint, int num_sms);
+std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const GemmOperand& Y0, long long kdim0,
+                      const GemmOperand* X1, const GemmOperand* Y1, long long kdim1, int rows,
+                      int ncols, int splits_hint, int num_sms);
 
 std::string launch_gemm(const GemmLaunch& L, int epi, cudaStream_t stream);
 

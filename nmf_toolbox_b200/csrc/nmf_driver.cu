@@ -1,0 +1,527 @@
+// nmf driver: the iteration loop of nmf.m (lines 143-225) for the Euclidean and
+// KL divergences, as a queue of device kernels with no host synchronisation
+// inside the loop.  Per iteration (nmf.m line numbers):
+//
+//   Euclidean                                       KL
+//   G_H = H H'                                      hs = H * 1                       (153)
+//   [cost of the previous iteration + stop test]    Q  = V ./ (W H)  [+ cost sums]   (152, 210)
+//   A = V H'   B = W G_H           (149-150)        [cost of the previous iteration + stop test]
+//   a_k = <W_k,A_k>  b_k = <W_k,B_k>                R  = Q H'   c_k = <W_k,R_k>      (152-153)
+//   W <- W.*(A + W b)./max(B + W a + lW, eps) (168) W <- W.*(R + W hs ws)./max(hs + W c + lW, eps)
+//   W <- W diag(1/|W_k|)               (169)        W <- W diag(1/|W_k|)
+//   G_W = W' W                                      Q  = V ./ (W H)                  (173, 183)
+//   H <- H.*(W'V)./max(G_W H + lH, eps) (180-199)   H <- H.*(W'Q)./max(ws + lH, eps) (183-199)
+//
+// The Euclidean cost 0.5*|V - W H|^2 (208) is evaluated through
+// 0.5*(|V|^2 - 2<W'V, H> + <G_W, G_H>) with the Gram matrices the updates need
+// anyway (or explicitly with cost_mode = NMFB_COST_DIRECT); it becomes
+// available once G_H of the *new* H exists, i.e. at the start of the next
+// iteration, and is finalised by one trailing Gram product after the last.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "comm.cuh"
+#include "engine.cuh"
+#include "ew_kernels.cuh"
+
+using namespace nmfb;
+
+struct NmfSession {
+  Arena ar;
+  int K = 0, Kp = 0, m = 0, n = 0;
+  long long ldw = 0, ldh = 0;
+  int divergence = NMFB_DIV_EUCLIDEAN;
+  bool W_fixed = false, H_fixed = false, direct_cost = false;
+  float lambda_w = 0.f, lambda_h = 0.f;
+  int maxiter = 100;
+  double tolerance = 1e-3;
+  int iters_enqueued = 0;
+  bool finalized = false;
+  double device_ms = 0.0;
+
+  float *Wm = nullptr, *Wt = nullptr, *Hm = nullptr, *Ht = nullptr;
+  float *A = nullptr, *B = nullptr, *Q = nullptr;
+  float *pcoef = nullptr, *qcoef = nullptr, *bvec = nullptr, *wsf = nullptr;
+  double *ab = nullptr, *norm2 = nullptr, *wsum = nullptr, *hs = nullptr, *scal = nullptr;
+  double *cost = nullptr, *vstats = nullptr;
+  int* stop = nullptr;
+  double vsq = 0.0;
+  const float* Vmma = nullptr;  // V as the tensor cores read it (tf32-rounded copy)
+
+  GramOp gramH, gramW;
+  GemmOp gemmA, gemmB, gemmH, gemmS, gemmR;
+  float* packed = nullptr;  // multi-GPU: [A | G_H | hs] contiguous fp32 for the single all-reduce
+  int* pinned = nullptr;    // host copy of stop[0..1]
+};
+
+namespace nmfdetail {
+
+struct D2FArgs {
+  const double* src;
+  float* dst;
+  int n;
+};
+__global__ void d2f_kernel(D2FArgs a, const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.n) a.dst[i] = static_cast<float>(a.src[i]);
+}
+
+int zero_async(nmfb_handle* h, void* p, size_t bytes) {
+  NMFB_CUDA(h, cudaMemsetAsync(p, 0, bytes, h->stream));
+  return NMFB_OK;
+}
+
+int normalize_defaults(const nmfb_config* in, nmfb_config* out) {
+  std::memset(out, 0, sizeof(*out));
+  if (in) *out = *in;
+  if (out->maxiter <= 0) out->maxiter = 100;           // nmf.m:404-406
+  if (!(out->tolerance > 0)) out->tolerance = 1e-3;    // nmf.m:409-411
+  if (out->W_sparsity < 0) out->W_sparsity = 0;        // nmf.m:321-333
+  if (out->H_sparsity < 0) out->H_sparsity = 0;
+  return 0;
+}
+
+}  // namespace nmfdetail
+using namespace nmfdetail;
+
+// ------------------------------------------------------------------ setup
+static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cfg_in) {
+  if (h->Vraw == nullptr) return h->fail(NMFB_ERR_NO_DATA, "nmf: call nmfb_set_V first");
+  if (K <= 0) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "nmf: num_basis_elems must be positive");
+  nmfb_config cfg;
+  normalize_defaults(cfg_in, &cfg);
+  switch (cfg.divergence) {
+    case NMFB_DIV_EUCLIDEAN:
+    case NMFB_DIV_KL:
+      break;
+    case NMFB_DIV_AB:
+      if (cfg.alpha == 0 && cfg.beta == 0)  // nmf.m:120-122
+        return h->fail(NMFB_ERR_AB_ZERO, "alpha = 0 and beta = 0 is not supported at this time.");
+      return h->fail(NMFB_ERR_UNSUPPORTED, "nmf: the AB divergence is outside the accelerated path");
+    case NMFB_DIV_IS:
+      return h->fail(NMFB_ERR_UNSUPPORTED, "nmf: the IS divergence is outside the accelerated path");
+    default:  // nmf.m:165-166 ('frobenius' included: nmf.m has no such case)
+      return h->fail(NMFB_ERR_DIVERGENCE,
+                     "No update equations defined for cost function with divergence type %d",
+                     cfg.divergence);
+  }
+  const int m = h->m, n = h->n;
+  s->K = K;
+  s->Kp = round_up(K, 32);
+  s->m = m;
+  s->n = n;
+  s->ldw = round_up(m, 4);
+  s->ldh = round_up(n, 4);
+  s->divergence = cfg.divergence;
+  s->W_fixed = cfg.W_fixed != 0;
+  s->H_fixed = cfg.H_fixed != 0;
+  s->direct_cost = cfg.cost_mode == NMFB_COST_DIRECT;
+  s->lambda_w = static_cast<float>(cfg.W_sparsity);
+  s->lambda_h = static_cast<float>(cfg.H_sparsity);
+  s->maxiter = cfg.maxiter;
+  s->tolerance = cfg.tolerance;
+  const int Kp = s->Kp;
+  const bool kl = s->divergence == NMFB_DIV_KL;
+  Arena* ar = &s->ar;
+
+  NMFB_TRY(ar->alloc(h, &s->Wm, static_cast<size_t>(Kp) * s->ldw));
+  NMFB_TRY(ar->alloc(h, &s->Wt, static_cast<size_t>(Kp) * s->ldw));
+  NMFB_TRY(ar->alloc(h, &s->Hm, static_cast<size_t>(Kp) * s->ldh));
+  NMFB_TRY(ar->alloc(h, &s->Ht, static_cast<size_t>(Kp) * s->ldh));
+  // packed = [A (Kp x ldw) | G_H (Kp x Kp, KL: unused) | ...]: one buffer so that a
+  // multi-GPU run can all-reduce it in a single call.
+  NMFB_TRY(ar->alloc(h, &s->packed, static_cast<size_t>(Kp) * s->ldw + static_cast<size_t>(Kp) * Kp));
+  s->A = s->packed;
+  NMFB_TRY(ar->alloc(h, &s->B, static_cast<size_t>(Kp) * s->ldw));
+  NMFB_TRY(ar->alloc(h, &s->pcoef, Kp));
+  NMFB_TRY(ar->alloc(h, &s->qcoef, Kp));
+  NMFB_TRY(ar->alloc(h, &s->bvec, Kp));
+  NMFB_TRY(ar->alloc(h, &s->wsf, Kp));
+  NMFB_TRY(ar->alloc(h, &s->ab, 2 * Kp));
+  NMFB_TRY(ar->alloc(h, &s->norm2, Kp));
+  NMFB_TRY(ar->alloc(h, &s->wsum, Kp));
+  NMFB_TRY(ar->alloc(h, &s->hs, Kp));
+  NMFB_TRY(ar->alloc(h, &s->scal, 4));
+  NMFB_TRY(ar->alloc(h, &s->cost, static_cast<size_t>(s->maxiter) + 1));
+  NMFB_TRY(ar->alloc(h, &s->stop, 2));
+  NMFB_CUDA(h, cudaMallocHost(&s->pinned, 2 * sizeof(int)));
+  s->pinned[0] = s->pinned[1] = 0;
+
+  // ---- initial factors (nmf.m:130-134; defaults nmf.m:277,298)
+  {
+    std::vector<float> tmp;
+    const float* Wsrc = cfg.W_init;
+    if (!Wsrc) {
+      tmp.resize(static_cast<size_t>(m) * K);
+      fill_uniform(tmp, cfg.seed * 2 + 1, true);
+      Wsrc = tmp.data();
+    }
+    NMFB_TRY(upload_colmajor(h, Wsrc, m, K, s->Wm, s->ldw));
+    NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    const float* Hsrc = cfg.H_init;
+    if (!Hsrc) {
+      tmp.resize(static_cast<size_t>(K) * n);
+      fill_uniform(tmp, cfg.seed * 2 + 2, true);
+      Hsrc = tmp.data();
+    }
+    NMFB_TRY(upload_H(h, ar, Hsrc, K, n, s->Hm, s->ldh));
+    NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  // W columns -> unit L2 (also for a user-supplied W_init, nmf.m:133); H is not rescaled
+  vec_sums_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, K, m, s->ldw, nullptr, s->norm2, nullptr);
+  NMFB_TRY(check_launch(h, "vec_sums(W init)"));
+  w_normalize_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, s->Wt, m, s->ldw, K, 1, 0, s->norm2,
+                                                            s->wsum, nullptr, nullptr);
+  NMFB_TRY(check_launch(h, "w_normalize(init)"));
+  round_copy_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, s->Ht, K, n, s->ldh, nullptr);
+  NMFB_TRY(check_launch(h, "round_copy(H init)"));
+  NMFB_TRY(zero_async(h, s->scal, 4 * sizeof(double)));
+  vec_sums_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, K, n, s->ldh, s->hs, nullptr, nullptr);
+  NMFB_TRY(check_launch(h, "vec_sums(H init)"));
+
+  // ---- V
+  if (kl) {
+    VStats st;
+    NMFB_TRY(compute_v_stats(h, true, &st, &s->vstats, nullptr, ar));
+    NMFB_TRY(ar->alloc(h, &s->Q, static_cast<size_t>(n) * h->ldv));
+  } else {
+    double* sq = nullptr;
+    NMFB_TRY(ar->alloc(h, &sq, 1));
+    NMFB_TRY(prepare_v_work(h, false, true, sq, nullptr));
+    NMFB_CUDA(h, cudaMemcpyAsync(&s->vsq, sq, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    s->Vmma = h->Vwork;
+  }
+
+  // ---- plan the contractions
+  const int* stop = s->stop;
+  const bool multi = comm_size(h->comm) > 1;
+  NMFB_TRY(plan_gram(h, ar, &s->gramW, s->Wt, Kp, m, s->ldw, stop));
+  if (!kl) {
+    NMFB_TRY(plan_gram(h, ar, &s->gramH, s->Ht, Kp, n, s->ldh, stop));
+    if (multi) {  // G_H must sit behind A in the packed buffer
+      s->gramH.g32 = s->packed + static_cast<size_t>(Kp) * s->ldw;
+    }
+    // A = V H'  (X = V, rows i contiguous -> MN-major; Y = H rows, K-major), B = W G_H
+    MatRef Xv{s->Vmma, m, n, h->ldv, true};
+    MatRef Yh{s->Ht, n, Kp, s->ldh, false};
+    MatRef Xw{s->Wt, m, Kp, s->ldw, true};
+    MatRef Yg{s->gramH.gtf, Kp, Kp, Kp, false};
+    const int tiles = (m + kTileM - 1) / kTileM * ((Kp + kMaxN - 1) / kMaxN);
+    const bool split = tiles * 2 <= h->num_sms;
+    if (multi || split) {
+      NMFB_TRY(plan_store(h, ar, &s->gemmA, Xv, Yh, n, nullptr, nullptr, 0, m, Kp, s->A, nullptr,
+                          s->ldw, split, stop));
+      NMFB_TRY(plan_store(h, ar, &s->gemmB, Xw, Yg, Kp, nullptr, nullptr, 0, m, Kp, s->B, nullptr,
+                          s->ldw, false, stop));
+    } else {
+      NMFB_TRY(plan_store(h, ar, &s->gemmA, Xv, Yh, n, &Xw, &Yg, Kp, m, Kp, s->A, s->B, s->ldw, false,
+                          stop));
+    }
+    // H update: N = W'V (X = V columns, K-major), D = G_W H (X = H, columns j contiguous -> MN-major)
+    MatRef Xvt{s->Vmma, m, n, h->ldv, false};
+    MatRef Yw{s->Wt, m, Kp, s->ldw, false};
+    MatRef Xh{s->Ht, n, Kp, s->ldh, true};
+    MatRef Ygw{s->gramW.gtf, Kp, Kp, Kp, false};
+    NMFB_TRY(plan_fused(h, &s->gemmH, EPI_HUPDATE, Xvt, Yw, m, &Xh, &Ygw, Kp, n, Kp, Kp, stop));
+    GemmArgs& a = s->gemmH.L.args;
+    a.Hm = s->Hm;
+    a.Hr32 = s->Ht;
+    a.Hc32 = nullptr;
+    a.ldh = s->ldh;
+    a.lambda = s->lambda_h;
+    a.scal = s->scal;
+    a.freeze = s->H_fixed ? 1 : 0;
+    if (s->direct_cost) {
+      MatRef Xs{s->Wt, m, Kp, s->ldw, true};
+      MatRef Ys{s->Ht, n, Kp, s->ldh, true};
+      NMFB_TRY(plan_fused(h, &s->gemmS, EPI_RESID, Xs, Ys, Kp, nullptr, nullptr, 0, m, round_up(n, 32),
+                          n, stop));
+      GemmArgs& r = s->gemmS.L.args;
+      r.Vsrc = s->Vmma;
+      r.ldv = h->ldv;
+      r.scal = s->scal + 2;
+    }
+  } else {
+    // S = W H (both operands MN-major), Q = V ./ S
+    MatRef Xs{s->Wt, m, Kp, s->ldw, true};
+    MatRef Ys{s->Ht, n, Kp, s->ldh, true};
+    NMFB_TRY(plan_fused(h, &s->gemmS, EPI_KLQ, Xs, Ys, Kp, nullptr, nullptr, 0, m, round_up(n, 32), n,
+                        stop));
+    GemmArgs& q = s->gemmS.L.args;
+    q.Vsrc = h->Vraw;
+    q.Qout = s->Q;
+    q.ldv = h->ldv;
+    q.scal = s->scal + 2;
+    // R = Q H'
+    MatRef Xq{s->Q, m, n, h->ldv, true};
+    MatRef Yh{s->Ht, n, Kp, s->ldh, false};
+    const int tiles = (m + kTileM - 1) / kTileM * ((Kp + kMaxN - 1) / kMaxN);
+    NMFB_TRY(plan_store(h, ar, &s->gemmR, Xq, Yh, n, nullptr, nullptr, 0, m, Kp, s->A, nullptr, s->ldw,
+                        tiles * 2 <= h->num_sms, stop));
+    // H update: N = W'Q, D = ws
+    MatRef Xqt{s->Q, m, n, h->ldv, false};
+    MatRef Yw{s->Wt, m, Kp, s->ldw, false};
+    NMFB_TRY(plan_fused(h, &s->gemmH, EPI_HUPDATE, Xqt, Yw, m, nullptr, nullptr, 0, n, Kp, Kp, stop));
+    GemmArgs& a = s->gemmH.L.args;
+    a.Hm = s->Hm;
+    a.Hr32 = s->Ht;
+    a.Hc32 = nullptr;
+    a.ldh = s->ldh;
+    a.lambda = s->lambda_h;
+    a.scal = s->scal;
+    a.dvec = s->wsf;
+    a.freeze = s->H_fixed ? 1 : 0;
+  }
+  if (s->W_fixed) NMFB_TRY(run_gram(h, s->gramW, nullptr));
+  D2FArgs da{s->wsum, s->wsf, Kp};
+  d2f_kernel<<<(Kp + 127) / 128, 128, 0, h->stream>>>(da, nullptr);
+  NMFB_TRY(check_launch(h, "d2f(ws)"));
+  return NMFB_OK;
+}
+
+// ------------------------------------------------------------------ one iteration
+static int enqueue_cost(nmfb_handle* h, NmfSession* s, int iter, int mode) {
+  CostArgs c{};
+  c.mode = mode;
+  c.iter = iter;
+  c.Kp = s->Kp;
+  c.GW = s->gramW.g32;
+  c.GH = s->gramH.g32;
+  c.vsq = s->vsq;
+  c.vstats = s->vstats;
+  c.scal = s->scal;
+  c.wsum = s->wsum;
+  c.n_wsum = s->Kp;
+  c.lambda_w = s->lambda_w;
+  c.lambda_h = s->lambda_h;
+  c.tolerance = s->tolerance;
+  c.cost = s->cost;
+  c.stop = s->stop;
+  cost_kernel<<<1, 256, 0, h->stream>>>(c);
+  return check_launch(h, "cost");
+}
+
+// Sum the per-rank partials of everything the W step and the cost need.
+static int allreduce_w_inputs(nmfb_handle* h, NmfSession* s, bool with_gram) {
+  if (comm_size(h->comm) <= 1) return NMFB_OK;
+  const size_t nA = static_cast<size_t>(s->Kp) * s->ldw;
+  const size_t count = nA + (with_gram ? static_cast<size_t>(s->Kp) * s->Kp : 0);
+  NMFB_TRY(comm_allreduce(h, s->packed, count, s->hs, s->Kp, s->scal, 4));
+  if (with_gram) {
+    const int cnt = s->Kp * s->Kp;
+    round_copy_kernel<<<dim3((cnt + 255) / 256, 1), 256, 0, h->stream>>>(s->gramH.g32, s->gramH.gtf, 1, cnt,
+                                                                       cnt, s->stop);
+    NMFB_TRY(check_launch(h, "round_copy(G_H)"));
+  }
+  return NMFB_OK;
+}
+
+static int enqueue_w_finish(nmfb_handle* h, NmfSession* s, int mode) {
+  const int Kp = s->Kp, K = s->K, m = s->m;
+  const int* stop = s->stop;
+  NMFB_TRY(zero_async(h, s->ab, 2 * Kp * sizeof(double)));
+  w_dots_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, s->A, mode == WSTEP_EUCLID ? s->B : nullptr,
+                                                       m, s->ldw, Kp, s->ab, stop);
+  NMFB_TRY(check_launch(h, "w_dots"));
+  w_coef_kernel<<<(Kp + 127) / 128, 128, 0, h->stream>>>(mode, Kp, s->ab, s->hs, s->wsum, s->pcoef,
+                                                         s->qcoef, s->bvec, stop);
+  NMFB_TRY(check_launch(h, "w_coef"));
+  NMFB_TRY(zero_async(h, s->norm2, Kp * sizeof(double)));
+  NMFB_TRY(zero_async(h, s->wsum, Kp * sizeof(double)));
+  w_update_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, s->A, mode == WSTEP_EUCLID ? s->B : nullptr,
+                                                         m, s->ldw, s->pcoef, s->qcoef, s->bvec,
+                                                         s->lambda_w, s->norm2, stop);
+  NMFB_TRY(check_launch(h, "w_update"));
+  w_normalize_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, s->Wt, m, s->ldw, K, 1, 0, s->norm2,
+                                                            s->wsum, nullptr, stop);
+  NMFB_TRY(check_launch(h, "w_normalize"));
+  return NMFB_OK;
+}
+
+static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
+  const int Kp = s->Kp, K = s->K, n = s->n;
+  const int* stop = s->stop;
+  const bool multi = comm_size(h->comm) > 1;
+  if (s->divergence == NMFB_DIV_EUCLIDEAN) {
+    if (!s->H_fixed || i == 0 || multi) NMFB_TRY(run_gram(h, s->gramH, stop));
+    if (s->W_fixed) {
+      if (multi) return h->fail(NMFB_ERR_UNSUPPORTED, "W_fixed with several GPUs");
+    } else {
+      NMFB_TRY(run_gemm(h, s->gemmA));
+    }
+    NMFB_TRY(allreduce_w_inputs(h, s, true));
+    if (i > 0 && !s->direct_cost) NMFB_TRY(enqueue_cost(h, s, i - 1, 0));
+    if (!s->W_fixed) {
+      if (s->gemmB.planned) NMFB_TRY(run_gemm(h, s->gemmB));
+      NMFB_TRY(enqueue_w_finish(h, s, WSTEP_EUCLID));
+      NMFB_TRY(run_gram(h, s->gramW, stop));
+    }
+    NMFB_TRY(run_gemm(h, s->gemmH));
+    if (s->direct_cost) {
+      NMFB_TRY(run_gemm(h, s->gemmS));
+      if (multi) NMFB_TRY(comm_allreduce(h, nullptr, 0, nullptr, 0, s->scal, 4));
+      NMFB_TRY(enqueue_cost(h, s, i, 1));
+    }
+  } else {
+    if (!s->H_fixed || i == 0) {
+      NMFB_TRY(zero_async(h, s->hs, Kp * sizeof(double)));
+      vec_sums_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, K, n, s->ldh, s->hs, nullptr, stop);
+      NMFB_TRY(check_launch(h, "vec_sums(H)"));
+    }
+    s->gemmS.L.args.want_cost = i > 0 ? 1 : 0;
+    NMFB_TRY(run_gemm(h, s->gemmS));  // Q = V ./ (W H) with the H of the previous iteration
+    if (!s->W_fixed) NMFB_TRY(run_gemm(h, s->gemmR));
+    NMFB_TRY(allreduce_w_inputs(h, s, false));
+    if (i > 0) NMFB_TRY(enqueue_cost(h, s, i - 1, 2));
+    if (!s->W_fixed) {
+      NMFB_TRY(enqueue_w_finish(h, s, WSTEP_KL));
+      D2FArgs da{s->wsum, s->wsf, Kp};
+      d2f_kernel<<<(Kp + 127) / 128, 128, 0, h->stream>>>(da, stop);
+      NMFB_TRY(check_launch(h, "d2f(ws)"));
+      s->gemmS.L.args.want_cost = 0;
+      NMFB_TRY(run_gemm(h, s->gemmS));  // refreshed V_hat (nmf.m:173)
+    }
+    NMFB_TRY(run_gemm(h, s->gemmH));
+  }
+  return NMFB_OK;
+}
+
+// cost of the last executed iteration (needs quantities of the final H)
+static int enqueue_final_cost(nmfb_handle* h, NmfSession* s) {
+  if (s->finalized || s->iters_enqueued == 0) return NMFB_OK;
+  s->finalized = true;
+  const int last = s->iters_enqueued - 1;
+  const bool multi = comm_size(h->comm) > 1;
+  if (s->divergence == NMFB_DIV_EUCLIDEAN) {
+    if (s->direct_cost) return NMFB_OK;
+    NMFB_TRY(run_gram(h, s->gramH, s->stop));
+    if (multi)
+      NMFB_TRY(comm_allreduce(h, s->gramH.g32, static_cast<size_t>(s->Kp) * s->Kp, nullptr, 0, s->scal, 4));
+    return enqueue_cost(h, s, last, 0);
+  }
+  s->gemmS.L.args.want_cost = 1;
+  NMFB_TRY(run_gemm(h, s->gemmS));
+  if (multi) NMFB_TRY(comm_allreduce(h, nullptr, 0, nullptr, 0, s->scal, 4));
+  return enqueue_cost(h, s, last, 2);
+}
+
+void nmf_session_release(nmfb_handle* h) {
+  if (h->sess) {
+    if (h->sess->pinned) cudaFreeHost(h->sess->pinned);
+    delete h->sess;
+    h->sess = nullptr;
+  }
+}
+
+// ------------------------------------------------------------------ C ABI
+extern "C" int nmfb_nmf_begin(nmfb_handle* h, int K, const nmfb_config* cfg) {
+  if (!h) return NMFB_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  nmf_session_release(h);
+  h->sess = new NmfSession();
+  int rc = nmf_setup(h, h->sess, K, cfg);
+  if (rc == NMFB_OK) {
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = h->fail(NMFB_ERR_CUDA, "nmf setup: %s", cudaGetErrorString(e));
+  }
+  if (rc != NMFB_OK) nmf_session_release(h);
+  return rc;
+}
+
+extern "C" int nmfb_nmf_step(nmfb_handle* h, int iters) {
+  if (!h || !h->sess) return NMFB_ERR_INVALID_ARGUMENT;
+  NmfSession* s = h->sess;
+  if (s->finalized) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "nmf_step after the cost was finalised");
+  cudaSetDevice(h->device);
+  iters = std::min(iters, s->maxiter - s->iters_enqueued);
+  if (iters <= 0) return NMFB_OK;
+  NMFB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  for (int k = 0; k < iters; ++k) {
+    NMFB_TRY(enqueue_iteration(h, s, s->iters_enqueued));
+    ++s->iters_enqueued;
+  }
+  NMFB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  NMFB_CUDA(h, cudaMemcpyAsync(s->pinned, s->stop, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  return NMFB_OK;
+}
+
+extern "C" int nmfb_nmf_sync(nmfb_handle* h, int* iters_done, double* device_ms) {
+  if (!h || !h->sess) return NMFB_ERR_INVALID_ARGUMENT;
+  NmfSession* s = h->sess;
+  NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  if (s->iters_enqueued > 0 && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess)
+    s->device_ms = ms;
+  if (iters_done) *iters_done = s->iters_enqueued;
+  if (device_ms) *device_ms = s->device_ms;
+  return NMFB_OK;
+}
+
+extern "C" int nmfb_nmf_end(nmfb_handle* h, float* W_out, float* H_out, double* cost_out, int* n_cost) {
+  if (!h || !h->sess) return NMFB_ERR_INVALID_ARGUMENT;
+  NmfSession* s = h->sess;
+  cudaSetDevice(h->device);
+  int rc = enqueue_final_cost(h, s);
+  if (rc == NMFB_OK) {
+    cudaError_t e = cudaMemcpyAsync(s->pinned, s->stop, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = h->fail(NMFB_ERR_CUDA, "nmf_end: %s", cudaGetErrorString(e));
+  }
+  if (rc == NMFB_OK) {
+    const int nc = s->pinned[1];
+    if (n_cost) *n_cost = nc;
+    if (cost_out && nc > 0) {
+      cudaError_t e = cudaMemcpy(cost_out, s->cost, nc * sizeof(double), cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) rc = h->fail(NMFB_ERR_CUDA, "cost download: %s", cudaGetErrorString(e));
+    }
+  }
+  if (rc == NMFB_OK && W_out) rc = download_colmajor(h, s->Wm, s->ldw, s->m, s->K, W_out);
+  if (rc == NMFB_OK && H_out) rc = download_H(h, s->Hm, s->ldh, s->K, s->n, H_out);
+  nmf_session_release(h);
+  return rc;
+}
+
+extern "C" int nmfb_nmf(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, float* H_out,
+                        double* cost_out, int* n_cost) {
+  NMFB_TRY(nmfb_nmf_begin(h, K, cfg));
+  NmfSession* s = h->sess;
+  // Queue the loop in chunks; the stop flag written by the cost kernel turns
+  // everything queued behind a converged iteration into no-ops, so the host only
+  // looks at it between chunks (and never waits for the chunk it just queued).
+  const int chunk = 16;
+  cudaEvent_t evs[2] = {nullptr, nullptr};
+  int rc = NMFB_OK;
+  for (int b = 0; b < 2 && rc == NMFB_OK; ++b)
+    if (cudaEventCreateWithFlags(&evs[b], cudaEventDisableTiming) != cudaSuccess)
+      rc = h->fail(NMFB_ERR_CUDA, "cudaEventCreate failed");
+  int* flags = nullptr;
+  if (rc == NMFB_OK && cudaMallocHost(&flags, 2 * sizeof(int)) != cudaSuccess)
+    rc = h->fail(NMFB_ERR_CUDA, "cudaMallocHost failed");
+  if (rc == NMFB_OK) {
+    flags[0] = flags[1] = 0;
+    int c = 0;
+    while (s->iters_enqueued < s->maxiter && rc == NMFB_OK) {
+      rc = nmfb_nmf_step(h, chunk);
+      if (rc != NMFB_OK) break;
+      if (c > 0) {  // look at the flag as of the end of the previous chunk
+        cudaEventSynchronize(evs[(c - 1) & 1]);
+        if (flags[(c - 1) & 1] != 0) break;
+      }
+      cudaMemcpyAsync(&flags[c & 1], s->stop, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+      cudaEventRecord(evs[c & 1], h->stream);
+      ++c;
+    }
+  }
+  for (int b = 0; b < 2; ++b)
+    if (evs[b]) cudaEventDestroy(evs[b]);
+  if (flags) cudaFreeHost(flags);
+  if (rc != NMFB_OK) {
+    nmf_session_release(h);
+    return rc;
+  }
+  return nmfb_nmf_end(h, W_out, H_out, cost_out, n_cost);
+}

@@ -18,10 +18,19 @@
 // and add it, round-to-nearest, into fp32 registers while the next chunk is
 // already accumulating.  Phase 1 (short: the K x K Gram products) is one chunk.
 //
-// Epilogues: EPI_STORE writes the raw sums (optionally one slab per split-K
-// slice); EPI_HUPDATE applies the fused multiplicative H update
-//   H <- H .* (N ./ max(D + lambda, eps))                  (nmf.m:180-181,199)
-// so that neither N = W'V nor D = W'V_hat ever exists in HBM.
+// Epilogues (thread = one output row, accumulator columns in registers):
+//   EPI_STORE    raw sums (optionally one slab per split-K slice)
+//   EPI_HUPDATE  fused multiplicative H update, H <- H .* (N ./ max(D + lambda, eps))
+//                (nmf.m:180-181,199): D is the second accumulator (Euclidean,
+//                D = (W'W) H) or a per-basis vector (KL, D = W' * ones = column
+//                sums of W, nmf.m:183-184); N and D never exist in HBM.
+//   EPI_RECON    acc is a tile of V_hat = W*H (ReconstructFromDecomposition.m:31): store it
+//   EPI_RESID    sum of (V - V_hat).^2 over the tile (nmf.m:208, nmfsc.m:161)
+//   EPI_KLQ      Q = V ./ V_hat written tf32-rounded (nmf.m:152,183) and, on request,
+//                sum(V .* log(V_hat)), sum(V_hat) for the KL cost (nmf.m:210)
+// Every kernel of an iteration loop starts by reading *stop: once the cost
+// kernel has detected convergence (nmf.m:221-224) the launches already queued
+// behind it become no-ops, so the host never has to synchronise per iteration.
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA
 // issuer, warps 2..9 = epilogue (TMEM lane quarter = warp & 3, column half =
@@ -50,16 +59,18 @@ constexpr int kMaxGroups = kMaxN / 16 / 2;  // 16-column groups per epilogue thr
 // eps even for single data (nmf.m:168,199); representable in fp32.
 #define NMFB_EPS 2.220446049250313e-16f
 
-enum { EPI_STORE = 0, EPI_HUPDATE = 1 };
+enum { EPI_STORE = 0, EPI_HUPDATE = 1, EPI_RECON = 2, EPI_RESID = 3, EPI_KLQ = 4 };
 
 struct GemmArgs {
   int rows;          // valid output rows (rows of X)
-  int ncols;         // valid output columns (padded K of this problem, multiple of 32)
+  int ncols;         // output columns (multiple of 32; rows of Y beyond its extent read as zero)
+  int ncols_valid;   // EPI_RECON / EPI_RESID / EPI_KLQ: columns that exist in V (<= ncols)
   int box_n;         // rows of the Y TMA box = min(ncols, 256)
   int nkb0;          // phase-0 k-blocks in total (over all splits)
   int kb_per_split;  // phase-0 k-blocks per split (blockIdx.z)
   int nkb1;          // phase-1 k-blocks (split 0 only); 0 = no second accumulator
   int xmn0, xmn1;    // X operand of phase 0 / 1 is MN-major (rows contiguous) instead of K-major
+  int ymn0, ymn1;    // same for the Y operand (its rows = output columns are contiguous)
   // EPI_STORE: out[z * split_stride + col * ldo + row]
   float* out0;
   float* out1;
@@ -72,7 +83,17 @@ struct GemmArgs {
   long long ldh;
   long long ldc;
   float lambda;
-  double* partials;  // [tiles*chunks][2]: sum(N .* Hnew), sum(Hnew)
+  const float* dvec;  // EPI_HUPDATE: if non-null, D[col] = dvec[col] replaces the second accumulator
+  double* scal;       // EPI_HUPDATE: scal[0] += sum(N .* tf32(Hnew)), scal[1] += sum(Hnew)
+                      // EPI_RESID:   scal[0] += sum((V - acc)^2)
+                      // EPI_KLQ:     scal[0] += sum(V .* log(acc)), scal[1] += sum(acc)   (if want_cost)
+  // EPI_RECON / EPI_RESID / EPI_KLQ: element (row, col) of the m x n problem lives at [col * ldv + row]
+  const float* Vsrc;
+  float* Qout;        // EPI_KLQ: Q; EPI_RECON: V_hat
+  long long ldv;
+  int want_cost;
+  int freeze;         // EPI_HUPDATE: leave H untouched (H_fixed, nmf.m:177) but still form the sums
+  const int* stop;    // device flag: non-zero = iteration loop already converged, do nothing
 };
 
 template <int EPI>
@@ -88,6 +109,7 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
   __shared__ uint32_t tmem_slot;
   __shared__ double red[kEpiWarps][2];
 
+  if (a.stop != nullptr && *a.stop != 0) return;  // uniform across the grid
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -152,7 +174,12 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       } else {
         tma_load_2d(xs, mx, &full_bar[stage], kb * kBlockK, r0, kEvictFirst);
       }
-      tma_load_2d(ys, my, &full_bar[stage], kb * kBlockK, n0, kEvictLast);
+      if (ph1 ? a.ymn1 : a.ymn0) {
+        for (int q = 0; q < (a.box_n >> 5); ++q)
+          tma_load_2d(ys + q * 4096, my, &full_bar[stage], n0 + q * 32, kb * kBlockK, kEvictLast);
+      } else {
+        tma_load_2d(ys, my, &full_bar[stage], kb * kBlockK, n0, kEvictLast);
+      }
       if (++stage == kStages) {
         stage = 0;
         phase ^= 1;
@@ -160,8 +187,6 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------ MMA issuer
-    const uint32_t idesc_k = make_idesc_tf32(kTileM, bn, 0, 0);
-    const uint32_t idesc_mn = make_idesc_tf32(kTileM, bn, 1, 0);
     int stage = 0;
     uint32_t phase = 0;
     for (int ch = 0; ch < nchunks; ++ch) {
@@ -174,6 +199,8 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       const bool ph1 = ch >= nchunk0;
       const int nkb = ph1 ? n1kb : min(kChunkKb, n0kb - ch * kChunkKb);
       const bool mn = ph1 ? (a.xmn1 != 0) : (a.xmn0 != 0);
+      const bool ymn = ph1 ? (a.ymn1 != 0) : (a.ymn0 != 0);
+      const uint32_t idesc = make_idesc_tf32(kTileM, bn, mn ? 1 : 0, ymn ? 1 : 0);
       const uint32_t d = tmem_base + static_cast<uint32_t>(buf * kMaxN);
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(&full_bar[stage], phase);
@@ -184,8 +211,9 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         for (int s = 0; s < kBlockK / kUmmaK; ++s) {
           const uint64_t adesc = mn ? make_desc_mnmajor_sw128_32b(xs + s * 1024, 4096, 512)
                                     : make_desc_kmajor_sw128(xs + s * (kUmmaK * 4));
-          const uint64_t bdesc = make_desc_kmajor_sw128(ys + s * (kUmmaK * 4));
-          mma_tf32_ss(d, adesc, bdesc, mn ? idesc_mn : idesc_k, (i == 0 && s == 0) ? 0u : 1u);
+          const uint64_t bdesc = ymn ? make_desc_mnmajor_sw128_32b(ys + s * 1024, 4096, 512)
+                                     : make_desc_kmajor_sw128(ys + s * (kUmmaK * 4));
+          mma_tf32_ss(d, adesc, bdesc, idesc, (i == 0 && s == 0) ? 0u : 1u);
         }
         tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
         if (++stage == kStages) {
@@ -268,60 +296,113 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         }
       }
     } else {
-      // fused multiplicative H update; thread = one sample (column of V / H)
-      float s_nh = 0.f, s_h = 0.f;
+      float s0 = 0.f, s1 = 0.f;  // per-thread partial sums (meaning depends on the epilogue)
+      if constexpr (EPI == EPI_HUPDATE) {
+        // fused multiplicative H update; thread = one sample (column of V / H)
+        const bool vecD = a.dvec != nullptr;
 #pragma unroll
-      for (int g = 0; g < kMaxGroups; ++g) {
-        if (g < g_count) {
-          float dv[16];
-          tmem_ld16(t1 + g * 16, dv);
-          tmem_ld_wait();
-          if (row_ok) {
-            const long long hoff = static_cast<long long>(col0 + g * 16) * a.ldh + row;
-            float h[16];
+        for (int g = 0; g < kMaxGroups; ++g) {
+          if (g < g_count) {
+            float dv[16];
+            if (vecD) {
 #pragma unroll
-            for (int t = 0; t < 16; ++t) h[t] = a.Hm[hoff + t * a.ldh];
+              for (int t = 0; t < 16; ++t) dv[t] = __ldg(a.dvec + col0 + g * 16 + t);
+            } else if (have1) {
+              tmem_ld16(t1 + g * 16, dv);
+              tmem_ld_wait();
+            } else {
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
-              const float nv = sum[g * 16 + t];
-              const float hn = h[t] * (nv / fmaxf(dv[t] + a.lambda, NMFB_EPS));
-              s_nh += nv * hn;
-              s_h += hn;
-              a.Hm[hoff + t * a.ldh] = hn;
-              h[t] = tf32_rn(hn);
-              a.Hr32[hoff + t * a.ldh] = h[t];
+              for (int t = 0; t < 16; ++t) dv[t] = 0.f;
             }
-            if (a.Hc32 != nullptr) {
-              float4* o = reinterpret_cast<float4*>(a.Hc32 + static_cast<long long>(row) * a.ldc +
-                                                    (col0 + g * 16));
+            if (row_ok) {
+              const long long hoff = static_cast<long long>(col0 + g * 16) * a.ldh + row;
+              float h[16];
 #pragma unroll
-              for (int t = 0; t < 4; ++t)
-                o[t] = make_float4(h[4 * t], h[4 * t + 1], h[4 * t + 2], h[4 * t + 3]);
+              for (int t = 0; t < 16; ++t) h[t] = a.Hm[hoff + t * a.ldh];
+#pragma unroll
+              for (int t = 0; t < 16; ++t) {
+                const float nv = sum[g * 16 + t];
+                float hn = h[t];
+                if (!a.freeze) {
+                  hn = h[t] * (nv / fmaxf(dv[t] + a.lambda, NMFB_EPS));
+                  a.Hm[hoff + t * a.ldh] = hn;
+                }
+                h[t] = tf32_rn(hn);
+                s0 += nv * h[t];
+                s1 += hn;
+                if (!a.freeze) a.Hr32[hoff + t * a.ldh] = h[t];
+              }
+              if (a.Hc32 != nullptr && !a.freeze) {
+                float4* o = reinterpret_cast<float4*>(a.Hc32 + static_cast<long long>(row) * a.ldc +
+                                                      (col0 + g * 16));
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                  o[t] = make_float4(h[4 * t], h[4 * t + 1], h[4 * t + 2], h[4 * t + 3]);
+              }
+            }
+          }
+        }
+      } else {
+        // acc = tile of V_hat; thread = one row i of V, columns j of V in registers
+        const int cols_ok = a.ncols_valid - col0;  // columns beyond the problem are padding
+#pragma unroll
+        for (int g = 0; g < kMaxGroups; ++g) {
+          if (g < g_count && row_ok) {
+            const long long off = static_cast<long long>(col0 + g * 16) * a.ldv + row;
+            if constexpr (EPI == EPI_RECON) {
+#pragma unroll
+              for (int t = 0; t < 16; ++t)
+                if (g * 16 + t < cols_ok) a.Qout[off + t * a.ldv] = sum[g * 16 + t];
+            } else {
+              float v[16];
+#pragma unroll
+              for (int t = 0; t < 16; ++t)
+                v[t] = (g * 16 + t < cols_ok) ? __ldg(a.Vsrc + off + t * a.ldv) : 0.f;
+              if constexpr (EPI == EPI_RESID) {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                  const float d = v[t] - sum[g * 16 + t];
+                  if (g * 16 + t < cols_ok) s0 = fmaf(d, d, s0);
+                }
+              } else {  // EPI_KLQ
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                  if (g * 16 + t < cols_ok) {
+                    const float sv = sum[g * 16 + t];
+                    a.Qout[off + t * a.ldv] = tf32_rn(v[t] / sv);
+                    if (a.want_cost) {
+                      s0 = fmaf(v[t], __logf(sv), s0);
+                      s1 += sv;
+                    }
+                  }
+                }
+              }
             }
           }
         }
       }
-      double d0 = row_ok ? static_cast<double>(s_nh) : 0.0;
-      double d1 = row_ok ? static_cast<double>(s_h) : 0.0;
+      if (EPI != EPI_RECON && a.scal != nullptr) {
+        double d0 = row_ok ? static_cast<double>(s0) : 0.0;
+        double d1 = row_ok ? static_cast<double>(s1) : 0.0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-      }
-      if (lane == 0) {
-        red[warp - 2][0] = d0;
-        red[warp - 2][1] = d1;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // epilogue warps only
-      if (warp == 2 && lane == 0) {
-        double p0 = 0.0, p1 = 0.0;
-        for (int w = 0; w < kEpiWarps; ++w) {
-          p0 += red[w][0];
-          p1 += red[w][1];
+        for (int o = 16; o > 0; o >>= 1) {
+          d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+          d1 += __shfl_xor_sync(0xffffffffu, d1, o);
         }
-        const long long p = (static_cast<long long>(blockIdx.x) * gridDim.y + blockIdx.y) * 2;
-        a.partials[p] = p0;
-        a.partials[p + 1] = p1;
+        if (lane == 0) {
+          red[warp - 2][0] = d0;
+          red[warp - 2][1] = d1;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // epilogue warps only
+        if (warp == 2 && lane == 0) {
+          double p0 = 0.0, p1 = 0.0;
+          for (int w = 0; w < kEpiWarps; ++w) {
+            p0 += red[w][0];
+            p1 += red[w][1];
+          }
+          atomicAdd(a.scal, p0);
+          atomicAdd(a.scal + 1, p1);
+        }
       }
     }
   }
