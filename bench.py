@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py - NMF update iterations/sec on BASELINE.json's north-star workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one multiplicative-update iteration of nmf.m (W update, H update,
+cost; nmf.m:143-225) on a synthetic dense V = max(U(0,1), 2^-24), 16384 x 16384,
+K = 256, Euclidean divergence (BASELINE.json configs[1]).  With N > 1 the same V
+is column-sharded over the ranks (strong scaling) and every iteration carries
+one packed all-reduce.
+
+`value`  : iterations/s with V, W, H resident in HBM, K iterations timed with
+           CUDA events on the engine's stream, max over ranks.
+`e2e`    : the same metric through the reference-facing call nmf(V, K, config)
+           with HOST buffers: upload of V / W_init / H_init, K iterations,
+           download of W, H and the cost trace all inside the timed region.
+`roofline`: the H-step contraction (panel_gemm, fused H update) timed per launch
+           with CUDA events inside the timed region.
+`cpu_baseline`: oracle/nmf_oracle.py (literal float64 restatement of nmf.m) on
+           this box's host cores, a bounded number of full-size iterations.
+--impl reference times that oracle alone (the reference is MATLAB and cannot
+run here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M = N_COLS = 16384
+K_BASIS = 256
+METRIC = "nmf_update_iterations_per_sec"
+UNIT = "iterations/s"
+WORKLOAD = "nmf.m euclidean MU, V=16384x16384 dense uniform, K=256, fp32 storage / tf32 tensor-core operands"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    """(tf32 TFLOP/s peak, hbm GB/s, source string).  tf32 runs at half the bf16 tensor rate."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        bf16 = float(p.get("bf16_tflops_sustained") or p.get("bf16_tflops"))
+        return bf16 / 2.0, float(p.get("hbm_gbs")), "MEASURED_PEAKS.json bf16_tflops_sustained/2 (tf32 = half the bf16 rate), of measured"
+    except Exception:
+        return 1590.0 / 2.0, 6650.0, "fallback 1.59 PFLOP/s bf16 / 2 (tf32 = half the bf16 rate), of fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_reference(steps_cap_seconds: float, rank0: bool):
+    """oracle nmf (literal nmf.m, float64, BLAS threads = all cores) on the full-size
+    workload for as many iterations as fit the time cap; returns (it/s, iters, cores)."""
+    import numpy as np
+    from oracle import nmf_oracle as O
+
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    t0 = time.time()
+    V = rng.random((M, N_COLS), dtype=np.float32).astype(np.float64)
+    np.maximum(V, 2.0 ** -24, out=V)
+    W0 = np.maximum(rng.random((M, K_BASIS)), O.EPS)
+    H0 = np.maximum(rng.random((K_BASIS, N_COLS)), O.EPS)
+    log(f"[cpu] inputs generated in {time.time() - t0:.1f}s")
+    # one untimed iteration tells how many fit the cap
+    t0 = time.time()
+    O.nmf(V, K_BASIS, dict(W_init=W0, H_init=H0, maxiter=1, tolerance=1e-300))
+    t1 = time.time() - t0
+    iters = max(1, min(5, int(steps_cap_seconds / max(t1, 1e-3))))
+    t0 = time.time()
+    O.nmf(V, K_BASIS, dict(W_init=W0, H_init=H0, maxiter=iters, tolerance=1e-300))
+    dt = time.time() - t0
+    log(f"[cpu] first iteration {t1:.2f}s; {iters} iterations in {dt:.2f}s")
+    return iters / dt, iters, cores
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    v, iters, cores = cpu_reference(45.0, True)
+    sample = f"{iters} full-size iterations of oracle.nmf_oracle.nmf (literal float64 nmf.m; every iteration costs the same)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "m": M, "n": N_COLS, "K": K_BASIS},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is MATLAB (no MATLAB/Octave in this image): this arm times the NumPy restatement of nmf.m on the host cores",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--m", type=int, default=M)
+    ap.add_argument("--n", type=int, default=N_COLS)
+    ap.add_argument("--k", type=int, default=K_BASIS)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from nmf_toolbox_b200 import api
+    from nmf_toolbox_b200.distributed import init_comm, shard_bounds
+
+    m, n, K = args.m, args.n, args.k
+    warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    h = api.Handle(local_rank)
+    init_comm(h, dist, rank, world)
+    lo, hi = shard_bounds(n, world, rank)
+    nl = hi - lo
+
+    # synthetic V generated on the device: column-major m x nl == torch tensor [nl][m]
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    Vd = torch.rand((nl, m), device=dev, generator=g, dtype=torch.float32).clamp_(min=2.0 ** -24)
+    rng = np.random.default_rng(7)
+    W0 = np.asfortranarray(np.maximum(rng.random((m, K), dtype=np.float32), 1e-7))
+    H0 = np.asfortranarray(np.maximum(rng.random((K, n), dtype=np.float32), 1e-7)[:, lo:hi])
+    total = warmup + args.steps
+    cfg = dict(divergence="euclidean", W_init=W0, H_init=H0, maxiter=total + 1, tolerance=1e-300)
+
+    # ------------------------------------------------------------ resident timing
+    h.set_V_device(Vd.data_ptr(), m, nl, m)
+    h.nmf_begin(K, cfg)
+    h.nmf_step(warmup)
+    h.nmf_sync()
+    sampler = ClockSampler(local_rank)
+    h.profile_enable(True)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = h.launch_count()
+    t0 = time.perf_counter()
+    h.nmf_step(args.steps)
+    done, dev_ms = h.nmf_sync()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = h.launch_count() - launches0
+    ms_w, ms_h, nprof = h.profile_get()
+    h.profile_enable(False)
+    _, _, cost = h.nmf_end(want_factors=False)
+    dev_ms = max_over_ranks(dev_ms)
+    wall_ms = max_over_ranks(wall_ms)
+    ms_w = max_over_ranks(ms_w)
+    ms_h = max_over_ranks(ms_h)
+    value = args.steps / (dev_ms / 1e3)
+    assert len(cost) == total and np.all(np.isfinite(cost)), "cost trace incomplete"
+    monotone = bool(np.all(np.diff(cost) <= 1e-6 * np.abs(cost[:-1])))
+
+    # ------------------------------------------------------------ end to end (host buffers)
+    e2e = None
+    if not args.no_e2e:
+        Vh = torch.empty((nl, m), dtype=torch.float32, pin_memory=True)
+        Vh.copy_(Vd)
+        torch.cuda.synchronize()
+        Vnp = Vh.numpy().T  # m x nl, column-major view of the pinned buffer
+        cfg2 = dict(cfg, maxiter=args.steps)
+        del Vd
+        torch.cuda.empty_cache()
+        h.set_V(Vnp[:, : min(nl, 256)])  # untimed: lets lazy CUDA state settle
+        barrier()
+        t0 = time.perf_counter()
+        h.set_V(Vnp)
+        W, H, c2 = h.nmf(K, cfg2)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        barrier()
+        el = max_over_ranks(el)
+        h2d = (Vnp.size + W0.size + H0.size) * 4
+        d2h = (W.size + H.size) * 4 + c2.size * 8
+        e2e = {"value": args.steps / el, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
+               "d2h_bytes_per_step": d2h / args.steps, "seconds": el,
+               "call": "Handle.set_V(V_host) + Handle.nmf(K, config) == nmfb_set_V + nmfb_nmf (C ABI), host buffers in and out"}
+
+    # ------------------------------------------------------------ report
+    if rank == 0:
+        Kp = (K + 31) // 32 * 32
+        peak_tf, hbm_gbs, src = measured_peaks()
+        flops_h = 2.0 * m * nl * Kp + 2.0 * nl * Kp * Kp
+        ach = flops_h / (ms_h * 1e-3) / 1e12 if ms_h > 0 else None
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f).get("h_step_gemm_dram_bytes_per_launch")
+        except Exception:
+            pass
+        f_alg = 4.0 * m * n * K + 4.0 * (m + n) * K * K
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "m": m, "n": n, "K": K, "columns_per_gpu": nl,
+                       "l2": "inputs_exceed_l2 (V shard %.0f MiB streamed twice per iteration)" % (m * nl * 4 / 2 ** 20),
+                       "parallelism": "columns of V and H sharded over %d GPU(s), W replicated" % world},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "algorithmic_tflops": f_alg * value / 1e12,
+            "tensor_frac_of_step": (f_alg * value / 1e12) / (peak_tf * world),
+            "roofline": {"bound": "tensor", "kernel": "panel_gemm_kernel<EPI_HUPDATE> (N = W'V fused with the H update)",
+                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": (ach / peak_tf) if ach else None,
+                         "traffic": traffic, "peak_source": src, "ms_per_launch": ms_h, "launches_timed": nprof,
+                         "w_step_gemm_ms_per_launch": ms_w,
+                         "hbm_gbs_of_V_stream": (m * nl * 4 / (ms_h * 1e-3) / 1e9) if ms_h > 0 else None,
+                         "hbm_peak_gbs": hbm_gbs},
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "cost_first_last": [float(cost[warmup]), float(cost[-1])],
+            "cost_monotone": monotone,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                v, iters, cores = cpu_reference(20.0, True)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                        "sample": f"{iters} full-size iterations of oracle.nmf_oracle.nmf (literal float64 nmf.m)"}
+            except MemoryError as e:  # pragma: no cover
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                        "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

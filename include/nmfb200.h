@@ -131,6 +131,10 @@ int nmfb_nmf_step(nmfb_handle* h, int iters);
  * and the device time (CUDA events on the handle's stream) they took in total. */
 int nmfb_nmf_sync(nmfb_handle* h, int* iters_done, double* device_ms);
 int nmfb_nmf_end(nmfb_handle* h, float* W_out, float* H_out, double* cost_out, int* n_cost);
+/* Optional per-kernel timing (CUDA events on the handle's stream around every
+ * launch of the two large contractions of the Euclidean nmf iteration). */
+int nmfb_profile_enable(nmfb_handle* h, int on);
+int nmfb_profile_get(nmfb_handle* h, double* ms_w_gemm, double* ms_h_gemm, int* count);
 /* Number of kernel launches issued by the handle since creation. */
 long long nmfb_launch_count(const nmfb_handle* h);
 

@@ -92,6 +92,8 @@ def _bind(lib):
         "nmfb_nmf_sync": ([P, PI, ctypes.POINTER(D)], I),
         "nmfb_nmf_end": ([P, P, P, P, PI], I),
         "nmfb_launch_count": ([P], LL),
+        "nmfb_profile_enable": ([P, I], I),
+        "nmfb_profile_get": ([P, ctypes.POINTER(D), ctypes.POINTER(D), PI], I),
         "nmfb_comm_unique_id": ([ctypes.c_char_p], I),
         "nmfb_comm_init": ([P, ctypes.c_char_p, I, I], I),
         "nmfb_version": ([], ctypes.c_char_p),
@@ -169,6 +171,15 @@ class Handle:
 
     def launch_count(self) -> int:
         return int(self.lib.nmfb_launch_count(self._h))
+
+    def profile_enable(self, on: bool = True):
+        self._check(self.lib.nmfb_profile_enable(self._h, int(on)))
+
+    def profile_get(self):
+        """Average device ms of the W-step and H-step contractions, and how many were timed."""
+        a, b, c = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int(0)
+        self._check(self.lib.nmfb_profile_get(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
 
     # -- config marshalling
     def _config(self, config, m, n, K, T=None, for_nmfsc=False):

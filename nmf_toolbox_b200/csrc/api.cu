@@ -120,17 +120,6 @@ extern "C" int nmfb_set_V_device(nmfb_handle* h, const float* V_dev, int m, int 
 
 // ------------------------------------------------------------------ ReconstructFromDecomposition
 namespace apidetail {
-// hi = tf32(x), lo = tf32(x - hi): x ~ hi + lo to ~2^-22 relative.
-__global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi,
-                                  float* __restrict__ lo, long long count) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float x = src[i];
-    const float h = tf32_rn(x);
-    hi[i] = h;
-    lo[i] = tf32_rn(x - h);
-  }
-}
 // unrounded shifted stack (RFD.m:37)
 __global__ void hstack_raw_kernel(const float* __restrict__ H, float* __restrict__ Hs, int K, int T, int n,
                                   long long ld) {
@@ -167,10 +156,10 @@ extern "C" int nmfb_reconstruct(nmfb_handle* h, const float* W, const float* H, 
   hstack_raw_kernel<<<vec_grid(n, KT), 256, 0, h->stream>>>(Hm, Hs, K, T, n, ldh);
   NMFB_TRY(check_launch(h, "hstack_raw"));
   const long long cw = static_cast<long long>(KTp) * ldw, ch = static_cast<long long>(KTp) * ldh;
-  split_tf32_kernel<<<1024, 256, 0, h->stream>>>(Wc, Xs, Xs + cw, cw);
+  split_copy_kernel<<<dim3(1024, 1), 256, 0, h->stream>>>(Wc, Xs, Xs + cw, 1, static_cast<int>(cw), cw);
   NMFB_TRY(check_launch(h, "split_tf32(W)"));
   NMFB_CUDA(h, cudaMemcpyAsync(Xs + 2 * cw, Xs, cw * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-  split_tf32_kernel<<<1024, 256, 0, h->stream>>>(Hs, Ys, Ys + 2 * ch, ch);
+  split_copy_kernel<<<dim3(1024, 1), 256, 0, h->stream>>>(Hs, Ys, Ys + 2 * ch, 1, static_cast<int>(ch), ch);
   NMFB_TRY(check_launch(h, "split_tf32(H)"));
   NMFB_CUDA(h, cudaMemcpyAsync(Ys + ch, Ys, ch * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
   GemmOp op;

@@ -1,5 +1,264 @@
+// cnmf driver: the iteration loop of cnmf.m (lines 175-258), Euclidean /
+// 'frobenius' divergence, in stacked form.
+//
+// With Wc = [W_1 ... W_T] (m x KT, which is exactly the column-major memory of
+// the reference's m x K x T tensor) and Hs = [H_1; ...; H_T] (KT x n, H_t = H
+// shifted right by t-1 columns with zero fill, cnmf.m:188) the reconstruction is
+// V_hat = Wc*Hs (ReconstructFromDecomposition.m:33-38) and
+//   - the T per-frame W updates of cnmf.m:187-194 (all computed from the same
+//     stale V_hat and H) are ONE nmf.m-style update of Wc with
+//     A = V*Hs', B = Wc*(Hs*Hs') and per-column dots <Wc_c, A_c>, <Wc_c, B_c>;
+//   - the H numerator / denominator of cnmf.m:218-227 are fold(Wc'*V) and
+//     fold((Wc'*Wc)*Hs) with fold(P)(k, j) = sum_t P(k + K(t-1), j + t - 1);
+//   - the Euclidean cost is 0.5*(|V|^2 - 2<Wc'V, Hs> + <Wc'Wc, Hs*Hs'>).
+// Basis k is normalised over all frames by |W(:,k,:)|_F / T (cnmf.m:196-199);
+// H is compensated for that only at initialisation (cnmf.m:163).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "comm.cuh"
 #include "engine.cuh"
+#include "ew_kernels.cuh"
+
+using namespace nmfb;
+
+namespace cnmfdetail {
+
+struct CnmfState {
+  Arena ar;
+  int K = 0, T = 0, KT = 0, KTp = 0, m = 0, n = 0;
+  long long ldw = 0, ldh = 0;
+  bool W_fixed = false, H_fixed = false, frobenius = false;
+  float lambda_w = 0.f, lambda_h = 0.f;
+  int maxiter = 100;
+  double tolerance = 1e-3;
+  float *Wm = nullptr, *Wt = nullptr, *Hm = nullptr, *Hs = nullptr;
+  float *A = nullptr, *B = nullptr, *P = nullptr, *D = nullptr;
+  float *pcoef = nullptr, *qcoef = nullptr, *bvec = nullptr, *hscale = nullptr;
+  double *ab = nullptr, *norm2 = nullptr, *wsum = nullptr, *scal = nullptr, *cost = nullptr;
+  int* stop = nullptr;
+  double vsq = 0.0;
+  GramOp gramH, gramW;
+  GemmOp gemmA, gemmP;
+};
+
+int zero_async(nmfb_handle* h, void* p, size_t bytes) {
+  NMFB_CUDA(h, cudaMemsetAsync(p, 0, bytes, h->stream));
+  return NMFB_OK;
+}
+
+int enqueue_cost(nmfb_handle* h, CnmfState* s, int iter) {
+  if (!s->frobenius) {
+    const int cnt = s->KTp * s->KTp;
+    gram_dot_kernel<<<std::min(64, (cnt + 1023) / 1024), 256, 0, h->stream>>>(s->gramW.g32, s->gramH.g32, cnt,
+                                                                               s->scal + 4, s->stop);
+    NMFB_TRY(check_launch(h, "gram_dot"));
+  }
+  CostArgs c{};
+  c.mode = s->frobenius ? 3 : 0;  // cnmf.m:239-248 has no 'frobenius' case
+  c.iter = iter;
+  c.Kp = s->KTp;
+  c.GW = s->gramW.g32;
+  c.GH = s->gramH.g32;
+  c.vsq = s->vsq;
+  c.scal = s->scal;
+  c.wsum = s->wsum;
+  c.n_wsum = s->KTp;
+  c.lambda_w = s->lambda_w;
+  c.lambda_h = s->lambda_h;
+  c.tolerance = s->tolerance;
+  c.cost = s->cost;
+  c.stop = s->stop;
+  cost_kernel<<<1, 256, 0, h->stream>>>(c);
+  return check_launch(h, "cost");
+}
+
+int enqueue_hstack(nmfb_handle* h, CnmfState* s, const int* stop) {
+  hstack_kernel<<<vec_grid(s->n, s->KT), 256, 0, h->stream>>>(s->Hm, s->Hs, s->K, s->T, s->n, s->ldh, stop);
+  return check_launch(h, "hstack");
+}
+
+int enqueue_iteration(nmfb_handle* h, CnmfState* s, int i) {
+  const int* stop = s->stop;
+  const int KT = s->KT, KTp = s->KTp, m = s->m;
+  if (!s->H_fixed || i == 0) {
+    NMFB_TRY(enqueue_hstack(h, s, stop));
+    NMFB_TRY(run_gram(h, s->gramH, stop));
+  }
+  if (i > 0) NMFB_TRY(enqueue_cost(h, s, i - 1));
+  if (!s->W_fixed) {
+    NMFB_TRY(run_gemm(h, s->gemmA));  // A = V Hs', B = Wc (Hs Hs')
+    NMFB_TRY(zero_async(h, s->ab, 2 * KTp * sizeof(double)));
+    w_dots_kernel<<<vec_grid(m, KT), 256, 0, h->stream>>>(s->Wm, s->A, s->B, m, s->ldw, KTp, s->ab, stop);
+    NMFB_TRY(check_launch(h, "w_dots"));
+    w_coef_kernel<<<(KTp + 127) / 128, 128, 0, h->stream>>>(WSTEP_EUCLID, KTp, s->ab, nullptr, nullptr,
+                                                            s->pcoef, s->qcoef, s->bvec, stop);
+    NMFB_TRY(check_launch(h, "w_coef"));
+    NMFB_TRY(zero_async(h, s->norm2, KTp * sizeof(double)));
+    NMFB_TRY(zero_async(h, s->wsum, KTp * sizeof(double)));
+    w_update_kernel<<<vec_grid(m, KT), 256, 0, h->stream>>>(s->Wm, s->A, s->B, m, s->ldw, s->pcoef, s->qcoef,
+                                                            s->bvec, s->lambda_w, s->norm2, stop);
+    NMFB_TRY(check_launch(h, "w_update"));
+    w_normalize_kernel<<<vec_grid(m, KT), 256, 0, h->stream>>>(s->Wm, s->Wt, m, s->ldw, s->K, s->T, 1,
+                                                               s->norm2, s->wsum, nullptr, stop);
+    NMFB_TRY(check_launch(h, "w_normalize"));
+    NMFB_TRY(run_gram(h, s->gramW, stop));
+  }
+  // P = Wc'V and D = (Wc'Wc) Hs, then fold over the frames and update H (cnmf.m:216-231)
+  NMFB_TRY(run_gemm(h, s->gemmP));
+  fold_update_kernel<<<vec_grid(s->n, s->K), 256, 0, h->stream>>>(s->P, s->D, s->Hm, s->K, s->T, s->n, s->ldh,
+                                                                  s->lambda_h, s->H_fixed ? 1 : 0, s->scal,
+                                                                  stop);
+  return check_launch(h, "fold_update");
+}
+
+int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_in, float* W_out,
+             float* H_out, double* cost_out, int* n_cost) {
+  if (h->Vraw == nullptr) return h->fail(NMFB_ERR_NO_DATA, "cnmf: call nmfb_set_V first");
+  if (K <= 0 || T <= 0) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "cnmf: K and context_len must be positive");
+  if (comm_size(h->comm) > 1)
+    return h->fail(NMFB_ERR_UNSUPPORTED, "cnmf: column sharding needs a (T-1)-column halo exchange; single GPU only");
+  nmfb_config cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  if (cfg_in) cfg = *cfg_in;
+  if (cfg.maxiter <= 0) cfg.maxiter = 100;         // cnmf.m:440-442
+  if (!(cfg.tolerance > 0)) cfg.tolerance = 1e-3;  // cnmf.m:445-447
+  if (cfg.W_sparsity < 0) cfg.W_sparsity = 0;
+  if (cfg.H_sparsity < 0) cfg.H_sparsity = 0;
+  switch (cfg.divergence) {
+    case NMFB_DIV_EUCLIDEAN:
+      break;
+    case NMFB_DIV_FROBENIUS:
+      s->frobenius = true;
+      break;
+    case NMFB_DIV_AB:
+      if (cfg.alpha == 0 && cfg.beta == 0)  // cnmf.m:133-135
+        return h->fail(NMFB_ERR_AB_ZERO, "alpha = 0 and beta = 0 is not supported at this time.");
+      return h->fail(NMFB_ERR_UNSUPPORTED, "cnmf: the AB divergence is outside the accelerated path");
+    case NMFB_DIV_KL:
+    case NMFB_DIV_IS:
+      return h->fail(NMFB_ERR_UNSUPPORTED, "cnmf: only the euclidean / frobenius divergence is accelerated");
+    default:
+      return h->fail(NMFB_ERR_DIVERGENCE, "unknown divergence %d", cfg.divergence);
+  }
+  const int m = h->m, n = h->n;
+  s->K = K;
+  s->T = T;
+  s->KT = K * T;
+  s->KTp = round_up(s->KT, 32);
+  s->m = m;
+  s->n = n;
+  s->ldw = round_up(m, 4);
+  s->ldh = round_up(n, 4);
+  s->W_fixed = cfg.W_fixed != 0;
+  s->H_fixed = cfg.H_fixed != 0;
+  s->lambda_w = static_cast<float>(cfg.W_sparsity);
+  s->lambda_h = static_cast<float>(cfg.H_sparsity);
+  s->maxiter = cfg.maxiter;
+  s->tolerance = cfg.tolerance;
+  const int KT = s->KT, KTp = s->KTp;
+  Arena* ar = &s->ar;
+  NMFB_TRY(ar->alloc(h, &s->Wm, static_cast<size_t>(KTp) * s->ldw));
+  NMFB_TRY(ar->alloc(h, &s->Wt, static_cast<size_t>(KTp) * s->ldw));
+  NMFB_TRY(ar->alloc(h, &s->Hm, static_cast<size_t>(K) * s->ldh));
+  NMFB_TRY(ar->alloc(h, &s->Hs, static_cast<size_t>(KTp) * s->ldh));
+  NMFB_TRY(ar->alloc(h, &s->A, static_cast<size_t>(KTp) * s->ldw));
+  NMFB_TRY(ar->alloc(h, &s->B, static_cast<size_t>(KTp) * s->ldw));
+  NMFB_TRY(ar->alloc(h, &s->P, static_cast<size_t>(KTp) * s->ldh));
+  NMFB_TRY(ar->alloc(h, &s->D, static_cast<size_t>(KTp) * s->ldh));
+  NMFB_TRY(ar->alloc(h, &s->pcoef, KTp));
+  NMFB_TRY(ar->alloc(h, &s->qcoef, KTp));
+  NMFB_TRY(ar->alloc(h, &s->bvec, KTp));
+  NMFB_TRY(ar->alloc(h, &s->hscale, KTp));
+  NMFB_TRY(ar->alloc(h, &s->ab, 2 * KTp));
+  NMFB_TRY(ar->alloc(h, &s->norm2, KTp));
+  NMFB_TRY(ar->alloc(h, &s->wsum, KTp));
+  NMFB_TRY(ar->alloc(h, &s->scal, 8));
+  NMFB_TRY(ar->alloc(h, &s->cost, static_cast<size_t>(s->maxiter) + 1));
+  NMFB_TRY(ar->alloc(h, &s->stop, 2));
+
+  {  // initial factors: defaults cnmf.m:311, 331-335 (rand; W normalised per basis)
+    std::vector<float> tmp;
+    const float* Wsrc = cfg.W_init;
+    if (!Wsrc) {
+      tmp.resize(static_cast<size_t>(m) * KT);
+      fill_uniform(tmp, cfg.seed * 2 + 1, false);
+      Wsrc = tmp.data();
+    }
+    NMFB_TRY(upload_colmajor(h, Wsrc, m, KT, s->Wm, s->ldw));
+    NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    const float* Hsrc = cfg.H_init;
+    if (!Hsrc) {
+      tmp.resize(static_cast<size_t>(K) * n);
+      fill_uniform(tmp, cfg.seed * 2 + 2, true);
+      Hsrc = tmp.data();
+    }
+    NMFB_TRY(upload_H(h, ar, Hsrc, K, n, s->Hm, s->ldh));
+    NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  // cnmf.m:157-166: W(:,k,:) /= w_norm, H(k,:) *= w_norm with w_norm = |W(:,k,:)|_F / T
+  vec_sums_kernel<<<vec_grid(m, KT), 256, 0, h->stream>>>(s->Wm, KT, m, s->ldw, nullptr, s->norm2, nullptr);
+  NMFB_TRY(check_launch(h, "vec_sums(W init)"));
+  w_normalize_kernel<<<vec_grid(m, KT), 256, 0, h->stream>>>(s->Wm, s->Wt, m, s->ldw, K, T, 1, s->norm2,
+                                                             s->wsum, s->hscale, nullptr);
+  NMFB_TRY(check_launch(h, "w_normalize(init)"));
+  row_scale_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, nullptr, n, s->ldh, s->hscale, 0);
+  NMFB_TRY(check_launch(h, "row_scale(H init)"));
+
+  double* sq = nullptr;
+  NMFB_TRY(ar->alloc(h, &sq, 1));
+  NMFB_TRY(prepare_v_work(h, false, true, sq, nullptr));
+  NMFB_CUDA(h, cudaMemcpyAsync(&s->vsq, sq, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+
+  const int* stop = s->stop;
+  NMFB_TRY(plan_gram(h, ar, &s->gramW, s->Wt, KTp, m, s->ldw, stop));
+  NMFB_TRY(plan_gram(h, ar, &s->gramH, s->Hs, KTp, n, s->ldh, stop));
+  {
+    MatRef Xv{h->Vwork, m, n, h->ldv, true};
+    MatRef Yh{s->Hs, n, KTp, s->ldh, false};
+    MatRef Xw{s->Wt, m, KTp, s->ldw, true};
+    MatRef Yg{s->gramH.gtf, KTp, KTp, KTp, false};
+    const int tiles = (m + kTileM - 1) / kTileM * ((KTp + kMaxN - 1) / kMaxN);
+    NMFB_TRY(plan_store(h, ar, &s->gemmA, Xv, Yh, n, &Xw, &Yg, KTp, m, KTp, s->A, s->B, s->ldw,
+                        tiles * 2 <= h->num_sms, stop));
+    MatRef Xvt{h->Vwork, m, n, h->ldv, false};
+    MatRef Yw{s->Wt, m, KTp, s->ldw, false};
+    MatRef Xh{s->Hs, n, KTp, s->ldh, true};
+    MatRef Ygw{s->gramW.gtf, KTp, KTp, KTp, false};
+    const int tiles_h = (n + kTileM - 1) / kTileM * ((KTp + kMaxN - 1) / kMaxN);
+    NMFB_TRY(plan_store(h, ar, &s->gemmP, Xvt, Yw, m, &Xh, &Ygw, KTp, n, KTp, s->P, s->D, s->ldh,
+                        tiles_h * 2 <= h->num_sms, stop));
+  }
+  if (s->W_fixed) NMFB_TRY(run_gram(h, s->gramW, nullptr));
+  // sum(H) for the sparsity term when H is never updated is accumulated by fold_update (freeze)
+
+  NMFB_TRY(run_chunked(h, s->maxiter, s->stop, [&](int i) { return enqueue_iteration(h, s, i); }));
+  // cost of the last executed iteration needs Hs Hs' of the final H
+  NMFB_TRY(enqueue_hstack(h, s, stop));
+  NMFB_TRY(run_gram(h, s->gramH, stop));
+  NMFB_TRY(enqueue_cost(h, s, s->maxiter - 1));
+  int flags[2] = {0, 0};
+  NMFB_CUDA(h, cudaMemcpyAsync(flags, s->stop, sizeof(flags), cudaMemcpyDeviceToHost, h->stream));
+  NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  const int nc = flags[1];
+  if (n_cost) *n_cost = nc;
+  if (cost_out && nc > 0)
+    NMFB_CUDA(h, cudaMemcpy(cost_out, s->cost, nc * sizeof(double), cudaMemcpyDeviceToHost));
+  if (W_out) NMFB_TRY(download_colmajor(h, s->Wm, s->ldw, m, KT, W_out));
+  if (H_out) NMFB_TRY(download_H(h, s->Hm, s->ldh, K, n, H_out));
+  return NMFB_OK;
+}
+
+}  // namespace cnmfdetail
+
 extern "C" int nmfb_cnmf(nmfb_handle* h, int K, int T, const nmfb_config* cfg, float* W_out, float* H_out,
                          double* cost_out, int* n_cost) {
-  return h ? h->fail(NMFB_ERR_UNSUPPORTED, "cnmf: not built yet") : NMFB_ERR_INVALID_ARGUMENT;
+  if (!h) return NMFB_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  cnmfdetail::CnmfState st;
+  int rc = cnmfdetail::cnmf_run(h, &st, K, T, cfg, W_out, H_out, cost_out, n_cost);
+  cudaStreamSynchronize(h->stream);
+  return rc;
 }

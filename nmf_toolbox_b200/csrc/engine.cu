@@ -19,14 +19,14 @@ int check_launch(nmfb_handle* h, const char* what) {
 }
 
 dim3 vec_grid(int len, int nvec, int threads) {
-  int bx = (len + threads * 4 - 1) / (threads * 4);
+  int bx = (len + threads * 16 - 1) / (threads * 16);
   bx = std::max(1, std::min(bx, 64));
   return dim3(bx, nvec, 1);
 }
 
 static int plan_common(nmfb_handle* h, GemmOp* op, const MatRef& X0, const MatRef& Y0,
                        long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1,
-                       int rows, int ncols, int splits_hint) {
+                       int rows, int ncols, int splits_hint, const ExtraSegs* segs = nullptr) {
   GemmOperand x0 = operand(X0), y0 = operand(Y0), x1{}, y1{};
   if (X1) {
     x1 = operand(*X1);
@@ -35,6 +35,10 @@ static int plan_common(nmfb_handle* h, GemmOp* op, const MatRef& X0, const MatRe
   std::string e = plan_gemm(&op->L, x0, y0, kdim0, X1 ? &x1 : nullptr, X1 ? &y1 : nullptr, kdim1,
                             rows, ncols, splits_hint, h->num_sms);
   if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "plan_gemm: %s", e.c_str());
+  for (int sgi = 0; segs && sgi < segs->n; ++sgi) {
+    e = add_segment(&op->L, sgi + 1, operand(segs->X[sgi]), operand(segs->Y[sgi]), h->num_sms, splits_hint);
+    if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "add_segment: %s", e.c_str());
+  }
   op->splits = static_cast<int>(op->L.grid.z);
   op->planned = true;
   return NMFB_OK;
@@ -43,9 +47,9 @@ static int plan_common(nmfb_handle* h, GemmOp* op, const MatRef& X0, const MatRe
 int plan_store(nmfb_handle* h, Arena* ar, GemmOp* op, const MatRef& X0, const MatRef& Y0,
                long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1, int rows,
                int ncols, float* out0, float* out1, long long ldo, bool allow_split,
-               const int* stop) {
+               const int* stop, const ExtraSegs* segs) {
   op->epi = EPI_STORE;
-  NMFB_TRY(plan_common(h, op, X0, Y0, kdim0, X1, Y1, kdim1, rows, ncols, allow_split ? 0 : 1));
+  NMFB_TRY(plan_common(h, op, X0, Y0, kdim0, X1, Y1, kdim1, rows, ncols, allow_split ? 0 : 1, segs));
   GemmArgs& a = op->L.args;
   a.stop = stop;
   a.out1 = out1;
@@ -65,9 +69,9 @@ int plan_store(nmfb_handle* h, Arena* ar, GemmOp* op, const MatRef& X0, const Ma
 
 int plan_fused(nmfb_handle* h, GemmOp* op, int epi, const MatRef& X0, const MatRef& Y0,
                long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1, int rows,
-               int ncols, int ncols_valid, const int* stop) {
+               int ncols, int ncols_valid, const int* stop, const ExtraSegs* segs) {
   op->epi = epi;
-  NMFB_TRY(plan_common(h, op, X0, Y0, kdim0, X1, Y1, kdim1, rows, ncols, 1));
+  NMFB_TRY(plan_common(h, op, X0, Y0, kdim0, X1, Y1, kdim1, rows, ncols, 1, segs));
   op->L.args.stop = stop;
   op->L.args.ncols_valid = ncols_valid;
   return NMFB_OK;
@@ -89,13 +93,24 @@ int run_gemm(nmfb_handle* h, const GemmOp& op) {
 }
 
 int plan_gram(nmfb_handle* h, Arena* ar, GramOp* op, const float* Mt, int nvec, int len,
-              long long ld, const int* stop) {
+              long long ld, const int* stop, const float* Mlo, int chunk_kb) {
   op->nvec = nvec;
   NMFB_TRY(ar->alloc(h, &op->g32, static_cast<size_t>(nvec) * nvec));
   NMFB_TRY(ar->alloc(h, &op->gtf, static_cast<size_t>(nvec) * nvec));
   MatRef M{Mt, len, nvec, ld, false};
   op->g.epi = EPI_STORE;
-  NMFB_TRY(plan_common(h, &op->g, M, M, len, nullptr, nullptr, 0, nvec, nvec, 0));
+  ExtraSegs segs;
+  if (Mlo) {
+    NMFB_TRY(ar->alloc(h, &op->glo, static_cast<size_t>(nvec) * nvec));
+    MatRef L{Mlo, len, nvec, ld, false};
+    segs.n = 2;
+    segs.X[0] = M;
+    segs.Y[0] = L;
+    segs.X[1] = L;
+    segs.Y[1] = M;
+  }
+  NMFB_TRY(plan_common(h, &op->g, M, M, len, nullptr, nullptr, 0, nvec, nvec, 0, Mlo ? &segs : nullptr));
+  op->g.L.args.chunk_kb = chunk_kb;
   GemmArgs& a = op->g.L.args;
   a.stop = stop;
   a.ldo = nvec;
@@ -112,7 +127,7 @@ int run_gram(nmfb_handle* h, const GramOp& op, const int* stop) {
   if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "%s", e.c_str());
   const int count = op.nvec * op.nvec;
   gram_reduce_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(op.g.parts, op.g.splits, count,
-                                                                 op.g32, op.gtf, count, stop);
+                                                                 op.g32, op.gtf, op.glo, count, stop);
   return check_launch(h, "gram_reduce");
 }
 

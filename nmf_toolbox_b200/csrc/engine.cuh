@@ -42,6 +42,10 @@ struct nmfb_handle {
   nmfb::Comm* comm = nullptr;
   NmfSession* sess = nullptr;
 
+  // optional per-kernel timing of the two large contractions (bench.py roofline)
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_ev[2];  // [0] W-step GEMM, [1] H-step GEMM: begin/end pairs
+
   int fail(int code, const char* fmt, ...) {
     char buf[1024];
     va_list ap;
@@ -112,13 +116,19 @@ inline GemmOperand operand(const MatRef& r) {
 // out0 = X0 * Y0' (+ out1 = X1 * Y1').  With allow_split the contraction of
 // phase 0 may be cut over several CTAs (EPI_STORE only); the slabs are summed
 // into out0 by run_gemm.
+// Extra phase-0 operand pairs: acc0 = X0*Y0' + Xs[0]*Ys[0]' (+ Xs[1]*Ys[1]'), all over kdim0.
+struct ExtraSegs {
+  int n = 0;
+  MatRef X[2];
+  MatRef Y[2];
+};
 int plan_store(nmfb_handle* h, Arena* ar, GemmOp* op, const MatRef& X0, const MatRef& Y0,
                long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1, int rows,
                int ncols, float* out0, float* out1, long long ldo, bool allow_split,
-               const int* stop);
+               const int* stop, const ExtraSegs* segs = nullptr);
 int plan_fused(nmfb_handle* h, GemmOp* op, int epi, const MatRef& X0, const MatRef& Y0,
                long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1, int rows,
-               int ncols, int ncols_valid, const int* stop);
+               int ncols, int ncols_valid, const int* stop, const ExtraSegs* segs = nullptr);
 int run_gemm(nmfb_handle* h, const GemmOp& op);
 
 // Gram matrix G = M M' of a factor stored as nvec contiguous vectors of length len
@@ -126,11 +136,14 @@ int run_gemm(nmfb_handle* h, const GemmOp& op);
 struct GramOp {
   GemmOp g;
   float* g32 = nullptr;
-  float* gtf = nullptr;
+  float* gtf = nullptr;  // tf32 head of g32
+  float* glo = nullptr;  // tf32 tail (only when planned with a split factor)
   int nvec = 0;
 };
+// Mlo != nullptr: the factor is given as a tf32 head/tail pair and the Gram matrix is formed at
+// fp32 accuracy from the three leading terms (hi*hi' + hi*lo' + lo*hi').
 int plan_gram(nmfb_handle* h, Arena* ar, GramOp* op, const float* Mt, int nvec, int len,
-              long long ld, const int* stop);
+              long long ld, const int* stop, const float* Mlo = nullptr, int chunk_kb = 0);
 int run_gram(nmfb_handle* h, const GramOp& op, const int* stop);
 
 dim3 vec_grid(int len, int nvec, int threads = 256);
@@ -155,5 +168,41 @@ int download_H(nmfb_handle* h, const float* Hm, long long ldh, int K, int n, flo
 void fill_uniform(std::vector<float>& v, unsigned long long seed, bool clamp_eps);
 
 int check_launch(nmfb_handle* h, const char* what);
+
+// Queue `maxiter` iterations in chunks.  The stop flag written by the cost
+// kernel turns everything queued behind a converged iteration into no-ops, so
+// the host only looks at the flag between chunks and never waits for the chunk
+// it has just queued.  enqueue(i) queues iteration i (0-based).
+template <class Fn>
+int run_chunked(nmfb_handle* h, int maxiter, const int* stop_dev, Fn enqueue, int chunk = 16) {
+  cudaEvent_t evs[2] = {nullptr, nullptr};
+  int* flags = nullptr;
+  int rc = NMFB_OK;
+  for (int b = 0; b < 2 && rc == NMFB_OK; ++b)
+    if (cudaEventCreateWithFlags(&evs[b], cudaEventDisableTiming) != cudaSuccess)
+      rc = h->fail(NMFB_ERR_CUDA, "cudaEventCreate failed");
+  if (rc == NMFB_OK && cudaMallocHost(&flags, 2 * sizeof(int)) != cudaSuccess)
+    rc = h->fail(NMFB_ERR_CUDA, "cudaMallocHost failed");
+  if (rc == NMFB_OK) {
+    flags[0] = flags[1] = 0;
+    int c = 0, i = 0;
+    while (i < maxiter && rc == NMFB_OK) {
+      const int end = i + chunk < maxiter ? i + chunk : maxiter;
+      for (; i < end && rc == NMFB_OK; ++i) rc = enqueue(i);
+      if (rc != NMFB_OK) break;
+      if (c > 0) {
+        cudaEventSynchronize(evs[(c - 1) & 1]);
+        if (flags[(c - 1) & 1] != 0) break;
+      }
+      cudaMemcpyAsync(&flags[c & 1], stop_dev, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+      cudaEventRecord(evs[c & 1], h->stream);
+      ++c;
+    }
+  }
+  for (int b = 0; b < 2; ++b)
+    if (evs[b]) cudaEventDestroy(evs[b]);
+  if (flags) cudaFreeHost(flags);
+  return rc;
+}
 
 }  // namespace nmfb

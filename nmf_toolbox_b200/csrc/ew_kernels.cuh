@@ -134,6 +134,18 @@ __global__ void round_copy_kernel(const float* __restrict__ src, float* __restri
       dst[c * ld + i] = tf32_rn(src[c * ld + i]);
 }
 
+// hi = tf32(x), lo = tf32(x - hi): x = hi + lo to ~2^-22 relative ("3xTF32" operand split)
+__global__ void split_copy_kernel(const float* __restrict__ src, float* __restrict__ hi,
+                                  float* __restrict__ lo, int nvec, int len, long long ld) {
+  for (int c = blockIdx.y; c < nvec; c += gridDim.y)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
+      const float x = src[c * ld + i];
+      const float h = tf32_rn(x);
+      hi[c * ld + i] = h;
+      lo[c * ld + i] = tf32_rn(x - h);
+    }
+}
+
 // out_sum[c] += sum_i M[c][i];  out_sq[c] += sum_i M[c][i]^2   (either may be null)
 __global__ void vec_sums_kernel(const float* __restrict__ M, int nvec, int len, long long ld,
                                 double* out_sum, double* out_sq, const int* stop) {
@@ -156,15 +168,17 @@ __global__ void vec_sums_kernel(const float* __restrict__ M, int nvec, int len, 
 
 // Sum split-K slabs of a Kp x Kp Gram matrix; write fp32 and tf32-rounded copies.
 __global__ void gram_reduce_kernel(const float* __restrict__ parts, int splits, long long slab,
-                                   float* __restrict__ g32, float* __restrict__ gtf, int count,
-                                   const int* stop) {
+                                   float* __restrict__ g32, float* __restrict__ gtf,
+                                   float* __restrict__ glo, int count, const int* stop) {
   NMFB_STOP_GUARD(stop);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   float s = 0.f;
   for (int z = 0; z < splits; ++z) s += parts[z * slab + i];
   g32[i] = s;
-  gtf[i] = tf32_rn(s);
+  const float hi = tf32_rn(s);
+  gtf[i] = hi;
+  if (glo) glo[i] = tf32_rn(s - hi);
 }
 // Same for a general matrix with split-K slabs (fp32 result only).
 __global__ void split_reduce_kernel(const float* __restrict__ parts, int splits, long long slab,
@@ -297,6 +311,18 @@ __global__ void row_scale_kernel(float* __restrict__ H, float* __restrict__ Ht, 
   }
 }
 
+// out += <GA, GB> over count fp32 entries (fp64 accumulation); feeds the trace form of the cost
+__global__ void gram_dot_kernel(const float* __restrict__ GA, const float* __restrict__ GB, int count,
+                                double* out, const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  __shared__ double sh[32];
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    acc[0] += static_cast<double>(GA[i]) * GB[i];
+  block_sum<1>(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(out, acc[0]);
+}
+
 // ---------------------------------------------------------------- cost + stop test
 struct CostArgs {
   int mode;             // 0 Euclid trace, 1 Euclid direct (scal[0] = sum (V-Vhat)^2), 2 KL, 3 sparsity terms only
@@ -306,7 +332,7 @@ struct CostArgs {
   const float* GH;
   double vsq;           // sum V^2                 (Euclid)
   const double* vstats; // [1] sum V, [2] sum V log V (KL)
-  double* scal;         // accumulators filled by the H-update / cost epilogues; reset here
+  double* scal;         // [0] <N,H> [1] sum H [2],[3] cost-epilogue sums [4] <G_W,G_H>; reset here
   const double* wsum;   // per-column sums of W (Kp_w entries)
   int n_wsum;
   double lambda_w, lambda_h;
@@ -319,10 +345,7 @@ __global__ void cost_kernel(CostArgs a) {
   if (a.stop[0] != 0) return;
   __shared__ double sh[64];
   double acc[2] = {0.0, 0.0};
-  if (a.mode == 0) {
-    for (int i = threadIdx.x; i < a.Kp * a.Kp; i += blockDim.x)
-      acc[0] += static_cast<double>(a.GW[i]) * a.GH[i];
-  }
+  acc[0] = threadIdx.x == 0 ? a.scal[4] : 0.0;
   for (int i = threadIdx.x; i < a.n_wsum; i += blockDim.x) acc[1] += a.wsum[i];
   block_sum<2>(acc, sh);
   if (threadIdx.x != 0) return;
@@ -341,7 +364,7 @@ __global__ void cost_kernel(CostArgs a) {
     const double prev = a.cost[a.iter - 1];
     if (c < prev && prev - c < a.tolerance) a.stop[0] = 1;  // nmf.m:221-224
   }
-  a.scal[0] = a.scal[1] = a.scal[2] = a.scal[3] = 0.0;
+  a.scal[0] = a.scal[1] = a.scal[2] = a.scal[3] = a.scal[4] = 0.0;
 }
 
 // ---------------------------------------------------------------- convolutive helpers
@@ -392,8 +415,8 @@ __global__ void fold_update_kernel(const float* __restrict__ P, const float* __r
 // Xnew = X - step * (Dp - Dn)   (nmfsc.m:148,154 / 200,205)
 __global__ void grad_step_kernel(const float* __restrict__ X, const float* __restrict__ Dp,
                                  const float* __restrict__ Dn, float* __restrict__ Xnew, int nvec,
-                                 int len, long long ld, const double* step) {
-  const float s = static_cast<float>(*step);
+                                 int len, long long ld, double step) {
+  const float s = static_cast<float>(step);
   const int c = blockIdx.y;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
     const long long o = static_cast<long long>(c) * ld + i;

@@ -74,6 +74,8 @@ std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const GemmOperand& Y
   a.ncols = ncols;
   a.box_n = std::min(ncols, kMaxN);
   a.nkb0 = static_cast<int>((kdim0 + kBlockK - 1) / kBlockK);
+  a.nkb_seg = a.nkb0;
+  a.chunk_kb = 0;
   a.nkb1 = (X1 != nullptr) ? static_cast<int>((kdim1 + kBlockK - 1) / kBlockK) : 0;
   a.xmn0 = X0.mn_major ? 1 : 0;
   a.xmn1 = (X1 && X1->mn_major) ? 1 : 0;
@@ -112,6 +114,38 @@ std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const GemmOperand& Y
     L->tmX1 = L->tmX0;
     L->tmY1 = L->tmY0;
   }
+  L->tmXb = L->tmXc = L->tmX0;
+  L->tmYb = L->tmYc = L->tmY0;
+  return "";
+}
+
+std::string add_segment(GemmLaunch* L, int seg, const GemmOperand& X, const GemmOperand& Y, int num_sms,
+                        int splits_hint) {
+  GemmArgs& a = L->args;
+  if (seg < 1 || seg > 2) return "add_segment: segment index must be 1 or 2";
+  if ((X.mn_major ? 1 : 0) != a.xmn0 || (Y.mn_major ? 1 : 0) != a.ymn0)
+    return "add_segment: operands must have the layout of segment 0";
+  std::string e;
+  CUtensorMap* tx = seg == 1 ? &L->tmXb : &L->tmXc;
+  CUtensorMap* ty = seg == 1 ? &L->tmYb : &L->tmYc;
+  e = X.mn_major ? make_tmap(tx, X.m, 32, 32, true) : make_tmap(tx, X.m, kBlockK, kTileM, false);
+  if (!e.empty()) return "Xseg " + e;
+  e = Y.mn_major ? make_tmap(ty, Y.m, 32, 32, true) : make_tmap(ty, Y.m, kBlockK, a.box_n, false);
+  if (!e.empty()) return "Yseg " + e;
+  a.nkb0 = a.nkb_seg * (seg + 1);
+  // redo the split bookkeeping for the longer contraction
+  int splits = 1;
+  a.kb_per_split = a.nkb0;
+  if (splits_hint != 1) {
+    if (splits_hint <= 0) {
+      splits = choose_splits(static_cast<int>(L->grid.x * L->grid.y), a.nkb0, num_sms, &a.kb_per_split);
+    } else {
+      int per = std::max(1, (a.nkb0 + splits_hint - 1) / splits_hint);
+      splits = std::max(1, (a.nkb0 + per - 1) / per);
+      a.kb_per_split = per;
+    }
+  }
+  L->grid.z = splits;
   return "";
 }
 
@@ -123,8 +157,8 @@ static cudaError_t set_smem_attr() {
 
 template <int EPI>
 static void launch_one(const GemmLaunch& L, cudaStream_t stream) {
-  panel_gemm_kernel<EPI><<<L.grid, kGemmThreads, kGemmSmemBytes, stream>>>(L.tmX0, L.tmY0, L.tmX1,
-                                                                          L.tmY1, L.args);
+  panel_gemm_kernel<EPI><<<L.grid, kGemmThreads, kGemmSmemBytes, stream>>>(
+      L.tmX0, L.tmY0, L.tmX1, L.tmY1, L.tmXb, L.tmYb, L.tmXc, L.tmYc, L.args);
 }
 
 std::string launch_gemm(const GemmLaunch& L, int epi, cudaStream_t stream) {

@@ -35,6 +35,7 @@ int choose_splits(int tiles, int nkb0, int num_sms, int* kb_per_split);
 
 struct GemmLaunch {
   CUtensorMap tmX0, tmY0, tmX1, tmY1;
+  CUtensorMap tmXb, tmYb, tmXc, tmYc;  // extra phase-0 segments (same shapes / majorness as X0, Y0)
   GemmArgs args;
   dim3 grid;
 };
@@ -45,6 +46,11 @@ struct GemmLaunch {
 std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const GemmOperand& Y0, long long kdim0,
                       const GemmOperand* X1, const GemmOperand* Y1, long long kdim1, int rows,
                       int ncols, int splits_hint, int num_sms);
+
+// Adds operand pair number `seg` (1 or 2) to phase 0: acc0 += Xs * Ys' over the same contraction.
+// Must be called after plan_gemm and before any split bookkeeping is read.
+std::string add_segment(GemmLaunch* L, int seg, const GemmOperand& X, const GemmOperand& Y, int num_sms,
+                        int splits_hint);
 
 std::string launch_gemm(const GemmLaunch& L, int epi, cudaStream_t stream);
 

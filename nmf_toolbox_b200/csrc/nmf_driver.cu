@@ -144,7 +144,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   NMFB_TRY(ar->alloc(h, &s->norm2, Kp));
   NMFB_TRY(ar->alloc(h, &s->wsum, Kp));
   NMFB_TRY(ar->alloc(h, &s->hs, Kp));
-  NMFB_TRY(ar->alloc(h, &s->scal, 4));
+  NMFB_TRY(ar->alloc(h, &s->scal, 8));
   NMFB_TRY(ar->alloc(h, &s->cost, static_cast<size_t>(s->maxiter) + 1));
   NMFB_TRY(ar->alloc(h, &s->stop, 2));
   NMFB_CUDA(h, cudaMallocHost(&s->pinned, 2 * sizeof(int)));
@@ -178,7 +178,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   NMFB_TRY(check_launch(h, "w_normalize(init)"));
   round_copy_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, s->Ht, K, n, s->ldh, nullptr);
   NMFB_TRY(check_launch(h, "round_copy(H init)"));
-  NMFB_TRY(zero_async(h, s->scal, 4 * sizeof(double)));
+  NMFB_TRY(zero_async(h, s->scal, 8 * sizeof(double)));
   vec_sums_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, K, n, s->ldh, s->hs, nullptr, nullptr);
   NMFB_TRY(check_launch(h, "vec_sums(H init)"));
 
@@ -186,11 +186,13 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   if (kl) {
     VStats st;
     NMFB_TRY(compute_v_stats(h, true, &st, &s->vstats, nullptr, ar));
+    NMFB_TRY(comm_allreduce(h, nullptr, 0, s->vstats, 4, nullptr, 0));  // global sums over all shards
     NMFB_TRY(ar->alloc(h, &s->Q, static_cast<size_t>(n) * h->ldv));
   } else {
     double* sq = nullptr;
     NMFB_TRY(ar->alloc(h, &sq, 1));
     NMFB_TRY(prepare_v_work(h, false, true, sq, nullptr));
+    NMFB_TRY(comm_allreduce(h, nullptr, 0, sq, 1, nullptr, 0));  // |V|^2 over all column shards
     NMFB_CUDA(h, cudaMemcpyAsync(&s->vsq, sq, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
     s->Vmma = h->Vwork;
@@ -285,6 +287,12 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
 
 // ------------------------------------------------------------------ one iteration
 static int enqueue_cost(nmfb_handle* h, NmfSession* s, int iter, int mode) {
+  if (mode == 0) {  // <G_W, G_H> of the trace identity (scal[4] is zero: reset by the previous cost kernel)
+    const int cnt = s->Kp * s->Kp;
+    gram_dot_kernel<<<std::min(64, (cnt + 1023) / 1024), 256, 0, h->stream>>>(s->gramW.g32, s->gramH.g32, cnt,
+                                                                               s->scal + 4, s->stop);
+    NMFB_TRY(check_launch(h, "gram_dot"));
+  }
   CostArgs c{};
   c.mode = mode;
   c.iter = iter;
@@ -310,7 +318,8 @@ static int allreduce_w_inputs(nmfb_handle* h, NmfSession* s, bool with_gram) {
   if (comm_size(h->comm) <= 1) return NMFB_OK;
   const size_t nA = static_cast<size_t>(s->Kp) * s->ldw;
   const size_t count = nA + (with_gram ? static_cast<size_t>(s->Kp) * s->Kp : 0);
-  NMFB_TRY(comm_allreduce(h, s->packed, count, s->hs, s->Kp, s->scal, 4));
+  const bool kl = s->divergence == NMFB_DIV_KL;  // hs is only formed (per iteration) by the KL path
+  NMFB_TRY(comm_allreduce(h, s->packed, count, kl ? s->hs : nullptr, kl ? s->Kp : 0, s->scal, 4));
   if (with_gram) {
     const int cnt = s->Kp * s->Kp;
     round_copy_kernel<<<dim3((cnt + 255) / 256, 1), 256, 0, h->stream>>>(s->gramH.g32, s->gramH.gtf, 1, cnt,
@@ -342,6 +351,55 @@ static int enqueue_w_finish(nmfb_handle* h, NmfSession* s, int mode) {
   return NMFB_OK;
 }
 
+// run_gemm bracketed by a CUDA-event pair when profiling is on
+static int run_timed(nmfb_handle* h, const GemmOp& op, int which) {
+  if (!h->profile) return run_gemm(h, op);
+  cudaEvent_t e0, e1;
+  NMFB_CUDA(h, cudaEventCreate(&e0));
+  NMFB_CUDA(h, cudaEventCreate(&e1));
+  h->prof_ev[which].push_back(e0);
+  h->prof_ev[which].push_back(e1);
+  NMFB_CUDA(h, cudaEventRecord(e0, h->stream));
+  NMFB_TRY(run_gemm(h, op));
+  NMFB_CUDA(h, cudaEventRecord(e1, h->stream));
+  return NMFB_OK;
+}
+
+extern "C" int nmfb_profile_enable(nmfb_handle* h, int on) {
+  if (!h) return NMFB_ERR_INVALID_ARGUMENT;
+  for (int w = 0; w < 2; ++w) {
+    for (cudaEvent_t e : h->prof_ev[w]) cudaEventDestroy(e);
+    h->prof_ev[w].clear();
+  }
+  h->profile = on != 0;
+  return NMFB_OK;
+}
+
+// Average device time (ms) of the W-step and H-step contractions recorded so far.
+extern "C" int nmfb_profile_get(nmfb_handle* h, double* ms_w, double* ms_h, int* count) {
+  if (!h) return NMFB_ERR_INVALID_ARGUMENT;
+  NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  double out[2] = {0.0, 0.0};
+  int cnt = 0;
+  for (int w = 0; w < 2; ++w) {
+    double tot = 0.0;
+    int c = 0;
+    for (size_t i = 0; i + 1 < h->prof_ev[w].size(); i += 2) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, h->prof_ev[w][i], h->prof_ev[w][i + 1]) == cudaSuccess) {
+        tot += ms;
+        ++c;
+      }
+    }
+    out[w] = c ? tot / c : 0.0;
+    cnt = std::max(cnt, c);
+  }
+  if (ms_w) *ms_w = out[0];
+  if (ms_h) *ms_h = out[1];
+  if (count) *count = cnt;
+  return NMFB_OK;
+}
+
 static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
   const int Kp = s->Kp, K = s->K, n = s->n;
   const int* stop = s->stop;
@@ -351,7 +409,7 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
     if (s->W_fixed) {
       if (multi) return h->fail(NMFB_ERR_UNSUPPORTED, "W_fixed with several GPUs");
     } else {
-      NMFB_TRY(run_gemm(h, s->gemmA));
+      NMFB_TRY(run_timed(h, s->gemmA, 0));
     }
     NMFB_TRY(allreduce_w_inputs(h, s, true));
     if (i > 0 && !s->direct_cost) NMFB_TRY(enqueue_cost(h, s, i - 1, 0));
@@ -360,14 +418,14 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
       NMFB_TRY(enqueue_w_finish(h, s, WSTEP_EUCLID));
       NMFB_TRY(run_gram(h, s->gramW, stop));
     }
-    NMFB_TRY(run_gemm(h, s->gemmH));
+    NMFB_TRY(run_timed(h, s->gemmH, 1));
     if (s->direct_cost) {
       NMFB_TRY(run_gemm(h, s->gemmS));
       if (multi) NMFB_TRY(comm_allreduce(h, nullptr, 0, nullptr, 0, s->scal, 4));
       NMFB_TRY(enqueue_cost(h, s, i, 1));
     }
   } else {
-    if (!s->H_fixed || i == 0) {
+    if (!s->H_fixed || i == 0 || multi) {
       NMFB_TRY(zero_async(h, s->hs, Kp * sizeof(double)));
       vec_sums_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, K, n, s->ldh, s->hs, nullptr, stop);
       NMFB_TRY(check_launch(h, "vec_sums(H)"));
@@ -489,36 +547,11 @@ extern "C" int nmfb_nmf(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_
                         double* cost_out, int* n_cost) {
   NMFB_TRY(nmfb_nmf_begin(h, K, cfg));
   NmfSession* s = h->sess;
-  // Queue the loop in chunks; the stop flag written by the cost kernel turns
-  // everything queued behind a converged iteration into no-ops, so the host only
-  // looks at it between chunks (and never waits for the chunk it just queued).
-  const int chunk = 16;
-  cudaEvent_t evs[2] = {nullptr, nullptr};
-  int rc = NMFB_OK;
-  for (int b = 0; b < 2 && rc == NMFB_OK; ++b)
-    if (cudaEventCreateWithFlags(&evs[b], cudaEventDisableTiming) != cudaSuccess)
-      rc = h->fail(NMFB_ERR_CUDA, "cudaEventCreate failed");
-  int* flags = nullptr;
-  if (rc == NMFB_OK && cudaMallocHost(&flags, 2 * sizeof(int)) != cudaSuccess)
-    rc = h->fail(NMFB_ERR_CUDA, "cudaMallocHost failed");
-  if (rc == NMFB_OK) {
-    flags[0] = flags[1] = 0;
-    int c = 0;
-    while (s->iters_enqueued < s->maxiter && rc == NMFB_OK) {
-      rc = nmfb_nmf_step(h, chunk);
-      if (rc != NMFB_OK) break;
-      if (c > 0) {  // look at the flag as of the end of the previous chunk
-        cudaEventSynchronize(evs[(c - 1) & 1]);
-        if (flags[(c - 1) & 1] != 0) break;
-      }
-      cudaMemcpyAsync(&flags[c & 1], s->stop, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-      cudaEventRecord(evs[c & 1], h->stream);
-      ++c;
-    }
-  }
-  for (int b = 0; b < 2; ++b)
-    if (evs[b]) cudaEventDestroy(evs[b]);
-  if (flags) cudaFreeHost(flags);
+  int rc = run_chunked(h, s->maxiter, s->stop, [&](int i) {
+    int r = enqueue_iteration(h, s, i);
+    if (r == NMFB_OK) ++s->iters_enqueued;
+    return r;
+  });
   if (rc != NMFB_OK) {
     nmf_session_release(h);
     return rc;

@@ -66,7 +66,10 @@ struct GemmArgs {
   int ncols;         // output columns (multiple of 32; rows of Y beyond its extent read as zero)
   int ncols_valid;   // EPI_RECON / EPI_RESID / EPI_KLQ: columns that exist in V (<= ncols)
   int box_n;         // rows of the Y TMA box = min(ncols, 256)
-  int nkb0;          // phase-0 k-blocks in total (over all splits)
+  int nkb0;          // phase-0 k-blocks in total (over all splits and segments)
+  int nkb_seg;       // phase 0 may be a sum over up to 3 operand pairs ("segments", e.g. the
+                     // hi/lo terms of a split-tf32 product); k-blocks per segment
+  int chunk_kb;      // k-blocks accumulated in TMEM before promotion to registers (<= 0: default)
   int kb_per_split;  // phase-0 k-blocks per split (blockIdx.z)
   int nkb1;          // phase-1 k-blocks (split 0 only); 0 = no second accumulator
   int xmn0, xmn1;    // X operand of phase 0 / 1 is MN-major (rows contiguous) instead of K-major
@@ -100,6 +103,8 @@ template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmY0,
                   const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmY1,
+                  const __grid_constant__ CUtensorMap tmXb, const __grid_constant__ CUtensorMap tmYb,
+                  const __grid_constant__ CUtensorMap tmXc, const __grid_constant__ CUtensorMap tmYc,
                   const GemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kStages];
@@ -121,7 +126,8 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
   const int kb_begin = split * a.kb_per_split;
   const int n0kb = max(0, min(a.nkb0, kb_begin + a.kb_per_split) - kb_begin);
   const int n1kb = (split == 0) ? a.nkb1 : 0;
-  const int nchunk0 = (n0kb + kChunkKb - 1) / kChunkKb;
+  const int chunk_kb = a.chunk_kb > 0 ? a.chunk_kb : kChunkKb;
+  const int nchunk0 = (n0kb + chunk_kb - 1) / chunk_kb;
   const int nchunks = nchunk0 + (n1kb > 0 ? 1 : 0);
 
   if (threadIdx.x == 0) {
@@ -160,9 +166,15 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       mbar_wait(&empty_bar[stage], phase ^ 1);
       mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
       const bool ph1 = it >= n0kb;
-      const int kb = ph1 ? (it - n0kb) : (kb_begin + it);
+      int kb = ph1 ? (it - n0kb) : (kb_begin + it);
       const CUtensorMap* mx = ph1 ? &tmX1 : &tmX0;
       const CUtensorMap* my = ph1 ? &tmY1 : &tmY0;
+      if (!ph1 && kb >= a.nkb_seg) {  // second / third operand pair of a segmented phase 0
+        const int seg = kb / a.nkb_seg;
+        kb -= seg * a.nkb_seg;
+        mx = seg == 1 ? &tmXb : &tmXc;
+        my = seg == 1 ? &tmYb : &tmYc;
+      }
       const uint32_t xs = sbase + stage * kStageBytes;
       const uint32_t ys = xs + kStageBytesX;
       // X is streamed once (evict-first); Y is re-read by every CTA (evict-last).
@@ -197,7 +209,7 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         tc_fence_after();
       }
       const bool ph1 = ch >= nchunk0;
-      const int nkb = ph1 ? n1kb : min(kChunkKb, n0kb - ch * kChunkKb);
+      const int nkb = ph1 ? n1kb : min(chunk_kb, n0kb - ch * chunk_kb);
       const bool mn = ph1 ? (a.xmn1 != 0) : (a.xmn0 != 0);
       const bool ymn = ph1 ? (a.ymn1 != 0) : (a.ymn0 != 0);
       const uint32_t idesc = make_idesc_tf32(kTileM, bn, mn ? 1 : 0, ymn ? 1 : 0);

@@ -257,8 +257,10 @@ def nmf(V, num_basis_elems, config=None, rng=None):
     V_hat = reconstruct_from_decomposition(W_all, H_all)  # nmf.m:139
     maxiter = int(cfg["maxiter"])
     cost = np.zeros(maxiter)  # nmf.m:141
-    ones_nm = np.ones((n, m))
-    ones_mn = np.ones((m, n))
+    # the dense ones(n, m) / ones(m, n) of nmf.m:152-156,184,187 (only the KL / IS branches use them)
+    needs_ones = div in ("kl_divergence", "kl", "is_divergence", "is")
+    ones_nm = np.ones((n, m)) if needs_ones else None
+    ones_mn = np.ones((m, n)) if needs_ones else None
 
     with np.errstate(divide="ignore", invalid="ignore"):
         for it in range(1, maxiter + 1):  # nmf.m:143

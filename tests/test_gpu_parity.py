@@ -1,0 +1,265 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via ctypes) against the CPU
+oracle and the committed golden fixtures, on the same seeded inputs.
+
+Stated tolerances (BASELINE.json north_star): cost curve within 1e-4 relative of
+the reference over the run, W*H reconstruction within 1e-3 relative (Frobenius).
+The kernels multiply tf32-rounded operands with fp32 accumulation; the oracle is
+float64."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from make_golden import CASES, inputs  # noqa: E402
+from oracle import nmf_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+COST_TOL = 1e-4
+RECON_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def api():
+    from nmf_toolbox_b200 import api as A
+
+    return A
+
+
+@pytest.fixture(scope="module")
+def handle(api):
+    h = api.Handle(0)
+    yield h
+    h.close()
+
+
+def recon_err(W, H, Wo, Ho):
+    R = O.reconstruct_from_decomposition(np.asarray(W, np.float64), np.asarray(H, np.float64))
+    Ro = O.reconstruct_from_decomposition(Wo, Ho)
+    return np.linalg.norm(R - Ro) / np.linalg.norm(Ro)
+
+
+def cost_err(c, co):
+    assert len(c) == len(co), (len(c), len(co))
+    return float(np.max(np.abs(c - co) / np.maximum(np.abs(co), 1e-300)))
+
+
+# ---------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_against_golden(api, handle, name):
+    alg, V, K, T, cfg = inputs(name)
+    g = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    if alg == "nmf":
+        W, H, c = api.nmf(V, K, cfg, handle=handle)
+    elif alg == "cnmf":
+        W, H, c = api.cnmf(V, K, T, cfg, handle=handle)
+    else:
+        W, H, c = api.nmfsc(V, K, cfg, handle=handle)
+    assert cost_err(c, g["cost"]) < COST_TOL
+    assert recon_err(W, H, g["W"].astype(np.float64), g["H"].astype(np.float64)) < RECON_TOL
+
+
+# ---------------------------------------------------------------- nmf
+@pytest.mark.parametrize("div", ["euclidean", "kl"])
+@pytest.mark.parametrize("m,n,K,iters", [(1024, 768, 32, 200), (257, 1030, 40, 60), (100, 64, 3, 30), (2048, 2048, 64, 100)])
+def test_nmf_vs_oracle(api, handle, div, m, n, K, iters):
+    rng = np.random.default_rng(m + n)
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    cfg = dict(divergence=div, W_init=np.maximum(rng.random((m, K)), O.EPS), H_init=np.maximum(rng.random((K, n)), O.EPS),
+               maxiter=iters, tolerance=1e-300)
+    W, H, c = api.nmf(V, K, cfg, handle=handle)
+    Wo, Ho, co = O.nmf(V, K, cfg)
+    assert cost_err(c, co) < COST_TOL
+    assert recon_err(W, H, Wo, Ho) < RECON_TOL
+    np.testing.assert_allclose((W.astype(np.float64) ** 2).sum(0), 1.0, rtol=1e-5)  # nmf.m:169
+
+
+def test_nmf_direct_cost_mode(api, handle):
+    alg, V, K, T, cfg = inputs("nmf_euclid_512")
+    Wo, Ho, co = O.nmf(V, K, cfg)
+    W, H, c = api.nmf(V, K, dict(cfg, cost_mode=api.COST_DIRECT), handle=handle)
+    assert cost_err(c, co) < 2e-5
+
+
+@pytest.mark.parametrize("div", ["euclidean", "kl"])
+def test_nmf_sparsity_terms(api, handle, div):
+    rng = np.random.default_rng(8)
+    V = np.maximum(rng.random((300, 500)), 2.0 ** -24)
+    cfg = dict(divergence=div, W_init=rng.random((300, 24)) + 1e-3, H_init=rng.random((24, 500)) + 1e-3,
+               W_sparsity=0.3, H_sparsity=0.7, maxiter=40, tolerance=1e-300)
+    W, H, c = api.nmf(V, 24, cfg, handle=handle)
+    Wo, Ho, co = O.nmf(V, 24, cfg)
+    assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
+
+
+@pytest.mark.parametrize("div", ["euclidean", "kl"])
+@pytest.mark.parametrize("which", ["W_fixed", "H_fixed"])
+def test_nmf_fixed_factor(api, handle, div, which):
+    """nmf.m:51-60,146,177: a fixed factor keeps its (normalised) initial value."""
+    rng = np.random.default_rng(9)
+    V = np.maximum(rng.random((200, 260)), 2.0 ** -24)
+    W0, H0 = rng.random((200, 12)) + 1e-3, rng.random((12, 260)) + 1e-3
+    cfg = dict(divergence=div, W_init=W0, H_init=H0, maxiter=25, tolerance=1e-300)
+    cfg[which] = True
+    W, H, c = api.nmf(V, 12, cfg, handle=handle)
+    Wo, Ho, co = O.nmf(V, 12, cfg)
+    assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
+    if which == "W_fixed":
+        np.testing.assert_allclose(W, W0 / np.sqrt((W0 ** 2).sum(0)), rtol=1e-5)  # nmf.m:133 still applies
+    else:
+        np.testing.assert_allclose(H, H0, rtol=1e-6)
+
+
+def test_nmf_stop_rule_and_trim(api, handle):
+    """nmf.m:221-224: the device-side stop test ends the loop at the same iteration as the oracle."""
+    alg, V, K, T, cfg = inputs("nmf_euclid_512")
+    _, _, full = O.nmf(V, K, cfg)
+    d = -np.diff(full)
+    tol = float(np.sort(d)[len(d) // 2]) * 1.0001
+    _, _, co = O.nmf(V, K, dict(cfg, tolerance=tol))
+    W, H, c = api.nmf(V, K, dict(cfg, tolerance=tol, cost_mode=api.COST_DIRECT), handle=handle)
+    assert 2 <= len(co) < 50 and len(c) == len(co)
+    assert cost_err(c, co) < COST_TOL
+    # defaults: maxiter <= 0 -> 100, tolerance <= 0 -> 1e-3 (nmf.m:404-411)
+    W, H, c = api.nmf(V[:64, :64], 4, dict(maxiter=0, tolerance=-1, seed=3), handle=handle)
+    assert 2 <= len(c) <= 100 and np.all(np.isfinite(c))
+
+
+@pytest.mark.parametrize("div", ["euclidean", "kl"])
+def test_nmf_exact_fixed_point(api, handle, div):
+    """V = W0*H0 with unit-L2 columns: factors do not move (to tf32 rounding), cost ~ 0."""
+    rng = np.random.default_rng(1)
+    W0 = rng.random((256, 8)) + 0.1
+    W0 /= np.sqrt((W0 ** 2).sum(0))
+    H0 = rng.random((8, 320)) + 0.1
+    V = W0 @ H0
+    W, H, c = api.nmf(V, 8, dict(divergence=div, W_init=W0, H_init=H0, maxiter=5, tolerance=1e-300,
+                                 cost_mode=api.COST_DIRECT), handle=handle)
+    np.testing.assert_allclose(W, W0, rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(H, H0, rtol=2e-3, atol=1e-6)
+    assert np.all(np.abs(c) < 1e-6 * 0.5 * (V ** 2).sum())
+
+
+def test_nmf_multi_source_cells(api, handle):
+    """nmf.m:11-16: cell-array inputs with a common sparsity level == one factorisation of the concatenation."""
+    rng = np.random.default_rng(12)
+    V = np.maximum(rng.random((150, 200)), 2.0 ** -24)
+    W0 = [rng.random((150, 5)) + 1e-3, rng.random((150, 7)) + 1e-3]
+    H0 = [rng.random((5, 200)) + 1e-3, rng.random((7, 200)) + 1e-3]
+    cfg = dict(W_init=W0, H_init=H0, W_sparsity=[0.1, 0.1], maxiter=20, tolerance=1e-300)
+    W, H, c = api.nmf(V, [5, 7], cfg, handle=handle)
+    Wo, Ho, co = O.nmf(V, [5, 7], cfg)
+    assert isinstance(W, list) and W[0].shape == (150, 5) and H[1].shape == (7, 200)
+    assert cost_err(c, co) < COST_TOL
+    assert recon_err(np.concatenate(W, 1), np.concatenate(H, 0), np.concatenate(Wo, 1), np.concatenate(Ho, 0)) < RECON_TOL
+
+
+def test_errors(api, handle):
+    V = np.ones((8, 8))
+    with pytest.raises(api.NmfbError) as e:  # nmf.m:165-166: nmf has no 'frobenius'
+        api.nmf(V, 2, dict(divergence="frobenius"), handle=handle)
+    assert e.value.code == 4
+    with pytest.raises(api.NmfbError) as e:
+        api.nmf(V, 2, dict(divergence="itakura"), handle=handle)
+    assert e.value.code == 4
+    with pytest.raises(api.NmfbError) as e:  # nmf.m:120-122
+        api.nmf(V, 2, dict(divergence="ab", alpha=0, beta=0), handle=handle)
+    assert e.value.code == 5
+    with pytest.raises(api.NmfbError) as e:  # nmfsc.m:57-59
+        api.nmfsc(-V, 2, dict(maxiter=2), handle=handle)
+    assert e.value.code == 6 and "Negative values in data!" in str(e.value)
+    with pytest.raises(api.NmfbError) as e:
+        api.nmf(V, 2, dict(divergence="is"), handle=handle)
+    assert e.value.code == 3
+
+
+# ---------------------------------------------------------------- cnmf
+@pytest.mark.parametrize("m,n,K,T,iters,lw,lh", [(129, 700, 8, 4, 60, 0, 0), (200, 1000, 16, 5, 40, 0.05, 0.1),
+                                                  (1025, 2000, 64, 8, 30, 0, 0), (64, 90, 3, 7, 25, 0, 0)])
+def test_cnmf_vs_oracle(api, handle, m, n, K, T, iters, lw, lh):
+    rng = np.random.default_rng(m)
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    cfg = dict(divergence="euclidean", W_init=rng.random((m, K, T)), H_init=np.maximum(rng.random((K, n)), O.EPS),
+               W_sparsity=lw, H_sparsity=lh, maxiter=iters, tolerance=1e-300)
+    W, H, c = api.cnmf(V, K, T, cfg, handle=handle)
+    Wo, Ho, co = O.cnmf(V, K, T, cfg)
+    assert W.shape == (m, K, T)
+    assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
+
+
+def test_cnmf_T1_equals_nmf(api, handle):
+    rng = np.random.default_rng(2)
+    V = np.maximum(rng.random((300, 400)), 2.0 ** -24)
+    W0 = rng.random((300, 10)) + 1e-3
+    W0 /= np.sqrt((W0 ** 2).sum(0))
+    H0 = rng.random((10, 400)) + 1e-3
+    cfg = dict(divergence="euclidean", W_init=W0, H_init=H0, maxiter=20, tolerance=1e-300)
+    W1, H1, c1 = api.nmf(V, 10, cfg, handle=handle)
+    W2, H2, c2 = api.cnmf(V, 10, 1, dict(cfg, W_init=W0[:, :, None]), handle=handle)
+    assert cost_err(c2, c1) < 2e-5
+    np.testing.assert_allclose(W2[:, :, 0], W1, rtol=2e-3, atol=1e-6)
+
+
+# ---------------------------------------------------------------- nmfsc / projfunc
+@pytest.mark.parametrize("sW,sH,iters", [(None, 0.7, 100), (None, None, 40), (0.5, 0.5, 40), (0.6, None, 10)])
+def test_nmfsc_vs_oracle(api, handle, sW, sH, iters):
+    rng = np.random.default_rng(2)
+    m, n, K = 512, 512, 16
+    V = rng.random((m, n)) * 3.0
+    H0 = rng.random((K, n))
+    H0 /= np.sqrt((H0 ** 2).sum(1, keepdims=True))
+    cfg = dict(W_init=rng.random((m, K)), H_init=H0, W_sparsity=sW, H_sparsity=sH, maxiter=iters, tolerance=1e-300)
+    W, H, c = api.nmfsc(V, K, cfg, handle=handle)
+    Wo, Ho, co = O.nmfsc(V, K, cfg)
+    assert cost_err(c, co) < COST_TOL
+    if sH:
+        Hd = H.astype(np.float64)
+        l1, l2 = np.abs(Hd).sum(1), np.sqrt((Hd ** 2).sum(1))
+        np.testing.assert_allclose((np.sqrt(n) - l1 / l2) / (np.sqrt(n) - 1), sH, atol=1e-4)  # rows keep sparseness
+        np.testing.assert_allclose(l2, 1.0, atol=1e-4)
+
+
+@pytest.mark.parametrize("N,sp", [(100, 0.7), (4096, 0.7), (1000, 0.3), (5000, 0.95), (20000, 0.5), (33, 0.9)])
+def test_projfunc_vs_oracle(api, handle, N, sp):
+    rng = np.random.default_rng(N)
+    s = rng.random(N)
+    k1 = np.sqrt(N) - (np.sqrt(N) - 1) * sp
+    v, it = api.projfunc(s, k1, 1.0, 1, handle=handle)
+    vo, ito = O.projfunc(s, k1, 1.0, 1)
+    assert it == ito
+    np.testing.assert_allclose(v, vo, atol=2e-5)
+    assert abs(v.astype(np.float64).sum() - k1) < 1e-3 * k1 and abs((v.astype(np.float64) ** 2).sum() - 1) < 1e-4
+    assert v.min() >= 0
+
+
+def test_projfunc_signed_and_batched(api, handle):
+    g = np.load(os.path.join(HERE, "golden", "projfunc.npz"))
+    rng = np.random.default_rng(99)
+    S = rng.random((6, 500))
+    for i, sp in enumerate([0.1, 0.3, 0.5, 0.7, 0.9, 0.95]):
+        k1 = np.sqrt(500) - (np.sqrt(500) - 1) * sp
+        v, it = api.projfunc(S[i], k1, 1.0, 1, handle=handle)
+        assert it == g["iters"][i]
+        np.testing.assert_allclose(v, g["v"][i], atol=2e-5)
+    s = np.random.default_rng(5).standard_normal((4, 777))
+    V, its = api.projfunc(s, 10.0, 2.0, 0, handle=handle)
+    for i in range(4):
+        vo, ito = O.projfunc(s[i], 10.0, 2.0, 0)
+        assert its[i] == ito
+        np.testing.assert_allclose(V[i], vo, atol=2e-5)
+
+
+# ---------------------------------------------------------------- ReconstructFromDecomposition
+def test_reconstruct(api, handle):
+    rng = np.random.default_rng(3)
+    W, H = rng.random((300, 24)), rng.random((24, 501))
+    R = api.ReconstructFromDecomposition(W, H, handle=handle)
+    np.testing.assert_allclose(R, W @ H, rtol=5e-6)
+    W3, H3 = rng.random((129, 8, 5)), rng.random((8, 333))
+    R = api.ReconstructFromDecomposition(W3, H3, handle=handle)
+    np.testing.assert_allclose(R, O.reconstruct_from_decomposition(W3, H3), rtol=5e-6, atol=1e-6)
+    R = api.ReconstructFromDecomposition([W[:, :10], W[:, 10:]], [H[:10], H[10:]], handle=handle)  # RFD.m:23-28
+    np.testing.assert_allclose(R, W @ H, rtol=5e-6)

@@ -1,0 +1,112 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol that
+include/nmfb200.h declares, fails loudly without a GPU (no CPU fallback), and the
+Python mirror marshals the reference's config conventions.  No compute calls here."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "nmfb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nmfb_[a-z_0-9]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+
+    g.build()
+    from nmf_toolbox_b200 import _lib
+
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    names = _declared_symbols()
+    assert len(names) >= 18, names
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/nmfb200.h but not exported"
+
+
+def test_bind_signatures(lib):
+    from nmf_toolbox_b200 import api
+
+    api._bind(lib)
+    assert lib.nmfb_version().decode().startswith("nmfb200")
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device creating a handle fails with a message; nothing computes on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from nmf_toolbox_b200 import api
+
+    with pytest.raises(api.NmfbError) as e:
+        api.Handle(0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "nmf_toolbox_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from nmf_toolbox_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.NmfbLibraryMissing):
+        _lib.load()
+
+
+def test_config_struct_layout():
+    from nmf_toolbox_b200 import api
+
+    # must match struct nmfb_config in include/nmfb200.h (x86-64 SysV layout)
+    assert ctypes.sizeof(api._Config) == 96
+    assert api._Config.W_init.offset == 24 and api._Config.maxiter.offset == 64
+    assert api._Config.tolerance.offset == 72 and api._Config.cost_mode.offset == 88
+
+
+def test_multi_source_mapping():
+    from nmf_toolbox_b200 import api
+
+    W = [np.ones((4, 2)), 2 * np.ones((4, 3))]
+    H = [np.ones((2, 5)), 3 * np.ones((3, 5))]
+    cfg = api._multi_source(dict(W_init=W, H_init=H, W_sparsity=[0.1, 0.1], H_fixed=[False, False]), [2, 3])
+    assert cfg["W_init"].shape == (4, 5) and cfg["H_init"].shape == (5, 5)
+    assert cfg["W_sparsity"] == 0.1 and cfg["H_fixed"] is False
+    with pytest.raises(api.NmfbError):  # nmf.m:317-318
+        api._multi_source(dict(W_sparsity=[0.1, 0.2, 0.3]), [2, 3])
+    with pytest.raises(api.NmfbError):  # nmf.m:301-302
+        api._multi_source(dict(W_init=[np.ones((4, 2))]), [2, 3])
+    with pytest.raises(api.NmfbError):  # per-source levels: not accelerated yet
+        api._multi_source(dict(W_sparsity=[0.1, 0.2]), [2, 3])
+
+
+def test_shard_bounds_cover_and_partition():
+    from nmf_toolbox_b200.distributed import pack_layout, shard_bounds
+
+    for n, P in [(16384, 8), (65536, 8), (1000, 3), (7, 8), (20000, 4)]:
+        edges = [shard_bounds(n, P, r) for r in range(P)]
+        assert edges[0][0] == 0 and edges[-1][1] == n
+        assert all(edges[i][1] == edges[i + 1][0] for i in range(P - 1))
+        sizes = [b - a for a, b in edges]
+        assert max(sizes) - min(sizes) <= 1
+    lay = pack_layout(8192, 128)  # config 3: 8192*128 + 128^2 floats ~ 4.26 MB
+    assert lay["total"] == 8192 * 128 + 128 * 128 and lay["G_H"][0] == 8192 * 128

@@ -1,0 +1,171 @@
+"""CPU tests of the oracle itself: golden fixtures, invariants derivable from the
+reference code, and the Gram / trace / stacked re-derivation
+that the CUDA path implements (oracle/restructured.py) against the literal form.
+
+PARITY UNPINNED: the reference has no tests or golden vectors and cannot run here
+(MATLAB); these are the pins we can add.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from make_golden import CASES, inputs, run  # noqa: E402
+from oracle import nmf_oracle as O  # noqa: E402
+from oracle import restructured as R  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_golden(name):
+    g = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    W, H, cost = run(name)
+    assert len(cost) == len(g["cost"])
+    np.testing.assert_allclose(cost, g["cost"], rtol=1e-9)
+    Vhat = O.reconstruct_from_decomposition(W, H)
+    np.testing.assert_allclose(np.linalg.norm(Vhat), float(g["vhat_norm"]), rtol=1e-9)
+    np.testing.assert_allclose(Vhat[:8, :8], g["vhat_sample"], rtol=1e-7)
+
+
+def test_projfunc_golden_and_constraints():
+    g = np.load(os.path.join(HERE, "golden", "projfunc.npz"))
+    rng = np.random.default_rng(99)
+    S = rng.random((6, 500))
+    for i, sp in enumerate([0.1, 0.3, 0.5, 0.7, 0.9, 0.95]):
+        k1 = np.sqrt(500) - (np.sqrt(500) - 1) * sp
+        v, it = O.projfunc(S[i], k1, 1.0, 1)
+        np.testing.assert_allclose(v, g["v"][i], atol=1e-12)
+        assert it == g["iters"][i]
+        # projfunc.m:3-7: sum(abs(v)) = k1, sum(v.^2) = k2, v >= 0
+        assert abs(v.sum() - k1) < 1e-9 and abs((v ** 2).sum() - 1.0) < 1e-9 and v.min() >= 0
+        v2, _ = O.projfunc(v, k1, 1.0, 1)  # idempotent
+        np.testing.assert_allclose(v2, v, atol=1e-9)
+
+
+def test_projfunc_signed():
+    rng = np.random.default_rng(5)
+    s = rng.standard_normal(300)
+    v, _ = O.projfunc(s, 8.0, 1.5, 0)
+    assert abs(np.abs(v).sum() - 8.0) < 1e-9 and abs((v ** 2).sum() - 1.5) < 1e-9
+    assert np.all(np.sign(v[v != 0]) == np.sign(s[v != 0]))
+
+
+@pytest.mark.parametrize("div", ["euclidean", "kl"])
+def test_exact_fixed_point(div):
+    """V = W0*H0 with unit-L2 W0 columns: neg == pos, nothing moves, cost 0 (nmf.m:149-153,180-184)."""
+    rng = np.random.default_rng(1)
+    W0 = rng.random((40, 5)) + 0.1
+    W0 /= np.sqrt((W0 ** 2).sum(0))
+    H0 = rng.random((5, 60)) + 0.1
+    W, H, cost = O.nmf(W0 @ H0, 5, dict(divergence=div, W_init=W0, H_init=H0, maxiter=5, tolerance=1e-300))
+    np.testing.assert_allclose(W, W0, rtol=1e-10)
+    np.testing.assert_allclose(H, H0, rtol=1e-10)
+    assert np.all(np.abs(cost) < 1e-12)  # rounding noise of sum(V.*log(V./V_hat) - V + V_hat) only
+
+
+@pytest.mark.parametrize("div", ["euclidean", "kl"])
+def test_cnmf_T1_equals_nmf(div):
+    rng = np.random.default_rng(2)
+    V = rng.random((50, 80)) + 1e-3
+    W0 = rng.random((50, 6)) + 1e-3
+    W0 /= np.sqrt((W0 ** 2).sum(0))
+    H0 = rng.random((6, 80)) + 1e-3
+    cfg = dict(divergence=div, W_init=W0, H_init=H0, maxiter=15, tolerance=1e-300)
+    W1, H1, c1 = O.nmf(V, 6, cfg)
+    W2, H2, c2 = O.cnmf(V, 6, 1, dict(cfg, W_init=W0[:, :, None]))
+    np.testing.assert_allclose(c1, c2, rtol=1e-10)
+    np.testing.assert_allclose(W1, W2[:, :, 0], rtol=1e-8)
+    np.testing.assert_allclose(H1, H2, rtol=1e-8)
+
+
+def test_nmf_invariants():
+    alg, V, K, T, cfg = inputs("nmf_euclid_sparse")
+    W, H, cost = O.nmf(V, K, cfg)
+    np.testing.assert_allclose((W ** 2).sum(0), 1.0, rtol=1e-12)  # nmf.m:169
+    alg, V, K, T, cfg = inputs("nmf_euclid_512")
+    _, _, cost = O.nmf(V, K, cfg)
+    assert np.all(np.diff(cost) <= 0)  # monotone on dense random V
+
+
+def test_stop_rule_and_trim():
+    """nmf.m:221-224: stop when 0 < cost(i-1) - cost(i) < tolerance; cost trimmed to executed iterations."""
+    alg, V, K, T, cfg = inputs("nmf_euclid_512")
+    _, _, full = O.nmf(V, K, cfg)
+    d = -np.diff(full)
+    tol = float(np.sort(d)[len(d) // 2])
+    first = int(np.argmax((d > 0) & (d < tol))) + 2  # 1-based iteration that triggers the break
+    _, _, c = O.nmf(V, K, dict(cfg, tolerance=tol))
+    assert len(c) == first
+    np.testing.assert_allclose(c, full[:first], rtol=1e-12)
+    # nmf.m:404-411: non-positive maxiter / tolerance are reset to 100 / 1e-3
+    _, _, c = O.nmf(V[:40, :40], 3, dict(maxiter=0, tolerance=-1), rng=np.random.default_rng(0))
+    assert 2 <= len(c) <= 100
+
+
+def test_nmfsc_rows_keep_sparseness():
+    alg, V, K, T, cfg = inputs("nmfsc_h07")
+    W, H, cost = O.nmfsc(V, K, dict(cfg, maxiter=15))
+    n = H.shape[1]
+    l1 = np.abs(H).sum(1)
+    l2 = np.sqrt((H ** 2).sum(1))
+    sp = (np.sqrt(n) - l1 / l2) / (np.sqrt(n) - 1)
+    np.testing.assert_allclose(sp, 0.7, atol=1e-9)
+    np.testing.assert_allclose(l2, 1.0, atol=1e-9)
+    assert len(cost) == 16 and np.all(np.diff(cost) <= 1e-12)
+
+
+def test_errors():
+    V = np.ones((4, 4))
+    with pytest.raises(ValueError):
+        O.nmf(V, 2, dict(divergence="frobenius", maxiter=2), rng=np.random.default_rng(0))  # nmf.m:165-166
+    with pytest.raises(ValueError):
+        O.nmf(V, 2, dict(divergence="ab", alpha=0, beta=0), rng=np.random.default_rng(0))  # nmf.m:120-122
+    with pytest.raises(ValueError):
+        O.nmfsc(-V, 2, dict(maxiter=2), rng=np.random.default_rng(0))  # nmfsc.m:57-59
+
+
+# ---------------------------------------------------------------- restructured forms
+@pytest.mark.parametrize("div,lw,lh", [("euclidean", 0, 0), ("euclidean", 0.1, 0.2), ("kl", 0, 0), ("kl", 0.05, 0.1)])
+@pytest.mark.parametrize("shards", [1, 3])
+def test_gram_form_matches_literal(div, lw, lh, shards):
+    rng = np.random.default_rng(3)
+    V = rng.random((70, 95)) + 1e-3
+    cfg = dict(divergence=div, W_init=rng.random((70, 7)) + 1e-3, H_init=rng.random((7, 95)) + 1e-3,
+               W_sparsity=lw, H_sparsity=lh, maxiter=25, tolerance=1e-300)
+    W1, H1, c1 = O.nmf(V, 7, cfg)
+    W2, H2, c2 = R.nmf_gram(V, 7, cfg, shards=shards)
+    np.testing.assert_allclose(c2, c1, rtol=1e-10)
+    np.testing.assert_allclose(W2 @ H2, W1 @ H1, rtol=1e-9)
+
+
+def test_stacked_cnmf_matches_literal():
+    rng = np.random.default_rng(4)
+    V = rng.random((60, 150)) + 1e-3
+    cfg = dict(divergence="euclidean", W_init=rng.random((60, 5, 4)), H_init=rng.random((5, 150)) + 1e-3,
+               W_sparsity=0.02, H_sparsity=0.03, maxiter=20, tolerance=1e-300)
+    W1, H1, c1 = O.cnmf(V, 5, 4, cfg)
+    W2, H2, c2 = R.cnmf_stacked(V, 5, 4, cfg)
+    np.testing.assert_allclose(c2, c1, rtol=1e-10)
+    np.testing.assert_allclose(W2, W1, rtol=1e-8)
+    np.testing.assert_allclose(H2, H1, rtol=1e-8)
+
+
+def test_sklearn_cross_check_plain_mu():
+    """Independent pin for the one textbook update in scope (nmfsc.m:182,232 = Lee-Seung MU)."""
+    sk = pytest.importorskip("sklearn.decomposition")
+    rng = np.random.default_rng(6)
+    V = rng.random((30, 40))
+    W0 = rng.random((30, 4)) + 0.1
+    H0 = rng.random((4, 40)) + 0.1
+    Vn = V / V.max()
+    # two plain MU sweeps in nmfsc order (H then W), no sparsity
+    W, H, cost = O.nmfsc(V, 4, dict(W_init=W0, H_init=H0, maxiter=3, tolerance=1e-300))
+    model = sk.NMF(n_components=4, init="custom", solver="mu", beta_loss="frobenius", max_iter=3, tol=0)
+    Wsk = model.fit_transform(Vn, W=W0.copy(), H=H0.copy())
+    # sklearn updates W first and does not renormalise; compare the objective only (same order of magnitude
+    # and both decreasing) - the two are different schedules of the same multiplicative rule.
+    obj_sk = 0.5 * np.linalg.norm(Vn - Wsk @ model.components_) ** 2
+    assert cost[-1] < cost[0] and obj_sk < cost[0]
+    assert abs(np.log(obj_sk / cost[-1])) < 0.5
