@@ -165,7 +165,7 @@ extern "C" int nmfb_reconstruct(nmfb_handle* h, const float* W, const float* H, 
   GemmOp op;
   MatRef X{Xs, m, 3 * KTp, ldw, true};
   MatRef Y{Ys, n, 3 * KTp, ldh, true};
-  NMFB_TRY(plan_fused(h, &op, EPI_RECON, X, Y, 3 * KTp, nullptr, nullptr, 0, m, round_up(n, 32), n,
+  NMFB_TRY(plan_fused(h, &op, EPI_RECON, X, Y, 3 * KTp, nullptr, nullptr, 0, m, round_up(n, 64), n,
                       nullptr));
   op.L.args.Qout = out;
   op.L.args.ldv = ldw;

@@ -1,11 +1,17 @@
 // Kernel-level test hooks (C ABI, device pointers in/out).  Used only by
 // tests/ to check panel_gemm against a plain fp32 matmul on the same GPU.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "gemm_host.cuh"
 
 using namespace nmfb;
+
+static int debug_cg() {  // NMFB_DEBUG_CG=2 runs the kernel-level tests on the CTA-pair kernel
+  const char* e = std::getenv("NMFB_DEBUG_CG");
+  return (e && e[0] == '2') ? 2 : 1;
+}
 
 static int fail(char* err, int errlen, const std::string& msg) {
   if (err && errlen > 0) {
@@ -42,7 +48,7 @@ int nmfb_debug_gemm_store(const nmfb_debug_mat* X0, const nmfb_debug_mat* Y0, lo
     y1 = GemmOperand{{Y1->base, Y1->inner, Y1->outer, Y1->pitch}, Y1->mn_major != 0};
   }
   std::string e = plan_gemm(&L, x0, y0, kdim0, two ? &x1 : nullptr, two ? &y1 : nullptr, kdim1, rows,
-                            ncols, splits, sms);
+                            ncols, splits, sms, debug_cg());
   if (!e.empty()) return fail(err, errlen, e);
   L.args.out0 = out0;
   L.args.out1 = out1;
@@ -69,7 +75,7 @@ int nmfb_debug_gemm_hupdate(const nmfb_debug_mat* X0, const nmfb_debug_mat* Y0, 
   GemmOperand y0{{Y0->base, Y0->inner, Y0->outer, Y0->pitch}, Y0->mn_major != 0};
   GemmOperand x1{{X1->base, X1->inner, X1->outer, X1->pitch}, X1->mn_major != 0};
   GemmOperand y1{{Y1->base, Y1->inner, Y1->outer, Y1->pitch}, Y1->mn_major != 0};
-  std::string e = plan_gemm(&L, x0, y0, kdim0, &x1, &y1, kdim1, rows, ncols, 1, sms);
+  std::string e = plan_gemm(&L, x0, y0, kdim0, &x1, &y1, kdim1, rows, ncols, 1, sms, debug_cg());
   if (!e.empty()) return fail(err, errlen, e);
   L.args.Hm = Hm;
   L.args.Hr32 = Hr32;

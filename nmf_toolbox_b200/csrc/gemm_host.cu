@@ -1,6 +1,7 @@
 #include "gemm_host.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -64,11 +65,21 @@ int choose_splits(int tiles, int nkb0, int num_sms, int* kb_per_split) {
   return splits;
 }
 
+bool pair_eligible(int rows, int ncols, bool y_mn_major0, bool y_mn_major1) {
+  const char* env = std::getenv("NMFB_CTA_GROUP");
+  if (env && env[0] == '1') return false;
+  if (rows <= kTileM) return false;  // a single 128-row tile: the partner CTA would idle
+  if ((y_mn_major0 || y_mn_major1) && ncols % 64 != 0) return false;  // 32-row boxes per CTA half
+  return true;
+}
+
 std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const GemmOperand& Y0, long long kdim0,
                       const GemmOperand* X1, const GemmOperand* Y1, long long kdim1, int rows,
-                      int ncols, int splits_hint, int num_sms) {
+                      int ncols, int splits_hint, int num_sms, int cg) {
   if (ncols <= 0 || ncols % 32 != 0) return "plan_gemm: ncols must be a positive multiple of 32";
+  if (cg != 1 && cg != 2) return "plan_gemm: cta group must be 1 or 2";
   std::memset(L, 0, sizeof(*L));
+  L->cg = cg;
   GemmArgs& a = L->args;
   a.rows = rows;
   a.ncols = ncols;
@@ -76,35 +87,37 @@ std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const GemmOperand& Y
   a.nkb0 = static_cast<int>((kdim0 + kBlockK - 1) / kBlockK);
   a.nkb_seg = a.nkb0;
   a.chunk_kb = 0;
+  if (const char* env = std::getenv("NMFB_CHUNK_KB")) a.chunk_kb = std::atoi(env);  // tuning experiments
   a.nkb1 = (X1 != nullptr) ? static_cast<int>((kdim1 + kBlockK - 1) / kBlockK) : 0;
   a.xmn0 = X0.mn_major ? 1 : 0;
   a.xmn1 = (X1 && X1->mn_major) ? 1 : 0;
   a.ymn0 = Y0.mn_major ? 1 : 0;
   a.ymn1 = (Y1 && Y1->mn_major) ? 1 : 0;
   a.ncols_valid = ncols;
-  const int tiles = (rows + kTileM - 1) / kTileM;
+  const int tile_rows = kTileM * cg;
+  const int tiles = (rows + tile_rows - 1) / tile_rows;
   const int chunks = (ncols + kMaxN - 1) / kMaxN;
   int splits = 1;
   a.kb_per_split = std::max(a.nkb0, 1);
   if (splits_hint != 1) {
     if (splits_hint <= 0) {
-      splits = choose_splits(tiles * chunks, a.nkb0, num_sms, &a.kb_per_split);
+      splits = choose_splits(tiles * chunks * cg, a.nkb0, num_sms, &a.kb_per_split);
     } else {
       int per = std::max(1, (a.nkb0 + splits_hint - 1) / splits_hint);
       splits = std::max(1, (a.nkb0 + per - 1) / per);
       a.kb_per_split = per;
     }
   }
-  L->grid = dim3(tiles, chunks, splits);
+  L->grid = dim3(tiles * cg, chunks, splits);
 
   std::string e;
   auto xmap = [&](CUtensorMap* tm, const GemmOperand& X) {
     return X.mn_major ? make_tmap(tm, X.m, 32, 32, true) : make_tmap(tm, X.m, kBlockK, kTileM, false);
   };
   if (!(e = xmap(&L->tmX0, X0)).empty()) return "X0 " + e;
-  auto ymap = [&](CUtensorMap* tm, const GemmOperand& Y) {
+  auto ymap = [&](CUtensorMap* tm, const GemmOperand& Y) {  // each CTA of a pair loads half of the slab
     return Y.mn_major ? make_tmap(tm, Y.m, 32, 32, true)
-                      : make_tmap(tm, Y.m, kBlockK, a.box_n, false);
+                      : make_tmap(tm, Y.m, kBlockK, a.box_n / cg, false);
   };
   if (!(e = ymap(&L->tmY0, Y0)).empty()) return "Y0 " + e;
   if (X1) {
@@ -130,7 +143,7 @@ std::string add_segment(GemmLaunch* L, int seg, const GemmOperand& X, const Gemm
   CUtensorMap* ty = seg == 1 ? &L->tmYb : &L->tmYc;
   e = X.mn_major ? make_tmap(tx, X.m, 32, 32, true) : make_tmap(tx, X.m, kBlockK, kTileM, false);
   if (!e.empty()) return "Xseg " + e;
-  e = Y.mn_major ? make_tmap(ty, Y.m, 32, 32, true) : make_tmap(ty, Y.m, kBlockK, a.box_n, false);
+  e = Y.mn_major ? make_tmap(ty, Y.m, 32, 32, true) : make_tmap(ty, Y.m, kBlockK, a.box_n / L->cg, false);
   if (!e.empty()) return "Yseg " + e;
   a.nkb0 = a.nkb_seg * (seg + 1);
   // redo the split bookkeeping for the longer contraction
@@ -149,40 +162,60 @@ std::string add_segment(GemmLaunch* L, int seg, const GemmOperand& X, const Gemm
   return "";
 }
 
-template <int EPI>
+template <int EPI, int CG>
 static cudaError_t set_smem_attr() {
-  return cudaFuncSetAttribute(panel_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              kGemmSmemBytes);
+  return cudaFuncSetAttribute(panel_gemm_kernel<EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              TileCfg<CG>::smem_bytes);
 }
 
 template <int EPI>
-static void launch_one(const GemmLaunch& L, cudaStream_t stream) {
-  panel_gemm_kernel<EPI><<<L.grid, kGemmThreads, kGemmSmemBytes, stream>>>(
+static cudaError_t launch_one(const GemmLaunch& L, cudaStream_t stream) {
+  if (L.cg == 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = L.grid;
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = TileCfg<2>::smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, panel_gemm_kernel<EPI, 2>, L.tmX0, L.tmY0, L.tmX1, L.tmY1, L.tmXb, L.tmYb,
+                              L.tmXc, L.tmYc, L.args);
+  }
+  panel_gemm_kernel<EPI, 1><<<L.grid, kGemmThreads, TileCfg<1>::smem_bytes, stream>>>(
       L.tmX0, L.tmY0, L.tmX1, L.tmY1, L.tmXb, L.tmYb, L.tmXc, L.tmYc, L.args);
+  return cudaGetLastError();
 }
 
 std::string launch_gemm(const GemmLaunch& L, int epi, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&]() {
-    cudaError_t e[5] = {set_smem_attr<EPI_STORE>(), set_smem_attr<EPI_HUPDATE>(),
-                        set_smem_attr<EPI_RECON>(), set_smem_attr<EPI_RESID>(),
-                        set_smem_attr<EPI_KLQ>()};
+    cudaError_t e[10] = {set_smem_attr<EPI_STORE, 1>(), set_smem_attr<EPI_HUPDATE, 1>(),
+                         set_smem_attr<EPI_RECON, 1>(), set_smem_attr<EPI_RESID, 1>(),
+                         set_smem_attr<EPI_KLQ, 1>(),   set_smem_attr<EPI_STORE, 2>(),
+                         set_smem_attr<EPI_HUPDATE, 2>(), set_smem_attr<EPI_RECON, 2>(),
+                         set_smem_attr<EPI_RESID, 2>(), set_smem_attr<EPI_KLQ, 2>()};
     for (cudaError_t x : e)
       if (x != cudaSuccess) attr_err = x;
   });
   if (attr_err != cudaSuccess)
     return std::string("cudaFuncSetAttribute(panel_gemm): ") + cudaGetErrorString(attr_err);
   if (epi != EPI_STORE && L.grid.z != 1) return "launch_gemm: fused epilogues require splits == 1";
+  cudaError_t e = cudaSuccess;
   switch (epi) {
-    case EPI_STORE: launch_one<EPI_STORE>(L, stream); break;
-    case EPI_HUPDATE: launch_one<EPI_HUPDATE>(L, stream); break;
-    case EPI_RECON: launch_one<EPI_RECON>(L, stream); break;
-    case EPI_RESID: launch_one<EPI_RESID>(L, stream); break;
-    case EPI_KLQ: launch_one<EPI_KLQ>(L, stream); break;
+    case EPI_STORE: e = launch_one<EPI_STORE>(L, stream); break;
+    case EPI_HUPDATE: e = launch_one<EPI_HUPDATE>(L, stream); break;
+    case EPI_RECON: e = launch_one<EPI_RECON>(L, stream); break;
+    case EPI_RESID: e = launch_one<EPI_RESID>(L, stream); break;
+    case EPI_KLQ: e = launch_one<EPI_KLQ>(L, stream); break;
     default: return "launch_gemm: unknown epilogue";
   }
-  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return std::string("panel_gemm launch: ") + cudaGetErrorString(e);
   return "";
 }

@@ -38,14 +38,18 @@ struct GemmLaunch {
   CUtensorMap tmXb, tmYb, tmXc, tmYc;  // extra phase-0 segments (same shapes / majorness as X0, Y0)
   GemmArgs args;
   dim3 grid;
+  int cg = 1;  // 2 = CTA-pair kernel (256-row tiles, cluster of two CTAs)
 };
+
+// Whether the CTA-pair kernel can run this problem (and is worth it).
+bool pair_eligible(int rows, int ncols, bool y_mn_major0, bool y_mn_major1);
 
 // Builds tensor maps + args for out = X0*Y0^T (+ second accumulator X1*Y1^T).
 //   rows  : valid rows of X (output rows);  ncols: output columns (multiple of 32)
 //   kdim0 : contraction length of phase 0;  kdim1: of phase 1 (0 = none)
 std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const GemmOperand& Y0, long long kdim0,
                       const GemmOperand* X1, const GemmOperand* Y1, long long kdim1, int rows,
-                      int ncols, int splits_hint, int num_sms);
+                      int ncols, int splits_hint, int num_sms, int cg = 1);
 
 // Adds operand pair number `seg` (1 or 2) to phase 0: acc0 += Xs * Ys' over the same contraction.
 // Must be called after plan_gemm and before any split bookkeeping is read.

@@ -240,7 +240,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     if (s->direct_cost) {
       MatRef Xs{s->Wt, m, Kp, s->ldw, true};
       MatRef Ys{s->Ht, n, Kp, s->ldh, true};
-      NMFB_TRY(plan_fused(h, &s->gemmS, EPI_RESID, Xs, Ys, Kp, nullptr, nullptr, 0, m, round_up(n, 32),
+      NMFB_TRY(plan_fused(h, &s->gemmS, EPI_RESID, Xs, Ys, Kp, nullptr, nullptr, 0, m, round_up(n, 64),
                           n, stop));
       GemmArgs& r = s->gemmS.L.args;
       r.Vsrc = s->Vmma;
@@ -251,7 +251,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     // S = W H (both operands MN-major), Q = V ./ S
     MatRef Xs{s->Wt, m, Kp, s->ldw, true};
     MatRef Ys{s->Ht, n, Kp, s->ldh, true};
-    NMFB_TRY(plan_fused(h, &s->gemmS, EPI_KLQ, Xs, Ys, Kp, nullptr, nullptr, 0, m, round_up(n, 32), n,
+    NMFB_TRY(plan_fused(h, &s->gemmS, EPI_KLQ, Xs, Ys, Kp, nullptr, nullptr, 0, m, round_up(n, 64), n,
                         stop));
     GemmArgs& q = s->gemmS.L.args;
     q.Vsrc = h->Vraw;

@@ -210,7 +210,7 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
       MatRef Xh{Whi, m, Kp, ldw, true}, Xl{Wlo, m, Kp, ldw, true};
       MatRef Yh{Hhi, n, Kp, ldh, true}, Yl{Hlo, n, Kp, ldh, true};
       ExtraSegs e = three(Xh, Xl, Yh, Yl);
-      NMFB_TRY(plan_fused(h, op, EPI_RESID, Xh, Yh, Kp, nullptr, nullptr, 0, m, round_up(n, 32), n, nullptr, &e));
+      NMFB_TRY(plan_fused(h, op, EPI_RESID, Xh, Yh, Kp, nullptr, nullptr, 0, m, round_up(n, 64), n, nullptr, &e));
       op->L.args.Vsrc = h->Vwork;
       op->L.args.ldv = h->ldv;
       op->L.args.scal = s->scal;

@@ -52,6 +52,18 @@ constexpr int kStageBytes = kStageBytesX + kStageBytesY;
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + kEpiWarps * 32;
 constexpr int kGemmSmemBytes = kStages * kStageBytes + 1024;
+
+// CTA-pair variant (CG = 2, tcgen05 cta_group::2): two CTAs of a cluster on neighbouring SMs
+// compute one 256 x N tile.  Each CTA loads its own 128 rows of X but only HALF of the Y
+// slab (the tensor core reads the other half from the partner's shared memory), so a stage
+// is 32 KB instead of 48 KB - a third less L2->SM traffic per flop and room for 6 stages.
+template <int CG>
+struct TileCfg {
+  static constexpr int stages = CG == 2 ? 6 : kStages;
+  static constexpr int ybytes = kStageBytesY / CG;
+  static constexpr int stage_bytes = kStageBytesX + ybytes;
+  static constexpr int smem_bytes = stages * stage_bytes + 1024;
+};
 constexpr uint32_t kTmemCols = 512;
 constexpr int kMaxGroups = kMaxN / 16 / 2;  // 16-column groups per epilogue thread
 
@@ -99,16 +111,18 @@ struct GemmArgs {
   const int* stop;    // device flag: non-zero = iteration loop already converged, do nothing
 };
 
-template <int EPI>
+template <int EPI, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmY0,
                   const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmY1,
                   const __grid_constant__ CUtensorMap tmXb, const __grid_constant__ CUtensorMap tmYb,
                   const __grid_constant__ CUtensorMap tmXc, const __grid_constant__ CUtensorMap tmYc,
                   const GemmArgs a) {
+  using TC = TileCfg<CG>;
+  constexpr int kNStages = TC::stages;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[kStages];
-  __shared__ uint64_t empty_bar[kStages];
+  __shared__ uint64_t full_bar[kNStages];
+  __shared__ uint64_t empty_bar[kNStages];
   __shared__ uint64_t tfull_bar[2];   // TMEM buffer holds a finished chunk
   __shared__ uint64_t tempty_bar[2];  // TMEM buffer has been drained
   __shared__ uint32_t tmem_slot;
@@ -119,7 +133,9 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
   const int lane = threadIdx.x & 31;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
-  const int r0 = blockIdx.x * kTileM;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
+  const int r0 = CG == 2 ? static_cast<int>(blockIdx.x >> 1) * (2 * kTileM) + static_cast<int>(rank) * kTileM
+                         : static_cast<int>(blockIdx.x) * kTileM;
   const int n0 = blockIdx.y * kMaxN;
   const int bn = min(a.ncols - n0, kMaxN);  // multiple of 32
   const int split = blockIdx.z;
@@ -131,13 +147,13 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
   const int nchunks = nchunk0 + (n1kb > 0 ? 1 : 0);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kNStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], kEpiWarps);
+      mbar_init(&tempty_bar[b], kEpiWarps * CG);  // the leader's barrier collects both CTAs' epilogues
     }
     fence_barrier_init();
     prefetch_tmap(&tmX0);
@@ -148,23 +164,36 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     }
   }
   if (warp == 1) {
-    tmem_alloc(&tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_pair(&tmem_slot, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(&tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------ TMA producer
-    const uint32_t tx_bytes = kStageBytesX + a.box_n * 128;
+    // bytes that land per stage in BOTH CTAs of a pair are counted on the leader's barrier
+    const int ybox = a.box_n / CG;  // rows of Y this CTA loads
+    const uint32_t tx_bytes = CG * (kStageBytesX + ybox * 128);
+    const int yrow0 = n0 + static_cast<int>(rank) * (bn / CG);
     const int total = n0kb + n1kb;
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0; it < total; ++it) {
       mbar_wait(&empty_bar[stage], phase ^ 1);
-      mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+      if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+      const uint32_t fb = CG == 2 ? map_to_cta(smem_u32(&full_bar[stage]), 0) : 0u;
+      auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint64_t pol) {
+        if constexpr (CG == 2) tma_load_2d_pair(dst, tm, fb, c0, c1, pol);
+        else tma_load_2d(dst, tm, &full_bar[stage], c0, c1, pol);
+      };
       const bool ph1 = it >= n0kb;
       int kb = ph1 ? (it - n0kb) : (kb_begin + it);
       const CUtensorMap* mx = ph1 ? &tmX1 : &tmX0;
@@ -175,49 +204,48 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         mx = seg == 1 ? &tmXb : &tmXc;
         my = seg == 1 ? &tmYb : &tmYc;
       }
-      const uint32_t xs = sbase + stage * kStageBytes;
+      const uint32_t xs = sbase + stage * TC::stage_bytes;
       const uint32_t ys = xs + kStageBytesX;
       // X is streamed once (evict-first); Y is re-read by every CTA (evict-last).
       if (ph1 ? a.xmn1 : a.xmn0) {
         // rows are the contiguous dimension: four 32(rows) x 32(k) boxes
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          tma_load_2d(xs + q * 4096, mx, &full_bar[stage], r0 + q * 32, kb * kBlockK, kEvictFirst);
+        for (int q = 0; q < 4; ++q) load(xs + q * 4096, mx, r0 + q * 32, kb * kBlockK, kEvictFirst);
       } else {
-        tma_load_2d(xs, mx, &full_bar[stage], kb * kBlockK, r0, kEvictFirst);
+        load(xs, mx, kb * kBlockK, r0, kEvictFirst);
       }
       if (ph1 ? a.ymn1 : a.ymn0) {
-        for (int q = 0; q < (a.box_n >> 5); ++q)
-          tma_load_2d(ys + q * 4096, my, &full_bar[stage], n0 + q * 32, kb * kBlockK, kEvictLast);
+        for (int q = 0; q < (ybox >> 5); ++q) load(ys + q * 4096, my, yrow0 + q * 32, kb * kBlockK, kEvictLast);
       } else {
-        tma_load_2d(ys, my, &full_bar[stage], kb * kBlockK, n0, kEvictLast);
+        load(ys, my, kb * kBlockK, yrow0, kEvictLast);
       }
-      if (++stage == kStages) {
+      if (++stage == kNStages) {
         stage = 0;
         phase ^= 1;
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------ MMA issuer
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ------------------------------------------------ MMA issuer (leader CTA of a pair)
     int stage = 0;
     uint32_t phase = 0;
     for (int ch = 0; ch < nchunks; ++ch) {
       const int buf = ch & 1;
       const int use = ch >> 1;
       if (use > 0) {
-        mbar_wait(&tempty_bar[buf], (use - 1) & 1);
+        if constexpr (CG == 2) mbar_wait_cluster(&tempty_bar[buf], (use - 1) & 1);
+        else mbar_wait(&tempty_bar[buf], (use - 1) & 1);
         tc_fence_after();
       }
       const bool ph1 = ch >= nchunk0;
       const int nkb = ph1 ? n1kb : min(chunk_kb, n0kb - ch * chunk_kb);
       const bool mn = ph1 ? (a.xmn1 != 0) : (a.xmn0 != 0);
       const bool ymn = ph1 ? (a.ymn1 != 0) : (a.ymn0 != 0);
-      const uint32_t idesc = make_idesc_tf32(kTileM, bn, mn ? 1 : 0, ymn ? 1 : 0);
+      const uint32_t idesc = make_idesc_tf32(kTileM * CG, bn, mn ? 1 : 0, ymn ? 1 : 0);
       const uint32_t d = tmem_base + static_cast<uint32_t>(buf * kMaxN);
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t xs = sbase + stage * kStageBytes;
+        const uint32_t xs = sbase + stage * TC::stage_bytes;
         const uint32_t ys = xs + kStageBytesX;
 #pragma unroll
         for (int s = 0; s < kBlockK / kUmmaK; ++s) {
@@ -225,15 +253,20 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
                                     : make_desc_kmajor_sw128(xs + s * (kUmmaK * 4));
           const uint64_t bdesc = ymn ? make_desc_mnmajor_sw128_32b(ys + s * 1024, 4096, 512)
                                      : make_desc_kmajor_sw128(ys + s * (kUmmaK * 4));
-          mma_tf32_ss(d, adesc, bdesc, idesc, (i == 0 && s == 0) ? 0u : 1u);
+          if constexpr (CG == 2) mma_tf32_ss_pair(d, adesc, bdesc, idesc, (i == 0 && s == 0) ? 0u : 1u);
+          else mma_tf32_ss(d, adesc, bdesc, idesc, (i == 0 && s == 0) ? 0u : 1u);
         }
-        tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-        if (++stage == kStages) {
+        // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+        if constexpr (CG == 2) tc_commit_pair(&empty_bar[stage], 0x3);
+        else tc_commit(&empty_bar[stage]);
+        if (++stage == kNStages) {
           stage = 0;
           phase ^= 1;
         }
       }
-      tc_commit(&tfull_bar[buf]);  // chunk complete
+      // chunk complete: wake the epilogue warps (of both CTAs)
+      if constexpr (CG == 2) tc_commit_pair(&tfull_bar[buf], 0x3);
+      else tc_commit(&tfull_bar[buf]);
     }
   } else if (warp >= 2) {
     // ------------------------------------------------ epilogue
@@ -268,7 +301,10 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_remote(map_to_cta(smem_u32(&tempty_bar[buf]), 0));
+        else mbar_arrive(&tempty_bar[buf]);
+      }
     }
     // second accumulator (if any) sits in the next buffer of the alternation
     const bool have1 = n1kb > 0;
@@ -420,10 +456,11 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();  // partner may still read our smem / TMEM
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 

@@ -17,6 +17,14 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=[1, 2], ids=["cta1", "cta_pair"])
+def cta_group(request):
+    """Every kernel-level test runs on the single-CTA kernel and on the CTA-pair (cta_group::2) kernel."""
+    os.environ["NMFB_DEBUG_CG"] = str(request.param)
+    yield request.param
+    os.environ.pop("NMFB_DEBUG_CG", None)
+
+
 class DebugMat(ctypes.Structure):
     _fields_ = [
         ("base", ctypes.c_void_p),
@@ -168,7 +176,7 @@ def test_fused_h_update():
     H0 = Hm.clone()
     Hr_in = Hr32.clone()
     tiles = (n + 127) // 128
-    partials = torch.zeros((tiles, 2), dtype=torch.float64, device=dev)
+    partials = torch.zeros((tiles, 2), dtype=torch.float64, device=dev)  # kernel accumulates into row 0
     Hc_out = torch.zeros((n, K), device=dev)
     err = ctypes.create_string_buffer(512)
     mx0, my0 = mat(Vt), mat(Wc)
