@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--m", type=int, default=M)
     ap.add_argument("--n", type=int, default=N_COLS)
     ap.add_argument("--k", type=int, default=K_BASIS)
+    ap.add_argument("--h-fixed", action="store_true", help="experiment: H_fixed=true (the H-step epilogue only forms sums)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,7 +203,7 @@ def main():
     W0 = np.asfortranarray(np.maximum(rng.random((m, K), dtype=np.float32), 1e-7))
     H0 = np.asfortranarray(np.maximum(rng.random((K, n), dtype=np.float32), 1e-7)[:, lo:hi])
     total = warmup + args.steps
-    cfg = dict(divergence="euclidean", W_init=W0, H_init=H0, maxiter=total + 1, tolerance=1e-300)
+    cfg = dict(divergence="euclidean", W_init=W0, H_init=H0, maxiter=total + 1, tolerance=1e-300, H_fixed=args.h_fixed)
 
     # ------------------------------------------------------------ resident timing
     h.set_V_device(Vd.data_ptr(), m, nl, m)
@@ -223,6 +224,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     launches = h.launch_count() - launches0
     ms_w, ms_h, nprof = h.profile_get()
+    breakdown = h.profile_get_all()
     h.profile_enable(False)
     _, _, cost = h.nmf_end(want_factors=False)
     dev_ms = max_over_ranks(dev_ms)
@@ -289,6 +291,7 @@ def main():
                          "hbm_peak_gbs": hbm_gbs},
             "e2e": e2e,
             "gpu_launches": int(launches),
+            "kernel_ms": breakdown,
             "clocks": clocks,
             "cost_first_last": [float(cost[warmup]), float(cost[-1])],
             "cost_monotone": monotone,

@@ -135,6 +135,8 @@ int nmfb_nmf_end(nmfb_handle* h, float* W_out, float* H_out, double* cost_out, i
  * launch of the two large contractions of the Euclidean nmf iteration). */
 int nmfb_profile_enable(nmfb_handle* h, int on);
 int nmfb_profile_get(nmfb_handle* h, double* ms_w_gemm, double* ms_h_gemm, int* count);
+/* ms_out[5]: W-step GEMM, H-step GEMM, gram(H)+cost, element-wise W step, gram(W) (averages). */
+int nmfb_profile_get_all(nmfb_handle* h, double* ms_out);
 /* Number of kernel launches issued by the handle since creation. */
 long long nmfb_launch_count(const nmfb_handle* h);
 

@@ -94,6 +94,7 @@ def _bind(lib):
         "nmfb_launch_count": ([P], LL),
         "nmfb_profile_enable": ([P, I], I),
         "nmfb_profile_get": ([P, ctypes.POINTER(D), ctypes.POINTER(D), PI], I),
+        "nmfb_profile_get_all": ([P, ctypes.POINTER(D)], I),
         "nmfb_comm_unique_id": ([ctypes.c_char_p], I),
         "nmfb_comm_init": ([P, ctypes.c_char_p, I, I], I),
         "nmfb_version": ([], ctypes.c_char_p),
@@ -180,6 +181,12 @@ class Handle:
         a, b, c = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int(0)
         self._check(self.lib.nmfb_profile_get(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return a.value, b.value, c.value
+
+    def profile_get_all(self):
+        """Average device ms of: W-step GEMM, H-step GEMM, gram(H)+cost, element-wise W step, gram(W)."""
+        arr = (ctypes.c_double * 5)()
+        self._check(self.lib.nmfb_profile_get_all(self._h, arr))
+        return dict(zip(["w_gemm", "h_gemm", "gram_h_cost", "w_elementwise", "gram_w"], [float(x) for x in arr]))
 
     # -- config marshalling
     def _config(self, config, m, n, K, T=None, for_nmfsc=False):

@@ -52,6 +52,9 @@ extern "C" int nmfb_create(nmfb_handle** out, int device) {
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
   if (e != cudaSuccess) {
@@ -68,11 +71,15 @@ extern "C" void nmfb_destroy(nmfb_handle* h) {
   cudaSetDevice(h->device);
   nmf_session_release(h);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->stream2) cudaStreamSynchronize(h->stream2);
   if (h->comm) comm_destroy(h->comm);
   if (h->Vown) cudaFree(h->Vown);
   if (h->Vwork) cudaFree(h->Vwork);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }

@@ -81,7 +81,7 @@ int enqueue_hstack(nmfb_handle* h, CnmfState* s, const int* stop) {
 
 int enqueue_iteration(nmfb_handle* h, CnmfState* s, int i) {
   const int* stop = s->stop;
-  const int KT = s->KT, KTp = s->KTp, m = s->m;
+  const int m = s->m;
   if (!s->H_fixed || i == 0) {
     NMFB_TRY(enqueue_hstack(h, s, stop));
     NMFB_TRY(run_gram(h, s->gramH, stop));
@@ -89,20 +89,22 @@ int enqueue_iteration(nmfb_handle* h, CnmfState* s, int i) {
   if (i > 0) NMFB_TRY(enqueue_cost(h, s, i - 1));
   if (!s->W_fixed) {
     NMFB_TRY(run_gemm(h, s->gemmA));  // A = V Hs', B = Wc (Hs Hs')
-    NMFB_TRY(zero_async(h, s->ab, 2 * KTp * sizeof(double)));
-    w_dots_kernel<<<vec_grid(m, KT), 256, 0, h->stream>>>(s->Wm, s->A, s->B, m, s->ldw, KTp, s->ab, stop);
-    NMFB_TRY(check_launch(h, "w_dots"));
-    w_coef_kernel<<<(KTp + 127) / 128, 128, 0, h->stream>>>(WSTEP_EUCLID, KTp, s->ab, nullptr, nullptr,
-                                                            s->pcoef, s->qcoef, s->bvec, stop);
-    NMFB_TRY(check_launch(h, "w_coef"));
-    NMFB_TRY(zero_async(h, s->norm2, KTp * sizeof(double)));
-    NMFB_TRY(zero_async(h, s->wsum, KTp * sizeof(double)));
-    w_update_kernel<<<vec_grid(m, KT), 256, 0, h->stream>>>(s->Wm, s->A, s->B, m, s->ldw, s->pcoef, s->qcoef,
-                                                            s->bvec, s->lambda_w, s->norm2, stop);
-    NMFB_TRY(check_launch(h, "w_update"));
-    w_normalize_kernel<<<vec_grid(m, KT), 256, 0, h->stream>>>(s->Wm, s->Wt, m, s->ldw, s->K, s->T, 1,
-                                                               s->norm2, s->wsum, nullptr, stop);
-    NMFB_TRY(check_launch(h, "w_normalize"));
+    WStepArgs w{};  // dots, multiplicative step and per-basis normalisation in one launch (CTA per basis)
+    w.mode = WSTEP_EUCLID;
+    w.W = s->Wm;
+    w.Wt = s->Wt;
+    w.A = s->A;
+    w.B = s->B;
+    w.m = m;
+    w.ld = s->ldw;
+    w.K = s->K;
+    w.T = s->T;
+    w.cnmf_style = 1;
+    w.wsum = s->wsum;
+    w.hs = nullptr;
+    w.lambda = s->lambda_w;
+    w.stop = stop;
+    NMFB_TRY(launch_w_step(h, w));
     NMFB_TRY(run_gram(h, s->gramW, stop));
   }
   // P = Wc'V and D = (Wc'Wc) Hs, then fold over the frames and update H (cnmf.m:216-231)
@@ -171,9 +173,9 @@ int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_
   NMFB_TRY(ar->alloc(h, &s->qcoef, KTp));
   NMFB_TRY(ar->alloc(h, &s->bvec, KTp));
   NMFB_TRY(ar->alloc(h, &s->hscale, KTp));
-  NMFB_TRY(ar->alloc(h, &s->ab, 2 * KTp));
-  NMFB_TRY(ar->alloc(h, &s->norm2, KTp));
-  NMFB_TRY(ar->alloc(h, &s->wsum, KTp));
+  NMFB_TRY(ar->alloc(h, &s->ab, 4 * KTp));  // [ab | norm2 | wsum]: WStepArgs::acc
+  s->norm2 = s->ab + 2 * KTp;
+  s->wsum = s->ab + 3 * KTp;
   NMFB_TRY(ar->alloc(h, &s->scal, 8));
   NMFB_TRY(ar->alloc(h, &s->cost, static_cast<size_t>(s->maxiter) + 1));
   NMFB_TRY(ar->alloc(h, &s->stop, 2));

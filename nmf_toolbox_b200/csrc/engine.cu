@@ -132,6 +132,24 @@ int run_gram(nmfb_handle* h, const GramOp& op, const int* stop) {
   return check_launch(h, "gram_reduce");
 }
 
+int run_gram_cost(nmfb_handle* h, const GramOp& op, unsigned int* ticket, const CostArgs& c, bool with_cost) {
+  std::string e = launch_gemm(op.g.L, EPI_STORE, h->stream);
+  ++h->launches;
+  if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "%s", e.c_str());
+  const int count = op.nvec * op.nvec;
+  gram_reduce_cost_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(op.g.parts, op.g.splits, count, op.g32,
+                                                                      op.gtf, count, ticket, c, with_cost ? 1 : 0);
+  return check_launch(h, "gram_reduce_cost");
+}
+
+int launch_w_step(nmfb_handle* h, const WStepArgs& a) {
+  if (a.m <= kWThreads * kWCache)
+    w_step_kernel<true><<<a.K, kWThreads, 0, h->stream>>>(a);
+  else
+    w_step_kernel<false><<<a.K, kWThreads, 0, h->stream>>>(a);
+  return check_launch(h, "w_step");
+}
+
 // ---------------------------------------------------------------- V
 int compute_v_stats(nmfb_handle* h, bool want_log, VStats* out, double** dev_stats_out,
                     unsigned int** dev_max_out, Arena* ar) {

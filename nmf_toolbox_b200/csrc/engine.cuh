@@ -26,7 +26,9 @@ struct nmfb_handle {
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // side stream: work that only depends on H runs beside the A GEMM
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   long long launches = 0;
 
@@ -44,7 +46,8 @@ struct nmfb_handle {
 
   // optional per-kernel timing of the two large contractions (bench.py roofline)
   bool profile = false;
-  std::vector<cudaEvent_t> prof_ev[2];  // [0] W-step GEMM, [1] H-step GEMM: begin/end pairs
+  // [0] W-step GEMM, [1] H-step GEMM, [2] gram(H)+cost, [3] element-wise W step, [4] gram(W)
+  std::vector<cudaEvent_t> prof_ev[5];
 
   int fail(int code, const char* fmt, ...) {
     char buf[1024];
@@ -168,6 +171,13 @@ int download_H(nmfb_handle* h, const float* Hm, long long ldh, int K, int n, flo
 void fill_uniform(std::vector<float>& v, unsigned long long seed, bool clamp_eps);
 
 int check_launch(nmfb_handle* h, const char* what);
+
+struct WStepArgs;
+// Cooperative launch of the fused W step (ew_kernels.cuh: w_step_kernel).
+int launch_w_step(nmfb_handle* h, const WStepArgs& a);
+struct CostArgs;
+// gram GEMM + (reduce, <G_W,G_H>, cost, stop test) in one follow-up kernel.
+int run_gram_cost(nmfb_handle* h, const GramOp& op, unsigned int* ticket, const CostArgs& c, bool with_cost);
 
 // Queue `maxiter` iterations in chunks.  The stop flag written by the cost
 // kernel turns everything queued behind a converged iteration into no-ops, so

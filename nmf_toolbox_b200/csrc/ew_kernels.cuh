@@ -10,6 +10,7 @@
 // so "vector c of a factor" (a column of W or a row of H) is always contiguous.
 // Kp = K rounded up to 32; padding vectors are all-zero and stay zero.
 #pragma once
+#include <cooperative_groups.h>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -173,8 +174,14 @@ __global__ void gram_reduce_kernel(const float* __restrict__ parts, int splits, 
   NMFB_STOP_GUARD(stop);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += parts[z * slab + i];
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains keep the loads in flight
+  int z = 0;
+  for (; z + 4 <= splits; z += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s4[u] += parts[(z + u) * slab + i];
+  }
+  for (; z < splits; ++z) s4[0] += parts[z * slab + i];
+  const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
   g32[i] = s;
   const float hi = tf32_rn(s);
   gtf[i] = hi;
@@ -261,6 +268,173 @@ __global__ void w_update_kernel(float* __restrict__ W, const float* __restrict__
   }
   block_sum<1>(acc, sh);
   if (threadIdx.x == 0 && norm2) atomicAdd(norm2 + c, acc[0]);
+}
+
+// The whole W step of nmf.m:149-169 / cnmf.m:187-199 in ONE launch, one CTA per basis vector:
+// everything the step needs is local to a column of W (cnmf: to the T frame-columns of one
+// basis), so the three dependent reductions are block-level and the column stays in registers:
+//   1  a_c = <W_c, A_c>, b_c = <W_c, B_c>                     (the diag(diag(.)) terms)
+//   2  W' = W .* (A + W p_c) ./ max(Bterm + W q_c + lambda, eps)            (nmf.m:168)
+//   3  W = W' / |W'_c| (nmf.m:169)  or  W(:,k,:) / (|W(:,k,:)|_F / T) (cnmf.m:196-199);
+//      tf32 copy; wsum[c] = sum_i W_ic
+// W, A and B are read once and W written once when T*m <= kWThreads*kWCache; longer columns
+// are re-read (L2 resident).
+constexpr int kWThreads = 1024;
+constexpr int kWCache = 16;
+struct WStepArgs {
+  int mode;        // WSTEP_EUCLID / WSTEP_KL
+  float* W;        // master, updated in place
+  float* Wt;       // tf32 copy
+  const float* A;  // numerator  (V H' or (V./V_hat) H')
+  const float* B;  // denominator matrix (Euclid: W (H H')); null for KL
+  int m;
+  long long ld;
+  int K, T;        // CTA k handles columns k + K*t, t < T (T = 1: plain nmf)
+  int cnmf_style;  // normalise per basis over all frames by |.|_F / T
+  double* wsum;    // [K*T] column sums of the new W (KL: holds the old ones on entry)
+  const double* hs;  // KL: row sums of H
+  float lambda;
+  const int* stop;
+};
+template <bool CACHED>
+__global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
+  NMFB_STOP_GUARD(a.stop);
+  __shared__ double sh[32 * 2];
+  __shared__ double bc[4];
+  const int k = blockIdx.x;
+  const int tid = threadIdx.x;
+  const bool kl = a.mode == WSTEP_KL;
+  const int total = a.T * a.m;  // elements of this basis
+  float wv[kWCache], av[kWCache], bv[kWCache];
+  double norm_basis = 0.0;
+
+  for (int t = 0; t < a.T; ++t) {
+    const int c = k + a.K * t;
+    const long long off = static_cast<long long>(c) * a.ld;
+    // ---- 1: column dots
+    float s0 = 0.f, s1 = 0.f;
+    if (CACHED) {
+#pragma unroll
+      for (int q = 0; q < kWCache; ++q) {
+        const int i = tid + q * kWThreads;
+        const bool ok = i < a.m;
+        wv[q] = ok ? a.W[off + i] : 0.f;
+        av[q] = ok ? a.A[off + i] : 0.f;
+        bv[q] = (ok && !kl) ? a.B[off + i] : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < kWCache; ++q) {
+        s0 = fmaf(wv[q], av[q], s0);
+        s1 = fmaf(wv[q], bv[q], s1);
+      }
+    } else {
+      for (int i = tid; i < a.m; i += kWThreads) {
+        const float w = a.W[off + i];
+        s0 = fmaf(w, a.A[off + i], s0);
+        if (!kl) s1 = fmaf(w, a.B[off + i], s1);
+      }
+    }
+    double acc[2] = {s0, s1};
+    block_sum<2>(acc, sh);
+    if (tid == 0) {
+      bc[0] = acc[0];
+      bc[1] = acc[1];
+    }
+    __syncthreads();
+    float pc, qc, bterm = 0.f;
+    if (kl) {  // nmf.m:152-153
+      pc = static_cast<float>(a.hs[c] * a.wsum[c]);
+      qc = static_cast<float>(bc[0]);
+      bterm = static_cast<float>(a.hs[c]);
+    } else {   // nmf.m:149-150
+      pc = static_cast<float>(bc[1]);
+      qc = static_cast<float>(bc[0]);
+    }
+    // ---- 2: multiplicative step + column norm
+    float s2 = 0.f;
+    if (CACHED) {
+#pragma unroll
+      for (int q = 0; q < kWCache; ++q) {
+        const float w = wv[q];
+        const float neg = av[q] + w * pc;
+        const float pos = (kl ? bterm : bv[q]) + w * qc;
+        const float wn = (tid + q * kWThreads < a.m) ? w * (neg / fmaxf(pos + a.lambda, NMFB_EPS)) : 0.f;
+        wv[q] = wn;
+        s2 = fmaf(wn, wn, s2);
+      }
+    } else {
+      for (int i = tid; i < a.m; i += kWThreads) {
+        const float w = a.W[off + i];
+        const float neg = a.A[off + i] + w * pc;
+        const float pos = (kl ? bterm : a.B[off + i]) + w * qc;
+        const float wn = w * (neg / fmaxf(pos + a.lambda, NMFB_EPS));
+        a.W[off + i] = wn;
+        s2 = fmaf(wn, wn, s2);
+      }
+    }
+    acc[0] = s2;
+    acc[1] = 0.0;
+    block_sum<2>(acc, sh);
+    if (tid == 0) bc[2] = acc[0];
+    __syncthreads();
+    norm_basis += bc[2];
+    if (!a.cnmf_style) {
+      // ---- 3 (nmf): unit L2 column, tf32 copy, column sum
+      const float mul = static_cast<float>(1.0 / sqrt(bc[2]));
+      float s3 = 0.f;
+      if (CACHED) {
+#pragma unroll
+        for (int q = 0; q < kWCache; ++q) {
+          const int i = tid + q * kWThreads;
+          if (i < a.m) {
+            const float w = wv[q] * mul;
+            a.W[off + i] = w;
+            a.Wt[off + i] = tf32_rn(w);
+            s3 += w;
+          }
+        }
+      } else {
+        for (int i = tid; i < a.m; i += kWThreads) {
+          const float w = a.W[off + i] * mul;
+          a.W[off + i] = w;
+          a.Wt[off + i] = tf32_rn(w);
+          s3 += w;
+        }
+      }
+      acc[0] = s3;
+      acc[1] = 0.0;
+      block_sum<2>(acc, sh);
+      if (tid == 0) a.wsum[c] = acc[0];
+    } else if (CACHED) {
+      // cnmf: the scale needs all T frames; park W' and come back
+#pragma unroll
+      for (int q = 0; q < kWCache; ++q) {
+        const int i = tid + q * kWThreads;
+        if (i < a.m) a.W[off + i] = wv[q];
+      }
+    }
+    __syncthreads();
+  }
+  if (a.cnmf_style) {
+    // ---- 3 (cnmf.m:196-199): W(:,k,:) /= |W(:,k,:)|_F / T
+    const float div = static_cast<float>(sqrt(norm_basis) / a.T);
+    for (int t = 0; t < a.T; ++t) {
+      const int c = k + a.K * t;
+      const long long off = static_cast<long long>(c) * a.ld;
+      float s3 = 0.f;
+      for (int i = tid; i < a.m; i += kWThreads) {
+        const float w = a.W[off + i] / div;
+        a.W[off + i] = w;
+        a.Wt[off + i] = tf32_rn(w);
+        s3 += w;
+      }
+      double acc[2] = {s3, 0.0};
+      block_sum<2>(acc, sh);
+      if (tid == 0) a.wsum[c] = acc[0];
+      __syncthreads();
+    }
+  }
+  (void)total;
 }
 
 // Column normalisation + tf32 copy + column sums.
@@ -365,6 +539,58 @@ __global__ void cost_kernel(CostArgs a) {
     if (c < prev && prev - c < a.tolerance) a.stop[0] = 1;  // nmf.m:221-224
   }
   a.scal[0] = a.scal[1] = a.scal[2] = a.scal[3] = a.scal[4] = 0.0;
+}
+
+// gram_reduce of G_H fused with <G_W, G_H> and the cost / stop test of the previous iteration:
+// every block reduces its share of the split-K slabs and adds its part of the inner product;
+// the last block to finish (ticket counter) finalises the cost exactly as cost_kernel does.
+__global__ void gram_reduce_cost_kernel(const float* __restrict__ parts, int splits, long long slab,
+                                        float* __restrict__ g32, float* __restrict__ gtf, int count,
+                                        unsigned int* ticket, CostArgs c, int with_cost) {
+  if (c.stop[0] != 0) return;
+  __shared__ double sh[64];
+  __shared__ bool last;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[2] = {0.0, 0.0};
+  if (i < count) {
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    int z = 0;
+    for (; z + 4 <= splits; z += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s4[u] += parts[(z + u) * slab + i];
+    }
+    for (; z < splits; ++z) s4[0] += parts[z * slab + i];
+    const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    g32[i] = s;
+    gtf[i] = tf32_rn(s);
+    if (with_cost) acc[0] = static_cast<double>(s) * c.GW[i];
+  }
+  if (!with_cost) return;
+  block_sum<2>(acc, sh);
+  if (threadIdx.x == 0) {
+    atomicAdd(c.scal + 4, acc[0]);
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  acc[0] = 0.0;
+  acc[1] = 0.0;
+  for (int k = threadIdx.x; k < c.n_wsum; k += blockDim.x) acc[1] += c.wsum[k];
+  block_sum<2>(acc, sh);
+  if (threadIdx.x != 0) return;
+  *ticket = 0u;
+  volatile double* sc = c.scal;
+  double cost = 0.5 * (c.vsq - 2.0 * sc[0] + sc[4]);
+  cost += c.lambda_w * acc[1] + c.lambda_h * sc[1];
+  c.cost[c.iter] = cost;
+  c.stop[1] = c.iter + 1;
+  if (c.iter > 0) {
+    const double prev = c.cost[c.iter - 1];
+    if (cost < prev && prev - cost < c.tolerance) c.stop[0] = 1;  // nmf.m:221-224
+  }
+  sc[0] = sc[1] = sc[2] = sc[3] = sc[4] = 0.0;
 }
 
 // ---------------------------------------------------------------- convolutive helpers

@@ -32,7 +32,7 @@ static EncodeTiledFn get_encode_fn(std::string* err) {
 }
 
 std::string make_tmap(CUtensorMap* out, const Mat2D& m, uint32_t box_inner, uint32_t box_outer,
-                      bool atom32b) {
+                      bool atom32b, bool no_swizzle) {
   std::string err;
   EncodeTiledFn fn = get_encode_fn(&err);
   if (!fn) return err;
@@ -44,7 +44,8 @@ std::string make_tmap(CUtensorMap* out, const Mat2D& m, uint32_t box_inner, uint
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(m.base), gdim, gstride,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE
+                             : (atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) +
@@ -129,6 +130,15 @@ std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const GemmOperand& Y
   }
   L->tmXb = L->tmXc = L->tmX0;
   L->tmYb = L->tmYc = L->tmY0;
+  L->tmH = L->tmX0;
+  return "";
+}
+
+std::string set_h_prefetch(GemmLaunch* L, const float* Hm, long long n, long long Kp, long long ldh) {
+  Mat2D m{Hm, n, Kp, ldh};
+  std::string e = make_tmap(&L->tmH, m, kTileM, 32, false, true);  // 128 samples x 32 basis rows, linear
+  if (!e.empty()) return "H tile " + e;
+  L->args.h_prefetch = 1;
   return "";
 }
 
@@ -184,10 +194,10 @@ static cudaError_t launch_one(const GemmLaunch& L, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, panel_gemm_kernel<EPI, 2>, L.tmX0, L.tmY0, L.tmX1, L.tmY1, L.tmXb, L.tmYb,
-                              L.tmXc, L.tmYc, L.args);
+                              L.tmXc, L.tmYc, L.tmH, L.args);
   }
   panel_gemm_kernel<EPI, 1><<<L.grid, kGemmThreads, TileCfg<1>::smem_bytes, stream>>>(
-      L.tmX0, L.tmY0, L.tmX1, L.tmY1, L.tmXb, L.tmYb, L.tmXc, L.tmYc, L.args);
+      L.tmX0, L.tmY0, L.tmX1, L.tmY1, L.tmXb, L.tmYb, L.tmXc, L.tmYc, L.tmH, L.args);
   return cudaGetLastError();
 }
 

@@ -28,7 +28,7 @@ struct GemmOperand {
 // Returns an empty string on success, else an error message.
 // atom32b selects the 128B-swizzle-with-32B-atom mode that MN-major fp32 operands need.
 std::string make_tmap(CUtensorMap* out, const Mat2D& m, uint32_t box_inner, uint32_t box_outer,
-                      bool atom32b);
+                      bool atom32b, bool no_swizzle = false);
 
 // Number of phase-0 k-blocks each split handles so that tiles*chunks*splits ~ fills the GPU.
 int choose_splits(int tiles, int nkb0, int num_sms, int* kb_per_split);
@@ -36,6 +36,7 @@ int choose_splits(int tiles, int nkb0, int num_sms, int* kb_per_split);
 struct GemmLaunch {
   CUtensorMap tmX0, tmY0, tmX1, tmY1;
   CUtensorMap tmXb, tmYb, tmXc, tmYc;  // extra phase-0 segments (same shapes / majorness as X0, Y0)
+  CUtensorMap tmH;                     // EPI_HUPDATE: H master tile (set_h_prefetch)
   GemmArgs args;
   dim3 grid;
   int cg = 1;  // 2 = CTA-pair kernel (256-row tiles, cluster of two CTAs)
@@ -55,6 +56,9 @@ std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const GemmOperand& Y
 // Must be called after plan_gemm and before any split bookkeeping is read.
 std::string add_segment(GemmLaunch* L, int seg, const GemmOperand& X, const GemmOperand& Y, int num_sms,
                         int splits_hint);
+
+// EPI_HUPDATE: let the kernel stage the H master tile through shared memory by TMA.
+std::string set_h_prefetch(GemmLaunch* L, const float* Hm, long long n, long long Kp, long long ldh);
 
 std::string launch_gemm(const GemmLaunch& L, int epi, cudaStream_t stream);
 

@@ -19,6 +19,7 @@
 // iteration, and is finalised by one trailing Gram product after the last.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -34,6 +35,7 @@ struct NmfSession {
   long long ldw = 0, ldh = 0;
   int divergence = NMFB_DIV_EUCLIDEAN;
   bool W_fixed = false, H_fixed = false, direct_cost = false;
+  bool overlap = false;  // gram(H) + cost run on the side stream next to the A GEMM
   float lambda_w = 0.f, lambda_h = 0.f;
   int maxiter = 100;
   double tolerance = 1e-3;
@@ -47,6 +49,7 @@ struct NmfSession {
   double *ab = nullptr, *norm2 = nullptr, *wsum = nullptr, *hs = nullptr, *scal = nullptr;
   double *cost = nullptr, *vstats = nullptr;
   int* stop = nullptr;
+  unsigned int* ticket = nullptr;
   double vsq = 0.0;
   const float* Vmma = nullptr;  // V as the tensor cores read it (tf32-rounded copy)
 
@@ -140,9 +143,10 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   NMFB_TRY(ar->alloc(h, &s->qcoef, Kp));
   NMFB_TRY(ar->alloc(h, &s->bvec, Kp));
   NMFB_TRY(ar->alloc(h, &s->wsf, Kp));
-  NMFB_TRY(ar->alloc(h, &s->ab, 2 * Kp));
-  NMFB_TRY(ar->alloc(h, &s->norm2, Kp));
-  NMFB_TRY(ar->alloc(h, &s->wsum, Kp));
+  NMFB_TRY(ar->alloc(h, &s->ab, 4 * Kp));  // [ab (2 Kp) | norm2 (Kp) | wsum (Kp)]: WStepArgs::acc
+  s->norm2 = s->ab + 2 * Kp;
+  s->wsum = s->ab + 3 * Kp;
+  NMFB_TRY(ar->alloc(h, &s->ticket, 1));
   NMFB_TRY(ar->alloc(h, &s->hs, Kp));
   NMFB_TRY(ar->alloc(h, &s->scal, 8));
   NMFB_TRY(ar->alloc(h, &s->cost, static_cast<size_t>(s->maxiter) + 1));
@@ -214,7 +218,14 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     MatRef Yg{s->gramH.gtf, Kp, Kp, Kp, false};
     const int tiles = (m + kTileM - 1) / kTileM * ((Kp + kMaxN - 1) / kMaxN);
     const bool split = tiles * 2 <= h->num_sms;
-    if (multi || split) {
+    {
+      // With B = W G_H as its own (small) launch, G_H is not needed until the A GEMM is over, so
+      // gram(H), <G_W,G_H>, the cost and the stop test overlap with it on SMs the GEMM leaves idle.
+      const char* env = std::getenv("NMFB_OVERLAP");
+      s->overlap = !multi && !s->direct_cost && !s->W_fixed && !(env && env[0] == '0') &&
+                   tiles < h->num_sms;  // a full wave of GEMM CTAs would leave no SM for the side stream
+    }
+    if (multi || split || s->overlap) {
       NMFB_TRY(plan_store(h, ar, &s->gemmA, Xv, Yh, n, nullptr, nullptr, 0, m, Kp, s->A, nullptr,
                           s->ldw, split, stop));
       NMFB_TRY(plan_store(h, ar, &s->gemmB, Xw, Yg, Kp, nullptr, nullptr, 0, m, Kp, s->B, nullptr,
@@ -223,12 +234,43 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
       NMFB_TRY(plan_store(h, ar, &s->gemmA, Xv, Yh, n, &Xw, &Yg, Kp, m, Kp, s->A, s->B, s->ldw, false,
                           stop));
     }
-    // H update: N = W'V (X = V columns, K-major), D = G_W H (X = H, columns j contiguous -> MN-major)
+    // H update: N = W'V, D = G_W H (X = H, columns j contiguous -> MN-major).
+    // Reading V with the contraction index contiguous (K-major) makes every TMA row a lone
+    // 128-byte DRAM access 64 KB away from the next one; with a row-major copy of V the same
+    // product reads 512-byte runs (MN-major X), worth ~15 % of this kernel.  The copy is made
+    // once per call when memory allows (it costs one more m x n buffer).
     MatRef Xvt{s->Vmma, m, n, h->ldv, false};
+    {
+      size_t free_b = 0, total_b = 0;
+      const long long ldn = round_up(n, 4);
+      const size_t need = static_cast<size_t>(m) * ldn * sizeof(float);
+      const char* env = std::getenv("NMFB_NO_VT");
+      if (!(env && env[0] == '1') && m >= 1024 && n >= 1024 &&
+          cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > need + (size_t(2) << 30)) {
+        float* Vrm = nullptr;
+        NMFB_TRY(ar->alloc(h, &Vrm, static_cast<size_t>(m) * ldn));
+        dim3 grid((n + 31) / 32, (m + 31) / 32);
+        // Vrm[i][j] = V[j][i]  (src is [n][ldv])
+        transpose_kernel<<<grid, dim3(32, 8), 0, h->stream>>>(s->Vmma, h->ldv, Vrm, ldn, m, n);
+        NMFB_TRY(check_launch(h, "transpose(V)"));
+        Xvt = MatRef{Vrm, n, m, ldn, true};
+      }
+    }
     MatRef Yw{s->Wt, m, Kp, s->ldw, false};
     MatRef Xh{s->Ht, n, Kp, s->ldh, true};
     MatRef Ygw{s->gramW.gtf, Kp, Kp, Kp, false};
     NMFB_TRY(plan_fused(h, &s->gemmH, EPI_HUPDATE, Xvt, Yw, m, &Xh, &Ygw, Kp, n, Kp, Kp, stop));
+    if (const char* env = std::getenv("NMFB_EXPERIMENT_HSTORE")) {  // timing experiment only: results are wrong
+      if (env[0] == '1') {
+        float *t0 = nullptr, *t1 = nullptr;
+        NMFB_TRY(ar->alloc(h, &t0, static_cast<size_t>(Kp) * s->ldh));
+        NMFB_TRY(ar->alloc(h, &t1, static_cast<size_t>(Kp) * s->ldh));
+        s->gemmH.epi = EPI_STORE;
+        s->gemmH.L.args.out0 = t0;
+        s->gemmH.L.args.out1 = t1;
+        s->gemmH.L.args.ldo = s->ldh;
+      }
+    }
     GemmArgs& a = s->gemmH.L.args;
     a.Hm = s->Hm;
     a.Hr32 = s->Ht;
@@ -237,6 +279,10 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     a.lambda = s->lambda_h;
     a.scal = s->scal;
     a.freeze = s->H_fixed ? 1 : 0;
+    if (!std::getenv("NMFB_NO_HPREFETCH")) {
+      std::string e = set_h_prefetch(&s->gemmH.L, s->Hm, n, Kp, s->ldh);
+      if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "%s", e.c_str());
+    }
     if (s->direct_cost) {
       MatRef Xs{s->Wt, m, Kp, s->ldw, true};
       MatRef Ys{s->Ht, n, Kp, s->ldh, true};
@@ -277,6 +323,10 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     a.scal = s->scal;
     a.dvec = s->wsf;
     a.freeze = s->H_fixed ? 1 : 0;
+    if (!std::getenv("NMFB_NO_HPREFETCH")) {
+      std::string e = set_h_prefetch(&s->gemmH.L, s->Hm, n, Kp, s->ldh);
+      if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "%s", e.c_str());
+    }
   }
   if (s->W_fixed) NMFB_TRY(run_gram(h, s->gramW, nullptr));
   D2FArgs da{s->wsum, s->wsf, Kp};
@@ -330,44 +380,60 @@ static int allreduce_w_inputs(nmfb_handle* h, NmfSession* s, bool with_gram) {
 }
 
 static int enqueue_w_finish(nmfb_handle* h, NmfSession* s, int mode) {
-  const int Kp = s->Kp, K = s->K, m = s->m;
-  const int* stop = s->stop;
-  NMFB_TRY(zero_async(h, s->ab, 2 * Kp * sizeof(double)));
-  w_dots_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, s->A, mode == WSTEP_EUCLID ? s->B : nullptr,
-                                                       m, s->ldw, Kp, s->ab, stop);
-  NMFB_TRY(check_launch(h, "w_dots"));
-  w_coef_kernel<<<(Kp + 127) / 128, 128, 0, h->stream>>>(mode, Kp, s->ab, s->hs, s->wsum, s->pcoef,
-                                                         s->qcoef, s->bvec, stop);
-  NMFB_TRY(check_launch(h, "w_coef"));
-  NMFB_TRY(zero_async(h, s->norm2, Kp * sizeof(double)));
-  NMFB_TRY(zero_async(h, s->wsum, Kp * sizeof(double)));
-  w_update_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, s->A, mode == WSTEP_EUCLID ? s->B : nullptr,
-                                                         m, s->ldw, s->pcoef, s->qcoef, s->bvec,
-                                                         s->lambda_w, s->norm2, stop);
-  NMFB_TRY(check_launch(h, "w_update"));
-  w_normalize_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, s->Wt, m, s->ldw, K, 1, 0, s->norm2,
-                                                            s->wsum, nullptr, stop);
-  NMFB_TRY(check_launch(h, "w_normalize"));
-  return NMFB_OK;
+  WStepArgs w{};
+  w.mode = mode;
+  w.W = s->Wm;
+  w.Wt = s->Wt;
+  w.A = s->A;
+  w.B = mode == WSTEP_EUCLID ? s->B : nullptr;
+  w.m = s->m;
+  w.ld = s->ldw;
+  w.K = s->K;
+  w.T = 1;
+  w.cnmf_style = 0;
+  w.wsum = s->wsum;
+  w.hs = s->hs;
+  w.lambda = s->lambda_w;
+  w.stop = s->stop;
+  return launch_w_step(h, w);
 }
 
-// run_gemm bracketed by a CUDA-event pair when profiling is on
-static int run_timed(nmfb_handle* h, const GemmOp& op, int which) {
-  if (!h->profile) return run_gemm(h, op);
-  cudaEvent_t e0, e1;
-  NMFB_CUDA(h, cudaEventCreate(&e0));
-  NMFB_CUDA(h, cudaEventCreate(&e1));
-  h->prof_ev[which].push_back(e0);
-  h->prof_ev[which].push_back(e1);
-  NMFB_CUDA(h, cudaEventRecord(e0, h->stream));
-  NMFB_TRY(run_gemm(h, op));
-  NMFB_CUDA(h, cudaEventRecord(e1, h->stream));
+static void fill_cost_args(NmfSession* s, CostArgs* c, int iter, int mode) {
+  c->mode = mode;
+  c->iter = iter;
+  c->Kp = s->Kp;
+  c->GW = s->gramW.g32;
+  c->GH = s->gramH.g32;
+  c->vsq = s->vsq;
+  c->vstats = s->vstats;
+  c->scal = s->scal;
+  c->wsum = s->wsum;
+  c->n_wsum = s->Kp;
+  c->lambda_w = s->lambda_w;
+  c->lambda_h = s->lambda_h;
+  c->tolerance = s->tolerance;
+  c->cost = s->cost;
+  c->stop = s->stop;
+}
+
+// CUDA-event pair around a group of launches when profiling is on
+static int prof_mark(nmfb_handle* h, int which) {
+  if (!h->profile) return NMFB_OK;
+  cudaEvent_t e;
+  NMFB_CUDA(h, cudaEventCreate(&e));
+  h->prof_ev[which].push_back(e);
+  NMFB_CUDA(h, cudaEventRecord(e, h->stream));
   return NMFB_OK;
+}
+static int run_timed(nmfb_handle* h, const GemmOp& op, int which) {
+  NMFB_TRY(prof_mark(h, which));
+  NMFB_TRY(run_gemm(h, op));
+  return prof_mark(h, which);
 }
 
 extern "C" int nmfb_profile_enable(nmfb_handle* h, int on) {
   if (!h) return NMFB_ERR_INVALID_ARGUMENT;
-  for (int w = 0; w < 2; ++w) {
+  for (int w = 0; w < 5; ++w) {
     for (cudaEvent_t e : h->prof_ev[w]) cudaEventDestroy(e);
     h->prof_ev[w].clear();
   }
@@ -376,6 +442,24 @@ extern "C" int nmfb_profile_enable(nmfb_handle* h, int on) {
 }
 
 // Average device time (ms) of the W-step and H-step contractions recorded so far.
+extern "C" int nmfb_profile_get_all(nmfb_handle* h, double* ms_out /* [5] */) {
+  if (!h || !ms_out) return NMFB_ERR_INVALID_ARGUMENT;
+  NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int w = 0; w < 5; ++w) {
+    double tot = 0.0;
+    int c = 0;
+    for (size_t i = 0; i + 1 < h->prof_ev[w].size(); i += 2) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, h->prof_ev[w][i], h->prof_ev[w][i + 1]) == cudaSuccess) {
+        tot += ms;
+        ++c;
+      }
+    }
+    ms_out[w] = c ? tot / c : 0.0;
+  }
+  return NMFB_OK;
+}
+
 extern "C" int nmfb_profile_get(nmfb_handle* h, double* ms_w, double* ms_h, int* count) {
   if (!h) return NMFB_ERR_INVALID_ARGUMENT;
   NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -405,18 +489,43 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
   const int* stop = s->stop;
   const bool multi = comm_size(h->comm) > 1;
   if (s->divergence == NMFB_DIV_EUCLIDEAN) {
-    if (!s->H_fixed || i == 0 || multi) NMFB_TRY(run_gram(h, s->gramH, stop));
+    const bool fused_cost = !multi && !s->direct_cost;  // reduce + <G_W,G_H> + cost in one kernel
+    if (fused_cost && s->overlap) {
+      CostArgs c{};
+      fill_cost_args(s, &c, i - 1, 0);
+      NMFB_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+      NMFB_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+      cudaStream_t main_stream = h->stream;
+      h->stream = h->stream2;
+      int rc = run_gram_cost(h, s->gramH, s->ticket, c, i > 0);
+      h->stream = main_stream;
+      NMFB_TRY(rc);
+      NMFB_CUDA(h, cudaEventRecord(h->ev_join, h->stream2));
+    } else if (fused_cost) {
+      CostArgs c{};
+      fill_cost_args(s, &c, i - 1, 0);
+      NMFB_TRY(prof_mark(h, 2));
+      NMFB_TRY(run_gram_cost(h, s->gramH, s->ticket, c, i > 0));
+      NMFB_TRY(prof_mark(h, 2));
+    } else if (!s->H_fixed || i == 0 || multi) {
+      NMFB_TRY(run_gram(h, s->gramH, stop));
+    }
     if (s->W_fixed) {
       if (multi) return h->fail(NMFB_ERR_UNSUPPORTED, "W_fixed with several GPUs");
     } else {
       NMFB_TRY(run_timed(h, s->gemmA, 0));
     }
+    if (fused_cost && s->overlap) NMFB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     NMFB_TRY(allreduce_w_inputs(h, s, true));
-    if (i > 0 && !s->direct_cost) NMFB_TRY(enqueue_cost(h, s, i - 1, 0));
+    if (i > 0 && !s->direct_cost && !fused_cost) NMFB_TRY(enqueue_cost(h, s, i - 1, 0));
     if (!s->W_fixed) {
       if (s->gemmB.planned) NMFB_TRY(run_gemm(h, s->gemmB));
+      NMFB_TRY(prof_mark(h, 3));
       NMFB_TRY(enqueue_w_finish(h, s, WSTEP_EUCLID));
+      NMFB_TRY(prof_mark(h, 3));
+      NMFB_TRY(prof_mark(h, 4));
       NMFB_TRY(run_gram(h, s->gramW, stop));
+      NMFB_TRY(prof_mark(h, 4));
     }
     NMFB_TRY(run_timed(h, s->gemmH, 1));
     if (s->direct_cost) {
@@ -456,6 +565,11 @@ static int enqueue_final_cost(nmfb_handle* h, NmfSession* s) {
   const bool multi = comm_size(h->comm) > 1;
   if (s->divergence == NMFB_DIV_EUCLIDEAN) {
     if (s->direct_cost) return NMFB_OK;
+    if (!multi) {
+      CostArgs c{};
+      fill_cost_args(s, &c, last, 0);
+      return run_gram_cost(h, s->gramH, s->ticket, c, true);
+    }
     NMFB_TRY(run_gram(h, s->gramH, s->stop));
     if (multi)
       NMFB_TRY(comm_allreduce(h, s->gramH.g32, static_cast<size_t>(s->Kp) * s->Kp, nullptr, 0, s->scal, 4));

@@ -108,6 +108,9 @@ struct GemmArgs {
   long long ldv;
   int want_cost;
   int freeze;         // EPI_HUPDATE: leave H untouched (H_fixed, nmf.m:177) but still form the sums
+  int h_prefetch;     // EPI_HUPDATE: the producer stages the tile of the H master in shared memory by
+                      // TMA (map tmH) as soon as the operand ring is idle, instead of the epilogue
+                      // fetching it with a chain of dependent global loads after the last MMA
   const int* stop;    // device flag: non-zero = iteration loop already converged, do nothing
 };
 
@@ -117,7 +120,7 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
                   const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmY1,
                   const __grid_constant__ CUtensorMap tmXb, const __grid_constant__ CUtensorMap tmYb,
                   const __grid_constant__ CUtensorMap tmXc, const __grid_constant__ CUtensorMap tmYc,
-                  const GemmArgs a) {
+                  const __grid_constant__ CUtensorMap tmH, const GemmArgs a) {
   using TC = TileCfg<CG>;
   constexpr int kNStages = TC::stages;
   extern __shared__ uint8_t smem_raw[];
@@ -125,6 +128,7 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
   __shared__ uint64_t empty_bar[kNStages];
   __shared__ uint64_t tfull_bar[2];   // TMEM buffer holds a finished chunk
   __shared__ uint64_t tempty_bar[2];  // TMEM buffer has been drained
+  __shared__ uint64_t h_bar;          // H master tile has landed (EPI_HUPDATE with h_prefetch)
   __shared__ uint32_t tmem_slot;
   __shared__ double red[kEpiWarps][2];
 
@@ -155,6 +159,7 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], kEpiWarps * CG);  // the leader's barrier collects both CTAs' epilogues
     }
+    mbar_init(&h_bar, 1);
     fence_barrier_init();
     prefetch_tmap(&tmX0);
     prefetch_tmap(&tmY0);
@@ -222,6 +227,22 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       if (++stage == kNStages) {
         stage = 0;
         phase ^= 1;
+      }
+    }
+    if constexpr (EPI == EPI_HUPDATE) {
+      if (a.h_prefetch) {
+        // the ring is not used again: wait until every stage has been consumed, then reuse the
+        // buffers for this CTA's 128-sample tile of the H master, [k][128 samples] fp32
+        for (int s2 = 0; s2 < kNStages; ++s2) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (++stage == kNStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        mbar_arrive_expect_tx(&h_bar, static_cast<uint32_t>(bn) * 512u);
+        for (int b = 0; b < (bn >> 5); ++b)
+          tma_load_2d(sbase + b * 16384, &tmH, &h_bar, r0, n0 + b * 32, kEvictNormal);
       }
     }
   } else if (warp == 1 && lane == 0 && rank == 0) {
@@ -346,8 +367,22 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     } else {
       float s0 = 0.f, s1 = 0.f;  // per-thread partial sums (meaning depends on the epilogue)
       if constexpr (EPI == EPI_HUPDATE) {
-        // fused multiplicative H update; thread = one sample (column of V / H)
+        // fused multiplicative H update; thread = one sample (column of V / H), 16 basis rows at
+        // a time.  Kept lean on purpose (fast division, warp-uniform branches hoisted): this code
+        // runs after the last MMA with nothing left to hide behind.
         const bool vecD = a.dvec != nullptr;
+        const bool staged = a.h_prefetch != 0;
+        const bool write = !a.freeze && row_ok;
+        const float* hsm = reinterpret_cast<const float*>(smem_raw + (sbase - smem_u32(smem_raw))) +
+                           (g_begin * 16) * kTileM + q * 32 + lane;
+        if (staged) mbar_wait(&h_bar, 0);
+        // 32-bit element offsets from two 64-bit bases (one IMAD per address instead of a
+        // 64-bit multiply-add chain); a tile spans at most 256 * ldh elements
+        const long long hbase = static_cast<long long>(col0) * a.ldh + (row_ok ? row : 0);
+        float* hm = a.Hm + hbase;
+        float* hr = a.Hr32 + hbase;
+        const unsigned ldh32 = static_cast<unsigned>(a.ldh);
+        const float lam = a.lambda;
 #pragma unroll
         for (int g = 0; g < kMaxGroups; ++g) {
           if (g < g_count) {
@@ -362,30 +397,37 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
 #pragma unroll
               for (int t = 0; t < 16; ++t) dv[t] = 0.f;
             }
-            if (row_ok) {
-              const long long hoff = static_cast<long long>(col0 + g * 16) * a.ldh + row;
-              float h[16];
+            float hv[16];
+            if (staged) {
 #pragma unroll
-              for (int t = 0; t < 16; ++t) h[t] = a.Hm[hoff + t * a.ldh];
+              for (int t = 0; t < 16; ++t) hv[t] = hsm[(g * 16 + t) * kTileM];
+            } else {
+#pragma unroll
+              for (int t = 0; t < 16; ++t) hv[t] = hm[(g * 16 + t) * ldh32];
+            }
+            if (!a.freeze) {
+#pragma unroll
+              for (int t = 0; t < 16; ++t)
+                hv[t] = hv[t] * __fdividef(sum[g * 16 + t], fmaxf(dv[t] + lam, NMFB_EPS));
+            }
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              dv[t] = tf32_rn(hv[t]);
+              s0 = fmaf(sum[g * 16 + t], dv[t], s0);
+              s1 += hv[t];
+            }
+            if (write) {
 #pragma unroll
               for (int t = 0; t < 16; ++t) {
-                const float nv = sum[g * 16 + t];
-                float hn = h[t];
-                if (!a.freeze) {
-                  hn = h[t] * (nv / fmaxf(dv[t] + a.lambda, NMFB_EPS));
-                  a.Hm[hoff + t * a.ldh] = hn;
-                }
-                h[t] = tf32_rn(hn);
-                s0 += nv * h[t];
-                s1 += hn;
-                if (!a.freeze) a.Hr32[hoff + t * a.ldh] = h[t];
+                hm[(g * 16 + t) * ldh32] = hv[t];
+                hr[(g * 16 + t) * ldh32] = dv[t];
               }
-              if (a.Hc32 != nullptr && !a.freeze) {
+              if (a.Hc32 != nullptr) {
                 float4* o = reinterpret_cast<float4*>(a.Hc32 + static_cast<long long>(row) * a.ldc +
                                                       (col0 + g * 16));
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
-                  o[t] = make_float4(h[4 * t], h[4 * t + 1], h[4 * t + 2], h[4 * t + 3]);
+                  o[t] = make_float4(dv[4 * t], dv[4 * t + 1], dv[4 * t + 2], dv[4 * t + 3]);
               }
             }
           }
