@@ -1,0 +1,100 @@
+// Host side of kl_fused_kernel: tensor maps, launch geometry, the two small finishing kernels.
+#include <algorithm>
+
+#include "engine.cuh"
+#include "ew_kernels.cuh"
+#include "kl_fused.cuh"
+
+namespace nmfb {
+
+struct KlOp {
+  CUtensorMap tmF, tmG1, tmG2, tmV;
+  KlArgs args;
+  dim3 grid;
+  int splits = 1;
+  float* parts = nullptr;
+  bool planned = false;
+};
+
+// F: [Kp][ldf] rows contiguous (length rows); G: [Kp][ldg] (length cols); VT: [cols][ldvt] (rows contiguous)
+int plan_kl(nmfb_handle* h, Arena* ar, KlOp* op, const float* F, long long ldf, const float* G, long long ldg,
+            const float* VT, long long ldvt, int rows, int cols, int Kp, const int* stop) {
+  if (Kp % 32 != 0 || Kp > kKlMaxKp) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "plan_kl: Kp must be 32..128");
+  std::string e;
+  if (!(e = make_tmap(&op->tmF, Mat2D{F, rows, Kp, ldf}, 32, 32, true)).empty()) return h->fail(NMFB_ERR_CUDA, "kl F %s", e.c_str());
+  if (!(e = make_tmap(&op->tmG1, Mat2D{G, cols, Kp, ldg}, 32, 32, true)).empty()) return h->fail(NMFB_ERR_CUDA, "kl G1 %s", e.c_str());
+  if (!(e = make_tmap(&op->tmG2, Mat2D{G, cols, Kp, ldg}, 32, Kp / 2, false)).empty()) return h->fail(NMFB_ERR_CUDA, "kl G2 %s", e.c_str());
+  if (!(e = make_tmap(&op->tmV, Mat2D{VT, rows, cols, ldvt}, kTileM, kKlTileC, false, true)).empty())
+    return h->fail(NMFB_ERR_CUDA, "kl V %s", e.c_str());
+  const int pairs = (rows + 2 * kTileM - 1) / (2 * kTileM);
+  const int total_tiles = (cols + kKlTileC - 1) / kKlTileC;
+  int splits = std::max(1, (h->num_sms / 2) / pairs);
+  splits = std::min(splits, total_tiles);
+  int per = (total_tiles + splits - 1) / splits;
+  per = (per + kKlOutChunk - 1) / kKlOutChunk * kKlOutChunk;  // whole accumulation chunks per split
+  splits = (total_tiles + per - 1) / per;
+  op->splits = splits;
+  op->grid = dim3(2 * pairs, splits, 1);
+  KlArgs& a = op->args;
+  a.rows = rows;
+  a.cols = cols;
+  a.Kp = Kp;
+  a.tiles_per_split = per;
+  a.want_cost = 0;
+  a.ldo = (rows + 3) / 4 * 4;
+  a.slab = static_cast<long long>(Kp) * a.ldo;
+  a.scal = nullptr;
+  a.stop = stop;
+  NMFB_TRY(ar->alloc(h, &op->parts, static_cast<size_t>(splits) * a.slab));
+  a.out = op->parts;
+  op->planned = true;
+  return NMFB_OK;
+}
+
+int run_kl(nmfb_handle* h, const KlOp& op) {
+  static cudaError_t attr = cudaFuncSetAttribute(kl_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKlSmemBytes);
+  if (attr != cudaSuccess) return h->fail(NMFB_ERR_CUDA, "cudaFuncSetAttribute(kl_fused): %s", cudaGetErrorString(attr));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = op.grid;
+  cfg.blockDim = dim3(kKlThreads);
+  cfg.dynamicSmemBytes = kKlSmemBytes;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kl_fused_kernel, op.tmF, op.tmG1, op.tmG2, op.tmV, op.args);
+  ++h->launches;
+  if (e != cudaSuccess) return h->fail(NMFB_ERR_CUDA, "launch of kl_fused failed: %s", cudaGetErrorString(e));
+  return NMFB_OK;
+}
+
+// H half: N = sum of the column-split slabs; H <- H .* N ./ max(ws + lambda, eps)  (nmf.m:183-184,199)
+__global__ void kl_h_finish_kernel(const float* __restrict__ parts, int splits, long long slab, long long ldo,
+                                   float* __restrict__ Hm, float* __restrict__ Ht, long long ldh,
+                                   const float* __restrict__ ws, float lambda, int n, int freeze, double* scal,
+                                   const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  __shared__ double sh[32];
+  const int k = blockIdx.y;
+  const float den = fmaxf(ws[k] + lambda, NMFB_EPS);
+  double acc[1] = {0.0};
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    float nv = 0.f;
+    for (int z = 0; z < splits; ++z) nv += parts[z * slab + k * ldo + j];
+    float hv = Hm[k * ldh + j];
+    if (!freeze) {
+      hv = hv * (nv / den);
+      Hm[k * ldh + j] = hv;
+      Ht[k * ldh + j] = tf32_rn(hv);
+    }
+    acc[0] += hv;
+  }
+  block_sum<1>(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(scal + 1, acc[0]);
+}
+
+}  // namespace nmfb

@@ -55,6 +55,8 @@ struct NmfSession {
 
   GramOp gramH, gramW;
   GemmOp gemmA, gemmB, gemmH, gemmS, gemmR;
+  KlOp klW, klH;         // fused KL halves (kl_fused.cuh)
+  bool kl_fused = false;
   float* packed = nullptr;  // multi-GPU: [A | G_H | hs] contiguous fp32 for the single all-reduce
   int* pinned = nullptr;    // host copy of stop[0..1]
 };
@@ -191,7 +193,6 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     VStats st;
     NMFB_TRY(compute_v_stats(h, true, &st, &s->vstats, nullptr, ar));
     NMFB_TRY(comm_allreduce(h, nullptr, 0, s->vstats, 4, nullptr, 0));  // global sums over all shards
-    NMFB_TRY(ar->alloc(h, &s->Q, static_cast<size_t>(n) * h->ldv));
   } else {
     double* sq = nullptr;
     NMFB_TRY(ar->alloc(h, &sq, 1));
@@ -294,7 +295,30 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
       r.scal = s->scal + 2;
     }
   } else {
-    // S = W H (both operands MN-major), Q = V ./ S
+    {
+      // Fused path: V_hat and Q = V ./ V_hat stay on chip (kl_fused.cuh).  Needs K <= 128 and a
+      // row-major copy of V for the H half.
+      size_t free_b = 0, total_b = 0;
+      const long long ldn = round_up(n, 4);
+      const size_t need = static_cast<size_t>(m) * ldn * sizeof(float);
+      const char* env = std::getenv("NMFB_KL_UNFUSED");
+      if (!(env && env[0] == '1') && Kp <= kKlMaxKp && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess &&
+          free_b > need + (size_t(1) << 30)) {
+        float* Vrm = nullptr;
+        NMFB_TRY(ar->alloc(h, &Vrm, static_cast<size_t>(m) * ldn));
+        dim3 grid((n + 31) / 32, (m + 31) / 32);
+        transpose_kernel<<<grid, dim3(32, 8), 0, h->stream>>>(h->Vraw, h->ldv, Vrm, ldn, m, n);
+        NMFB_TRY(check_launch(h, "transpose(V)"));
+        NMFB_TRY(plan_kl(h, ar, &s->klW, s->Wt, s->ldw, s->Ht, s->ldh, h->Vraw, h->ldv, m, n, Kp, stop));
+        NMFB_TRY(plan_kl(h, ar, &s->klH, s->Ht, s->ldh, s->Wt, s->ldw, Vrm, ldn, n, m, Kp, stop));
+        s->klW.args.scal = s->scal + 2;
+        s->kl_fused = true;
+      }
+    }
+    if (!s->kl_fused) {
+    // Unfused fallback (K > 128 or not enough memory for the row-major copy of V):
+    // S = W H (both operands MN-major), Q = V ./ S materialised in HBM
+    NMFB_TRY(ar->alloc(h, &s->Q, static_cast<size_t>(n) * h->ldv));
     MatRef Xs{s->Wt, m, Kp, s->ldw, true};
     MatRef Ys{s->Ht, n, Kp, s->ldh, true};
     NMFB_TRY(plan_fused(h, &s->gemmS, EPI_KLQ, Xs, Ys, Kp, nullptr, nullptr, 0, m, round_up(n, 64), n,
@@ -326,6 +350,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     if (!std::getenv("NMFB_NO_HPREFETCH")) {
       std::string e = set_h_prefetch(&s->gemmH.L, s->Hm, n, Kp, s->ldh);
       if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "%s", e.c_str());
+    }
     }
   }
   if (s->W_fixed) NMFB_TRY(run_gram(h, s->gramW, nullptr));
@@ -539,9 +564,23 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
       vec_sums_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, K, n, s->ldh, s->hs, nullptr, stop);
       NMFB_TRY(check_launch(h, "vec_sums(H)"));
     }
-    s->gemmS.L.args.want_cost = i > 0 ? 1 : 0;
-    NMFB_TRY(run_gemm(h, s->gemmS));  // Q = V ./ (W H) with the H of the previous iteration
-    if (!s->W_fixed) NMFB_TRY(run_gemm(h, s->gemmR));
+    if (s->kl_fused) {
+      // R = (V ./ (W H)) H' (+ the cost sums of the previous iteration) in one fused kernel
+      if (!s->W_fixed || i > 0) {
+        s->klW.args.want_cost = i > 0 ? 1 : 0;
+        NMFB_TRY(run_kl(h, s->klW));
+        if (!s->W_fixed) {
+          const long long cnt = s->klW.args.slab;
+          split_reduce_kernel<<<static_cast<int>(std::min<long long>((cnt + 255) / 256, 2048)), 256, 0, h->stream>>>(
+              s->klW.parts, s->klW.splits, cnt, s->A, cnt, stop);
+          NMFB_TRY(check_launch(h, "split_reduce(R)"));
+        }
+      }
+    } else {
+      s->gemmS.L.args.want_cost = i > 0 ? 1 : 0;
+      NMFB_TRY(run_gemm(h, s->gemmS));  // Q = V ./ (W H) with the H of the previous iteration
+      if (!s->W_fixed) NMFB_TRY(run_gemm(h, s->gemmR));
+    }
     NMFB_TRY(allreduce_w_inputs(h, s, false));
     if (i > 0) NMFB_TRY(enqueue_cost(h, s, i - 1, 2));
     if (!s->W_fixed) {
@@ -549,10 +588,21 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
       D2FArgs da{s->wsum, s->wsf, Kp};
       d2f_kernel<<<(Kp + 127) / 128, 128, 0, h->stream>>>(da, stop);
       NMFB_TRY(check_launch(h, "d2f(ws)"));
-      s->gemmS.L.args.want_cost = 0;
-      NMFB_TRY(run_gemm(h, s->gemmS));  // refreshed V_hat (nmf.m:173)
+      if (!s->kl_fused) {
+        s->gemmS.L.args.want_cost = 0;
+        NMFB_TRY(run_gemm(h, s->gemmS));  // refreshed V_hat (nmf.m:173)
+      }
     }
-    NMFB_TRY(run_gemm(h, s->gemmH));
+    if (s->kl_fused) {
+      // N' = (V ./ (W H))' W with the refreshed V_hat, then the H update on the summed slabs
+      NMFB_TRY(run_kl(h, s->klH));
+      kl_h_finish_kernel<<<dim3(std::max(1, std::min(64, (n + 1023) / 1024)), K), 256, 0, h->stream>>>(s->klH.parts, s->klH.splits, s->klH.args.slab,
+                                                                s->klH.args.ldo, s->Hm, s->Ht, s->ldh, s->wsf,
+                                                                s->lambda_h, n, s->H_fixed ? 1 : 0, s->scal, stop);
+      NMFB_TRY(check_launch(h, "kl_h_finish"));
+    } else {
+      NMFB_TRY(run_gemm(h, s->gemmH));
+    }
   }
   return NMFB_OK;
 }
@@ -575,8 +625,13 @@ static int enqueue_final_cost(nmfb_handle* h, NmfSession* s) {
       NMFB_TRY(comm_allreduce(h, s->gramH.g32, static_cast<size_t>(s->Kp) * s->Kp, nullptr, 0, s->scal, 4));
     return enqueue_cost(h, s, last, 0);
   }
-  s->gemmS.L.args.want_cost = 1;
-  NMFB_TRY(run_gemm(h, s->gemmS));
+  if (s->kl_fused) {
+    s->klW.args.want_cost = 1;
+    NMFB_TRY(run_kl(h, s->klW));
+  } else {
+    s->gemmS.L.args.want_cost = 1;
+    NMFB_TRY(run_gemm(h, s->gemmS));
+  }
   if (multi) NMFB_TRY(comm_allreduce(h, nullptr, 0, nullptr, 0, s->scal, 4));
   return enqueue_cost(h, s, last, 2);
 }
