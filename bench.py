@@ -27,7 +27,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -59,44 +58,60 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
-
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled (NVML, every ~2 ms) while the timed region runs."""
 
     def __init__(self, index: int):
         self.index = index
         self.samples = []
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self._nvml = None
 
     def _run(self):
+        nv = self._nvml
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
+                self.samples.append((nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetCurrentClocksEventReasons(self._h),
+                                     nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0))
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.002)
 
     def start(self):
+        if self._nvml is None:
+            return
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
 
     def stop(self):
         self._stop.set()
         if self._t:
-            self._t.join(timeout=6)
-        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
-        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for i, nm in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+            self._t.join(timeout=2)
+        if self._nvml is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        nv = self._nvml
+        sm = sorted(s[0] for s in self.samples)
+        bits = 0
+        for s in self.samples:
+            bits |= int(s[1])
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = [k for k, v in names.items() if bits & int(v)]
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        pw = sorted(s[2] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": mx, "reasons": reasons,
+                "power_w_median": pw[len(pw) // 2], "samples": len(self.samples)}
 
 
 def cpu_reference(steps_cap_seconds: float, rank0: bool):

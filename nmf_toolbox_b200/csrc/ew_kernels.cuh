@@ -593,6 +593,36 @@ __global__ void gram_reduce_cost_kernel(const float* __restrict__ parts, int spl
   sc[0] = sc[1] = sc[2] = sc[3] = sc[4] = 0.0;
 }
 
+// Unfused H update for problems with too few sample tiles to fill the GPU (small column
+// shards): N = W'V was formed with split-K and summed, D = (W'W) H stored next to it.
+//   H <- H .* N ./ max(D + lambda, eps)  (nmf.m:180-181,199); scal[0] += <N, tf32(Hnew)>, scal[1] += sum Hnew
+__global__ void h_finish_kernel(const float* __restrict__ N, const float* __restrict__ D, float* __restrict__ Hm,
+                                float* __restrict__ Ht, long long ld, int n, float lambda, int freeze,
+                                double* scal, const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  __shared__ double sh[64];
+  const int k = blockIdx.y;
+  double acc[2] = {0.0, 0.0};
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const long long o = static_cast<long long>(k) * ld + j;
+    const float nv = N[o];
+    float hv = Hm[o];
+    if (!freeze) {
+      hv = hv * __fdividef(nv, fmaxf(D[o] + lambda, NMFB_EPS));
+      Hm[o] = hv;
+    }
+    const float hr = tf32_rn(hv);
+    if (!freeze) Ht[o] = hr;
+    acc[0] += static_cast<double>(nv) * hr;
+    acc[1] += hv;
+  }
+  block_sum<2>(acc, sh);
+  if (threadIdx.x == 0) {
+    atomicAdd(scal + 0, acc[0]);
+    atomicAdd(scal + 1, acc[1]);
+  }
+}
+
 // ---------------------------------------------------------------- convolutive helpers
 // Hs[k + K*t][j] = tf32(H[k][j - t]) for j >= t, else 0   (cnmf.m:188, RFD.m:37)
 __global__ void hstack_kernel(const float* __restrict__ H, float* __restrict__ Hs, int K, int T, int n,

@@ -36,6 +36,8 @@ struct NmfSession {
   int divergence = NMFB_DIV_EUCLIDEAN;
   bool W_fixed = false, H_fixed = false, direct_cost = false;
   bool overlap = false;  // gram(H) + cost run on the side stream next to the A GEMM
+  bool h_split = false;  // too few sample tiles for the fused H update: split-K GEMM + h_finish
+  float *Nbuf = nullptr, *Dbuf = nullptr;
   float lambda_w = 0.f, lambda_h = 0.f;
   int maxiter = 100;
   double tolerance = 1e-3;
@@ -260,7 +262,21 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     MatRef Yw{s->Wt, m, Kp, s->ldw, false};
     MatRef Xh{s->Ht, n, Kp, s->ldh, true};
     MatRef Ygw{s->gramW.gtf, Kp, Kp, Kp, false};
+    {
+      // The fused H update needs the whole contraction in one CTA pair; with few sample tiles
+      // (small column shards on many GPUs) that leaves most SMs idle, so the contraction is
+      // split over CTAs instead and the update runs as a separate element-wise kernel.
+      const int pair_ctas = (n + 2 * kTileM - 1) / (2 * kTileM) * 2 * ((Kp + kMaxN - 1) / kMaxN);
+      s->h_split = pair_ctas * 2 <= h->num_sms && n > kTileM;
+      if (const char* env = std::getenv("NMFB_H_SPLIT")) s->h_split = env[0] == '1';  // tests force either path
+    }
+    if (s->h_split) {
+      NMFB_TRY(ar->alloc(h, &s->Nbuf, static_cast<size_t>(Kp) * s->ldh));
+      NMFB_TRY(ar->alloc(h, &s->Dbuf, static_cast<size_t>(Kp) * s->ldh));
+      NMFB_TRY(plan_store(h, ar, &s->gemmH, Xvt, Yw, m, &Xh, &Ygw, Kp, n, Kp, s->Nbuf, s->Dbuf, s->ldh, true, stop));
+    } else {
     NMFB_TRY(plan_fused(h, &s->gemmH, EPI_HUPDATE, Xvt, Yw, m, &Xh, &Ygw, Kp, n, Kp, Kp, stop));
+    }
     if (const char* env = std::getenv("NMFB_EXPERIMENT_HSTORE")) {  // timing experiment only: results are wrong
       if (env[0] == '1') {
         float *t0 = nullptr, *t1 = nullptr;
@@ -273,16 +289,18 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
       }
     }
     GemmArgs& a = s->gemmH.L.args;
-    a.Hm = s->Hm;
-    a.Hr32 = s->Ht;
-    a.Hc32 = nullptr;
-    a.ldh = s->ldh;
-    a.lambda = s->lambda_h;
-    a.scal = s->scal;
-    a.freeze = s->H_fixed ? 1 : 0;
-    if (!std::getenv("NMFB_NO_HPREFETCH")) {
-      std::string e = set_h_prefetch(&s->gemmH.L, s->Hm, n, Kp, s->ldh);
-      if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "%s", e.c_str());
+    if (!s->h_split) {
+      a.Hm = s->Hm;
+      a.Hr32 = s->Ht;
+      a.Hc32 = nullptr;
+      a.ldh = s->ldh;
+      a.lambda = s->lambda_h;
+      a.scal = s->scal;
+      a.freeze = s->H_fixed ? 1 : 0;
+      if (!std::getenv("NMFB_NO_HPREFETCH")) {
+        std::string e = set_h_prefetch(&s->gemmH.L, s->Hm, n, Kp, s->ldh);
+        if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "%s", e.c_str());
+      }
     }
     if (s->direct_cost) {
       MatRef Xs{s->Wt, m, Kp, s->ldw, true};
@@ -552,7 +570,16 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
       NMFB_TRY(run_gram(h, s->gramW, stop));
       NMFB_TRY(prof_mark(h, 4));
     }
-    NMFB_TRY(run_timed(h, s->gemmH, 1));
+    if (s->h_split) {
+      NMFB_TRY(prof_mark(h, 1));
+      NMFB_TRY(run_gemm(h, s->gemmH));  // N (split-K, summed) and D = G_W H
+      h_finish_kernel<<<dim3(std::max(1, std::min(64, (n + 1023) / 1024)), K), 256, 0, h->stream>>>(
+          s->Nbuf, s->Dbuf, s->Hm, s->Ht, s->ldh, n, s->lambda_h, s->H_fixed ? 1 : 0, s->scal, stop);
+      NMFB_TRY(check_launch(h, "h_finish"));
+      NMFB_TRY(prof_mark(h, 1));
+    } else {
+      NMFB_TRY(run_timed(h, s->gemmH, 1));
+    }
     if (s->direct_cost) {
       NMFB_TRY(run_gemm(h, s->gemmS));
       if (multi) NMFB_TRY(comm_allreduce(h, nullptr, 0, nullptr, 0, s->scal, 4));

@@ -77,6 +77,45 @@ def test_nmf_vs_oracle(api, handle, div, m, n, K, iters):
     np.testing.assert_allclose((W.astype(np.float64) ** 2).sum(0), 1.0, rtol=1e-5)  # nmf.m:169
 
 
+@pytest.mark.parametrize("m,n,K,iters", [(700, 900, 128, 40), (1000, 333, 100, 30), (513, 1025, 96, 30)])
+def test_nmf_kl_fused_kernel_shapes(api, handle, m, n, K, iters):
+    """KL with K up to 128 runs on the fused kernel (kl_fused.cuh): ragged sizes, several column splits."""
+    rng = np.random.default_rng(K + m)
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    cfg = dict(divergence="kl_divergence", W_init=rng.random((m, K)) + 1e-3, H_init=rng.random((K, n)) + 1e-3,
+               W_sparsity=0.05, H_sparsity=0.02, maxiter=iters, tolerance=1e-300)
+    W, H, c = api.nmf(V, K, cfg, handle=handle)
+    Wo, Ho, co = O.nmf(V, K, cfg)
+    assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
+
+
+def test_nmf_kl_large_K_fallback(api, handle):
+    """K > 128 exceeds the fused kernel's tensor-memory plan: the unfused path must give the same answers."""
+    rng = np.random.default_rng(77)
+    m, n, K = 400, 500, 150
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    cfg = dict(divergence="kl", W_init=rng.random((m, K)) + 1e-3, H_init=rng.random((K, n)) + 1e-3, maxiter=25,
+               tolerance=1e-300)
+    W, H, c = api.nmf(V, K, cfg, handle=handle)
+    Wo, Ho, co = O.nmf(V, K, cfg)
+    assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
+
+
+@pytest.mark.parametrize("h_split", ["0", "1"])
+def test_nmf_euclid_both_h_paths(api, handle, h_split, monkeypatch):
+    """The H step is either fused into the W'V contraction (many sample tiles) or a split-K
+    contraction + element-wise update (few tiles, e.g. small column shards): same answers."""
+    monkeypatch.setenv("NMFB_H_SPLIT", h_split)
+    rng = np.random.default_rng(31)
+    m, n, K = 600, 1500, 48
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    cfg = dict(divergence="euclidean", W_init=rng.random((m, K)) + 1e-3, H_init=rng.random((K, n)) + 1e-3,
+               W_sparsity=0.02, H_sparsity=0.05, maxiter=40, tolerance=1e-300)
+    W, H, c = api.nmf(V, K, cfg, handle=handle)
+    Wo, Ho, co = O.nmf(V, K, cfg)
+    assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
+
+
 def test_nmf_direct_cost_mode(api, handle):
     alg, V, K, T, cfg = inputs("nmf_euclid_512")
     Wo, Ho, co = O.nmf(V, K, cfg)
