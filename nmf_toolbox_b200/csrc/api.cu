@@ -1,6 +1,7 @@
 // C ABI: handle lifetime, V upload, ReconstructFromDecomposition, projfunc.
 // (nmf / cnmf / nmfsc live in their *_driver.cu files.)
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -51,6 +52,7 @@ extern "C" int nmfb_create(nmfb_handle** out, int device) {
   nmfb_handle* h = new nmfb_handle();
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
+  // (stream priorities were tried for the side stream: no gain, slightly slower large GEMMs)
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);

@@ -94,7 +94,7 @@ int run_gemm(nmfb_handle* h, const GemmOp& op) {
 }
 
 int plan_gram(nmfb_handle* h, Arena* ar, GramOp* op, const float* Mt, int nvec, int len,
-              long long ld, const int* stop, const float* Mlo, int chunk_kb) {
+              long long ld, const int* stop, const float* Mlo, int chunk_kb, int max_ctas) {
   op->nvec = nvec;
   NMFB_TRY(ar->alloc(h, &op->g32, static_cast<size_t>(nvec) * nvec));
   NMFB_TRY(ar->alloc(h, &op->gtf, static_cast<size_t>(nvec) * nvec));
@@ -110,7 +110,13 @@ int plan_gram(nmfb_handle* h, Arena* ar, GramOp* op, const float* Mt, int nvec, 
     segs.X[1] = L;
     segs.Y[1] = M;
   }
-  NMFB_TRY(plan_common(h, &op->g, M, M, len, nullptr, nullptr, 0, nvec, nvec, 0, Mlo ? &segs : nullptr));
+  int splits_hint = 0;
+  if (max_ctas > 0) {
+    const int cg = pair_eligible(nvec, nvec, false, false) ? 2 : 1;
+    const int tiles = (nvec + kTileM * cg - 1) / (kTileM * cg) * cg * ((nvec + kMaxN - 1) / kMaxN);
+    splits_hint = std::max(2, max_ctas / std::max(1, tiles));
+  }
+  NMFB_TRY(plan_common(h, &op->g, M, M, len, nullptr, nullptr, 0, nvec, nvec, splits_hint, Mlo ? &segs : nullptr));
   op->g.L.args.chunk_kb = chunk_kb;
   GemmArgs& a = op->g.L.args;
   a.stop = stop;
@@ -122,23 +128,27 @@ int plan_gram(nmfb_handle* h, Arena* ar, GramOp* op, const float* Mt, int nvec, 
   return NMFB_OK;
 }
 
-int run_gram(nmfb_handle* h, const GramOp& op, const int* stop) {
+int run_gram(nmfb_handle* h, const GramOp& op, const int* stop, unsigned int* ticket, unsigned int* gate,
+             unsigned int gate_value) {
   std::string e = launch_gemm(op.g.L, EPI_STORE, h->stream);
   ++h->launches;
   if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "%s", e.c_str());
   const int count = op.nvec * op.nvec;
   gram_reduce_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(op.g.parts, op.g.splits, count,
-                                                                 op.g32, op.gtf, op.glo, count, stop);
+                                                                 op.g32, op.gtf, op.glo, count, stop, ticket, gate,
+                                                                 gate_value);
   return check_launch(h, "gram_reduce");
 }
 
-int run_gram_cost(nmfb_handle* h, const GramOp& op, unsigned int* ticket, const CostArgs& c, bool with_cost) {
+int run_gram_cost(nmfb_handle* h, const GramOp& op, unsigned int* ticket, const CostArgs& c, bool with_cost,
+                  unsigned int* gate, unsigned int gate_value) {
   std::string e = launch_gemm(op.g.L, EPI_STORE, h->stream);
   ++h->launches;
   if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "%s", e.c_str());
   const int count = op.nvec * op.nvec;
   gram_reduce_cost_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(op.g.parts, op.g.splits, count, op.g32,
-                                                                      op.gtf, count, ticket, c, with_cost ? 1 : 0);
+                                                                      op.gtf, count, ticket, c, with_cost ? 1 : 0,
+                                                                      gate, gate_value);
   return check_launch(h, "gram_reduce_cost");
 }
 

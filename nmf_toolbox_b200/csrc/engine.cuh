@@ -146,8 +146,10 @@ struct GramOp {
 // Mlo != nullptr: the factor is given as a tf32 head/tail pair and the Gram matrix is formed at
 // fp32 accuracy from the three leading terms (hi*hi' + hi*lo' + lo*hi').
 int plan_gram(nmfb_handle* h, Arena* ar, GramOp* op, const float* Mt, int nvec, int len,
-              long long ld, const int* stop, const float* Mlo = nullptr, int chunk_kb = 0);
-int run_gram(nmfb_handle* h, const GramOp& op, const int* stop);
+              long long ld, const int* stop, const float* Mlo = nullptr, int chunk_kb = 0,
+              int max_ctas = 0 /* 0 = whole GPU; else cap the grid (Gram running beside a large GEMM) */);
+int run_gram(nmfb_handle* h, const GramOp& op, const int* stop, unsigned int* ticket = nullptr,
+             unsigned int* gate = nullptr, unsigned int gate_value = 0);
 
 dim3 vec_grid(int len, int nvec, int threads = 256);
 
@@ -177,7 +179,8 @@ struct WStepArgs;
 int launch_w_step(nmfb_handle* h, const WStepArgs& a);
 struct CostArgs;
 // gram GEMM + (reduce, <G_W,G_H>, cost, stop test) in one follow-up kernel.
-int run_gram_cost(nmfb_handle* h, const GramOp& op, unsigned int* ticket, const CostArgs& c, bool with_cost);
+int run_gram_cost(nmfb_handle* h, const GramOp& op, unsigned int* ticket, const CostArgs& c, bool with_cost,
+                  unsigned int* gate = nullptr, unsigned int gate_value = 0);
 
 // Queue `maxiter` iterations in chunks.  The stop flag written by the cost
 // kernel turns everything queued behind a converged iteration into no-ops, so

@@ -168,11 +168,41 @@ __global__ void vec_sums_kernel(const float* __restrict__ M, int nvec, int len, 
 }
 
 // Sum split-K slabs of a Kp x Kp Gram matrix; write fp32 and tf32-rounded copies.
+// gate (optional): the last block to finish publishes gate_value for a concurrently running
+// consumer (ptx.cuh: gate_publish / gate_wait).
 __global__ void gram_reduce_kernel(const float* __restrict__ parts, int splits, long long slab,
                                    float* __restrict__ g32, float* __restrict__ gtf,
-                                   float* __restrict__ glo, int count, const int* stop) {
+                                   float* __restrict__ glo, int count, const int* stop,
+                                   unsigned int* ticket = nullptr, unsigned int* gate = nullptr,
+                                   unsigned int gate_value = 0) {
   NMFB_STOP_GUARD(stop);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gate != nullptr) {
+    if (i < count) {
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+      int z = 0;
+      for (; z + 4 <= splits; z += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s4[u] += parts[(z + u) * slab + i];
+      }
+      for (; z < splits; ++z) s4[0] += parts[z * slab + i];
+      const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      g32[i] = s;
+      const float hi = tf32_rn(s);
+      gtf[i] = hi;
+      if (glo) glo[i] = tf32_rn(s - hi);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+        *ticket = 0u;
+        __threadfence();
+        gate_publish(gate, gate_value);
+      }
+    }
+    return;
+  }
   if (i >= count) return;
   float s4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains keep the loads in flight
   int z = 0;
@@ -546,7 +576,8 @@ __global__ void cost_kernel(CostArgs a) {
 // the last block to finish (ticket counter) finalises the cost exactly as cost_kernel does.
 __global__ void gram_reduce_cost_kernel(const float* __restrict__ parts, int splits, long long slab,
                                         float* __restrict__ g32, float* __restrict__ gtf, int count,
-                                        unsigned int* ticket, CostArgs c, int with_cost) {
+                                        unsigned int* ticket, CostArgs c, int with_cost,
+                                        unsigned int* gate = nullptr, unsigned int gate_value = 0) {
   if (c.stop[0] != 0) return;
   __shared__ double sh[64];
   __shared__ bool last;
@@ -565,16 +596,25 @@ __global__ void gram_reduce_cost_kernel(const float* __restrict__ parts, int spl
     gtf[i] = tf32_rn(s);
     if (with_cost) acc[0] = static_cast<double>(s) * c.GW[i];
   }
-  if (!with_cost) return;
+  if (!with_cost && gate == nullptr) return;
   block_sum<2>(acc, sh);
+  __threadfence();
   if (threadIdx.x == 0) {
-    atomicAdd(c.scal + 4, acc[0]);
+    if (with_cost) atomicAdd(c.scal + 4, acc[0]);
     __threadfence();
     last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
   if (!last) return;
   __threadfence();
+  if (!with_cost) {
+    if (threadIdx.x == 0) {
+      *ticket = 0u;
+      __threadfence();
+      gate_publish(gate, gate_value);
+    }
+    return;
+  }
   acc[0] = 0.0;
   acc[1] = 0.0;
   for (int k = threadIdx.x; k < c.n_wsum; k += blockDim.x) acc[1] += c.wsum[k];
@@ -591,6 +631,10 @@ __global__ void gram_reduce_cost_kernel(const float* __restrict__ parts, int spl
     if (cost < prev && prev - cost < c.tolerance) c.stop[0] = 1;  // nmf.m:221-224
   }
   sc[0] = sc[1] = sc[2] = sc[3] = sc[4] = 0.0;
+  if (gate != nullptr) {
+    __threadfence();
+    gate_publish(gate, gate_value);
+  }
 }
 
 // Unfused H update for problems with too few sample tiles to fill the GPU (small column

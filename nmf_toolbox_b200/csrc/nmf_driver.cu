@@ -35,7 +35,10 @@ struct NmfSession {
   long long ldw = 0, ldh = 0;
   int divergence = NMFB_DIV_EUCLIDEAN;
   bool W_fixed = false, H_fixed = false, direct_cost = false;
-  bool overlap = false;  // gram(H) + cost run on the side stream next to the A GEMM
+  bool overlap = false;  // the Gram products (and the cost) run on the side stream BESIDE the two large
+                         // contractions, which wait for them at a device-side gate before their short phase 1
+  bool gate_h = false;   // H-step contraction small enough to leave SMs for gram(W)
+  unsigned int* gates = nullptr;  // [0] G_H ready for iteration i (value i+1), [1] G_W ready
   bool h_split = false;  // too few sample tiles for the fused H update: split-K GEMM + h_finish
   float *Nbuf = nullptr, *Dbuf = nullptr;
   float lambda_w = 0.f, lambda_h = 0.f;
@@ -150,7 +153,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   NMFB_TRY(ar->alloc(h, &s->ab, 4 * Kp));  // [ab (2 Kp) | norm2 (Kp) | wsum (Kp)]: WStepArgs::acc
   s->norm2 = s->ab + 2 * Kp;
   s->wsum = s->ab + 3 * Kp;
-  NMFB_TRY(ar->alloc(h, &s->ticket, 1));
+  NMFB_TRY(ar->alloc(h, &s->ticket, 2));
   NMFB_TRY(ar->alloc(h, &s->hs, Kp));
   NMFB_TRY(ar->alloc(h, &s->scal, 8));
   NMFB_TRY(ar->alloc(h, &s->cost, static_cast<size_t>(s->maxiter) + 1));
@@ -208,9 +211,23 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   // ---- plan the contractions
   const int* stop = s->stop;
   const bool multi = comm_size(h->comm) > 1;
-  NMFB_TRY(plan_gram(h, ar, &s->gramW, s->Wt, Kp, m, s->ldw, stop));
   if (!kl) {
-    NMFB_TRY(plan_gram(h, ar, &s->gramH, s->Ht, Kp, n, s->ldh, stop));
+    // decide up front which Gram products run beside a large contraction (see below)
+    const int tilesA = (m + kTileM - 1) / kTileM * ((Kp + kMaxN - 1) / kMaxN);
+    const int ctasA = ((m + 2 * kTileM - 1) / (2 * kTileM)) * 2 * ((Kp + kMaxN - 1) / kMaxN);
+    const int ctasH = ((n + 2 * kTileM - 1) / (2 * kTileM)) * 2 * ((Kp + kMaxN - 1) / kMaxN);
+    const char* env = std::getenv("NMFB_OVERLAP");
+    s->h_split = ctasH * 2 <= h->num_sms && n > kTileM;
+    if (const char* e2 = std::getenv("NMFB_H_SPLIT")) s->h_split = e2[0] == '1';  // tests force either path
+    s->overlap = !multi && !s->direct_cost && !s->W_fixed && !s->H_fixed && !(tilesA * 2 <= h->num_sms) &&
+                 !(env && env[0] == '0') && m > kTileM && ctasA + 8 <= h->num_sms;
+    s->gate_h = s->overlap && !s->h_split && ctasH + 8 <= h->num_sms;
+  }
+  NMFB_TRY(plan_gram(h, ar, &s->gramW, s->Wt, Kp, m, s->ldw, stop, nullptr, 0,
+                     s->gate_h ? h->num_sms - (((n + 2 * kTileM - 1) / (2 * kTileM)) * 2 * ((Kp + kMaxN - 1) / kMaxN)) : 0));
+  if (!kl) {
+    NMFB_TRY(plan_gram(h, ar, &s->gramH, s->Ht, Kp, n, s->ldh, stop, nullptr, 0,
+                       s->overlap ? h->num_sms - (((m + 2 * kTileM - 1) / (2 * kTileM)) * 2 * ((Kp + kMaxN - 1) / kMaxN)) : 0));
     if (multi) {  // G_H must sit behind A in the packed buffer
       s->gramH.g32 = s->packed + static_cast<size_t>(Kp) * s->ldw;
     }
@@ -222,13 +239,13 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     const int tiles = (m + kTileM - 1) / kTileM * ((Kp + kMaxN - 1) / kMaxN);
     const bool split = tiles * 2 <= h->num_sms;
     {
-      // With B = W G_H as its own (small) launch, G_H is not needed until the A GEMM is over, so
-      // gram(H), <G_W,G_H>, the cost and the stop test overlap with it on SMs the GEMM leaves idle.
-      const char* env = std::getenv("NMFB_OVERLAP");
-      s->overlap = !multi && !s->direct_cost && !s->W_fixed && !(env && env[0] == '0') &&
-                   tiles < h->num_sms;  // a full wave of GEMM CTAs would leave no SM for the side stream
+      // B = W G_H is the short phase 1 of the A GEMM, so G_H is not needed until the long phase 0
+      // is over: gram(H), <G_W,G_H>, the cost and the stop test run on the side stream on SMs the
+      // GEMM leaves idle, and the GEMM's producer waits at a gate before its first phase-1 load.
+      // (A grid that fills every SM would leave the side stream nothing to run on: no overlap then.)
+      NMFB_TRY(ar->alloc(h, &s->gates, 2));
     }
-    if (multi || split || s->overlap) {
+    if (multi || split) {
       NMFB_TRY(plan_store(h, ar, &s->gemmA, Xv, Yh, n, nullptr, nullptr, 0, m, Kp, s->A, nullptr,
                           s->ldw, split, stop));
       NMFB_TRY(plan_store(h, ar, &s->gemmB, Xw, Yg, Kp, nullptr, nullptr, 0, m, Kp, s->B, nullptr,
@@ -236,6 +253,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     } else {
       NMFB_TRY(plan_store(h, ar, &s->gemmA, Xv, Yh, n, &Xw, &Yg, Kp, m, Kp, s->A, s->B, s->ldw, false,
                           stop));
+      if (s->overlap) s->gemmA.L.args.gate = s->gates + 0;
     }
     // H update: N = W'V, D = G_W H (X = H, columns j contiguous -> MN-major).
     // Reading V with the contraction index contiguous (K-major) makes every TMA row a lone
@@ -266,9 +284,6 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
       // The fused H update needs the whole contraction in one CTA pair; with few sample tiles
       // (small column shards on many GPUs) that leaves most SMs idle, so the contraction is
       // split over CTAs instead and the update runs as a separate element-wise kernel.
-      const int pair_ctas = (n + 2 * kTileM - 1) / (2 * kTileM) * 2 * ((Kp + kMaxN - 1) / kMaxN);
-      s->h_split = pair_ctas * 2 <= h->num_sms && n > kTileM;
-      if (const char* env = std::getenv("NMFB_H_SPLIT")) s->h_split = env[0] == '1';  // tests force either path
     }
     if (s->h_split) {
       NMFB_TRY(ar->alloc(h, &s->Nbuf, static_cast<size_t>(Kp) * s->ldh));
@@ -277,6 +292,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     } else {
     NMFB_TRY(plan_fused(h, &s->gemmH, EPI_HUPDATE, Xvt, Yw, m, &Xh, &Ygw, Kp, n, Kp, Kp, stop));
     }
+    if (s->gate_h) s->gemmH.L.args.gate = s->gates + 1;
     if (const char* env = std::getenv("NMFB_EXPERIMENT_HSTORE")) {  // timing experiment only: results are wrong
       if (env[0] == '1') {
         float *t0 = nullptr, *t1 = nullptr;
@@ -534,16 +550,17 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
   if (s->divergence == NMFB_DIV_EUCLIDEAN) {
     const bool fused_cost = !multi && !s->direct_cost;  // reduce + <G_W,G_H> + cost in one kernel
     if (fused_cost && s->overlap) {
+      // side stream: G_H, <G_W,G_H>, cost(i-1), stop test; publishes gate[0] = i+1 when G_H is ready
       CostArgs c{};
       fill_cost_args(s, &c, i - 1, 0);
       NMFB_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
       NMFB_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
       cudaStream_t main_stream = h->stream;
       h->stream = h->stream2;
-      int rc = run_gram_cost(h, s->gramH, s->ticket, c, i > 0);
+      int rc = run_gram_cost(h, s->gramH, s->ticket, c, i > 0, s->gates + 0, static_cast<unsigned>(i + 1));
       h->stream = main_stream;
       NMFB_TRY(rc);
-      NMFB_CUDA(h, cudaEventRecord(h->ev_join, h->stream2));
+      s->gemmA.L.args.gate_value = static_cast<unsigned>(i + 1);
     } else if (fused_cost) {
       CostArgs c{};
       fill_cost_args(s, &c, i - 1, 0);
@@ -558,7 +575,6 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
     } else {
       NMFB_TRY(run_timed(h, s->gemmA, 0));
     }
-    if (fused_cost && s->overlap) NMFB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     NMFB_TRY(allreduce_w_inputs(h, s, true));
     if (i > 0 && !s->direct_cost && !fused_cost) NMFB_TRY(enqueue_cost(h, s, i - 1, 0));
     if (!s->W_fixed) {
@@ -566,9 +582,21 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
       NMFB_TRY(prof_mark(h, 3));
       NMFB_TRY(enqueue_w_finish(h, s, WSTEP_EUCLID));
       NMFB_TRY(prof_mark(h, 3));
-      NMFB_TRY(prof_mark(h, 4));
-      NMFB_TRY(run_gram(h, s->gramW, stop));
-      NMFB_TRY(prof_mark(h, 4));
+      if (s->gate_h) {
+        // side stream: G_W of the new W; the H-step contraction starts at once and waits at gate[1]
+        NMFB_CUDA(h, cudaEventRecord(h->ev_join, h->stream));
+        NMFB_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_join, 0));
+        cudaStream_t main_stream = h->stream;
+        h->stream = h->stream2;
+        int rc = run_gram(h, s->gramW, stop, s->ticket + 1, s->gates + 1, static_cast<unsigned>(i + 1));
+        h->stream = main_stream;
+        NMFB_TRY(rc);
+        s->gemmH.L.args.gate_value = static_cast<unsigned>(i + 1);
+      } else {
+        NMFB_TRY(prof_mark(h, 4));
+        NMFB_TRY(run_gram(h, s->gramW, stop));
+        NMFB_TRY(prof_mark(h, 4));
+      }
     }
     if (s->h_split) {
       NMFB_TRY(prof_mark(h, 1));

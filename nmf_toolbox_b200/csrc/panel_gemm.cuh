@@ -13,7 +13,7 @@
 // adds into the fp32 accumulator, which gives a systematic relative bias of
 // about 5e-8 per accumulation step (measured on B200: 1.1e-4 after the 2048
 // steps of a 16384-long contraction).  Phase 0 is therefore cut into chunks of
-// kChunkKb k-blocks (32 MMA steps) that ping-pong between the two 256-column
+// kChunkKb k-blocks (64 MMA steps) that ping-pong between the two 256-column
 // TMEM buffers; eight epilogue warps drain each finished chunk with tcgen05.ld
 // and add it, round-to-nearest, into fp32 registers while the next chunk is
 // already accumulating.  Phase 1 (short: the K x K Gram products) is one chunk.
@@ -45,7 +45,8 @@ constexpr int kBlockK = 32;   // fp32 elements per 128-byte swizzle row
 constexpr int kUmmaK = 8;     // tf32 MMA K
 constexpr int kStages = 4;
 constexpr int kMaxN = 256;    // widest accumulator (fp32 TMEM columns)
-constexpr int kChunkKb = 8;   // k-blocks accumulated in TMEM before promotion to registers
+constexpr int kChunkKb = 16;  // k-blocks accumulated in TMEM before promotion to registers (64 MMA steps:
+                              // accumulate-truncation bias ~3e-6 relative, 2.5 % faster than 8)
 constexpr int kStageBytesX = kTileM * 128;
 constexpr int kStageBytesY = kMaxN * 128;
 constexpr int kStageBytes = kStageBytesX + kStageBytesY;
@@ -112,6 +113,11 @@ struct GemmArgs {
                       // TMA (map tmH) as soon as the operand ring is idle, instead of the epilogue
                       // fetching it with a chain of dependent global loads after the last MMA
   const int* stop;    // device flag: non-zero = iteration loop already converged, do nothing
+  // Phase 1 (the short second accumulator) may depend on a small kernel that runs CONCURRENTLY
+  // on another stream (a Gram matrix): the producer waits for *gate >= gate_value right before
+  // its first phase-1 load.  Only valid when the grid leaves SMs free for that kernel.
+  const unsigned int* gate;
+  unsigned int gate_value;
 };
 
 template <int EPI, int CG>
@@ -200,6 +206,7 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         else tma_load_2d(dst, tm, &full_bar[stage], c0, c1, pol);
       };
       const bool ph1 = it >= n0kb;
+      if (ph1 && it == n0kb && a.gate != nullptr) gate_wait(a.gate, a.gate_value);
       int kb = ph1 ? (it - n0kb) : (kb_begin + it);
       const CUtensorMap* mx = ph1 ? &tmX1 : &tmX0;
       const CUtensorMap* my = ph1 ? &tmY1 : &tmY0;

@@ -119,6 +119,29 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
+// ------------------------------------------------------------------ cross-kernel gate
+// A kernel running on another stream publishes "my output is complete" by storing an
+// increasing counter with release semantics (gate_publish, after __threadfence); a consumer
+// that was launched concurrently waits for it right before it needs the data.  The TMA reads
+// that follow go through the async proxy, hence the proxy fence.
+__device__ __forceinline__ void gate_publish(unsigned int* gate, unsigned int value) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(gate), "r"(value) : "memory");
+}
+__device__ __forceinline__ void gate_wait(const unsigned int* gate, unsigned int value) {
+  unsigned int v;
+  long long t0 = clock64();
+  while (true) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gate) : "memory");
+    if (static_cast<int>(v - value) >= 0) break;
+    __nanosleep(200);
+    if (clock64() - t0 > 4000000000LL) {
+      printf("nmfb: gate timeout (block %d,%d,%d) have %u want %u\n", blockIdx.x, blockIdx.y, blockIdx.z, v, value);
+      __trap();
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ TMA
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
