@@ -152,6 +152,14 @@ int run_gram_cost(nmfb_handle* h, const GramOp& op, unsigned int* ticket, const 
   return check_launch(h, "gram_reduce_cost");
 }
 
+int run_gram_post_allreduce(nmfb_handle* h, const GramOp& op, unsigned int* ticket, const CostArgs& c,
+                            bool with_cost) {
+  const int count = op.nvec * op.nvec;  // "one slab" = the reduced matrix itself
+  gram_reduce_cost_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(op.g32, 1, count, op.g32, op.gtf, count,
+                                                                      ticket, c, with_cost ? 1 : 0, nullptr, 0);
+  return check_launch(h, "gram_post_allreduce");
+}
+
 int launch_w_step(nmfb_handle* h, const WStepArgs& a) {
   if (a.m <= kWThreads * kWCache)
     w_step_kernel<true><<<a.K, kWThreads, 0, h->stream>>>(a);

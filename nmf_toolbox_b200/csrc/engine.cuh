@@ -182,6 +182,10 @@ struct CostArgs;
 int run_gram_cost(nmfb_handle* h, const GramOp& op, unsigned int* ticket, const CostArgs& c, bool with_cost,
                   unsigned int* gate = nullptr, unsigned int gate_value = 0);
 
+// After an all-reduce of a Gram matrix (multi-GPU): tf32 copy, <G_W,G_H>, cost and stop test in one kernel.
+int run_gram_post_allreduce(nmfb_handle* h, const GramOp& op, unsigned int* ticket, const CostArgs& c,
+                            bool with_cost);
+
 // Queue `maxiter` iterations in chunks.  The stop flag written by the cost
 // kernel turns everything queued behind a converged iteration into no-ops, so
 // the host only looks at the flag between chunks and never waits for the chunk

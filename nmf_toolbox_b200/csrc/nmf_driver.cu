@@ -38,6 +38,7 @@ struct NmfSession {
   bool overlap = false;  // the Gram products (and the cost) run on the side stream BESIDE the two large
                          // contractions, which wait for them at a device-side gate before their short phase 1
   bool gate_h = false;   // H-step contraction small enough to leave SMs for gram(W)
+  bool side_gh = false;  // several GPUs: gram(H) runs beside the A GEMM, joined before the all-reduce
   unsigned int* gates = nullptr;  // [0] G_H ready for iteration i (value i+1), [1] G_W ready
   bool h_split = false;  // too few sample tiles for the fused H update: split-K GEMM + h_finish
   float *Nbuf = nullptr, *Dbuf = nullptr;
@@ -221,13 +222,16 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     if (const char* e2 = std::getenv("NMFB_H_SPLIT")) s->h_split = e2[0] == '1';  // tests force either path
     s->overlap = !multi && !s->direct_cost && !s->W_fixed && !s->H_fixed && !(tilesA * 2 <= h->num_sms) &&
                  !(env && env[0] == '0') && m > kTileM && ctasA + 8 <= h->num_sms;
-    s->gate_h = s->overlap && !s->h_split && ctasH + 8 <= h->num_sms;
+    const bool can_side = !s->direct_cost && !s->W_fixed && !s->H_fixed && !(env && env[0] == '0') && m > kTileM &&
+                          ctasA + 8 <= h->num_sms;
+    // the split-K H step is planned with a reduced SM budget when it runs beside gram(W) (see below)
+    s->gate_h = (s->overlap && !s->h_split && ctasH + 8 <= h->num_sms) || (can_side && s->h_split);
+    s->side_gh = multi && can_side;
   }
-  NMFB_TRY(plan_gram(h, ar, &s->gramW, s->Wt, Kp, m, s->ldw, stop, nullptr, 0,
-                     s->gate_h ? h->num_sms - (((n + 2 * kTileM - 1) / (2 * kTileM)) * 2 * ((Kp + kMaxN - 1) / kMaxN)) : 0));
+  NMFB_TRY(plan_gram(h, ar, &s->gramW, s->Wt, Kp, m, s->ldw, stop, nullptr, 0, s->gate_h ? 20 : 0));
   if (!kl) {
     NMFB_TRY(plan_gram(h, ar, &s->gramH, s->Ht, Kp, n, s->ldh, stop, nullptr, 0,
-                       s->overlap ? h->num_sms - (((m + 2 * kTileM - 1) / (2 * kTileM)) * 2 * ((Kp + kMaxN - 1) / kMaxN)) : 0));
+                       (s->overlap || s->side_gh) ? 20 : 0));
     if (multi) {  // G_H must sit behind A in the packed buffer
       s->gramH.g32 = s->packed + static_cast<size_t>(Kp) * s->ldw;
     }
@@ -288,7 +292,11 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     if (s->h_split) {
       NMFB_TRY(ar->alloc(h, &s->Nbuf, static_cast<size_t>(Kp) * s->ldh));
       NMFB_TRY(ar->alloc(h, &s->Dbuf, static_cast<size_t>(Kp) * s->ldh));
-      NMFB_TRY(plan_store(h, ar, &s->gemmH, Xvt, Yw, m, &Xh, &Ygw, Kp, n, Kp, s->Nbuf, s->Dbuf, s->ldh, true, stop));
+      const int sms = h->num_sms;
+      if (s->gate_h) h->num_sms = std::max(16, sms - 20);  // leave SMs for the Gram product running beside it
+      int rc = plan_store(h, ar, &s->gemmH, Xvt, Yw, m, &Xh, &Ygw, Kp, n, Kp, s->Nbuf, s->Dbuf, s->ldh, true, stop);
+      h->num_sms = sms;
+      NMFB_TRY(rc);
     } else {
     NMFB_TRY(plan_fused(h, &s->gemmH, EPI_HUPDATE, Xvt, Yw, m, &Xh, &Ygw, Kp, n, Kp, Kp, stop));
     }
@@ -429,7 +437,7 @@ static int allreduce_w_inputs(nmfb_handle* h, NmfSession* s, bool with_gram) {
   const size_t count = nA + (with_gram ? static_cast<size_t>(s->Kp) * s->Kp : 0);
   const bool kl = s->divergence == NMFB_DIV_KL;  // hs is only formed (per iteration) by the KL path
   NMFB_TRY(comm_allreduce(h, s->packed, count, kl ? s->hs : nullptr, kl ? s->Kp : 0, s->scal, 4));
-  if (with_gram) {
+  if (with_gram && s->direct_cost) {  // otherwise run_gram_post_allreduce makes the tf32 copy
     const int cnt = s->Kp * s->Kp;
     round_copy_kernel<<<dim3((cnt + 255) / 256, 1), 256, 0, h->stream>>>(s->gramH.g32, s->gramH.gtf, 1, cnt,
                                                                        cnt, s->stop);
@@ -567,6 +575,15 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
       NMFB_TRY(prof_mark(h, 2));
       NMFB_TRY(run_gram_cost(h, s->gramH, s->ticket, c, i > 0));
       NMFB_TRY(prof_mark(h, 2));
+    } else if (s->side_gh) {
+      NMFB_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+      NMFB_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+      cudaStream_t main_stream = h->stream;
+      h->stream = h->stream2;
+      int rc = run_gram(h, s->gramH, stop);
+      h->stream = main_stream;
+      NMFB_TRY(rc);
+      NMFB_CUDA(h, cudaEventRecord(h->ev_join, h->stream2));
     } else if (!s->H_fixed || i == 0 || multi) {
       NMFB_TRY(run_gram(h, s->gramH, stop));
     }
@@ -575,8 +592,15 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
     } else {
       NMFB_TRY(run_timed(h, s->gemmA, 0));
     }
+    if (s->side_gh) NMFB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     NMFB_TRY(allreduce_w_inputs(h, s, true));
-    if (i > 0 && !s->direct_cost && !fused_cost) NMFB_TRY(enqueue_cost(h, s, i - 1, 0));
+    if (multi && !s->direct_cost) {
+      CostArgs c{};
+      fill_cost_args(s, &c, i - 1, 0);
+      NMFB_TRY(run_gram_post_allreduce(h, s->gramH, s->ticket, c, i > 0));
+    } else if (i > 0 && !s->direct_cost && !fused_cost) {
+      NMFB_TRY(enqueue_cost(h, s, i - 1, 0));
+    }
     if (!s->W_fixed) {
       if (s->gemmB.planned) NMFB_TRY(run_gemm(h, s->gemmB));
       NMFB_TRY(prof_mark(h, 3));
@@ -676,9 +700,10 @@ static int enqueue_final_cost(nmfb_handle* h, NmfSession* s) {
       return run_gram_cost(h, s->gramH, s->ticket, c, true);
     }
     NMFB_TRY(run_gram(h, s->gramH, s->stop));
-    if (multi)
-      NMFB_TRY(comm_allreduce(h, s->gramH.g32, static_cast<size_t>(s->Kp) * s->Kp, nullptr, 0, s->scal, 4));
-    return enqueue_cost(h, s, last, 0);
+    NMFB_TRY(comm_allreduce(h, s->gramH.g32, static_cast<size_t>(s->Kp) * s->Kp, nullptr, 0, s->scal, 4));
+    CostArgs c{};
+    fill_cost_args(s, &c, last, 0);
+    return run_gram_post_allreduce(h, s->gramH, s->ticket, c, true);
   }
   if (s->kl_fused) {
     s->klW.args.want_cost = 1;
