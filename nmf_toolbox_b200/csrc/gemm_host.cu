@@ -142,6 +142,14 @@ std::string set_h_prefetch(GemmLaunch* L, const float* Hm, long long n, long lon
   return "";
 }
 
+std::string set_v_prefetch(GemmLaunch* L, const float* V, long long m, long long n, long long ldv) {
+  Mat2D mm{V, m, n, ldv};
+  std::string e = make_tmap(&L->tmH, mm, kTileM, 32, false, true);  // 128 rows x 32 columns, linear
+  if (!e.empty()) return "V tile " + e;
+  L->args.h_prefetch = 1;
+  return "";
+}
+
 std::string add_segment(GemmLaunch* L, int seg, const GemmOperand& X, const GemmOperand& Y, int num_sms,
                         int splits_hint) {
   GemmArgs& a = L->args;

@@ -59,6 +59,8 @@ std::string add_segment(GemmLaunch* L, int seg, const GemmOperand& X, const Gemm
 
 // EPI_HUPDATE: let the kernel stage the H master tile through shared memory by TMA.
 std::string set_h_prefetch(GemmLaunch* L, const float* Hm, long long n, long long Kp, long long ldh);
+// EPI_RESID / EPI_KLQ: same staging for the tile of V (m x n column-major, leading dimension ldv).
+std::string set_v_prefetch(GemmLaunch* L, const float* V, long long m, long long n, long long ldv);
 
 std::string launch_gemm(const GemmLaunch& L, int epi, cudaStream_t stream);
 

@@ -4,6 +4,7 @@
 #include "engine.cuh"
 #include "ew_kernels.cuh"
 #include "kl_fused.cuh"
+#include "resid_fused.cuh"
 
 namespace nmfb {
 
@@ -69,6 +70,60 @@ int run_kl(nmfb_handle* h, const KlOp& op) {
   cudaError_t e = cudaLaunchKernelEx(&cfg, kl_fused_kernel, op.tmF, op.tmG1, op.tmG2, op.tmV, op.args);
   ++h->launches;
   if (e != cudaSuccess) return h->fail(NMFB_ERR_CUDA, "launch of kl_fused failed: %s", cudaGetErrorString(e));
+  return NMFB_OK;
+}
+
+// ---------------------------------------------------------------- resid_fused (nmfsc objective)
+struct ResidOp {
+  CUtensorMap tmFhi, tmFlo, tmGhi, tmGlo, tmV;
+  ResidArgs args;
+  dim3 grid;
+  bool planned = false;
+};
+
+// W (head, tail): [Kp][ldw] columns contiguous over m rows; H (head, tail): [Kp][ldh] over n columns;
+// V: column-major m x n (leading dimension ldv); scal[0] receives sum (V - W H)^2.
+int plan_resid(nmfb_handle* h, ResidOp* op, const float* Whi, const float* Wlo, long long ldw, const float* Hhi,
+               const float* Hlo, long long ldh, const float* V, long long ldv, int m, int n, int Kp, double* scal) {
+  if (Kp % 32 != 0 || Kp > kKlMaxKp) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "plan_resid: Kp must be 32..128");
+  std::string e;
+  if (!(e = make_tmap(&op->tmFhi, Mat2D{Whi, m, Kp, ldw}, 32, 32, true)).empty()) return h->fail(NMFB_ERR_CUDA, "resid W %s", e.c_str());
+  if (!(e = make_tmap(&op->tmFlo, Mat2D{Wlo, m, Kp, ldw}, 32, 32, true)).empty()) return h->fail(NMFB_ERR_CUDA, "resid W %s", e.c_str());
+  if (!(e = make_tmap(&op->tmGhi, Mat2D{Hhi, n, Kp, ldh}, 32, 32, true)).empty()) return h->fail(NMFB_ERR_CUDA, "resid H %s", e.c_str());
+  if (!(e = make_tmap(&op->tmGlo, Mat2D{Hlo, n, Kp, ldh}, 32, 32, true)).empty()) return h->fail(NMFB_ERR_CUDA, "resid H %s", e.c_str());
+  if (!(e = make_tmap(&op->tmV, Mat2D{V, m, n, ldv}, kTileM, kKlTileC, false, true)).empty())
+    return h->fail(NMFB_ERR_CUDA, "resid V %s", e.c_str());
+  const int pairs = (m + 2 * kTileM - 1) / (2 * kTileM);
+  const int total_tiles = (n + kKlTileC - 1) / kKlTileC;
+  int splits = std::max(1, (h->num_sms / 2) / pairs);
+  splits = std::min(splits, total_tiles);
+  const int per = (total_tiles + splits - 1) / splits;
+  splits = (total_tiles + per - 1) / per;
+  op->grid = dim3(2 * pairs, splits, 1);
+  op->args = ResidArgs{m, n, Kp, per, scal};
+  op->planned = true;
+  return NMFB_OK;
+}
+
+int run_resid(nmfb_handle* h, const ResidOp& op) {
+  static cudaError_t attr =
+      cudaFuncSetAttribute(resid_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemBytes);
+  if (attr != cudaSuccess) return h->fail(NMFB_ERR_CUDA, "cudaFuncSetAttribute(resid_fused): %s", cudaGetErrorString(attr));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = op.grid;
+  cfg.blockDim = dim3(64 + kKlEpiWarps * 32);
+  cfg.dynamicSmemBytes = kRsSmemBytes;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, resid_fused_kernel, op.tmFhi, op.tmFlo, op.tmGhi, op.tmGlo, op.tmV, op.args);
+  ++h->launches;
+  if (e != cudaSuccess) return h->fail(NMFB_ERR_CUDA, "launch of resid_fused failed: %s", cudaGetErrorString(e));
   return NMFB_OK;
 }
 

@@ -336,6 +336,8 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
       r.Vsrc = s->Vmma;
       r.ldv = h->ldv;
       r.scal = s->scal + 2;
+      std::string pe = set_v_prefetch(&s->gemmS.L, s->Vmma, m, n, h->ldv);
+      if (!pe.empty()) return h->fail(NMFB_ERR_CUDA, "%s", pe.c_str());
     }
   } else {
     {
@@ -371,6 +373,10 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     q.Qout = s->Q;
     q.ldv = h->ldv;
     q.scal = s->scal + 2;
+    {
+      std::string pe = set_v_prefetch(&s->gemmS.L, h->Vraw, m, n, h->ldv);
+      if (!pe.empty()) return h->fail(NMFB_ERR_CUDA, "%s", pe.c_str());
+    }
     // R = Q H'
     MatRef Xq{s->Q, m, n, h->ldv, true};
     MatRef Yh{s->Ht, n, Kp, s->ldh, false};

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <ctime>
 #include <vector>
 
 #include "comm.cuh"
@@ -40,11 +41,14 @@ struct State {
   int* fail;
   GramOp gramW, gramH;
   GemmOp gemmN, gemmD, gemmA, gemmB, residCur, residH, residW;
+  ResidOp rsCur, rsH, rsW;  // streaming objective kernel (resid_fused.cuh), K <= 128
+  bool fused_resid = false;
 };
 
-int objective(nmfb_handle* h, State* s, const GemmOp& op, double* out) {
+int objective(nmfb_handle* h, State* s, const GemmOp& op, const ResidOp& rs, double* out) {
   NMFB_CUDA(h, cudaMemsetAsync(s->scal, 0, 2 * sizeof(double), h->stream));
-  NMFB_TRY(run_gemm(h, op));
+  if (s->fused_resid) NMFB_TRY(run_resid(h, rs));
+  else NMFB_TRY(run_gemm(h, op));
   double v[2];
   int failed = 0;
   NMFB_CUDA(h, cudaMemcpyAsync(v, s->scal, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
@@ -215,23 +219,49 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
       op->L.args.ldv = h->ldv;
       op->L.args.scal = s->scal;
       op->L.args.chunk_kb = kChunk;
+      std::string pe = set_v_prefetch(&op->L, h->Vwork, m, n, h->ldv);
+      if (!pe.empty()) return h->fail(NMFB_ERR_CUDA, "%s", pe.c_str());
       return static_cast<int>(NMFB_OK);
     };
-    NMFB_TRY(plan_resid(&s->residCur, s->Wt, s->Wl, s->Ht, s->Hl));
-    NMFB_TRY(plan_resid(&s->residH, s->Wt, s->Wl, s->Hnt, s->Hnl));
-    NMFB_TRY(plan_resid(&s->residW, s->Wnt, s->Wnl, s->Ht, s->Hl));
+    s->fused_resid = Kp <= kKlMaxKp && std::getenv("NMFB_RESID_UNFUSED") == nullptr;
+    if (s->fused_resid) {
+      NMFB_TRY(nmfb::plan_resid(h, &s->rsCur, s->Wt, s->Wl, ldw, s->Ht, s->Hl, ldh, h->Vwork, h->ldv, m, n, Kp, s->scal));
+      NMFB_TRY(nmfb::plan_resid(h, &s->rsH, s->Wt, s->Wl, ldw, s->Hnt, s->Hnl, ldh, h->Vwork, h->ldv, m, n, Kp, s->scal));
+      NMFB_TRY(nmfb::plan_resid(h, &s->rsW, s->Wnt, s->Wnl, ldw, s->Ht, s->Hl, ldh, h->Vwork, h->ldv, m, n, Kp, s->scal));
+    } else {
+      NMFB_TRY(plan_resid(&s->residCur, s->Wt, s->Wl, s->Ht, s->Hl));
+      NMFB_TRY(plan_resid(&s->residH, s->Wt, s->Wl, s->Hnt, s->Hnl));
+      NMFB_TRY(plan_resid(&s->residW, s->Wnt, s->Wnl, s->Ht, s->Hl));
+    }
   }
 
+  const bool trace = std::getenv("NMFB_TRACE") != nullptr;
+  double tr[6] = {0, 0, 0, 0, 0, 0};
+  int ntrials = 0;
+  auto now = [] {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  };
+  auto lap = [&](int slot, double& t0) {
+    if (!trace) return;
+    cudaStreamSynchronize(h->stream);
+    const double t1 = now();
+    tr[slot] += t1 - t0;
+    t0 = t1;
+  };
   std::vector<double> cost(static_cast<size_t>(cfg.maxiter) + 1, 0.0);  // nmfsc.m:137
-  NMFB_TRY(objective(h, s, s->residCur, &cost[0]));                      // nmfsc.m:138-139
+  NMFB_TRY(objective(h, s, s->residCur, s->rsCur, &cost[0]));                      // nmfsc.m:138-139
   double stepW = 1.0, stepH = 1.0;                                       // nmfsc.m:133-134
   int ncost = cfg.maxiter + 1;
   bool done = false;
   for (int it = 1; it <= cfg.maxiter && !done; ++it) {
+    double tl = now();
     if (!H_fixed) {
       NMFB_TRY(run_gram(h, s->gramW, nullptr));
       NMFB_TRY(run_gemm(h, s->gemmN));  // N = W'V (144)
       NMFB_TRY(run_gemm(h, s->gemmD));  // D = W'V_hat = (W'W)H (145)
+      lap(0, tl);
       if (sH > 0) {
         const double begobj = cost[it - 1];  // nmfsc.m:149
         while (true) {
@@ -239,8 +269,11 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
           NMFB_TRY(check_launch(h, "grad_step(H)"));
           NMFB_TRY(project(h, s, s->Hnew, K, n, ldh, L1s));  // nmfsc.m:155-157
           NMFB_TRY(split_to(h, s->Hnew, s->Hnt, s->Hnl, K, n, ldh));
+          lap(1, tl);
+          ++ntrials;
           double newobj;
-          NMFB_TRY(objective(h, s, s->residH, &newobj));  // nmfsc.m:160-161
+          NMFB_TRY(objective(h, s, s->residH, s->rsH, &newobj));  // nmfsc.m:160-161
+          lap(2, tl);
           if (newobj <= begobj) break;                    // nmfsc.m:164-166
           stepH /= 2;                                     // nmfsc.m:169
           if (stepH < 1e-200) {                           // nmfsc.m:170-174
@@ -266,20 +299,21 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
         NMFB_TRY(split_to(h, s->Wm, s->Wt, s->Wl, K, m, ldw));
       }
     }
+    lap(3, tl);
     if (!W_fixed) {
       NMFB_TRY(run_gram(h, s->gramH, nullptr));
       NMFB_TRY(run_gemm(h, s->gemmA));  // A = V H' (194)
       NMFB_TRY(run_gemm(h, s->gemmB));  // B = V_hat H' = W (H H') (195)
       if (sW > 0) {
         double begobj;
-        NMFB_TRY(objective(h, s, s->residCur, &begobj));  // nmfsc.m:193,197
+        NMFB_TRY(objective(h, s, s->residCur, s->rsCur, &begobj));  // nmfsc.m:193,197
         while (true) {
           grad_step_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, s->B, s->A, s->Wnew, K, m, ldw, stepW);
           NMFB_TRY(check_launch(h, "grad_step(W)"));
           NMFB_TRY(project(h, s, s->Wnew, K, m, ldw, L1a));  // nmfsc.m:206-208
           NMFB_TRY(split_to(h, s->Wnew, s->Wnt, s->Wnl, K, m, ldw));
           double newobj;
-          NMFB_TRY(objective(h, s, s->residW, &newobj));  // nmfsc.m:211-212
+          NMFB_TRY(objective(h, s, s->residW, s->rsW, &newobj));  // nmfsc.m:211-212
           if (newobj <= begobj) break;
           stepW /= 2;
           if (stepW < 1e-200) {  // nmfsc.m:221-225
@@ -299,12 +333,18 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
         NMFB_TRY(split_to(h, s->Wm, s->Wt, s->Wl, K, m, ldw));
       }
     }
-    NMFB_TRY(objective(h, s, s->residCur, &cost[it]));  // nmfsc.m:237-238
+    lap(4, tl);
+    NMFB_TRY(objective(h, s, s->residCur, s->rsCur, &cost[it]));  // nmfsc.m:237-238
+    lap(5, tl);
     if (it > 1 && cost[it] < cost[it - 1] && cost[it - 1] - cost[it] < cfg.tolerance) {  // 241-244
       ncost = it + 1;
       done = true;
     }
   }
+  if (trace)
+    fprintf(stderr, "[nmfb] nmfsc per-phase ms over the run: gradient GEMMs %.2f, trial prep (step+projfunc+split) %.2f, "
+                    "trial objective %.2f (%d trials), copies %.2f, W step %.2f, final objective %.2f\n",
+            tr[0], tr[1], tr[2], ntrials, tr[3], tr[4], tr[5]);
   if (n_cost) *n_cost = ncost;
   if (cost_out) std::memcpy(cost_out, cost.data(), static_cast<size_t>(ncost) * sizeof(double));
   if (W_out) NMFB_TRY(download_colmajor(h, s->Wm, ldw, m, K, W_out));

@@ -236,7 +236,8 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         phase ^= 1;
       }
     }
-    if constexpr (EPI == EPI_HUPDATE) {
+    if constexpr (EPI == EPI_HUPDATE || EPI == EPI_RESID || EPI == EPI_KLQ) {
+      // (EPI_RESID / EPI_KLQ: the staged tile is the 128-row x bn-column tile of V)
       if (a.h_prefetch) {
         // the ring is not used again: wait until every stage has been consumed, then reuse the
         // buffers for this CTA's 128-sample tile of the H master, [k][128 samples] fp32
@@ -442,6 +443,10 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       } else {
         // acc = tile of V_hat; thread = one row i of V, columns j of V in registers
         const int cols_ok = a.ncols_valid - col0;  // columns beyond the problem are padding
+        const bool staged = (EPI == EPI_RESID || EPI == EPI_KLQ) && a.h_prefetch != 0;
+        const float* vsm = reinterpret_cast<const float*>(smem_raw + (sbase - smem_u32(smem_raw))) +
+                           (g_begin * 16) * kTileM + q * 32 + lane;
+        if (staged) mbar_wait(&h_bar, 0);  // V tile staged by TMA: [column][128 rows]
 #pragma unroll
         for (int g = 0; g < kMaxGroups; ++g) {
           if (g < g_count && row_ok) {
@@ -454,7 +459,9 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
               float v[16];
 #pragma unroll
               for (int t = 0; t < 16; ++t)
-                v[t] = (g * 16 + t < cols_ok) ? __ldg(a.Vsrc + off + t * a.ldv) : 0.f;
+                v[t] = (g * 16 + t < cols_ok)
+                           ? (staged ? vsm[(g * 16 + t) * kTileM] : __ldg(a.Vsrc + off + t * a.ldv))
+                           : 0.f;
               if constexpr (EPI == EPI_RESID) {
 #pragma unroll
                 for (int t = 0; t < 16; ++t) {
