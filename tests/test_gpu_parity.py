@@ -116,6 +116,19 @@ def test_nmf_euclid_both_h_paths(api, handle, h_split, monkeypatch):
     assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
 
 
+@pytest.mark.parametrize("m,n,K,h_split", [(700, 900, 300, "1"), (700, 900, 300, "0"), (900, 700, 512, "1"), (64, 50, 70, "1")])
+def test_nmf_euclid_more_bases_than_one_column_chunk(api, handle, m, n, K, h_split, monkeypatch):
+    """K > 256 spans several 256-wide accumulator chunks (grid.y > 1); K > m, n is legal too."""
+    monkeypatch.setenv("NMFB_H_SPLIT", h_split)
+    rng = np.random.default_rng(K)
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    cfg = dict(divergence="euclidean", W_init=rng.random((m, K)) + 1e-3, H_init=rng.random((K, n)) + 1e-3, maxiter=20,
+               tolerance=1e-300)
+    W, H, c = api.nmf(V, K, cfg, handle=handle)
+    Wo, Ho, co = O.nmf(V, K, cfg)
+    assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
+
+
 def test_nmf_direct_cost_mode(api, handle):
     alg, V, K, T, cfg = inputs("nmf_euclid_512")
     Wo, Ho, co = O.nmf(V, K, cfg)
