@@ -74,7 +74,7 @@ extern "C" void nmfb_destroy(nmfb_handle* h) {
   nmf_session_release(h);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->stream2) cudaStreamSynchronize(h->stream2);
-  if (h->comm) comm_destroy(h->comm);
+  if (h->comm) comm_destroy(h);
   if (h->Vown) cudaFree(h->Vown);
   if (h->Vwork) cudaFree(h->Vwork);
   if (h->ev0) cudaEventDestroy(h->ev0);

@@ -64,7 +64,8 @@ struct NmfSession {
   GemmOp gemmA, gemmB, gemmH, gemmS, gemmR;
   KlOp klW, klH;         // fused KL halves (kl_fused.cuh)
   bool kl_fused = false;
-  float* packed = nullptr;  // multi-GPU: [A | G_H | hs] contiguous fp32 for the single all-reduce
+  float* packed = nullptr;  // multi-GPU: [A | G_H] contiguous fp32 for the single all-reduce
+  char* region = nullptr;   // multi-GPU: allocation shared with the peers ([packed | hs | scal | flags])
   int* pinned = nullptr;    // host copy of stop[0..1]
 };
 
@@ -145,7 +146,22 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   NMFB_TRY(ar->alloc(h, &s->Ht, static_cast<size_t>(Kp) * s->ldh));
   // packed = [A (Kp x ldw) | G_H (Kp x Kp, KL: unused) | ...]: one buffer so that a
   // multi-GPU run can all-reduce it in a single call.
-  NMFB_TRY(ar->alloc(h, &s->packed, static_cast<size_t>(Kp) * s->ldw + static_cast<size_t>(Kp) * Kp));
+  // With several GPUs the doubles that travel with it (hs, scal) and the barrier flags of the
+  // peer-memory all-reduce live behind it in the SAME allocation, owned by the communicator and
+  // mapped into the other ranks (comm_acquire_region).
+  const size_t packed_floats = static_cast<size_t>(Kp) * s->ldw + static_cast<size_t>(Kp) * Kp;
+  const bool share = comm_size(h->comm) > 1;
+  const size_t dbl_off = (packed_floats * sizeof(float) + 255) / 256 * 256;
+  if (share) {
+    char* region = nullptr;
+    NMFB_TRY(comm_acquire_region(h, dbl_off + (static_cast<size_t>(Kp) + 8) * sizeof(double), &region));
+    s->packed = reinterpret_cast<float*>(region);
+    s->hs = reinterpret_cast<double*>(region + dbl_off);
+    s->scal = s->hs + Kp;
+    s->region = region;
+  } else {
+    NMFB_TRY(ar->alloc(h, &s->packed, packed_floats));
+  }
   s->A = s->packed;
   NMFB_TRY(ar->alloc(h, &s->B, static_cast<size_t>(Kp) * s->ldw));
   NMFB_TRY(ar->alloc(h, &s->pcoef, Kp));
@@ -156,8 +172,10 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   s->norm2 = s->ab + 2 * Kp;
   s->wsum = s->ab + 3 * Kp;
   NMFB_TRY(ar->alloc(h, &s->ticket, 2));
-  NMFB_TRY(ar->alloc(h, &s->hs, Kp));
-  NMFB_TRY(ar->alloc(h, &s->scal, 8));
+  if (!share) {
+    NMFB_TRY(ar->alloc(h, &s->hs, Kp));
+    NMFB_TRY(ar->alloc(h, &s->scal, 8));
+  }
   NMFB_TRY(ar->alloc(h, &s->cost, static_cast<size_t>(s->maxiter) + 1));
   NMFB_TRY(ar->alloc(h, &s->stop, 2));
   NMFB_CUDA(h, cudaMallocHost(&s->pinned, 2 * sizeof(int)));
