@@ -55,10 +55,12 @@ NcclApi* nccl_api() {
 using namespace ncclbind;
 
 constexpr int kMaxRanks = 8;
+constexpr int kMaxBlocks = 256;                                   // grid cap of the all-reduce kernel
+constexpr size_t kFlagBytes = kMaxBlocks * kMaxRanks * sizeof(int);  // one flag array (opening / closing)
+constexpr size_t kHeader = 2 * kFlagBytes;                        // region = [flags | data]
 struct PeerTable {
   char* base[kMaxRanks];  // base[q] = rank q's registered region as seen from this process
   int rank, nranks;
-  size_t sig_off;
 };
 
 struct Comm {
@@ -70,7 +72,6 @@ struct Comm {
   char* region = nullptr;   // allocation owned by the communicator: [flags 256 B | data]
   size_t region_bytes = 0;  // capacity incl. the flag header
   int epoch = 0;
-  double* dtmp = nullptr;  // local scratch for the fp64 sums
 };
 
 // ---------------------------------------------------------------- peer-memory all-reduce kernels
@@ -82,20 +83,21 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// Every block signals (idempotent) and waits until all ranks have reached `epoch`.
-__device__ __forceinline__ void p2p_barrier(const PeerTable& t, int epoch) {
-  __threadfence_system();
+// Block b of every rank meets block b of all other ranks (flags[b][rank] in each rank's region
+// header, monotone epochs).  The release store of the signalling thread follows the bar.sync, so it
+// publishes the whole block's earlier writes (and, by stream order, those of earlier kernels).
+__device__ __forceinline__ void p2p_block_barrier(const PeerTable& t, size_t flags_off, int epoch) {
   __syncthreads();
   if (threadIdx.x < t.nranks) {
     const int q = threadIdx.x;
-    int* peer_sig = reinterpret_cast<int*>(t.base[q] + t.sig_off);
-    st_release_sys(peer_sig + t.rank, epoch);
-    const int* my_sig = reinterpret_cast<const int*>(t.base[t.rank] + t.sig_off);
+    const size_t row = flags_off + static_cast<size_t>(blockIdx.x) * kMaxRanks * sizeof(int);
+    st_release_sys(reinterpret_cast<int*>(t.base[q] + row) + t.rank, epoch);
+    const int* mine = reinterpret_cast<const int*>(t.base[t.rank] + row) + q;
     long long t0 = clock64();
-    while (ld_acquire_sys(my_sig + q) - epoch < 0) {
-      __nanosleep(100);
+    while (ld_acquire_sys(mine) - epoch < 0) {
       if (clock64() - t0 > 8000000000LL) {
-        printf("nmfb: peer barrier timeout (rank %d waiting for rank %d, epoch %d)\n", t.rank, q, epoch);
+        printf("nmfb: peer barrier timeout (rank %d block %d waiting for rank %d, epoch %d)\n", t.rank, blockIdx.x, q,
+               epoch);
         __trap();
       }
     }
@@ -136,10 +138,12 @@ __device__ __forceinline__ void p2p_reduce_slice(const PeerTable& t, size_t f_of
   }
 }
 
+// One kernel per all-reduce.  Blocks never wait for other blocks of their own GPU: when the kernel
+// has finished on a rank, every block has passed its closing barrier, hence every block of every
+// rank has finished reading and writing - which is all the next kernel in the stream needs.
 __global__ void __launch_bounds__(512)
-p2p_allreduce_kernel(PeerTable t, int epoch, size_t f_off, size_t nf, size_t d1_off, int n1, size_t d2_off, int n2,
-                     double* dtmp) {
-  p2p_barrier(t, epoch);  // every rank's partial results are complete and visible
+p2p_allreduce_kernel(PeerTable t, int epoch, size_t f_off, size_t nf, size_t d1_off, int n1, size_t d2_off, int n2) {
+  p2p_block_barrier(t, 0, epoch);  // every rank's partial results are complete and visible
   const int N = t.nranks;
   // fp32 part: rank r owns float4 slice r
   const size_t n4 = (nf + 3) / 4;
@@ -154,24 +158,29 @@ p2p_allreduce_kernel(PeerTable t, int epoch, size_t f_off, size_t nf, size_t d1_
     case 7: p2p_reduce_slice<7>(t, f_off, lo, hi); break;
     default: p2p_reduce_slice<8>(t, f_off, lo, hi); break;
   }
-  // fp64 scalars: every rank forms the same sums (rank order) into local scratch
+  // fp64 scalars (block 0 only): every rank forms the same sums in rank order, keeps them in
+  // registers across the closing barrier and then overwrites its own copy
+  double dsum[2] = {0.0, 0.0};
   if (blockIdx.x == 0) {
-    for (int i = threadIdx.x; i < n1 + n2; i += blockDim.x) {
-      const size_t off = i < n1 ? d1_off + static_cast<size_t>(i) * 8 : d2_off + static_cast<size_t>(i - n1) * 8;
-      double a = 0.0;
-      for (int q = 0; q < N; ++q) a += __ldcv(reinterpret_cast<const double*>(t.base[q] + off));
-      dtmp[i] = a;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = threadIdx.x + u * blockDim.x;
+      if (i < n1 + n2) {
+        const size_t off = i < n1 ? d1_off + static_cast<size_t>(i) * 8 : d2_off + static_cast<size_t>(i - n1) * 8;
+        for (int q = 0; q < N; ++q) dsum[u] += __ldcv(reinterpret_cast<const double*>(t.base[q] + off));
+      }
     }
   }
-  __threadfence_system();
-}
-
-__global__ void p2p_finish_kernel(PeerTable t, int epoch, size_t d1_off, int n1, size_t d2_off, int n2,
-                                  const double* dtmp) {
-  p2p_barrier(t, epoch);  // all peers have written their slices into our buffer and read our scalars
-  for (int i = threadIdx.x; i < n1 + n2; i += blockDim.x) {
-    const size_t off = i < n1 ? d1_off + static_cast<size_t>(i) * 8 : d2_off + static_cast<size_t>(i - n1) * 8;
-    *reinterpret_cast<double*>(t.base[t.rank] + off) = dtmp[i];
+  p2p_block_barrier(t, kFlagBytes, epoch);  // all reads of our data and writes into it are done
+  if (blockIdx.x == 0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = threadIdx.x + u * blockDim.x;
+      if (i < n1 + n2) {
+        const size_t off = i < n1 ? d1_off + static_cast<size_t>(i) * 8 : d2_off + static_cast<size_t>(i - n1) * 8;
+        *reinterpret_cast<double*>(t.base[t.rank] + off) = dsum[u];
+      }
+    }
   }
 }
 
@@ -211,15 +220,15 @@ int comm_allreduce(nmfb_handle* h, float* f, size_t nf, double* d1, size_t n1, d
     const size_t d1_off = n1 ? reinterpret_cast<const char*>(d1) - b : 0;
     const size_t d2_off = n2 ? reinterpret_cast<const char*>(d2) - b : 0;
     const size_t n4 = (nf + 3) / 4 / c->nranks;
-    const int blocks = static_cast<int>(std::max<size_t>(1, std::min<size_t>(2 * h->num_sms, (n4 + 2047) / 2048)));
-    const int e1 = ++c->epoch, e2 = ++c->epoch;
-    p2p_allreduce_kernel<<<blocks, 512, 0, h->stream>>>(c->table, e1, f_off, nf, d1_off, static_cast<int>(n1), d2_off,
-                                                         static_cast<int>(n2), c->dtmp);
-    p2p_finish_kernel<<<1, 256, 0, h->stream>>>(c->table, e2, d1_off, static_cast<int>(n1), d2_off,
-                                                 static_cast<int>(n2), c->dtmp);
-    h->launches += 2;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return h->fail(NMFB_ERR_CUDA, "peer all-reduce launch failed: %s", cudaGetErrorString(e));
+    // one co-resident block per SM at most: blocks spin on their peers
+    const int cap = std::min(h->num_sms, kMaxBlocks);
+    const int blocks = static_cast<int>(std::max<size_t>(1, std::min<size_t>(cap, (n4 + 2047) / 2048)));
+    const int e = ++c->epoch;
+    p2p_allreduce_kernel<<<blocks, 512, 0, h->stream>>>(c->table, e, f_off, nf, d1_off, static_cast<int>(n1), d2_off,
+                                                         static_cast<int>(n2));
+    h->launches += 1;
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return h->fail(NMFB_ERR_CUDA, "peer all-reduce launch failed: %s", cudaGetErrorString(ce));
     return NMFB_OK;
   }
   NcclApi* api = nccl_api();
@@ -250,8 +259,6 @@ static void region_release(nmfb_handle* h, Comm* c, bool collective) {
       cudaFree(one);
     }
   }
-  if (c->dtmp) cudaFree(c->dtmp);
-  c->dtmp = nullptr;
   cudaFree(c->region);
   c->region = nullptr;
   c->region_bytes = 0;
@@ -306,14 +313,12 @@ static int region_export(nmfb_handle* h, Comm* c) {
   cudaFree(flag);
   c->table.rank = c->rank;
   c->table.nranks = c->nranks;
-  c->table.sig_off = 0;
   c->epoch = 0;
   if (bad != 0.f) {
     for (int q = 0; q < c->nranks; ++q)
       if (q != c->rank && c->table.base[q]) cudaIpcCloseMemHandle(c->table.base[q]);
     return NMFB_OK;  // NCCL path
   }
-  NMFB_CUDA(h, cudaMalloc(&c->dtmp, 1024 * sizeof(double)));
   c->p2p = true;
   return NMFB_OK;
 }
@@ -322,7 +327,6 @@ int comm_acquire_region(nmfb_handle* h, size_t bytes, char** data) {
   Comm* c = h->comm;
   *data = nullptr;
   if (!c) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "comm_acquire_region without a communicator");
-  constexpr size_t kHeader = 256;  // barrier flags
   bytes = (bytes + 255) / 256 * 256;
   if (c->region && c->region_bytes >= bytes + kHeader) {
     // reuse: the mapping, the flags and the epoch counter carry on; only the data is cleared.  Safe
