@@ -58,8 +58,11 @@ typedef enum nmfb_divergence {
                               euclidean but the reference's cost switch has no such
                               case, so cost = sparsity terms only (cnmf.m:239-251).
                               nmf.m rejects it (NMFB_ERR_DIVERGENCE).                */
-  NMFB_DIV_IS = 3,         /* recognised, NMFB_ERR_UNSUPPORTED (nmf.m:154-156)        */
-  NMFB_DIV_AB = 4          /* recognised, NMFB_ERR_UNSUPPORTED (nmf.m:157-164)        */
+  NMFB_DIV_IS = 3,         /* 'is_divergence' | 'is'  nmf.m:154-156,185-187,211-212 (nmfb_nmf on one
+                              GPU; nmfb_cnmf and multi-GPU: NMFB_ERR_UNSUPPORTED)     */
+  NMFB_DIV_AB = 4          /* 'ab_divergence' | 'ab'  nmf.m:157-164,188-195,213-214 with config
+                              alpha, beta; alpha == 0 selects the dual updates
+                              (nmf.m:124-128); same availability as NMFB_DIV_IS       */
 } nmfb_divergence;
 
 typedef enum nmfb_cost_mode {
@@ -76,7 +79,7 @@ typedef enum nmfb_cost_mode {
  *   *_sparsity < 0      -> 0      (nmf.m:321-333); nmfsc clamps to <= 1 (nmfsc.m:90,103) */
 typedef struct nmfb_config {
   int divergence;        /* nmfb_divergence (ignored by nmfb_nmfsc)                     */
-  double alpha, beta;    /* only consulted for NMFB_DIV_AB (-> NMFB_ERR_AB_ZERO check)  */
+  double alpha, beta;    /* NMFB_DIV_AB only (nmf.m:23-28); both 0 -> NMFB_ERR_AB_ZERO  */
   const float* W_init;   /* m x K (x T) column-major, or NULL                           */
   const float* H_init;   /* K x n_local column-major, or NULL                           */
   double W_sparsity;     /* lambda_W (nmf/cnmf) or Hoyer sparseness of W columns (nmfsc) */

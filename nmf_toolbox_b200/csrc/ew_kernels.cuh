@@ -325,6 +325,8 @@ struct WStepArgs {
   const double* hs;  // KL: row sums of H
   float lambda;
   const int* stop;
+  float expo;      // AB divergence: both gradients are raised to 1/alpha (dual: 1/beta) first
+                   // (nmf.m:159-163); 0 or 1 = plain ratio
 };
 template <bool CACHED>
 __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
@@ -382,12 +384,17 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
     }
     // ---- 2: multiplicative step + column norm
     float s2 = 0.f;
+    const bool powered = a.expo != 0.f && a.expo != 1.f;
     if (CACHED) {
 #pragma unroll
       for (int q = 0; q < kWCache; ++q) {
         const float w = wv[q];
-        const float neg = av[q] + w * pc;
-        const float pos = (kl ? bterm : bv[q]) + w * qc;
+        float neg = av[q] + w * pc;
+        float pos = (kl ? bterm : bv[q]) + w * qc;
+        if (powered) {
+          neg = powf(neg, a.expo);
+          pos = powf(pos, a.expo);
+        }
         const float wn = (tid + q * kWThreads < a.m) ? w * (neg / fmaxf(pos + a.lambda, NMFB_EPS)) : 0.f;
         wv[q] = wn;
         s2 = fmaf(wn, wn, s2);
@@ -395,8 +402,12 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
     } else {
       for (int i = tid; i < a.m; i += kWThreads) {
         const float w = a.W[off + i];
-        const float neg = a.A[off + i] + w * pc;
-        const float pos = (kl ? bterm : a.B[off + i]) + w * qc;
+        float neg = a.A[off + i] + w * pc;
+        float pos = (kl ? bterm : a.B[off + i]) + w * qc;
+        if (powered) {
+          neg = powf(neg, a.expo);
+          pos = powf(pos, a.expo);
+        }
         const float wn = w * (neg / fmaxf(pos + a.lambda, NMFB_EPS));
         a.W[off + i] = wn;
         s2 = fmaf(wn, wn, s2);
@@ -529,7 +540,9 @@ __global__ void gram_dot_kernel(const float* __restrict__ GA, const float* __res
 
 // ---------------------------------------------------------------- cost + stop test
 struct CostArgs {
-  int mode;             // 0 Euclid trace, 1 Euclid direct (scal[0] = sum (V-Vhat)^2), 2 KL, 3 sparsity terms only
+  int mode;             // 0 Euclid trace, 1 Euclid direct (scal[0] = sum (V-Vhat)^2), 2 KL, 3 sparsity terms only,
+                        // 4 IS (scal[2] = divergence), 5 AB (scal[2] = bracket sum of nmf.m:214, times ab_scale)
+  double ab_scale;      // -1 / (alpha * beta)
   int iter;             // 0-based index into cost[]
   int Kp;
   const float* GW;      // Kp x Kp fp32 Gram matrices (trace mode)
@@ -560,6 +573,10 @@ __global__ void cost_kernel(CostArgs a) {
     c = 0.5 * a.scal[2];
   } else if (a.mode == 2) {
     c = a.vstats[2] - a.scal[2] - a.vstats[1] + a.scal[3];
+  } else if (a.mode == 4) {
+    c = a.scal[2];
+  } else if (a.mode == 5) {
+    c = a.ab_scale * a.scal[2];
   }
   c += a.lambda_w * acc[1] + a.lambda_h * a.scal[1];
   a.cost[a.iter] = c;
@@ -642,17 +659,23 @@ __global__ void gram_reduce_cost_kernel(const float* __restrict__ parts, int spl
 //   H <- H .* N ./ max(D + lambda, eps)  (nmf.m:180-181,199); scal[0] += <N, tf32(Hnew)>, scal[1] += sum Hnew
 __global__ void h_finish_kernel(const float* __restrict__ N, const float* __restrict__ D, float* __restrict__ Hm,
                                 float* __restrict__ Ht, long long ld, int n, float lambda, int freeze,
-                                double* scal, const int* stop) {
+                                double* scal, const int* stop, float expo = 0.f) {
   NMFB_STOP_GUARD(stop);
   __shared__ double sh[64];
   const int k = blockIdx.y;
   double acc[2] = {0.0, 0.0};
+  const bool powered = expo != 0.f && expo != 1.f;  // AB divergence (nmf.m:190-194)
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const long long o = static_cast<long long>(k) * ld + j;
-    const float nv = N[o];
+    float nv = N[o];
     float hv = Hm[o];
     if (!freeze) {
-      hv = hv * __fdividef(nv, fmaxf(D[o] + lambda, NMFB_EPS));
+      float dv = D[o];
+      if (powered) {
+        nv = powf(nv, expo);
+        dv = powf(dv, expo);
+      }
+      hv = hv * (powered ? nv / fmaxf(dv + lambda, NMFB_EPS) : __fdividef(nv, fmaxf(dv + lambda, NMFB_EPS)));
       Hm[o] = hv;
     }
     const float hr = tf32_rn(hv);

@@ -213,7 +213,8 @@ std::string launch_gemm(const GemmLaunch& L, int epi, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&]() {
-    cudaError_t e[10] = {set_smem_attr<EPI_STORE, 1>(), set_smem_attr<EPI_HUPDATE, 1>(),
+    cudaError_t e[12] = {set_smem_attr<EPI_ABQ, 1>(),   set_smem_attr<EPI_ABQ, 2>(),
+                         set_smem_attr<EPI_STORE, 1>(), set_smem_attr<EPI_HUPDATE, 1>(),
                          set_smem_attr<EPI_RECON, 1>(), set_smem_attr<EPI_RESID, 1>(),
                          set_smem_attr<EPI_KLQ, 1>(),   set_smem_attr<EPI_STORE, 2>(),
                          set_smem_attr<EPI_HUPDATE, 2>(), set_smem_attr<EPI_RECON, 2>(),
@@ -231,6 +232,7 @@ std::string launch_gemm(const GemmLaunch& L, int epi, cudaStream_t stream) {
     case EPI_RECON: e = launch_one<EPI_RECON>(L, stream); break;
     case EPI_RESID: e = launch_one<EPI_RESID>(L, stream); break;
     case EPI_KLQ: e = launch_one<EPI_KLQ>(L, stream); break;
+    case EPI_ABQ: e = launch_one<EPI_ABQ>(L, stream); break;
     default: return "launch_gemm: unknown epilogue";
   }
   if (e == cudaSuccess) e = cudaGetLastError();

@@ -65,17 +65,6 @@ struct KlArgs {
   const int* stop;
 };
 
-__device__ __forceinline__ float fast_rcp(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float fast_lg2(float x) {
-  float r;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-
 __device__ __forceinline__ void mma_tf32_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc,
                                                  uint32_t idesc, uint32_t accumulate) {
   asm volatile(

@@ -62,6 +62,13 @@ struct NmfSession {
 
   GramOp gramH, gramW;
   GemmOp gemmA, gemmB, gemmH, gemmS, gemmR;
+  // IS / AB divergences ("two-weight" updates: both gradients are contractions with an element-wise
+  // function of V and V_hat, nmf.m:154-164,185-195)
+  bool two_weight = false;
+  float* Q2 = nullptr;   // Qp next to Q = Qn
+  GemmOp gemmRb, gemmHn, gemmHd;
+  float expo = 0.f;      // outer exponent of the AB gradients (1/alpha, dual: 1/beta)
+  double ab_scale = 0.0; // -1/(alpha beta) of the AB cost (nmf.m:214)
   KlOp klW, klH;         // fused KL halves (kl_fused.cuh)
   bool kl_fused = false;
   float* packed = nullptr;  // multi-GPU: [A | G_H] contiguous fp32 for the single all-reduce
@@ -100,6 +107,65 @@ int normalize_defaults(const nmfb_config* in, nmfb_config* out) {
 }  // namespace nmfdetail
 using namespace nmfdetail;
 
+// ------------------------------------------------------------------ IS / AB divergences
+// Per half iteration: V_hat = W H on the tensor cores with the two weight matrices
+//   IS        Qn = V ./ V_hat.^2                  Qp = 1 ./ V_hat                  (nmf.m:155-156)
+//   AB        Qn = V.^a .* V_hat.^(b-1)           Qp = V_hat.^(a+b-1)              (nmf.m:162-163)
+//   AB, a = 0 Qn = V.^(a-1) .* V_hat.^b           Qp = V.^(a+b-1)                  (nmf.m:159-160)
+// written by the epilogue (EPI_ABQ), then  W: A = Qn H', B = Qp H'  and the Euclidean-shaped W step
+// (neg = A + W diag(<W_k,B_k>), pos = B + W diag(<W_k,A_k>), both raised to 1/a or 1/b for AB);
+// H: N = W' Qn, D = W' Qp, H <- H .* N^e ./ max(D^e + lambda, eps).  The divergence itself
+// (nmf.m:211-214) is summed by the same epilogue one V_hat later, as for KL.
+static int plan_two_weight(nmfb_handle* h, NmfSession* s, const nmfb_config& cfg) {
+  Arena* ar = &s->ar;
+  const int m = s->m, n = s->n, Kp = s->Kp;
+  const int* stop = s->stop;
+  int mode = ABQ_IS;
+  if (s->divergence == NMFB_DIV_AB) {
+    const bool dual = cfg.alpha == 0;  // nmf.m:124-128
+    mode = dual ? ABQ_AB_DUAL : ABQ_AB;
+    s->expo = static_cast<float>(1.0 / (dual ? cfg.beta : cfg.alpha));
+    s->ab_scale = -1.0 / (cfg.alpha * cfg.beta);
+  }
+  NMFB_TRY(ar->alloc(h, &s->Q, static_cast<size_t>(n) * h->ldv));
+  NMFB_TRY(ar->alloc(h, &s->Q2, static_cast<size_t>(n) * h->ldv));
+  NMFB_TRY(ar->alloc(h, &s->Nbuf, static_cast<size_t>(Kp) * s->ldh));
+  NMFB_TRY(ar->alloc(h, &s->Dbuf, static_cast<size_t>(Kp) * s->ldh));
+  MatRef Xs{s->Wt, m, Kp, s->ldw, true};
+  MatRef Ys{s->Ht, n, Kp, s->ldh, true};
+  NMFB_TRY(plan_fused(h, &s->gemmS, EPI_ABQ, Xs, Ys, Kp, nullptr, nullptr, 0, m, round_up(n, 64), n, stop));
+  GemmArgs& q = s->gemmS.L.args;
+  q.Vsrc = h->Vraw;
+  q.Qout = s->Q;
+  q.Qout2 = s->Q2;
+  q.ldv = h->ldv;
+  q.scal = s->scal + 2;
+  q.ab_mode = mode;
+  q.ab_alpha = static_cast<float>(cfg.alpha);
+  q.ab_beta = static_cast<float>(cfg.beta);
+  {
+    std::string pe = set_v_prefetch(&s->gemmS.L, h->Vraw, m, n, h->ldv);
+    if (!pe.empty()) return h->fail(NMFB_ERR_CUDA, "%s", pe.c_str());
+  }
+  // W step: A = Qn H', B = Qp H'
+  MatRef Yh{s->Ht, n, Kp, s->ldh, false};
+  const int tilesW = (m + kTileM - 1) / kTileM * ((Kp + kMaxN - 1) / kMaxN);
+  const bool splitW = tilesW * 2 <= h->num_sms;
+  MatRef Xn{s->Q, m, n, h->ldv, true};
+  MatRef Xp{s->Q2, m, n, h->ldv, true};
+  NMFB_TRY(plan_store(h, ar, &s->gemmR, Xn, Yh, n, nullptr, nullptr, 0, m, Kp, s->A, nullptr, s->ldw, splitW, stop));
+  NMFB_TRY(plan_store(h, ar, &s->gemmRb, Xp, Yh, n, nullptr, nullptr, 0, m, Kp, s->B, nullptr, s->ldw, splitW, stop));
+  // H step: N = W' Qn, D = W' Qp
+  MatRef Yw{s->Wt, m, Kp, s->ldw, false};
+  const int tilesH = (n + kTileM - 1) / kTileM * ((Kp + kMaxN - 1) / kMaxN);
+  const bool splitH = tilesH * 2 <= h->num_sms;
+  MatRef Xnt{s->Q, m, n, h->ldv, false};
+  MatRef Xpt{s->Q2, m, n, h->ldv, false};
+  NMFB_TRY(plan_store(h, ar, &s->gemmHn, Xnt, Yw, m, nullptr, nullptr, 0, n, Kp, s->Nbuf, nullptr, s->ldh, splitH, stop));
+  NMFB_TRY(plan_store(h, ar, &s->gemmHd, Xpt, Yw, m, nullptr, nullptr, 0, n, Kp, s->Dbuf, nullptr, s->ldh, splitH, stop));
+  return NMFB_OK;
+}
+
 // ------------------------------------------------------------------ setup
 static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cfg_in) {
   if (h->Vraw == nullptr) return h->fail(NMFB_ERR_NO_DATA, "nmf: call nmfb_set_V first");
@@ -113,9 +179,11 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     case NMFB_DIV_AB:
       if (cfg.alpha == 0 && cfg.beta == 0)  // nmf.m:120-122
         return h->fail(NMFB_ERR_AB_ZERO, "alpha = 0 and beta = 0 is not supported at this time.");
-      return h->fail(NMFB_ERR_UNSUPPORTED, "nmf: the AB divergence is outside the accelerated path");
+      [[fallthrough]];
     case NMFB_DIV_IS:
-      return h->fail(NMFB_ERR_UNSUPPORTED, "nmf: the IS divergence is outside the accelerated path");
+      if (comm_size(h->comm) > 1)
+        return h->fail(NMFB_ERR_UNSUPPORTED, "nmf: the IS / AB divergences run on one GPU only");
+      break;
     default:  // nmf.m:165-166 ('frobenius' included: nmf.m has no such case)
       return h->fail(NMFB_ERR_DIVERGENCE,
                      "No update equations defined for cost function with divergence type %d",
@@ -138,6 +206,8 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   s->tolerance = cfg.tolerance;
   const int Kp = s->Kp;
   const bool kl = s->divergence == NMFB_DIV_KL;
+  const bool tw = s->divergence == NMFB_DIV_IS || s->divergence == NMFB_DIV_AB;
+  s->two_weight = tw;
   Arena* ar = &s->ar;
 
   NMFB_TRY(ar->alloc(h, &s->Wm, static_cast<size_t>(Kp) * s->ldw));
@@ -214,7 +284,9 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   NMFB_TRY(check_launch(h, "vec_sums(H init)"));
 
   // ---- V
-  if (kl) {
+  if (tw) {
+    // the weights are formed from the fp32 V in the epilogue of V_hat = W H; nothing to prepare
+  } else if (kl) {
     VStats st;
     NMFB_TRY(compute_v_stats(h, true, &st, &s->vstats, nullptr, ar));
     NMFB_TRY(comm_allreduce(h, nullptr, 0, s->vstats, 4, nullptr, 0));  // global sums over all shards
@@ -231,6 +303,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   // ---- plan the contractions
   const int* stop = s->stop;
   const bool multi = comm_size(h->comm) > 1;
+  if (tw) return plan_two_weight(h, s, cfg);
   if (!kl) {
     // decide up front which Gram products run beside a large contraction (see below)
     const int tilesA = (m + kTileM - 1) / kTileM * ((Kp + kMaxN - 1) / kMaxN);
@@ -451,6 +524,7 @@ static int enqueue_cost(nmfb_handle* h, NmfSession* s, int iter, int mode) {
   c.tolerance = s->tolerance;
   c.cost = s->cost;
   c.stop = s->stop;
+  c.ab_scale = s->ab_scale;
   cost_kernel<<<1, 256, 0, h->stream>>>(c);
   return check_launch(h, "cost");
 }
@@ -576,7 +650,43 @@ extern "C" int nmfb_profile_get(nmfb_handle* h, double* ms_w, double* ms_h, int*
   return NMFB_OK;
 }
 
+static int enqueue_iteration_two_weight(nmfb_handle* h, NmfSession* s, int i) {
+  const int K = s->K, n = s->n;
+  const int cost_mode = s->divergence == NMFB_DIV_IS ? 4 : 5;
+  s->gemmS.L.args.want_cost = i > 0 ? 1 : 0;
+  NMFB_TRY(run_gemm(h, s->gemmS));  // weights from the current V_hat (+ divergence of iteration i-1)
+  if (i > 0) NMFB_TRY(enqueue_cost(h, s, i - 1, cost_mode));
+  if (!s->W_fixed) {
+    NMFB_TRY(run_gemm(h, s->gemmR));
+    NMFB_TRY(run_gemm(h, s->gemmRb));
+    WStepArgs w{};
+    w.mode = WSTEP_EUCLID;  // same shape: neg = A + W diag(<W,B>), pos = B + W diag(<W,A>)
+    w.W = s->Wm;
+    w.Wt = s->Wt;
+    w.A = s->A;
+    w.B = s->B;
+    w.m = s->m;
+    w.ld = s->ldw;
+    w.K = s->K;
+    w.T = 1;
+    w.wsum = s->wsum;
+    w.hs = s->hs;
+    w.lambda = s->lambda_w;
+    w.stop = s->stop;
+    w.expo = s->expo;
+    NMFB_TRY(launch_w_step(h, w));
+    s->gemmS.L.args.want_cost = 0;
+    NMFB_TRY(run_gemm(h, s->gemmS));  // refreshed V_hat (nmf.m:173)
+  }
+  NMFB_TRY(run_gemm(h, s->gemmHn));
+  NMFB_TRY(run_gemm(h, s->gemmHd));
+  h_finish_kernel<<<dim3(std::max(1, std::min(64, (n + 1023) / 1024)), K), 256, 0, h->stream>>>(
+      s->Nbuf, s->Dbuf, s->Hm, s->Ht, s->ldh, n, s->lambda_h, s->H_fixed ? 1 : 0, s->scal, s->stop, s->expo);
+  return check_launch(h, "h_finish");
+}
+
 static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
+  if (s->two_weight) return enqueue_iteration_two_weight(h, s, i);
   const int Kp = s->Kp, K = s->K, n = s->n;
   const int* stop = s->stop;
   const bool multi = comm_size(h->comm) > 1;
@@ -717,6 +827,11 @@ static int enqueue_final_cost(nmfb_handle* h, NmfSession* s) {
   s->finalized = true;
   const int last = s->iters_enqueued - 1;
   const bool multi = comm_size(h->comm) > 1;
+  if (s->two_weight) {
+    s->gemmS.L.args.want_cost = 1;
+    NMFB_TRY(run_gemm(h, s->gemmS));
+    return enqueue_cost(h, s, last, s->divergence == NMFB_DIV_IS ? 4 : 5);
+  }
   if (s->divergence == NMFB_DIV_EUCLIDEAN) {
     if (s->direct_cost) return NMFB_OK;
     if (!multi) {

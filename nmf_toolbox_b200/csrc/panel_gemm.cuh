@@ -28,6 +28,9 @@
 //   EPI_RESID    sum of (V - V_hat).^2 over the tile (nmf.m:208, nmfsc.m:161)
 //   EPI_KLQ      Q = V ./ V_hat written tf32-rounded (nmf.m:152,183) and, on request,
 //                sum(V .* log(V_hat)), sum(V_hat) for the KL cost (nmf.m:210)
+//   EPI_ABQ      the two element-wise weight matrices of the IS / AB updates (nmf.m:154-164,
+//                185-195), tf32-rounded: Qn multiplies H' / W' in the negative gradient, Qp in
+//                the positive one; on request the sum of the per-element divergence (nmf.m:211-214)
 // Every kernel of an iteration loop starts by reading *stop: once the cost
 // kernel has detected convergence (nmf.m:221-224) the launches already queued
 // behind it become no-ops, so the host never has to synchronise per iteration.
@@ -72,7 +75,8 @@ constexpr int kMaxGroups = kMaxN / 16 / 2;  // 16-column groups per epilogue thr
 // eps even for single data (nmf.m:168,199); representable in fp32.
 #define NMFB_EPS 2.220446049250313e-16f
 
-enum { EPI_STORE = 0, EPI_HUPDATE = 1, EPI_RECON = 2, EPI_RESID = 3, EPI_KLQ = 4 };
+enum { EPI_STORE = 0, EPI_HUPDATE = 1, EPI_RECON = 2, EPI_RESID = 3, EPI_KLQ = 4, EPI_ABQ = 5 };
+enum { ABQ_IS = 0, ABQ_AB = 1, ABQ_AB_DUAL = 2 };
 
 struct GemmArgs {
   int rows;          // valid output rows (rows of X)
@@ -103,9 +107,13 @@ struct GemmArgs {
   double* scal;       // EPI_HUPDATE: scal[0] += sum(N .* tf32(Hnew)), scal[1] += sum(Hnew)
                       // EPI_RESID:   scal[0] += sum((V - acc)^2)
                       // EPI_KLQ:     scal[0] += sum(V .* log(acc)), scal[1] += sum(acc)   (if want_cost)
+                      // EPI_ABQ:     scal[0] += sum of the per-element divergence          (if want_cost)
   // EPI_RECON / EPI_RESID / EPI_KLQ: element (row, col) of the m x n problem lives at [col * ldv + row]
   const float* Vsrc;
-  float* Qout;        // EPI_KLQ: Q; EPI_RECON: V_hat
+  float* Qout;        // EPI_KLQ: Q; EPI_RECON: V_hat; EPI_ABQ: Qn
+  float* Qout2;       // EPI_ABQ: Qp
+  int ab_mode;        // EPI_ABQ: ABQ_IS / ABQ_AB / ABQ_AB_DUAL (alpha == 0, nmf.m:124-128)
+  float ab_alpha, ab_beta;
   long long ldv;
   int want_cost;
   int freeze;         // EPI_HUPDATE: leave H untouched (H_fixed, nmf.m:177) but still form the sums
@@ -119,6 +127,89 @@ struct GemmArgs {
   const unsigned int* gate;
   unsigned int gate_value;
 };
+
+// EPI_ABQ: 16 columns of one row.  The mode is uniform over the launch, so the three variants are
+// separate straight-line blocks (only one of them is ever fetched).
+template <int MODE>
+__device__ __forceinline__ void abq_group_mode(const GemmArgs& a, const float (&v)[16], const float* sum, int ncols,
+                                               float* qn_out, float* qp_out, float& s0) {
+  const float al = a.ab_alpha, be = a.ab_beta;
+  // exponents of log2 V and log2 V_hat: Qn = V^c0 V_hat^c1, Qp = V^c2 V_hat^c3
+  const float c0 = MODE == ABQ_AB ? al : al - 1.f, c1 = MODE == ABQ_AB ? be - 1.f : be;
+  const float c2 = MODE == ABQ_AB ? 0.f : al + be - 1.f, c3 = MODE == ABQ_AB ? al + be - 1.f : 0.f;
+  const float rs = 1.f / (al + be);  // alpha + beta == 0: Inf, as the reference's division
+  const long long ldv = a.ldv;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    if (t < ncols) {
+      const float sv = sum[t], vv = v[t];
+      float qn, qp;
+      if (MODE == ABQ_IS) {  // nmf.m:155-156,186-187
+        const float r = fast_rcp(sv);
+        qp = r;
+        qn = vv * r * r;
+        if (a.want_cost) s0 += 0.6931471805599453f * fast_lg2(sv * fast_rcp(vv)) + vv * r - 1.f;  // nmf.m:212
+      } else {               // nmf.m:159-163,190-194: powers as exp2(c log2 x); x.^0 == 1 (no 0 * inf)
+        const float lv = fast_lg2(vv), ls = fast_lg2(sv);
+        auto term = [](float c, float l) { return c == 0.f ? 0.f : c * l; };
+        qn = fast_ex2(term(c0, lv) + term(c1, ls));
+        qp = fast_ex2(term(c2, lv) + term(c3, ls));
+        if (a.want_cost)     // nmf.m:214 (the prefactor is applied by the cost kernel)
+          s0 += fast_ex2(term(al, lv) + term(be, ls)) -
+                (al * fast_ex2(term(al + be, lv)) + be * fast_ex2(term(al + be, ls)) + be) * rs;
+      }
+      qn_out[t * ldv] = tf32_rn(qn);
+      qp_out[t * ldv] = tf32_rn(qp);
+    }
+  }
+}
+template <int MODE, int NG>
+__device__ __forceinline__ void abq_tile(const GemmArgs& a, const float (&sum)[NG * 16], int g_count, int col0, int row,
+                                         int cols_ok, bool staged, const float* vsm, int vsm_stride, float& s0) {
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    if (g < g_count) {
+      const long long off = static_cast<long long>(col0 + g * 16) * a.ldv + row;
+      float v[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t)
+        v[t] = (g * 16 + t < cols_ok) ? (staged ? vsm[(g * 16 + t) * vsm_stride] : __ldg(a.Vsrc + off + t * a.ldv)) : 0.f;
+      abq_group_mode<MODE>(a, v, &sum[g * 16], cols_ok - g * 16, a.Qout + off, a.Qout2 + off, s0);
+    }
+  }
+}
+
+// Rolled variant: accumulator groups come from TMEM one at a time (see `direct` in the kernel).
+template <int MODE>  // MODE < 0: EPI_KLQ
+__device__ __noinline__ void q_tile_direct(const GemmArgs& a, uint32_t taddr, int g_count, int col0, int row,
+                                           bool row_ok, int cols_ok, bool staged, const float* vsm, int vsm_stride, float& s0,
+                                           float& s1) {
+#pragma unroll 1
+  for (int g = 0; g < g_count; ++g) {
+    float sv[16], v[16];
+    tmem_ld16(taddr + g * 16, sv);  // warp-collective: every lane gets here, rows beyond m included
+    const long long off = static_cast<long long>(col0 + g * 16) * a.ldv + row;
+    const int nc = row_ok ? cols_ok - g * 16 : 0;
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+      v[t] = (t < nc) ? (staged ? vsm[(g * 16 + t) * vsm_stride] : __ldg(a.Vsrc + off + t * a.ldv)) : 0.f;
+    tmem_ld_wait();
+    if constexpr (MODE < 0) {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        if (t < nc) {
+          a.Qout[off + t * a.ldv] = tf32_rn(v[t] * fast_rcp(sv[t]));
+          if (a.want_cost) {
+            s0 = fmaf(v[t], fast_lg2(sv[t]), s0);
+            s1 += sv[t];
+          }
+        }
+      }
+    } else {
+      abq_group_mode<MODE>(a, v, sv, nc, a.Qout + off, a.Qout2 + off, s0);
+    }
+  }
+}
 
 template <int EPI, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -236,8 +327,8 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         phase ^= 1;
       }
     }
-    if constexpr (EPI == EPI_HUPDATE || EPI == EPI_RESID || EPI == EPI_KLQ) {
-      // (EPI_RESID / EPI_KLQ: the staged tile is the 128-row x bn-column tile of V)
+    if constexpr (EPI == EPI_HUPDATE || EPI == EPI_RESID || EPI == EPI_KLQ || EPI == EPI_ABQ) {
+      // (EPI_RESID / EPI_KLQ / EPI_ABQ: the staged tile is the 128-row x bn-column tile of V)
       if (a.h_prefetch) {
         // the ring is not used again: wait until every stage has been consumed, then reuse the
         // buffers for this CTA's 128-sample tile of the H master, [k][128 samples] fp32
@@ -312,8 +403,17 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
 #pragma unroll
     for (int i = 0; i < kMaxGroups * 16; ++i) sum[i] = 0.f;
 
+    // EPI_KLQ / EPI_ABQ with a single accumulation chunk (K <= 512, the usual case): the epilogue
+    // reads the accumulator straight from TMEM in a ROLLED loop over the column groups.  Unrolled
+    // (as the register-resident sums require) it is ~8k straight-line instructions executed once per
+    // CTA, and the kernel was instruction-fetch bound (stall_no_inst on 80 % of the samples).
+    const bool direct = (EPI == EPI_KLQ || EPI == EPI_ABQ) && nchunk0 == 1 && n1kb == 0;
+    if (direct) {
+      mbar_wait(&tfull_bar[0], 0);
+      tc_fence_after();
+    }
     // promote finished phase-0 chunks from TMEM into registers
-    for (int ch = 0; ch < nchunk0; ++ch) {
+    for (int ch = 0; ch < (direct ? 0 : nchunk0); ++ch) {
       const int buf = ch & 1;
       mbar_wait(&tfull_bar[buf], (ch >> 1) & 1);
       tc_fence_after();
@@ -443,10 +543,32 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       } else {
         // acc = tile of V_hat; thread = one row i of V, columns j of V in registers
         const int cols_ok = a.ncols_valid - col0;  // columns beyond the problem are padding
-        const bool staged = (EPI == EPI_RESID || EPI == EPI_KLQ) && a.h_prefetch != 0;
+        const bool staged = (EPI == EPI_RESID || EPI == EPI_KLQ || EPI == EPI_ABQ) && a.h_prefetch != 0;
         const float* vsm = reinterpret_cast<const float*>(smem_raw + (sbase - smem_u32(smem_raw))) +
                            (g_begin * 16) * kTileM + q * 32 + lane;
         if (staged) mbar_wait(&h_bar, 0);  // V tile staged by TMA: [column][128 rows]
+        if ((EPI == EPI_KLQ || EPI == EPI_ABQ) && direct) {
+          const uint32_t ta = tlane + static_cast<uint32_t>(g_begin * 16);
+          if constexpr (EPI == EPI_KLQ) {
+            q_tile_direct<-1>(a, ta, g_count, col0, row, row_ok, cols_ok, staged, vsm, kTileM, s0, s1);
+          } else {
+            if (a.ab_mode == ABQ_IS)
+              q_tile_direct<ABQ_IS>(a, ta, g_count, col0, row, row_ok, cols_ok, staged, vsm, kTileM, s0, s1);
+            else if (a.ab_mode == ABQ_AB)
+              q_tile_direct<ABQ_AB>(a, ta, g_count, col0, row, row_ok, cols_ok, staged, vsm, kTileM, s0, s1);
+            else
+              q_tile_direct<ABQ_AB_DUAL>(a, ta, g_count, col0, row, row_ok, cols_ok, staged, vsm, kTileM, s0, s1);
+          }
+        } else if constexpr (EPI == EPI_ABQ) {
+          if (row_ok) {
+            if (a.ab_mode == ABQ_IS)
+              abq_tile<ABQ_IS, kMaxGroups>(a, sum, g_count, col0, row, cols_ok, staged, vsm, kTileM, s0);
+            else if (a.ab_mode == ABQ_AB)
+              abq_tile<ABQ_AB, kMaxGroups>(a, sum, g_count, col0, row, cols_ok, staged, vsm, kTileM, s0);
+            else
+              abq_tile<ABQ_AB_DUAL, kMaxGroups>(a, sum, g_count, col0, row, cols_ok, staged, vsm, kTileM, s0);
+          }
+        } else {
 #pragma unroll
         for (int g = 0; g < kMaxGroups; ++g) {
           if (g < g_count && row_ok) {
@@ -468,14 +590,14 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
                   const float d = v[t] - sum[g * 16 + t];
                   if (g * 16 + t < cols_ok) s0 = fmaf(d, d, s0);
                 }
-              } else {  // EPI_KLQ
+              } else if constexpr (EPI == EPI_KLQ) {
 #pragma unroll
                 for (int t = 0; t < 16; ++t) {
                   if (g * 16 + t < cols_ok) {
                     const float sv = sum[g * 16 + t];
-                    a.Qout[off + t * a.ldv] = tf32_rn(v[t] / sv);
+                    a.Qout[off + t * a.ldv] = tf32_rn(v[t] * fast_rcp(sv));
                     if (a.want_cost) {
-                      s0 = fmaf(v[t], __logf(sv), s0);
+                      s0 = fmaf(v[t], fast_lg2(sv), s0);  // log2: scaled by ln 2 below
                       s1 += sv;
                     }
                   }
@@ -484,6 +606,8 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
             }
           }
         }
+        }
+        if constexpr (EPI == EPI_KLQ) s0 *= 0.6931471805599453f;
       }
       if (EPI != EPI_RECON && a.scal != nullptr) {
         double d0 = row_ok ? static_cast<double>(s0) : 0.0;

@@ -355,4 +355,23 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_ma
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// Single-instruction MUFU approximations (2 ulp / 2^-22): everything they feed is rounded to tf32
+// (2^-11) right afterwards.  The IEEE versions expand to range-check slow paths that, unrolled over a
+// 128-column epilogue, made the kernels instruction-fetch bound.
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 }  // namespace nmfb

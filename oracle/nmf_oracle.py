@@ -222,11 +222,12 @@ def _cost(divergence, V, V_hat, alpha, beta):
         if divergence in ("is_divergence", "is"):
             return np.sum(np.sum(np.log(V_hat / V) + (V / V_hat) - 1))
         if divergence in ("ab_divergence", "ab"):
-            return (-1.0 / (alpha * beta)) * np.sum(
+            # IEEE division as in MATLAB: alpha*beta == 0 or alpha+beta == 0 give Inf / NaN, no error
+            return (np.float64(-1.0) / np.float64(alpha * beta)) * np.sum(
                 np.sum(
                     V ** alpha * V_hat ** beta
                     - (alpha * V ** (alpha + beta) + beta * V_hat ** (alpha + beta) + beta)
-                    / (alpha + beta)
+                    / np.float64(alpha + beta)
                 )
             )
     return 0.0

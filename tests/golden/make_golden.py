@@ -25,6 +25,10 @@ CASES = {
     "nmf_euclid_sparse": ("nmf", 200, 333, 24, 1, 40, dict(divergence="euclidean", W_sparsity=0.1, H_sparsity=0.2)),
     "nmf_kl_300": ("nmf", 300, 257, 20, 1, 40, dict(divergence="kl")),
     "nmf_kl_sparse": ("nmf", 129, 400, 8, 1, 30, dict(divergence="kl_divergence", W_sparsity=0.05, H_sparsity=0.1)),
+    "nmf_is_200": ("nmf", 200, 260, 12, 1, 40, dict(divergence="is")),
+    "nmf_ab_half_half": ("nmf", 257, 300, 10, 1, 40, dict(divergence="ab", alpha=0.5, beta=0.5)),
+    "nmf_ab_2_1_sparse": ("nmf", 150, 400, 8, 1, 30, dict(divergence="ab_divergence", alpha=2, beta=1, W_sparsity=0.05,
+                                                           H_sparsity=0.1)),
     "cnmf_euclid": ("cnmf", 129, 700, 8, 4, 40, dict(divergence="euclidean")),
     "cnmf_frobenius_sparse": ("cnmf", 100, 300, 6, 3, 20, dict(divergence="frobenius", W_sparsity=0.05, H_sparsity=0.1)),
     "nmfsc_h07": ("nmfsc", 512, 512, 16, 1, 60, dict(H_sparsity=0.7)),
@@ -61,7 +65,10 @@ def run(name):
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]  # optional: regenerate just these cases
     for name in CASES:
+        if only and name not in only:
+            continue
         W, H, cost = run(name)
         Vhat = O.reconstruct_from_decomposition(W, H)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), cost=cost, W=W.astype(np.float32), H=H.astype(np.float32),

@@ -223,9 +223,77 @@ def test_errors(api, handle):
     with pytest.raises(api.NmfbError) as e:  # nmfsc.m:57-59
         api.nmfsc(-V, 2, dict(maxiter=2), handle=handle)
     assert e.value.code == 6 and "Negative values in data!" in str(e.value)
-    with pytest.raises(api.NmfbError) as e:
-        api.nmf(V, 2, dict(divergence="is"), handle=handle)
+    with pytest.raises(api.NmfbError) as e:  # cnmf.m:179-185: IS / AB exist only for nmf in this build
+        api.cnmf(V, 2, 2, dict(divergence="is"), handle=handle)
     assert e.value.code == 3
+
+
+# ---------------------------------------------------------------- nmf, IS and AB divergences
+@pytest.mark.parametrize("div,alpha,beta,lw,lh", [
+    ("is", 1, 1, 0, 0), ("is", 1, 1, 0.05, 0.1),            # nmf.m:154-156,185-187,211-212
+    ("ab", 1, 1, 0, 0), ("ab", 0.5, 0.5, 0, 0), ("ab", 2, 1, 0.05, 0.1),  # nmf.m:161-163,192-194,213-214
+    ("ab", 0.5, 1.0, 0, 0), ("ab", 1.5, -0.5, 0.02, 0),
+])
+@pytest.mark.parametrize("m,n,K,iters", [(257, 330, 8, 40), (1024, 768, 32, 60)])
+def test_nmf_is_ab_vs_oracle(api, handle, div, alpha, beta, lw, lh, m, n, K, iters):
+    rng = np.random.default_rng(m + n)
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    cfg = dict(divergence=div, alpha=alpha, beta=beta, W_init=np.maximum(rng.random((m, K)), O.EPS),
+               H_init=np.maximum(rng.random((K, n)), O.EPS), maxiter=iters, tolerance=1e-300,
+               W_sparsity=lw, H_sparsity=lh)
+    W, H, c = api.nmf(V, K, cfg, handle=handle)
+    Wo, Ho, co = O.nmf(V, K, cfg)
+    assert cost_err(c, co) < COST_TOL
+    assert recon_err(W, H, Wo, Ho) < RECON_TOL
+    np.testing.assert_allclose((W.astype(np.float64) ** 2).sum(0), 1.0, rtol=1e-5)  # nmf.m:169
+
+
+def test_nmf_ab_nonfinite_cost(api, handle):
+    """alpha + beta == 0 and alpha * beta == 0 divide by zero in the reference's cost (nmf.m:214): the
+    cost entries are Inf / NaN there and here, the factors are still the reference's."""
+    m, n, K = 300, 200, 6
+    rng = np.random.default_rng(5)
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    for alpha, beta in [(1, -1), (1, 0)]:
+        cfg = dict(divergence="ab", alpha=alpha, beta=beta, W_init=rng.random((m, K)) + 1e-3,
+                   H_init=rng.random((K, n)) + 1e-3, maxiter=20, tolerance=1e-300)
+        W, H, c = api.nmf(V, K, cfg, handle=handle)
+        with np.errstate(all="ignore"):
+            Wo, Ho, co = O.nmf(V, K, cfg)
+        assert len(c) == len(co) and not np.isfinite(co).any() and not np.isfinite(c).any()
+        assert np.array_equal(np.isnan(c), np.isnan(co))
+        assert recon_err(W, H, Wo, Ho) < RECON_TOL
+
+
+def test_nmf_ab_dual_updates(api, handle):
+    """alpha == 0 selects the dual update equations (nmf.m:124-128,159-160,190-191).  On the
+    reference they collapse H within a few iterations, so the factors are compared after two."""
+    m, n, K = 300, 260, 6
+    rng = np.random.default_rng(9)
+    V = 0.5 + rng.random((m, n))
+    for beta in (1.0, 2.0):
+        cfg = dict(divergence="ab", alpha=0, beta=beta, W_init=rng.random((m, K)) + 1e-3,
+                   H_init=rng.random((K, n)) + 1e-3, maxiter=2, tolerance=1e-300)
+        W, H, c = api.nmf(V, K, cfg, handle=handle)
+        with np.errstate(all="ignore"):
+            Wo, Ho, co = O.nmf(V, K, cfg)
+        assert np.isfinite(Wo).all() and np.isfinite(Ho).all()
+        np.testing.assert_allclose(W, Wo, rtol=5e-3, atol=1e-6)
+        np.testing.assert_allclose(H, Ho, rtol=5e-3, atol=1e-12)
+        assert np.array_equal(np.isfinite(c), np.isfinite(co))
+
+
+@pytest.mark.parametrize("fixed", ["W", "H"])
+def test_nmf_is_fixed_factor(api, handle, fixed):
+    m, n, K = 200, 300, 5
+    rng = np.random.default_rng(17)
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    cfg = dict(divergence="is", W_init=rng.random((m, K)) + 1e-3, H_init=rng.random((K, n)) + 1e-3, maxiter=25,
+               tolerance=1e-300, W_fixed=fixed == "W", H_fixed=fixed == "H")
+    W, H, c = api.nmf(V, K, cfg, handle=handle)
+    Wo, Ho, co = O.nmf(V, K, cfg)
+    assert cost_err(c, co) < COST_TOL
+    assert recon_err(W, H, Wo, Ho) < RECON_TOL
 
 
 # ---------------------------------------------------------------- cnmf
