@@ -89,6 +89,15 @@ typedef struct nmfb_config {
   double tolerance;
   unsigned long long seed; /* only used when an init pointer is NULL                    */
   int cost_mode;         /* nmfb_cost_mode                                              */
+  /* Optional per-basis overrides for nmfb_nmf (NULL = the scalars above apply to every basis).
+   * They carry the reference's multi-source convention (cell arrays, nmf.m:11-16,51-60,
+   * 284-400) across the C boundary: the caller concatenates the sources' bases and passes, for
+   * every basis column k < K, the setting of the source it belongs to.  Exact, because the
+   * per-source loops of nmf.m:144-171 / 175-201 never refresh V_hat between sources.       */
+  const double* W_sparsity_k; /* K values of lambda_W (negative -> 0)                      */
+  const double* H_sparsity_k; /* K values of lambda_H                                      */
+  const int* W_fixed_k;       /* K flags: basis k of W is held fixed (nmf.m:145)           */
+  const int* H_fixed_k;       /* K flags: row k of H is held fixed (nmf.m:176)             */
 } nmfb_config;
 
 /* ---- handle ------------------------------------------------------------- */

@@ -119,6 +119,36 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
       if (w && !mxIsEmpty(w)) { W0 = to_single(w); c.W_init = W0.data(); }
       if (hh && !mxIsEmpty(hh)) { H0 = to_single(hh); c.H_init = H0.data(); }
     }
+    // per-basis vectors (what nmf.m's per-source cell settings become after concatenating the
+    // sources, see matlab/nmf.m): numeric vectors with one entry per basis column
+    std::vector<double> lwk, lhk;
+    std::vector<int> fwk, fhk;
+    auto vec_field = [&](const char* name, std::vector<double>* d, std::vector<int>* i) {
+      const mxArray* f = (cfg && mxIsStruct(cfg)) ? mxGetField(cfg, 0, name) : nullptr;
+      if (!f || mxIsEmpty(f)) return false;
+      if (static_cast<int>(mxGetNumberOfElements(f)) != K)
+        mexErrMsgIdAndTxt("nmfb:config", "%s needs one value per basis", name);
+      const mxArray* dbl = f;
+      mxArray* conv_arr = nullptr;
+      if (!mxIsDouble(f)) {
+        mxArray* in = const_cast<mxArray*>(f);
+        mexCallMATLAB(1, &conv_arr, 1, &in, "double");
+        dbl = conv_arr;
+      }
+      const double* p = mxGetPr(dbl);
+      for (int k = 0; k < K; ++k) {
+        if (d) d->push_back(p[k]);
+        if (i) i->push_back(p[k] != 0);
+      }
+      if (conv_arr) mxDestroyArray(conv_arr);
+      return true;
+    };
+    if (cmd == "nmf") {
+      if (vec_field("W_sparsity_k", &lwk, nullptr)) c.W_sparsity_k = lwk.data();
+      if (vec_field("H_sparsity_k", &lhk, nullptr)) c.H_sparsity_k = lhk.data();
+      if (vec_field("W_fixed_k", nullptr, &fwk)) c.W_fixed_k = fwk.data();
+      if (vec_field("H_fixed_k", nullptr, &fhk)) c.H_fixed_k = fhk.data();
+    }
     const int maxiter = c.maxiter > 0 ? c.maxiter : 100;
     std::vector<float> W(static_cast<size_t>(m) * K * T), H(static_cast<size_t>(K) * n);
     std::vector<double> cost(maxiter + 1);

@@ -68,6 +68,10 @@ class _Config(ctypes.Structure):
         ("tolerance", ctypes.c_double),
         ("seed", ctypes.c_ulonglong),
         ("cost_mode", ctypes.c_int),
+        ("W_sparsity_k", ctypes.c_void_p),
+        ("H_sparsity_k", ctypes.c_void_p),
+        ("W_fixed_k", ctypes.c_void_p),
+        ("H_fixed_k", ctypes.c_void_p),
     ]
 
 
@@ -215,6 +219,16 @@ class Handle:
         c.H_sparsity = float(cfg.get("H_sparsity") or 0)
         c.W_fixed = int(bool(cfg.get("W_fixed") or False))
         c.H_fixed = int(bool(cfg.get("H_fixed") or False))
+        # per-basis overrides (what a multi-source call with different per-source settings becomes)
+        for key, dt in (("W_sparsity_k", np.float64), ("H_sparsity_k", np.float64), ("W_fixed_k", np.int32),
+                        ("H_fixed_k", np.int32)):
+            v = cfg.get(key)
+            if v is not None:
+                arr = np.ascontiguousarray(np.asarray(v).astype(dt).ravel())
+                if arr.size != K:
+                    raise NmfbError(1, f"{key} needs one value per basis ({K}), got {arr.size}")
+                keep.append(arr)
+                setattr(c, key, arr.ctypes.data)
         mi = cfg.get("maxiter")
         c.maxiter = int(mi) if mi is not None else 0
         tol = cfg.get("tolerance")
@@ -335,11 +349,13 @@ def _split(a, sizes, axis):
     return [np.asfortranarray(p) for p in np.split(a, idx, axis=axis)]
 
 
-def _multi_source(config, sizes):
-    """nmf.m:11-16, 284-309: cell-array inputs.  The per-source loops of the
-    reference never refresh V_hat between sources, so S sources with a common
-    sparsity level and no fixed source are exactly one factorisation with the
-    bases concatenated; that case is mapped onto the single-source engine."""
+def _multi_source(config, sizes, per_basis=False):
+    """nmf.m:11-16, 284-400: cell-array inputs.  The per-source loops of the
+    reference (nmf.m:144-171, 175-201) never refresh V_hat between sources, so S
+    sources are exactly one factorisation with the bases concatenated; settings
+    that differ between sources (sparsity levels, fixed sources: the
+    semi-supervised use of nmf.m:51-60) become per-basis vectors
+    (``nmfb_config::*_k``) when the engine supports them (``per_basis``: nmf)."""
     cfg = dict(config or {})
     S = len(sizes)
     for key in ("W_sparsity", "H_sparsity", "W_fixed", "H_fixed"):
@@ -351,8 +367,12 @@ def _multi_source(config, sizes):
                 cfg[key] = None
             elif len(set(v)) == 1:
                 cfg[key] = v[0]
+            elif per_basis:
+                vals = [max(float(x), 0.0) for x in v] if key.endswith("sparsity") else [int(bool(x)) for x in v]
+                cfg[key + "_k"] = np.repeat(np.asarray(vals), sizes)
+                cfg[key] = None
             else:
-                raise NmfbError(3, f"per-source {key} values are not supported by the accelerated path yet")
+                raise NmfbError(3, f"per-source {key} values are not supported by this function's accelerated path")
     for key, axis in (("W_init", 1), ("H_init", 0)):
         v = cfg.get(key)
         if isinstance(v, (list, tuple)) and len(v) > 0:
@@ -368,7 +388,7 @@ def nmf(V, num_basis_elems, config=None, handle: Optional[Handle] = None):
     h.set_V(V)
     if isinstance(num_basis_elems, (list, tuple)):
         sizes = [int(k) for k in num_basis_elems]
-        cfg = _multi_source(config, sizes)
+        cfg = _multi_source(config, sizes, per_basis=True)
         W, H, cost = h.nmf(sum(sizes), cfg)
         if len(sizes) == 1 and not isinstance((config or {}).get("W_init"), (list, tuple)):
             return W, H, cost

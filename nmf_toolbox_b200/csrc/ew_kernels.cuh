@@ -327,6 +327,8 @@ struct WStepArgs {
   const int* stop;
   float expo;      // AB divergence: both gradients are raised to 1/alpha (dual: 1/beta) first
                    // (nmf.m:159-163); 0 or 1 = plain ratio
+  const float* lambda_k;  // optional per-basis lambda_W / fixed flags (multi-source runs, nmf.m:145,168)
+  const int* fixed_k;
 };
 template <bool CACHED>
 __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
@@ -337,6 +339,8 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
   const int tid = threadIdx.x;
   const bool kl = a.mode == WSTEP_KL;
   const int total = a.T * a.m;  // elements of this basis
+  if (a.fixed_k != nullptr && a.fixed_k[k] != 0) return;  // basis of a fixed source: untouched, not renormalised
+  const float lambda = a.lambda_k != nullptr ? a.lambda_k[k] : a.lambda;
   float wv[kWCache], av[kWCache], bv[kWCache];
   double norm_basis = 0.0;
 
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
           neg = powf(neg, a.expo);
           pos = powf(pos, a.expo);
         }
-        const float wn = (tid + q * kWThreads < a.m) ? w * (neg / fmaxf(pos + a.lambda, NMFB_EPS)) : 0.f;
+        const float wn = (tid + q * kWThreads < a.m) ? w * (neg / fmaxf(pos + lambda, NMFB_EPS)) : 0.f;
         wv[q] = wn;
         s2 = fmaf(wn, wn, s2);
       }
@@ -408,7 +412,7 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
           neg = powf(neg, a.expo);
           pos = powf(pos, a.expo);
         }
-        const float wn = w * (neg / fmaxf(pos + a.lambda, NMFB_EPS));
+        const float wn = w * (neg / fmaxf(pos + lambda, NMFB_EPS));
         a.W[off + i] = wn;
         s2 = fmaf(wn, wn, s2);
       }
@@ -552,6 +556,8 @@ struct CostArgs {
   double* scal;         // [0] <N,H> [1] sum H [2],[3] cost-epilogue sums [4] <G_W,G_H>; reset here
   const double* wsum;   // per-column sums of W (Kp_w entries)
   int n_wsum;
+  const float* lamw_k;  // optional per-basis lambda_W: the W term is sum_k lamw_k[k] wsum[k] and the
+                        // H-step kernels have already weighted scal[1] (host passes lambda_w = lambda_h = 1)
   double lambda_w, lambda_h;
   double tolerance;
   double* cost;
@@ -563,7 +569,8 @@ __global__ void cost_kernel(CostArgs a) {
   __shared__ double sh[64];
   double acc[2] = {0.0, 0.0};
   acc[0] = threadIdx.x == 0 ? a.scal[4] : 0.0;
-  for (int i = threadIdx.x; i < a.n_wsum; i += blockDim.x) acc[1] += a.wsum[i];
+  for (int i = threadIdx.x; i < a.n_wsum; i += blockDim.x)
+    acc[1] += a.lamw_k != nullptr ? a.wsum[i] * static_cast<double>(a.lamw_k[i]) : a.wsum[i];
   block_sum<2>(acc, sh);
   if (threadIdx.x != 0) return;
   double c = 0.0;
@@ -634,7 +641,8 @@ __global__ void gram_reduce_cost_kernel(const float* __restrict__ parts, int spl
   }
   acc[0] = 0.0;
   acc[1] = 0.0;
-  for (int k = threadIdx.x; k < c.n_wsum; k += blockDim.x) acc[1] += c.wsum[k];
+  for (int k = threadIdx.x; k < c.n_wsum; k += blockDim.x)
+    acc[1] += c.lamw_k != nullptr ? c.wsum[k] * static_cast<double>(c.lamw_k[k]) : c.wsum[k];
   block_sum<2>(acc, sh);
   if (threadIdx.x != 0) return;
   *ticket = 0u;
@@ -659,11 +667,16 @@ __global__ void gram_reduce_cost_kernel(const float* __restrict__ parts, int spl
 //   H <- H .* N ./ max(D + lambda, eps)  (nmf.m:180-181,199); scal[0] += <N, tf32(Hnew)>, scal[1] += sum Hnew
 __global__ void h_finish_kernel(const float* __restrict__ N, const float* __restrict__ D, float* __restrict__ Hm,
                                 float* __restrict__ Ht, long long ld, int n, float lambda, int freeze,
-                                double* scal, const int* stop, float expo = 0.f) {
+                                double* scal, const int* stop, float expo = 0.f,
+                                const float* lambda_k = nullptr, const int* fixed_k = nullptr) {
   NMFB_STOP_GUARD(stop);
   __shared__ double sh[64];
   const int k = blockIdx.y;
   double acc[2] = {0.0, 0.0};
+  // per-basis settings of a multi-source run: scal[1] then receives the lambda-weighted sum
+  if (lambda_k != nullptr) lambda = lambda_k[k];
+  if (fixed_k != nullptr && fixed_k[k] != 0) freeze = 1;
+  const double wgt = lambda_k != nullptr ? static_cast<double>(lambda) : 1.0;
   const bool powered = expo != 0.f && expo != 1.f;  // AB divergence (nmf.m:190-194)
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const long long o = static_cast<long long>(k) * ld + j;
@@ -683,6 +696,7 @@ __global__ void h_finish_kernel(const float* __restrict__ N, const float* __rest
     acc[0] += static_cast<double>(nv) * hr;
     acc[1] += hv;
   }
+  acc[1] *= wgt;
   block_sum<2>(acc, sh);
   if (threadIdx.x == 0) {
     atomicAdd(scal + 0, acc[0]);

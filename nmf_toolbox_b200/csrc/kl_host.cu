@@ -131,10 +131,13 @@ int run_resid(nmfb_handle* h, const ResidOp& op) {
 __global__ void kl_h_finish_kernel(const float* __restrict__ parts, int splits, long long slab, long long ldo,
                                    float* __restrict__ Hm, float* __restrict__ Ht, long long ldh,
                                    const float* __restrict__ ws, float lambda, int n, int freeze, double* scal,
-                                   const int* stop) {
+                                   const int* stop, const float* lambda_k = nullptr, const int* fixed_k = nullptr) {
   NMFB_STOP_GUARD(stop);
   __shared__ double sh[32];
   const int k = blockIdx.y;
+  if (lambda_k != nullptr) lambda = lambda_k[k];  // multi-source run: scal[1] receives the weighted sum
+  if (fixed_k != nullptr && fixed_k[k] != 0) freeze = 1;
+  const double wgt = lambda_k != nullptr ? static_cast<double>(lambda) : 1.0;
   const float den = fmaxf(ws[k] + lambda, NMFB_EPS);
   double acc[1] = {0.0};
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -148,6 +151,7 @@ __global__ void kl_h_finish_kernel(const float* __restrict__ parts, int splits, 
     }
     acc[0] += hv;
   }
+  acc[0] *= wgt;
   block_sum<1>(acc, sh);
   if (threadIdx.x == 0) atomicAdd(scal + 1, acc[0]);
 }

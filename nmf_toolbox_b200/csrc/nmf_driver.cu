@@ -44,6 +44,10 @@ struct NmfSession {
   bool h_split = false;  // too few sample tiles for the fused H update: split-K GEMM + h_finish
   float *Nbuf = nullptr, *Dbuf = nullptr;
   float lambda_w = 0.f, lambda_h = 0.f;
+  // per-basis settings of a multi-source run (nmfb_config::*_k); null = the scalars apply
+  bool per_basis = false;
+  float *lamW_k = nullptr, *lamH_k = nullptr;
+  int *fixW_k = nullptr, *fixH_k = nullptr;
   int maxiter = 100;
   double tolerance = 1e-3;
   int iters_enqueued = 0;
@@ -205,6 +209,30 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   s->maxiter = cfg.maxiter;
   s->tolerance = cfg.tolerance;
   const int Kp = s->Kp;
+  // ---- per-basis overrides (multi-source runs): collapse to the scalars when they are uniform
+  std::vector<float> lw(Kp, 0.f), lh(Kp, 0.f);
+  std::vector<int> fw(Kp, 1), fh(Kp, 1);  // padding rows/columns are never touched
+  if (cfg.W_sparsity_k || cfg.H_sparsity_k || cfg.W_fixed_k || cfg.H_fixed_k) {
+    bool uniform = true;
+    for (int k = 0; k < K; ++k) {
+      lw[k] = static_cast<float>(cfg.W_sparsity_k ? std::max(0.0, cfg.W_sparsity_k[k]) : cfg.W_sparsity);
+      lh[k] = static_cast<float>(cfg.H_sparsity_k ? std::max(0.0, cfg.H_sparsity_k[k]) : cfg.H_sparsity);
+      fw[k] = cfg.W_fixed_k ? (cfg.W_fixed_k[k] != 0) : (cfg.W_fixed != 0);
+      fh[k] = cfg.H_fixed_k ? (cfg.H_fixed_k[k] != 0) : (cfg.H_fixed != 0);
+      uniform = uniform && lw[k] == lw[0] && lh[k] == lh[0] && fw[k] == fw[0] && fh[k] == fh[0];
+    }
+    if (uniform) {
+      s->lambda_w = lw[0];
+      s->lambda_h = lh[0];
+      s->W_fixed = fw[0] != 0;
+      s->H_fixed = fh[0] != 0;
+    } else {
+      s->per_basis = true;
+      s->W_fixed = s->H_fixed = false;  // the masks decide per basis; every kernel of the iteration runs
+      if (comm_size(h->comm) > 1 && (cfg.W_fixed_k || cfg.W_fixed))
+        return h->fail(NMFB_ERR_UNSUPPORTED, "fixed W sources with several GPUs");
+    }
+  }
   const bool kl = s->divergence == NMFB_DIV_KL;
   const bool tw = s->divergence == NMFB_DIV_IS || s->divergence == NMFB_DIV_AB;
   s->two_weight = tw;
@@ -242,6 +270,17 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   s->norm2 = s->ab + 2 * Kp;
   s->wsum = s->ab + 3 * Kp;
   NMFB_TRY(ar->alloc(h, &s->ticket, 2));
+  if (s->per_basis) {
+    NMFB_TRY(ar->alloc(h, &s->lamW_k, Kp));
+    NMFB_TRY(ar->alloc(h, &s->lamH_k, Kp));
+    NMFB_TRY(ar->alloc(h, &s->fixW_k, Kp));
+    NMFB_TRY(ar->alloc(h, &s->fixH_k, Kp));
+    NMFB_CUDA(h, cudaMemcpyAsync(s->lamW_k, lw.data(), Kp * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    NMFB_CUDA(h, cudaMemcpyAsync(s->lamH_k, lh.data(), Kp * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    NMFB_CUDA(h, cudaMemcpyAsync(s->fixW_k, fw.data(), Kp * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    NMFB_CUDA(h, cudaMemcpyAsync(s->fixH_k, fh.data(), Kp * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    NMFB_CUDA(h, cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
+  }
   if (!share) {
     NMFB_TRY(ar->alloc(h, &s->hs, Kp));
     NMFB_TRY(ar->alloc(h, &s->scal, 8));
@@ -312,6 +351,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     const char* env = std::getenv("NMFB_OVERLAP");
     s->h_split = ctasH * 2 <= h->num_sms && n > kTileM;
     if (const char* e2 = std::getenv("NMFB_H_SPLIT")) s->h_split = e2[0] == '1';  // tests force either path
+    if (s->per_basis) s->h_split = true;  // per-basis lambda / fixed rows live in h_finish, not in the fused epilogue
     s->overlap = !multi && !s->direct_cost && !s->W_fixed && !s->H_fixed && !(tilesA * 2 <= h->num_sms) &&
                  !(env && env[0] == '0') && m > kTileM && ctasA + 8 <= h->num_sms;
     const bool can_side = !s->direct_cost && !s->W_fixed && !s->H_fixed && !(env && env[0] == '0') && m > kTileM &&
@@ -451,6 +491,8 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
         s->kl_fused = true;
       }
     }
+    if (!s->kl_fused && s->per_basis)
+      return h->fail(NMFB_ERR_UNSUPPORTED, "per-source settings with the unfused KL path (K > 128)");
     if (!s->kl_fused) {
     // Unfused fallback (K > 128 or not enough memory for the row-major copy of V):
     // S = W H (both operands MN-major), Q = V ./ S materialised in HBM
@@ -519,8 +561,9 @@ static int enqueue_cost(nmfb_handle* h, NmfSession* s, int iter, int mode) {
   c.scal = s->scal;
   c.wsum = s->wsum;
   c.n_wsum = s->Kp;
-  c.lambda_w = s->lambda_w;
-  c.lambda_h = s->lambda_h;
+  c.lambda_w = s->per_basis ? 1.0 : s->lambda_w;
+  c.lamw_k = s->lamW_k;
+  c.lambda_h = s->per_basis ? 1.0 : s->lambda_h;
   c.tolerance = s->tolerance;
   c.cost = s->cost;
   c.stop = s->stop;
@@ -561,6 +604,8 @@ static int enqueue_w_finish(nmfb_handle* h, NmfSession* s, int mode) {
   w.hs = s->hs;
   w.lambda = s->lambda_w;
   w.stop = s->stop;
+  w.lambda_k = s->lamW_k;
+  w.fixed_k = s->fixW_k;
   return launch_w_step(h, w);
 }
 
@@ -575,8 +620,9 @@ static void fill_cost_args(NmfSession* s, CostArgs* c, int iter, int mode) {
   c->scal = s->scal;
   c->wsum = s->wsum;
   c->n_wsum = s->Kp;
-  c->lambda_w = s->lambda_w;
-  c->lambda_h = s->lambda_h;
+  c->lambda_w = s->per_basis ? 1.0 : s->lambda_w;
+  c->lambda_h = s->per_basis ? 1.0 : s->lambda_h;
+  c->lamw_k = s->lamW_k;
   c->tolerance = s->tolerance;
   c->cost = s->cost;
   c->stop = s->stop;
@@ -674,6 +720,8 @@ static int enqueue_iteration_two_weight(nmfb_handle* h, NmfSession* s, int i) {
     w.lambda = s->lambda_w;
     w.stop = s->stop;
     w.expo = s->expo;
+    w.lambda_k = s->lamW_k;
+    w.fixed_k = s->fixW_k;
     NMFB_TRY(launch_w_step(h, w));
     s->gemmS.L.args.want_cost = 0;
     NMFB_TRY(run_gemm(h, s->gemmS));  // refreshed V_hat (nmf.m:173)
@@ -681,7 +729,8 @@ static int enqueue_iteration_two_weight(nmfb_handle* h, NmfSession* s, int i) {
   NMFB_TRY(run_gemm(h, s->gemmHn));
   NMFB_TRY(run_gemm(h, s->gemmHd));
   h_finish_kernel<<<dim3(std::max(1, std::min(64, (n + 1023) / 1024)), K), 256, 0, h->stream>>>(
-      s->Nbuf, s->Dbuf, s->Hm, s->Ht, s->ldh, n, s->lambda_h, s->H_fixed ? 1 : 0, s->scal, s->stop, s->expo);
+      s->Nbuf, s->Dbuf, s->Hm, s->Ht, s->ldh, n, s->lambda_h, s->H_fixed ? 1 : 0, s->scal, s->stop, s->expo, s->lamH_k,
+      s->fixH_k);
   return check_launch(h, "h_finish");
 }
 
@@ -761,7 +810,8 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
       NMFB_TRY(prof_mark(h, 1));
       NMFB_TRY(run_gemm(h, s->gemmH));  // N (split-K, summed) and D = G_W H
       h_finish_kernel<<<dim3(std::max(1, std::min(64, (n + 1023) / 1024)), K), 256, 0, h->stream>>>(
-          s->Nbuf, s->Dbuf, s->Hm, s->Ht, s->ldh, n, s->lambda_h, s->H_fixed ? 1 : 0, s->scal, stop);
+          s->Nbuf, s->Dbuf, s->Hm, s->Ht, s->ldh, n, s->lambda_h, s->H_fixed ? 1 : 0, s->scal, stop, 0.f, s->lamH_k,
+          s->fixH_k);
       NMFB_TRY(check_launch(h, "h_finish"));
       NMFB_TRY(prof_mark(h, 1));
     } else {
@@ -812,7 +862,8 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
       NMFB_TRY(run_kl(h, s->klH));
       kl_h_finish_kernel<<<dim3(std::max(1, std::min(64, (n + 1023) / 1024)), K), 256, 0, h->stream>>>(s->klH.parts, s->klH.splits, s->klH.args.slab,
                                                                 s->klH.args.ldo, s->Hm, s->Ht, s->ldh, s->wsf,
-                                                                s->lambda_h, n, s->H_fixed ? 1 : 0, s->scal, stop);
+                                                                s->lambda_h, n, s->H_fixed ? 1 : 0, s->scal, stop,
+                                                                s->lamH_k, s->fixH_k);
       NMFB_TRY(check_launch(h, "kl_h_finish"));
     } else {
       NMFB_TRY(run_gemm(h, s->gemmH));

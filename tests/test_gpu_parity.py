@@ -296,6 +296,36 @@ def test_nmf_is_fixed_factor(api, handle, fixed):
     assert recon_err(W, H, Wo, Ho) < RECON_TOL
 
 
+# ---------------------------------------------------------------- nmf, multi-source cell arrays
+@pytest.mark.parametrize("div", ["euclidean", "kl", "is"])
+@pytest.mark.parametrize("case", ["sparsity", "w_fixed", "h_fixed", "mixed"])
+def test_nmf_multi_source_per_source_settings(api, handle, div, case):
+    """nmf.m:11-16,51-60,144-201: sources with different sparsity levels / held fixed (the
+    semi-supervised use: a pre-trained dictionary stays fixed while another one is learned)."""
+    m, n, sizes = 300, 420, [6, 10, 4]
+    rng = np.random.default_rng(31)
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    W0 = [rng.random((m, k)) + 1e-3 for k in sizes]
+    H0 = [rng.random((k, n)) + 1e-3 for k in sizes]
+    cfg = dict(divergence=div, W_init=W0, H_init=H0, maxiter=30, tolerance=1e-300)
+    if case in ("sparsity", "mixed"):
+        cfg.update(W_sparsity=[0.0, 0.2, 0.05], H_sparsity=[0.3, 0.0, 0.1])
+    if case in ("w_fixed", "mixed"):
+        cfg.update(W_fixed=[True, False, False])
+    if case in ("h_fixed", "mixed"):
+        cfg.update(H_fixed=[False, False, True])
+    W, H, c = api.nmf(V, sizes, cfg, handle=handle)
+    Wo, Ho, co = O.nmf(V, sizes, cfg)
+    assert isinstance(W, list) and [w.shape[1] for w in W] == sizes and [x.shape[0] for x in H] == sizes
+    assert cost_err(c, co) < COST_TOL
+    assert recon_err(np.concatenate(W, 1), np.concatenate(H, 0), np.concatenate(Wo, 1), np.concatenate(Ho, 0)) < RECON_TOL
+    if case in ("w_fixed", "mixed"):  # the fixed dictionary is returned as normalised at the start (nmf.m:132)
+        Wn = W0[0] / np.sqrt((W0[0] ** 2).sum(0))
+        np.testing.assert_allclose(W[0], Wn, rtol=2e-6)
+    if case in ("h_fixed", "mixed"):
+        np.testing.assert_allclose(H[2], H0[2], rtol=2e-6)
+
+
 # ---------------------------------------------------------------- cnmf
 @pytest.mark.parametrize("m,n,K,T,iters,lw,lh", [(129, 700, 8, 4, 60, 0, 0), (200, 1000, 16, 5, 40, 0.05, 0.1),
                                                   (1025, 2000, 64, 8, 30, 0, 0), (64, 90, 3, 7, 25, 0, 0)])

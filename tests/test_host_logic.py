@@ -78,9 +78,10 @@ def test_config_struct_layout():
     from nmf_toolbox_b200 import api
 
     # must match struct nmfb_config in include/nmfb200.h (x86-64 SysV layout)
-    assert ctypes.sizeof(api._Config) == 96
+    assert ctypes.sizeof(api._Config) == 128
     assert api._Config.W_init.offset == 24 and api._Config.maxiter.offset == 64
     assert api._Config.tolerance.offset == 72 and api._Config.cost_mode.offset == 88
+    assert api._Config.W_sparsity_k.offset == 96 and api._Config.H_fixed_k.offset == 120
 
 
 def test_multi_source_mapping():
@@ -95,8 +96,15 @@ def test_multi_source_mapping():
         api._multi_source(dict(W_sparsity=[0.1, 0.2, 0.3]), [2, 3])
     with pytest.raises(api.NmfbError):  # nmf.m:301-302
         api._multi_source(dict(W_init=[np.ones((4, 2))]), [2, 3])
-    with pytest.raises(api.NmfbError):  # per-source levels: not accelerated yet
+    with pytest.raises(api.NmfbError):  # per-source levels: only nmf maps them (cnmf does not)
         api._multi_source(dict(W_sparsity=[0.1, 0.2]), [2, 3])
+    # nmf: settings that differ between sources become per-basis vectors (nmfb_config::*_k)
+    cfg = api._multi_source(dict(W_sparsity=[0.1, 0.2], H_sparsity=[-1, 0.5], W_fixed=[True, False], H_fixed=[0, 0]),
+                            [2, 3], per_basis=True)
+    np.testing.assert_allclose(cfg["W_sparsity_k"], [0.1, 0.1, 0.2, 0.2, 0.2])
+    np.testing.assert_allclose(cfg["H_sparsity_k"], [0, 0, 0.5, 0.5, 0.5])  # nmf.m:321-333 clamps negatives
+    assert list(cfg["W_fixed_k"]) == [1, 1, 0, 0, 0] and cfg["W_fixed"] is None
+    assert cfg["H_fixed"] == 0 and "H_fixed_k" not in cfg
 
 
 def test_shard_bounds_cover_and_partition():
