@@ -261,18 +261,23 @@ def main():
         del Vd
         torch.cuda.empty_cache()
         h.set_V(Vnp[:, : min(nl, 256)])  # untimed: lets lazy CUDA state settle
-        barrier()
-        t0 = time.perf_counter()
-        h.set_V(Vnp)
-        W, H, c2 = h.nmf(K, cfg2)
-        torch.cuda.synchronize()
-        el = time.perf_counter() - t0
-        barrier()
-        el = max_over_ranks(el)
+        # three complete calls, median reported (single calls show sporadic host-side stalls of ~0.1 s:
+        # page faults of the fresh output arrays, driver housekeeping)
+        runs = []
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            h.set_V(Vnp)
+            W, H, c2 = h.nmf(K, cfg2)
+            torch.cuda.synchronize()
+            el = time.perf_counter() - t0
+            barrier()
+            runs.append(max_over_ranks(el))
+        el = sorted(runs)[1]
         h2d = (Vnp.size + W0.size + H0.size) * 4
         d2h = (W.size + H.size) * 4 + c2.size * 8
         e2e = {"value": args.steps / el, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
-               "d2h_bytes_per_step": d2h / args.steps, "seconds": el,
+               "d2h_bytes_per_step": d2h / args.steps, "seconds": el, "runs_seconds": runs,
                "call": "Handle.set_V(V_host) + Handle.nmf(K, config) == nmfb_set_V + nmfb_nmf (C ABI), host buffers in and out"}
 
     # ------------------------------------------------------------ report

@@ -105,6 +105,12 @@ int nmfb_create(nmfb_handle** out, int device);
 void nmfb_destroy(nmfb_handle* h);
 const char* nmfb_last_error(const nmfb_handle* h); /* h may be NULL: last create error */
 
+/* The handle keeps the device blocks of finished calls for reuse by the next call of the same
+ * shape (cudaMalloc / cudaFree of GiB-sized blocks cost as much as ~100 iterations); at most a
+ * third of the device memory, released on allocation failure, by nmfb_destroy and by this call.
+ * NMFB_NO_POOL=1 in the environment disables the cache. */
+int nmfb_trim(nmfb_handle* h);
+
 /* Upload V (m x n column-major float32, host memory; pinned or pageable). */
 int nmfb_set_V(nmfb_handle* h, const float* V_host, int m, int n);
 /* Adopt a V that already lives on the handle's device (column-major, leading

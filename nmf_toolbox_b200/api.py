@@ -83,6 +83,7 @@ def _bind(lib):
     sig = {
         "nmfb_create": ([ctypes.POINTER(P), I], I),
         "nmfb_destroy": ([P], None),
+        "nmfb_trim": ([P], ctypes.c_int),
         "nmfb_last_error": ([P], ctypes.c_char_p),
         "nmfb_set_V": ([P, P, I, I], I),
         "nmfb_set_V_device": ([P, P, I, I, LL], I),
@@ -151,6 +152,10 @@ class Handle:
             raise NmfbError(rc, self.lib.nmfb_last_error(self._h).decode())
 
     # -- data
+    def trim(self):
+        """Release the device blocks cached from earlier calls (``nmfb_trim``)."""
+        self._check(self.lib.nmfb_trim(self._h))
+
     def set_V(self, V):
         V = np.asarray(V)
         if V.ndim != 2:

@@ -52,6 +52,10 @@ extern "C" int nmfb_create(nmfb_handle** out, int device) {
   nmfb_handle* h = new nmfb_handle();
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
+  {
+    const char* np_env = std::getenv("NMFB_NO_POOL");
+    h->pool.cap = (np_env && np_env[0] == '1') ? 0 : prop.totalGlobalMem / 3;
+  }
   // (stream priorities were tried for the side stream: no gain, slightly slower large GEMMs)
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
@@ -59,6 +63,7 @@ extern "C" int nmfb_create(nmfb_handle** out, int device) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+  if (e == cudaSuccess) e = cudaMallocHost(&h->pinned, 8 * sizeof(int));
   if (e != cudaSuccess) {
     g_create_error = std::string("handle creation failed: ") + cudaGetErrorString(e);
     delete h;
@@ -77,6 +82,8 @@ extern "C" void nmfb_destroy(nmfb_handle* h) {
   if (h->comm) comm_destroy(h);
   if (h->Vown) cudaFree(h->Vown);
   if (h->Vwork) cudaFree(h->Vwork);
+  h->pool.trim();
+  if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -86,9 +93,20 @@ extern "C" void nmfb_destroy(nmfb_handle* h) {
   delete h;
 }
 
+extern "C" int nmfb_trim(nmfb_handle* h) {
+  if (!h) return NMFB_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  h->pool.trim();
+  return NMFB_OK;
+}
+
 static void drop_V(nmfb_handle* h) {
-  if (h->Vown) cudaFree(h->Vown);
+  if (h->Vown) {
+    cudaStreamSynchronize(h->stream);
+    dev_free(h, h->Vown, h->Vown_bytes);
+  }
   h->Vown = nullptr;
+  h->Vown_bytes = 0;
   h->Vraw = nullptr;
 }
 
@@ -100,7 +118,10 @@ extern "C" int nmfb_set_V(nmfb_handle* h, const float* V_host, int m, int n) {
   drop_V(h);
   const long long ld = round_up(m, 4);
   const size_t bytes = static_cast<size_t>(n) * ld * sizeof(float);
-  NMFB_CUDA(h, cudaMalloc(&h->Vown, bytes));
+  void* vp = nullptr;
+  NMFB_CUDA(h, dev_alloc(h, &vp, bytes));
+  h->Vown = static_cast<float*>(vp);
+  h->Vown_bytes = bytes;
   if (ld != m) NMFB_CUDA(h, cudaMemsetAsync(h->Vown, 0, bytes, h->stream));
   h->Vraw = h->Vown;
   h->m = m;

@@ -22,6 +22,48 @@ inline long long round_up_ll(long long x, long long q) { return (x + q - 1) / q 
 
 struct NmfSession;  // nmf_driver.cu
 
+// Device blocks handed back by finished calls, kept for the next call of the same shape: a
+// factorisation allocates ~4 GiB in a few dozen blocks and cudaMalloc / cudaFree of GiB-sized blocks
+// cost 30-150 ms per call (measured), as much as 100 iterations at the north-star size.  Exact-size
+// reuse only; bounded by `cap` (a third of the device memory; NMFB_NO_POOL=1 disables), trimmed when
+// an allocation fails, and released by nmfb_trim / nmfb_destroy.
+struct BlockPool {
+  struct Blk {
+    void* p;
+    size_t bytes;
+  };
+  std::vector<Blk> blocks;
+  size_t held = 0, cap = 0;
+  void* take(size_t bytes) {
+    for (size_t i = blocks.size(); i-- > 0;)
+      if (blocks[i].bytes == bytes) {
+        void* p = blocks[i].p;
+        blocks.erase(blocks.begin() + static_cast<long>(i));
+        held -= bytes;
+        return p;
+      }
+    return nullptr;
+  }
+  void give(void* p, size_t bytes) {
+    if (bytes > cap) {
+      cudaFree(p);
+      return;
+    }
+    blocks.push_back({p, bytes});
+    held += bytes;
+    while (held > cap && !blocks.empty()) {  // oldest first
+      held -= blocks.front().bytes;
+      cudaFree(blocks.front().p);
+      blocks.erase(blocks.begin());
+    }
+  }
+  void trim() {
+    for (Blk& b : blocks) cudaFree(b.p);
+    blocks.clear();
+    held = 0;
+  }
+};
+
 struct nmfb_handle {
   int device = 0;
   int num_sms = 148;
@@ -35,6 +77,12 @@ struct nmfb_handle {
   // V as given (uploaded copy or adopted device pointer)
   const float* Vraw = nullptr;
   float* Vown = nullptr;
+  size_t Vown_bytes = 0;
+  BlockPool pool;
+  // pinned host scratch, allocated once per handle (cudaMallocHost / cudaFreeHost synchronise the
+  // device and took up to 0.8 s when issued per call next to a large pinned user buffer):
+  // [0..1] session stop flag / cost count, [2..3] run_chunked flags
+  int* pinned = nullptr;
   int m = 0, n = 0;
   long long ldv = 0;
   // working copy (tf32-rounded / rescaled), allocated on demand, same shape as Vraw
@@ -76,21 +124,51 @@ namespace nmfb {
     if (rc__ != NMFB_OK) return rc__; \
   } while (0)
 
-// Device allocations that live as long as one algorithm call / session.
+// cudaMalloc through the handle's block pool (a failed allocation empties the pool and retries)
+inline cudaError_t dev_alloc(nmfb_handle* h, void** p, size_t bytes) {
+  *p = h->pool.take(bytes);
+  if (*p) return cudaSuccess;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess && h->pool.held > 0) {
+    cudaGetLastError();
+    h->pool.trim();
+    e = cudaMalloc(p, bytes);
+  }
+  return e;
+}
+inline void dev_free(nmfb_handle* h, void* p, size_t bytes) {
+  if (p) h->pool.give(p, bytes);
+}
+
+// Device allocations that live as long as one algorithm call / session (zero-filled).
 struct Arena {
-  std::vector<void*> ptrs;
+  struct Blk {
+    void* p;
+    size_t bytes;
+  };
+  std::vector<Blk> blocks;
+  nmfb_handle* owner = nullptr;
   ~Arena() { release(); }
   void release() {
-    for (void* p : ptrs) cudaFree(p);
-    ptrs.clear();
+    if (owner && !blocks.empty()) {  // nothing of this call may still be running when the blocks are reused
+      cudaStreamSynchronize(owner->stream);
+      if (owner->stream2) cudaStreamSynchronize(owner->stream2);
+    }
+    for (Blk& b : blocks) {
+      if (owner) dev_free(owner, b.p, b.bytes);
+      else cudaFree(b.p);
+    }
+    blocks.clear();
   }
   template <class T>
   int alloc(nmfb_handle* h, T** out, size_t count) {
     void* p = nullptr;
-    const size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
-    NMFB_CUDA(h, cudaMalloc(&p, bytes ? bytes : 256));
-    ptrs.push_back(p);
-    NMFB_CUDA(h, cudaMemsetAsync(p, 0, bytes ? bytes : 256, h->stream));
+    size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
+    if (bytes == 0) bytes = 256;
+    owner = h;
+    NMFB_CUDA(h, dev_alloc(h, &p, bytes));
+    blocks.push_back({p, bytes});
+    NMFB_CUDA(h, cudaMemsetAsync(p, 0, bytes, h->stream));
     *out = static_cast<T*>(p);
     return NMFB_OK;
   }
@@ -198,8 +276,7 @@ int run_chunked(nmfb_handle* h, int maxiter, const int* stop_dev, Fn enqueue, in
   for (int b = 0; b < 2 && rc == NMFB_OK; ++b)
     if (cudaEventCreateWithFlags(&evs[b], cudaEventDisableTiming) != cudaSuccess)
       rc = h->fail(NMFB_ERR_CUDA, "cudaEventCreate failed");
-  if (rc == NMFB_OK && cudaMallocHost(&flags, 2 * sizeof(int)) != cudaSuccess)
-    rc = h->fail(NMFB_ERR_CUDA, "cudaMallocHost failed");
+  flags = h->pinned + 2;
   if (rc == NMFB_OK) {
     flags[0] = flags[1] = 0;
     int c = 0, i = 0;
@@ -218,7 +295,7 @@ int run_chunked(nmfb_handle* h, int maxiter, const int* stop_dev, Fn enqueue, in
   }
   for (int b = 0; b < 2; ++b)
     if (evs[b]) cudaEventDestroy(evs[b]);
-  if (flags) cudaFreeHost(flags);
+  cudaStreamSynchronize(h->stream);  // the last flag copy must not land after the scratch is reused
   return rc;
 }
 

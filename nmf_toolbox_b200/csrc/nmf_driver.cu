@@ -287,7 +287,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   }
   NMFB_TRY(ar->alloc(h, &s->cost, static_cast<size_t>(s->maxiter) + 1));
   NMFB_TRY(ar->alloc(h, &s->stop, 2));
-  NMFB_CUDA(h, cudaMallocHost(&s->pinned, 2 * sizeof(int)));
+  s->pinned = h->pinned;
   s->pinned[0] = s->pinned[1] = 0;
 
   // ---- initial factors (nmf.m:130-134; defaults nmf.m:277,298)
@@ -403,7 +403,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
       const size_t need = static_cast<size_t>(m) * ldn * sizeof(float);
       const char* env = std::getenv("NMFB_NO_VT");
       if (!(env && env[0] == '1') && m >= 1024 && n >= 1024 &&
-          cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > need + (size_t(2) << 30)) {
+          cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b + h->pool.held > need + (size_t(2) << 30)) {
         float* Vrm = nullptr;
         NMFB_TRY(ar->alloc(h, &Vrm, static_cast<size_t>(m) * ldn));
         dim3 grid((n + 31) / 32, (m + 31) / 32);
@@ -479,7 +479,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
       const size_t need = static_cast<size_t>(m) * ldn * sizeof(float);
       const char* env = std::getenv("NMFB_KL_UNFUSED");
       if (!(env && env[0] == '1') && Kp <= kKlMaxKp && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess &&
-          free_b > need + (size_t(1) << 30)) {
+          free_b + h->pool.held > need + (size_t(1) << 30)) {
         float* Vrm = nullptr;
         NMFB_TRY(ar->alloc(h, &Vrm, static_cast<size_t>(m) * ldn));
         dim3 grid((n + 31) / 32, (m + 31) / 32);
@@ -909,7 +909,6 @@ static int enqueue_final_cost(nmfb_handle* h, NmfSession* s) {
 
 void nmf_session_release(nmfb_handle* h) {
   if (h->sess) {
-    if (h->sess->pinned) cudaFreeHost(h->sess->pinned);
     delete h->sess;
     h->sess = nullptr;
   }
