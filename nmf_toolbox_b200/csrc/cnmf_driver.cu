@@ -1,5 +1,6 @@
-// cnmf driver: the iteration loop of cnmf.m (lines 175-258), Euclidean /
-// 'frobenius' divergence, in stacked form.
+// cnmf driver: the iteration loop of cnmf.m (lines 175-258) in stacked form.  Euclidean /
+// 'frobenius' run on the Gram path described here; KL, IS and AB (which cnmf.m treats as one
+// alpha-beta family, cnmf.m:137-147) on the two-weight path further down.
 //
 // With Wc = [W_1 ... W_T] (m x KT, which is exactly the column-major memory of
 // the reference's m x K x T tensor) and Hs = [H_1; ...; H_T] (KT x n, H_t = H
@@ -41,6 +42,13 @@ struct CnmfState {
   double vsq = 0.0;
   GramOp gramH, gramW;
   GemmOp gemmA, gemmP;
+  // KL / IS / AB: element-wise weights Qn, Qp of V_hat = Wc Hs (see plan_two_weight in nmf_driver.cu)
+  bool two_weight = false, kl_quirk = false;
+  float *Q = nullptr, *Q2 = nullptr;
+  GemmOp gemmS, gemmRa, gemmRb, gemmPn, gemmPd;
+  float expo = 0.f;
+  double ab_scale = 0.0;
+  int cost_mode = 0;
 };
 
 int zero_async(nmfb_handle* h, void* p, size_t bytes) {
@@ -49,14 +57,15 @@ int zero_async(nmfb_handle* h, void* p, size_t bytes) {
 }
 
 int enqueue_cost(nmfb_handle* h, CnmfState* s, int iter) {
-  if (!s->frobenius) {
+  if (!s->frobenius && !s->two_weight) {
     const int cnt = s->KTp * s->KTp;
     gram_dot_kernel<<<std::min(64, (cnt + 1023) / 1024), 256, 0, h->stream>>>(s->gramW.g32, s->gramH.g32, cnt,
                                                                                s->scal + 4, s->stop);
     NMFB_TRY(check_launch(h, "gram_dot"));
   }
   CostArgs c{};
-  c.mode = s->frobenius ? 3 : 0;  // cnmf.m:239-248 has no 'frobenius' case
+  c.mode = s->two_weight ? s->cost_mode : s->frobenius ? 3 : 0;  // cnmf.m:239-248 has no 'frobenius' case
+  c.ab_scale = s->ab_scale;
   c.iter = iter;
   c.Kp = s->KTp;
   c.GW = s->gramW.g32;
@@ -79,7 +88,49 @@ int enqueue_hstack(nmfb_handle* h, CnmfState* s, const int* stop) {
   return check_launch(h, "hstack");
 }
 
+// KL / IS / AB (cnmf.m:177-233 with alpha, beta from cnmf.m:137-147): both gradients of every frame
+// are contractions with Qn = V^a V_hat^(b-1), Qp = V_hat^(a+b-1) (dual: V^(a-1) V_hat^b, V^(a+b-1)),
+// so with the stacked operands A = Qn Hs', B = Qp Hs' feed the same per-column update as the
+// Euclidean path, and the H gradients are fold(Wc' Qn), fold(Wc' Qp) - except that the KL branch
+// of cnmf.m:221-222 leaves V_pos unshifted.
+int enqueue_iteration_two_weight(nmfb_handle* h, CnmfState* s, int i) {
+  const int* stop = s->stop;
+  if (!s->H_fixed || i == 0) NMFB_TRY(enqueue_hstack(h, s, stop));
+  s->gemmS.L.args.want_cost = i > 0 ? 1 : 0;
+  NMFB_TRY(run_gemm(h, s->gemmS));
+  if (i > 0) NMFB_TRY(enqueue_cost(h, s, i - 1));
+  if (!s->W_fixed) {
+    NMFB_TRY(run_gemm(h, s->gemmRa));
+    NMFB_TRY(run_gemm(h, s->gemmRb));
+    WStepArgs w{};
+    w.mode = WSTEP_EUCLID;
+    w.W = s->Wm;
+    w.Wt = s->Wt;
+    w.A = s->A;
+    w.B = s->B;
+    w.m = s->m;
+    w.ld = s->ldw;
+    w.K = s->K;
+    w.T = s->T;
+    w.cnmf_style = 1;
+    w.wsum = s->wsum;
+    w.lambda = s->lambda_w;
+    w.stop = stop;
+    w.expo = s->expo;
+    NMFB_TRY(launch_w_step(h, w));
+    s->gemmS.L.args.want_cost = 0;
+    NMFB_TRY(run_gemm(h, s->gemmS));  // refreshed V_hat (cnmf.m:204)
+  }
+  NMFB_TRY(run_gemm(h, s->gemmPn));
+  NMFB_TRY(run_gemm(h, s->gemmPd));
+  fold_update_kernel<<<vec_grid(s->n, s->K), 256, 0, h->stream>>>(s->P, s->D, s->Hm, s->K, s->T, s->n, s->ldh,
+                                                                  s->lambda_h, s->H_fixed ? 1 : 0, s->scal, stop,
+                                                                  s->expo, s->kl_quirk ? 1 : 0);
+  return check_launch(h, "fold_update");
+}
+
 int enqueue_iteration(nmfb_handle* h, CnmfState* s, int i) {
+  if (s->two_weight) return enqueue_iteration_two_weight(h, s, i);
   const int* stop = s->stop;
   const int m = s->m;
   if (!s->H_fixed || i == 0) {
@@ -115,6 +166,19 @@ int enqueue_iteration(nmfb_handle* h, CnmfState* s, int i) {
   return check_launch(h, "fold_update");
 }
 
+int cnmf_finish(nmfb_handle* h, CnmfState* s, float* W_out, float* H_out, double* cost_out, int* n_cost) {
+  int flags[2] = {0, 0};
+  NMFB_CUDA(h, cudaMemcpyAsync(flags, s->stop, sizeof(flags), cudaMemcpyDeviceToHost, h->stream));
+  NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  const int nc = flags[1];
+  if (n_cost) *n_cost = nc;
+  if (cost_out && nc > 0)
+    NMFB_CUDA(h, cudaMemcpy(cost_out, s->cost, nc * sizeof(double), cudaMemcpyDeviceToHost));
+  if (W_out) NMFB_TRY(download_colmajor(h, s->Wm, s->ldw, s->m, s->KT, W_out));
+  if (H_out) NMFB_TRY(download_H(h, s->Hm, s->ldh, s->K, s->n, H_out));
+  return NMFB_OK;
+}
+
 int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_in, float* W_out,
              float* H_out, double* cost_out, int* n_cost) {
   if (h->Vraw == nullptr) return h->fail(NMFB_ERR_NO_DATA, "cnmf: call nmfb_set_V first");
@@ -137,10 +201,21 @@ int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_
     case NMFB_DIV_AB:
       if (cfg.alpha == 0 && cfg.beta == 0)  // cnmf.m:133-135
         return h->fail(NMFB_ERR_AB_ZERO, "alpha = 0 and beta = 0 is not supported at this time.");
-      return h->fail(NMFB_ERR_UNSUPPORTED, "cnmf: the AB divergence is outside the accelerated path");
-    case NMFB_DIV_KL:
-    case NMFB_DIV_IS:
-      return h->fail(NMFB_ERR_UNSUPPORTED, "cnmf: only the euclidean / frobenius divergence is accelerated");
+      s->two_weight = true;
+      s->cost_mode = 5;
+      break;
+    case NMFB_DIV_KL:  // cnmf.m:141-143
+      cfg.alpha = 1;
+      cfg.beta = 0;
+      s->two_weight = s->kl_quirk = true;
+      s->cost_mode = 4;
+      break;
+    case NMFB_DIV_IS:  // cnmf.m:144-146
+      cfg.alpha = 1;
+      cfg.beta = -1;
+      s->two_weight = true;
+      s->cost_mode = 4;
+      break;
     default:
       return h->fail(NMFB_ERR_DIVERGENCE, "unknown divergence %d", cfg.divergence);
   }
@@ -215,6 +290,46 @@ int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_
   NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
 
   const int* stop = s->stop;
+  if (s->two_weight) {
+    const bool dual = cfg.alpha == 0;  // cnmf.m:149-153
+    s->expo = static_cast<float>(1.0 / (dual ? cfg.beta : cfg.alpha));
+    s->ab_scale = -1.0 / (cfg.alpha * cfg.beta);
+    NMFB_TRY(ar->alloc(h, &s->Q, static_cast<size_t>(n) * h->ldv));
+    NMFB_TRY(ar->alloc(h, &s->Q2, static_cast<size_t>(n) * h->ldv));
+    MatRef Xs{s->Wt, m, KTp, s->ldw, true};
+    MatRef Ys{s->Hs, n, KTp, s->ldh, true};
+    NMFB_TRY(plan_fused(h, &s->gemmS, EPI_ABQ, Xs, Ys, KTp, nullptr, nullptr, 0, m, round_up(n, 64), n, stop));
+    GemmArgs& q = s->gemmS.L.args;
+    q.Vsrc = h->Vraw;
+    q.Qout = s->Q;
+    q.Qout2 = s->Q2;
+    q.ldv = h->ldv;
+    q.scal = s->scal + 2;
+    q.ab_mode = cfg.divergence == NMFB_DIV_IS ? ABQ_IS : dual ? ABQ_AB_DUAL : ABQ_AB;
+    q.ab_alpha = static_cast<float>(cfg.alpha);
+    q.ab_beta = static_cast<float>(cfg.beta);
+    q.ab_cost_kl = cfg.divergence == NMFB_DIV_KL ? 1 : 0;
+    std::string pe = set_v_prefetch(&s->gemmS.L, h->Vraw, m, n, h->ldv);
+    if (!pe.empty()) return h->fail(NMFB_ERR_CUDA, "%s", pe.c_str());
+    MatRef Yh{s->Hs, n, KTp, s->ldh, false};
+    MatRef Xn{s->Q, m, n, h->ldv, true}, Xp{s->Q2, m, n, h->ldv, true};
+    const int tiles = (m + kTileM - 1) / kTileM * ((KTp + kMaxN - 1) / kMaxN);
+    const bool split = tiles * 2 <= h->num_sms;
+    NMFB_TRY(plan_store(h, ar, &s->gemmRa, Xn, Yh, n, nullptr, nullptr, 0, m, KTp, s->A, nullptr, s->ldw, split, stop));
+    NMFB_TRY(plan_store(h, ar, &s->gemmRb, Xp, Yh, n, nullptr, nullptr, 0, m, KTp, s->B, nullptr, s->ldw, split, stop));
+    MatRef Yw{s->Wt, m, KTp, s->ldw, false};
+    MatRef Xnt{s->Q, m, n, h->ldv, false}, Xpt{s->Q2, m, n, h->ldv, false};
+    const int tiles_h = (n + kTileM - 1) / kTileM * ((KTp + kMaxN - 1) / kMaxN);
+    const bool split_h = tiles_h * 2 <= h->num_sms;
+    NMFB_TRY(plan_store(h, ar, &s->gemmPn, Xnt, Yw, m, nullptr, nullptr, 0, n, KTp, s->P, nullptr, s->ldh, split_h, stop));
+    NMFB_TRY(plan_store(h, ar, &s->gemmPd, Xpt, Yw, m, nullptr, nullptr, 0, n, KTp, s->D, nullptr, s->ldh, split_h, stop));
+    NMFB_TRY(run_chunked(h, s->maxiter, s->stop, [&](int i) { return enqueue_iteration(h, s, i); }));
+    NMFB_TRY(enqueue_hstack(h, s, stop));
+    s->gemmS.L.args.want_cost = 1;
+    NMFB_TRY(run_gemm(h, s->gemmS));
+    NMFB_TRY(enqueue_cost(h, s, s->maxiter - 1));
+    return cnmf_finish(h, s, W_out, H_out, cost_out, n_cost);
+  }
   NMFB_TRY(plan_gram(h, ar, &s->gramW, s->Wt, KTp, m, s->ldw, stop));
   NMFB_TRY(plan_gram(h, ar, &s->gramH, s->Hs, KTp, n, s->ldh, stop));
   {
@@ -241,16 +356,7 @@ int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_
   NMFB_TRY(enqueue_hstack(h, s, stop));
   NMFB_TRY(run_gram(h, s->gramH, stop));
   NMFB_TRY(enqueue_cost(h, s, s->maxiter - 1));
-  int flags[2] = {0, 0};
-  NMFB_CUDA(h, cudaMemcpyAsync(flags, s->stop, sizeof(flags), cudaMemcpyDeviceToHost, h->stream));
-  NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
-  const int nc = flags[1];
-  if (n_cost) *n_cost = nc;
-  if (cost_out && nc > 0)
-    NMFB_CUDA(h, cudaMemcpy(cost_out, s->cost, nc * sizeof(double), cudaMemcpyDeviceToHost));
-  if (W_out) NMFB_TRY(download_colmajor(h, s->Wm, s->ldw, m, KT, W_out));
-  if (H_out) NMFB_TRY(download_H(h, s->Hm, s->ldh, K, n, H_out));
-  return NMFB_OK;
+  return cnmf_finish(h, s, W_out, H_out, cost_out, n_cost);
 }
 
 }  // namespace cnmfdetail

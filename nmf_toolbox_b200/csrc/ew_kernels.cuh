@@ -719,19 +719,28 @@ __global__ void hstack_kernel(const float* __restrict__ H, float* __restrict__ H
 // H <- H .* neg ./ max(pos + lambda, eps) (cnmf.m:231); scal[0] += <neg, tf32(Hnew)>, scal[1] += sum Hnew
 __global__ void fold_update_kernel(const float* __restrict__ P, const float* __restrict__ D,
                                    float* __restrict__ H, int K, int T, int n, long long ld,
-                                   float lambda, int freeze, double* scal, const int* stop) {
+                                   float lambda, int freeze, double* scal, const int* stop,
+                                   float expo = 0.f, int pos_unshifted = 0) {
+  // expo: outer exponent of both gradients (AB divergence, cnmf.m:229-232); pos_unshifted: the KL
+  // branch of cnmf.m:221-222 does not shift V_pos
   NMFB_STOP_GUARD(stop);
   __shared__ double sh[64];
   const int k = blockIdx.y;
   double acc[2] = {0.0, 0.0};
+  const bool powered = expo != 0.f && expo != 1.f;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     float neg = 0.f, pos = 0.f;
     for (int t = 0; t < T; ++t) {
       if (j + t < n) {
         const long long o = static_cast<long long>(k + K * t) * ld + j + t;
         neg += P[o];
-        pos += D[o];
+        if (!pos_unshifted) pos += D[o];
       }
+      if (pos_unshifted) pos += D[static_cast<long long>(k + K * t) * ld + j];
+    }
+    if (powered) {
+      neg = powf(neg, expo);
+      pos = powf(pos, expo);
     }
     float h = H[k * ld + j];
     if (!freeze) {

@@ -113,6 +113,7 @@ struct GemmArgs {
   float* Qout;        // EPI_KLQ: Q; EPI_RECON: V_hat; EPI_ABQ: Qn
   float* Qout2;       // EPI_ABQ: Qp
   int ab_mode;        // EPI_ABQ: ABQ_IS / ABQ_AB / ABQ_AB_DUAL (alpha == 0, nmf.m:124-128)
+  int ab_cost_kl;     // EPI_ABQ: the summed divergence is KL's (cnmf.m:243 reaches KL as alpha = 1, beta = 0)
   float ab_alpha, ab_beta;
   long long ldv;
   int want_cost;
@@ -154,9 +155,13 @@ __device__ __forceinline__ void abq_group_mode(const GemmArgs& a, const float (&
         auto term = [](float c, float l) { return c == 0.f ? 0.f : c * l; };
         qn = fast_ex2(term(c0, lv) + term(c1, ls));
         qp = fast_ex2(term(c2, lv) + term(c3, ls));
-        if (a.want_cost)     // nmf.m:214 (the prefactor is applied by the cost kernel)
-          s0 += fast_ex2(term(al, lv) + term(be, ls)) -
-                (al * fast_ex2(term(al + be, lv)) + be * fast_ex2(term(al + be, ls)) + be) * rs;
+        if (a.want_cost) {
+          if (a.ab_cost_kl)  // cnmf.m:243
+            s0 += vv * 0.6931471805599453f * (lv - ls) - vv + sv;
+          else               // nmf.m:214 (the prefactor is applied by the cost kernel)
+            s0 += fast_ex2(term(al, lv) + term(be, ls)) -
+                  (al * fast_ex2(term(al + be, lv)) + be * fast_ex2(term(al + be, ls)) + be) * rs;
+        }
       }
       qn_out[t * ldv] = tf32_rn(qn);
       qp_out[t * ldv] = tf32_rn(qp);

@@ -223,9 +223,9 @@ def test_errors(api, handle):
     with pytest.raises(api.NmfbError) as e:  # nmfsc.m:57-59
         api.nmfsc(-V, 2, dict(maxiter=2), handle=handle)
     assert e.value.code == 6 and "Negative values in data!" in str(e.value)
-    with pytest.raises(api.NmfbError) as e:  # cnmf.m:179-185: IS / AB exist only for nmf in this build
-        api.cnmf(V, 2, 2, dict(divergence="is"), handle=handle)
-    assert e.value.code == 3
+    with pytest.raises(api.NmfbError) as e:  # cnmf.m:133-135
+        api.cnmf(V, 2, 2, dict(divergence="ab", alpha=0, beta=0), handle=handle)
+    assert e.value.code == 5
 
 
 # ---------------------------------------------------------------- nmf, IS and AB divergences
@@ -334,6 +334,24 @@ def test_cnmf_vs_oracle(api, handle, m, n, K, T, iters, lw, lh):
     V = np.maximum(rng.random((m, n)), 2.0 ** -24)
     cfg = dict(divergence="euclidean", W_init=rng.random((m, K, T)), H_init=np.maximum(rng.random((K, n)), O.EPS),
                W_sparsity=lw, H_sparsity=lh, maxiter=iters, tolerance=1e-300)
+    W, H, c = api.cnmf(V, K, T, cfg, handle=handle)
+    Wo, Ho, co = O.cnmf(V, K, T, cfg)
+    assert W.shape == (m, K, T)
+    assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
+
+
+@pytest.mark.parametrize("div,alpha,beta", [("kl", 1, 1), ("is", 1, 1), ("ab", 0.5, 0.5), ("ab", 2, 1), ("ab", 1, 1),
+                                            ("kl_divergence", 1, 1)])
+@pytest.mark.parametrize("m,n,K,T,iters,lw,lh", [(129, 700, 8, 4, 40, 0, 0), (200, 500, 6, 5, 30, 0.05, 0.1),
+                                                  (513, 1000, 64, 8, 15, 0, 0)])
+def test_cnmf_kl_is_ab_vs_oracle(api, handle, div, alpha, beta, m, n, K, T, iters, lw, lh):
+    """cnmf.m:137-147,177-233: KL / IS / AB as one alpha-beta family (with the unshifted V_pos of the
+    KL branch, cnmf.m:221-222)."""
+    rng = np.random.default_rng(m + T)
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    cfg = dict(divergence=div, alpha=alpha, beta=beta, W_init=rng.random((m, K, T)) + 1e-3,
+               H_init=np.maximum(rng.random((K, n)), O.EPS), W_sparsity=lw, H_sparsity=lh, maxiter=iters,
+               tolerance=1e-300)
     W, H, c = api.cnmf(V, K, T, cfg, handle=handle)
     Wo, Ho, co = O.cnmf(V, K, T, cfg)
     assert W.shape == (m, K, T)
