@@ -58,8 +58,8 @@ typedef enum nmfb_divergence {
                               euclidean but the reference's cost switch has no such
                               case, so cost = sparsity terms only (cnmf.m:239-251).
                               nmf.m rejects it (NMFB_ERR_DIVERGENCE).                */
-  NMFB_DIV_IS = 3,         /* 'is_divergence' | 'is'  nmf.m:154-156,185-187,211-212 (nmfb_nmf and
-                              nmfb_cnmf, cnmf.m:144-146; one GPU)                     */
+  NMFB_DIV_IS = 3,         /* 'is_divergence' | 'is'  nmf.m:154-156,185-187,211-212 (nmfb_nmf, also
+                              column-sharded; nmfb_cnmf, cnmf.m:144-146)              */
   NMFB_DIV_AB = 4          /* 'ab_divergence' | 'ab'  nmf.m:157-164,188-195,213-214 with config
                               alpha, beta; alpha == 0 selects the dual updates
                               (nmf.m:124-128); same availability as NMFB_DIV_IS       */

@@ -185,8 +185,6 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
         return h->fail(NMFB_ERR_AB_ZERO, "alpha = 0 and beta = 0 is not supported at this time.");
       [[fallthrough]];
     case NMFB_DIV_IS:
-      if (comm_size(h->comm) > 1)
-        return h->fail(NMFB_ERR_UNSUPPORTED, "nmf: the IS / AB divergences run on one GPU only");
       break;
     default:  // nmf.m:165-166 ('frobenius' included: nmf.m has no such case)
       return h->fail(NMFB_ERR_DIVERGENCE,
@@ -247,7 +245,9 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   // With several GPUs the doubles that travel with it (hs, scal) and the barrier flags of the
   // peer-memory all-reduce live behind it in the SAME allocation, owned by the communicator and
   // mapped into the other ranks (comm_acquire_region).
-  const size_t packed_floats = static_cast<size_t>(Kp) * s->ldw + static_cast<size_t>(Kp) * Kp;
+  // (IS / AB: [A | B], both W-step matrices are sums over the column shards)
+  const size_t packed_floats =
+      static_cast<size_t>(Kp) * s->ldw + (tw ? static_cast<size_t>(Kp) * s->ldw : static_cast<size_t>(Kp) * Kp);
   const bool share = comm_size(h->comm) > 1;
   const size_t dbl_off = (packed_floats * sizeof(float) + 255) / 256 * 256;
   if (share) {
@@ -261,7 +261,8 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     NMFB_TRY(ar->alloc(h, &s->packed, packed_floats));
   }
   s->A = s->packed;
-  NMFB_TRY(ar->alloc(h, &s->B, static_cast<size_t>(Kp) * s->ldw));
+  if (tw) s->B = s->packed + static_cast<size_t>(Kp) * s->ldw;
+  else NMFB_TRY(ar->alloc(h, &s->B, static_cast<size_t>(Kp) * s->ldw));
   NMFB_TRY(ar->alloc(h, &s->pcoef, Kp));
   NMFB_TRY(ar->alloc(h, &s->qcoef, Kp));
   NMFB_TRY(ar->alloc(h, &s->bvec, Kp));
@@ -699,12 +700,19 @@ extern "C" int nmfb_profile_get(nmfb_handle* h, double* ms_w, double* ms_h, int*
 static int enqueue_iteration_two_weight(nmfb_handle* h, NmfSession* s, int i) {
   const int K = s->K, n = s->n;
   const int cost_mode = s->divergence == NMFB_DIV_IS ? 4 : 5;
+  const bool multi = comm_size(h->comm) > 1;
   s->gemmS.L.args.want_cost = i > 0 ? 1 : 0;
   NMFB_TRY(run_gemm(h, s->gemmS));  // weights from the current V_hat (+ divergence of iteration i-1)
-  if (i > 0) NMFB_TRY(enqueue_cost(h, s, i - 1, cost_mode));
   if (!s->W_fixed) {
     NMFB_TRY(run_gemm(h, s->gemmR));
     NMFB_TRY(run_gemm(h, s->gemmRb));
+  }
+  if (multi) {  // column shards: A, B and the cost sums are partial (one all-reduce, as for euclidean / KL)
+    if (s->W_fixed) return h->fail(NMFB_ERR_UNSUPPORTED, "W_fixed with several GPUs");
+    NMFB_TRY(comm_allreduce(h, s->packed, 2 * static_cast<size_t>(s->Kp) * s->ldw, nullptr, 0, s->scal, 4));
+  }
+  if (i > 0) NMFB_TRY(enqueue_cost(h, s, i - 1, cost_mode));
+  if (!s->W_fixed) {
     WStepArgs w{};
     w.mode = WSTEP_EUCLID;  // same shape: neg = A + W diag(<W,B>), pos = B + W diag(<W,A>)
     w.W = s->Wm;
@@ -881,6 +889,7 @@ static int enqueue_final_cost(nmfb_handle* h, NmfSession* s) {
   if (s->two_weight) {
     s->gemmS.L.args.want_cost = 1;
     NMFB_TRY(run_gemm(h, s->gemmS));
+    if (multi) NMFB_TRY(comm_allreduce(h, nullptr, 0, nullptr, 0, s->scal, 4));
     return enqueue_cost(h, s, last, s->divergence == NMFB_DIV_IS ? 4 : 5);
   }
   if (s->divergence == NMFB_DIV_EUCLIDEAN) {

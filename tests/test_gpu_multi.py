@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("div", ["euclidean", "kl"])
+@pytest.mark.parametrize("div", ["euclidean", "kl", "is"])
 def test_two_gpu_matches_single_and_oracle(div, tmp_path):
     import torch
 
