@@ -124,6 +124,15 @@ int nmfb_set_V_device(nmfb_handle* h, const float* V_dev, int m, int n, long lon
  * reference's trimmed cost vector (nmf.m:222).  Outputs may be NULL. */
 int nmfb_nmf(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, float* H_out,
              double* cost_out, int* n_cost);
+/* [W, H, cost] = lnmf(V, num_basis_elems, config)  (lnmf.m:1).
+ * KL-type updates with unit-sum bases and H <- sqrt(H .* W'(V./V_hat)) (lnmf.m:63-83) on the fused
+ * KL kernels (num_basis_elems <= 128, one GPU).  config: W_init, H_init, W_fixed, H_fixed, maxiter,
+ * tolerance (divergence and sparsity fields are ignored: lnmf.m has none).  As in the reference the
+ * cost vector is NOT trimmed when the loop stops early (lnmf.m:88-90): *n_cost == maxiter, entries
+ * after the stopping iteration are 0. */
+int nmfb_lnmf(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, float* H_out, double* cost_out,
+              int* n_cost);
+
 /* W_out: m*K*T floats (m x K x T column-major). */
 int nmfb_cnmf(nmfb_handle* h, int K, int T, const nmfb_config* cfg, float* W_out, float* H_out,
               double* cost_out, int* n_cost);

@@ -154,6 +154,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     std::vector<double> cost(maxiter + 1);
     int ncost = 0;
     if (cmd == "nmf") check(nmfb_nmf(h, K, &c, W.data(), H.data(), cost.data(), &ncost));
+    else if (cmd == "lnmf") check(nmfb_lnmf(h, K, &c, W.data(), H.data(), cost.data(), &ncost));
     else if (conv) check(nmfb_cnmf(h, K, T, &c, W.data(), H.data(), cost.data(), &ncost));
     else check(nmfb_nmfsc(h, K, &c, W.data(), H.data(), cost.data(), &ncost));
     plhs[0] = from_single(W, m, K, T);

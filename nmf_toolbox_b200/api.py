@@ -88,6 +88,7 @@ def _bind(lib):
         "nmfb_set_V": ([P, P, I, I], I),
         "nmfb_set_V_device": ([P, P, I, I, LL], I),
         "nmfb_nmf": ([P, I, ctypes.POINTER(_Config), P, P, P, PI], I),
+        "nmfb_lnmf": ([P, I, ctypes.POINTER(_Config), P, P, P, PI], I),
         "nmfb_cnmf": ([P, I, I, ctypes.POINTER(_Config), P, P, P, PI], I),
         "nmfb_nmfsc": ([P, I, ctypes.POINTER(_Config), P, P, P, PI], I),
         "nmfb_reconstruct": ([P, P, P, I, I, I, I, P], I),
@@ -255,6 +256,17 @@ class Handle:
         del keep
         return W, H, cost[: nc.value].copy()
 
+    def lnmf(self, K: int, config=None):
+        m, n = self.shape
+        c, keep, maxiter = self._config(dict(config or {}, divergence="kl"), m, n, K)
+        W = np.empty((m, K), dtype=np.float32, order="F")
+        H = np.empty((K, n), dtype=np.float32, order="F")
+        cost = np.zeros(maxiter, dtype=np.float64)
+        nc = ctypes.c_int(0)
+        self._check(self.lib.nmfb_lnmf(self._h, K, ctypes.byref(c), _ptr(W), _ptr(H), _ptr(cost), ctypes.byref(nc)))
+        del keep
+        return W, H, cost[: nc.value].copy()
+
     def cnmf(self, K: int, T: int, config=None):
         m, n = self.shape
         c, keep, maxiter = self._config(config, m, n, K, T)
@@ -399,6 +411,13 @@ def nmf(V, num_basis_elems, config=None, handle: Optional[Handle] = None):
             return W, H, cost
         return _split(W, sizes, 1), _split(H, sizes, 0), cost
     return h.nmf(int(num_basis_elems), config)
+
+
+def lnmf(V, num_basis_elems, config=None, handle: Optional[Handle] = None):
+    """``[W, H, cost] = lnmf(V, num_basis_elems, config)`` (lnmf.m:1)."""
+    h = handle or default_handle()
+    h.set_V(V)
+    return h.lnmf(int(num_basis_elems), config)
 
 
 def cnmf(V, num_basis_elems, context_len, config=None, handle: Optional[Handle] = None):

@@ -255,7 +255,8 @@ __global__ void w_dots_kernel(const float* __restrict__ W, const float* __restri
 //   W' = W .* (A + W*p_c) ./ max(Bterm + W*q_c + lambda, eps)
 // Euclidean (nmf.m:149-150): p = <W_c,B_c>, q = <W_c,A_c>, Bterm = B
 // KL        (nmf.m:152-153): p = hs_c*ws_c, q = <W_c,R_c>, Bterm = hs_c
-enum { WSTEP_EUCLID = 0, WSTEP_KL = 1, WSTEP_PLAIN = 2 };
+// LNMF      (lnmf.m:74-75):  W' = W .* R ./ max(hs_c, eps), then unit column SUM instead of unit L2
+enum { WSTEP_EUCLID = 0, WSTEP_KL = 1, WSTEP_PLAIN = 2, WSTEP_LNMF = 3 };
 __global__ void w_coef_kernel(int mode, int Kp, const double* ab, const double* hs, const double* ws,
                               float* p, float* q, float* bvec, const int* stop) {
   NMFB_STOP_GUARD(stop);
@@ -337,7 +338,8 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
   __shared__ double bc[4];
   const int k = blockIdx.x;
   const int tid = threadIdx.x;
-  const bool kl = a.mode == WSTEP_KL;
+  const bool lnmf = a.mode == WSTEP_LNMF;
+  const bool kl = a.mode == WSTEP_KL || lnmf;  // no B matrix
   const int total = a.T * a.m;  // elements of this basis
   if (a.fixed_k != nullptr && a.fixed_k[k] != 0) return;  // basis of a fixed source: untouched, not renormalised
   const float lambda = a.lambda_k != nullptr ? a.lambda_k[k] : a.lambda;
@@ -378,7 +380,11 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
     }
     __syncthreads();
     float pc, qc, bterm = 0.f;
-    if (kl) {  // nmf.m:152-153
+    if (lnmf) {  // lnmf.m:74
+      pc = 0.f;
+      qc = 0.f;
+      bterm = static_cast<float>(a.hs[c]);
+    } else if (kl) {  // nmf.m:152-153
       pc = static_cast<float>(a.hs[c] * a.wsum[c]);
       qc = static_cast<float>(bc[0]);
       bterm = static_cast<float>(a.hs[c]);
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
         }
         const float wn = (tid + q * kWThreads < a.m) ? w * (neg / fmaxf(pos + lambda, NMFB_EPS)) : 0.f;
         wv[q] = wn;
-        s2 = fmaf(wn, wn, s2);
+        s2 = lnmf ? s2 + wn : fmaf(wn, wn, s2);
       }
     } else {
       for (int i = tid; i < a.m; i += kWThreads) {
@@ -414,7 +420,7 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
         }
         const float wn = w * (neg / fmaxf(pos + lambda, NMFB_EPS));
         a.W[off + i] = wn;
-        s2 = fmaf(wn, wn, s2);
+        s2 = lnmf ? s2 + wn : fmaf(wn, wn, s2);
       }
     }
     acc[0] = s2;
@@ -425,7 +431,7 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
     norm_basis += bc[2];
     if (!a.cnmf_style) {
       // ---- 3 (nmf): unit L2 column, tf32 copy, column sum
-      const float mul = static_cast<float>(1.0 / sqrt(bc[2]));
+      const float mul = static_cast<float>(lnmf ? 1.0 / bc[2] : 1.0 / sqrt(bc[2]));  // lnmf.m:75 / nmf.m:169
       float s3 = 0.f;
       if (CACHED) {
 #pragma unroll
@@ -505,11 +511,15 @@ __global__ void w_normalize_kernel(float* __restrict__ W, float* __restrict__ Wt
     } else {
       mul = static_cast<float>(1.0 / sqrt(norm2[c]));
     }
+    if (cnmf_style == 2) {  // lnmf.m:63: norm2 holds the column SUM
+      div = 1.f;
+      mul = static_cast<float>(1.0 / norm2[c]);
+    }
   }
   double acc[1] = {0.0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     float w = W[off + i];
-    if (T >= 1) w = cnmf_style ? (w / div) : (w * mul);
+    if (T >= 1) w = (cnmf_style == 1) ? (w / div) : (w * mul);
     W[off + i] = w;
     Wt[off + i] = tf32_rn(w);
     acc[0] += w;
@@ -556,6 +566,7 @@ struct CostArgs {
   double* scal;         // [0] <N,H> [1] sum H [2],[3] cost-epilogue sums [4] <G_W,G_H>; reset here
   const double* wsum;   // per-column sums of W (Kp_w entries)
   int n_wsum;
+  int stop_le;          // lnmf.m:88: stop if cost <= previous and the decrease <= tolerance
   const float* lamw_k;  // optional per-basis lambda_W: the W term is sum_k lamw_k[k] wsum[k] and the
                         // H-step kernels have already weighted scal[1] (host passes lambda_w = lambda_h = 1)
   double lambda_w, lambda_h;
@@ -590,7 +601,8 @@ __global__ void cost_kernel(CostArgs a) {
   a.stop[1] = a.iter + 1;
   if (a.iter > 0) {
     const double prev = a.cost[a.iter - 1];
-    if (c < prev && prev - c < a.tolerance) a.stop[0] = 1;  // nmf.m:221-224
+    if (a.stop_le ? (c <= prev && prev - c <= a.tolerance) : (c < prev && prev - c < a.tolerance))
+      a.stop[0] = 1;  // nmf.m:221-224 / lnmf.m:88
   }
   a.scal[0] = a.scal[1] = a.scal[2] = a.scal[3] = a.scal[4] = 0.0;
 }

@@ -131,7 +131,8 @@ int run_resid(nmfb_handle* h, const ResidOp& op) {
 __global__ void kl_h_finish_kernel(const float* __restrict__ parts, int splits, long long slab, long long ldo,
                                    float* __restrict__ Hm, float* __restrict__ Ht, long long ldh,
                                    const float* __restrict__ ws, float lambda, int n, int freeze, double* scal,
-                                   const int* stop, const float* lambda_k = nullptr, const int* fixed_k = nullptr) {
+                                   const int* stop, const float* lambda_k = nullptr, const int* fixed_k = nullptr,
+                                   int lnmf = 0) {
   NMFB_STOP_GUARD(stop);
   __shared__ double sh[32];
   const int k = blockIdx.y;
@@ -145,7 +146,7 @@ __global__ void kl_h_finish_kernel(const float* __restrict__ parts, int splits, 
     for (int z = 0; z < splits; ++z) nv += parts[z * slab + k * ldo + j];
     float hv = Hm[k * ldh + j];
     if (!freeze) {
-      hv = hv * (nv / den);
+      hv = lnmf ? sqrtf(hv * nv) : hv * (nv / den);  // lnmf.m:81 / nmf.m:183-184,199
       Hm[k * ldh + j] = hv;
       Ht[k * ldh + j] = tf32_rn(hv);
     }

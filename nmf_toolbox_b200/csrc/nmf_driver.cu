@@ -68,6 +68,7 @@ struct NmfSession {
   GemmOp gemmA, gemmB, gemmH, gemmS, gemmR;
   // IS / AB divergences ("two-weight" updates: both gradients are contractions with an element-wise
   // function of V and V_hat, nmf.m:154-164,185-195)
+  bool lnmf = false;     // lnmf.m: KL-type updates with unit-sum bases and a square-root H step
   bool two_weight = false;
   float* Q2 = nullptr;   // Qp next to Q = Qn
   GemmOp gemmRb, gemmHn, gemmHd;
@@ -171,11 +172,19 @@ static int plan_two_weight(nmfb_handle* h, NmfSession* s, const nmfb_config& cfg
 }
 
 // ------------------------------------------------------------------ setup
-static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cfg_in) {
+static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cfg_in, bool lnmf = false) {
   if (h->Vraw == nullptr) return h->fail(NMFB_ERR_NO_DATA, "nmf: call nmfb_set_V first");
   if (K <= 0) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "nmf: num_basis_elems must be positive");
   nmfb_config cfg;
   normalize_defaults(cfg_in, &cfg);
+  s->lnmf = lnmf;
+  if (lnmf) {  // lnmf.m has no divergence / sparsity options (lnmf.m:95-135)
+    cfg.divergence = NMFB_DIV_KL;
+    cfg.W_sparsity = cfg.H_sparsity = 0;
+    cfg.W_sparsity_k = cfg.H_sparsity_k = nullptr;
+    cfg.W_fixed_k = cfg.H_fixed_k = nullptr;
+    if (comm_size(h->comm) > 1) return h->fail(NMFB_ERR_UNSUPPORTED, "lnmf: one GPU only");
+  }
   switch (cfg.divergence) {
     case NMFB_DIV_EUCLIDEAN:
     case NMFB_DIV_KL:
@@ -312,9 +321,11 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   // W columns -> unit L2 (also for a user-supplied W_init, nmf.m:133); H is not rescaled
-  vec_sums_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, K, m, s->ldw, nullptr, s->norm2, nullptr);
+  // (lnmf.m:63: unit column SUM instead)
+  vec_sums_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, K, m, s->ldw, lnmf ? s->norm2 : nullptr,
+                                                         lnmf ? nullptr : s->norm2, nullptr);
   NMFB_TRY(check_launch(h, "vec_sums(W init)"));
-  w_normalize_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, s->Wt, m, s->ldw, K, 1, 0, s->norm2,
+  w_normalize_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, s->Wt, m, s->ldw, K, 1, lnmf ? 2 : 0, s->norm2,
                                                             s->wsum, nullptr, nullptr);
   NMFB_TRY(check_launch(h, "w_normalize(init)"));
   round_copy_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, s->Ht, K, n, s->ldh, nullptr);
@@ -492,6 +503,8 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
         s->kl_fused = true;
       }
     }
+    if (!s->kl_fused && s->lnmf)
+      return h->fail(NMFB_ERR_UNSUPPORTED, "lnmf needs the fused KL kernel (num_basis_elems <= 128)");
     if (!s->kl_fused && s->per_basis)
       return h->fail(NMFB_ERR_UNSUPPORTED, "per-source settings with the unfused KL path (K > 128)");
     if (!s->kl_fused) {
@@ -569,6 +582,7 @@ static int enqueue_cost(nmfb_handle* h, NmfSession* s, int iter, int mode) {
   c.cost = s->cost;
   c.stop = s->stop;
   c.ab_scale = s->ab_scale;
+  c.stop_le = s->lnmf ? 1 : 0;
   cost_kernel<<<1, 256, 0, h->stream>>>(c);
   return check_launch(h, "cost");
 }
@@ -856,7 +870,7 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
     NMFB_TRY(allreduce_w_inputs(h, s, false));
     if (i > 0) NMFB_TRY(enqueue_cost(h, s, i - 1, 2));
     if (!s->W_fixed) {
-      NMFB_TRY(enqueue_w_finish(h, s, WSTEP_KL));
+      NMFB_TRY(enqueue_w_finish(h, s, s->lnmf ? WSTEP_LNMF : WSTEP_KL));
       D2FArgs da{s->wsum, s->wsf, Kp};
       d2f_kernel<<<(Kp + 127) / 128, 128, 0, h->stream>>>(da, stop);
       NMFB_TRY(check_launch(h, "d2f(ws)"));
@@ -871,7 +885,7 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
       kl_h_finish_kernel<<<dim3(std::max(1, std::min(64, (n + 1023) / 1024)), K), 256, 0, h->stream>>>(s->klH.parts, s->klH.splits, s->klH.args.slab,
                                                                 s->klH.args.ldo, s->Hm, s->Ht, s->ldh, s->wsf,
                                                                 s->lambda_h, n, s->H_fixed ? 1 : 0, s->scal, stop,
-                                                                s->lamH_k, s->fixH_k);
+                                                                s->lamH_k, s->fixH_k, s->lnmf ? 1 : 0);
       NMFB_TRY(check_launch(h, "kl_h_finish"));
     } else {
       NMFB_TRY(run_gemm(h, s->gemmH));
@@ -924,18 +938,21 @@ void nmf_session_release(nmfb_handle* h) {
 }
 
 // ------------------------------------------------------------------ C ABI
-extern "C" int nmfb_nmf_begin(nmfb_handle* h, int K, const nmfb_config* cfg) {
+static int nmf_begin_impl(nmfb_handle* h, int K, const nmfb_config* cfg, bool lnmf) {
   if (!h) return NMFB_ERR_INVALID_ARGUMENT;
   cudaSetDevice(h->device);
   nmf_session_release(h);
   h->sess = new NmfSession();
-  int rc = nmf_setup(h, h->sess, K, cfg);
+  int rc = nmf_setup(h, h->sess, K, cfg, lnmf);
   if (rc == NMFB_OK) {
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) rc = h->fail(NMFB_ERR_CUDA, "nmf setup: %s", cudaGetErrorString(e));
   }
   if (rc != NMFB_OK) nmf_session_release(h);
   return rc;
+}
+extern "C" int nmfb_nmf_begin(nmfb_handle* h, int K, const nmfb_config* cfg) {
+  return nmf_begin_impl(h, K, cfg, false);
 }
 
 extern "C" int nmfb_nmf_step(nmfb_handle* h, int iters) {
@@ -978,7 +995,8 @@ extern "C" int nmfb_nmf_end(nmfb_handle* h, float* W_out, float* H_out, double* 
     if (e != cudaSuccess) rc = h->fail(NMFB_ERR_CUDA, "nmf_end: %s", cudaGetErrorString(e));
   }
   if (rc == NMFB_OK) {
-    const int nc = s->pinned[1];
+    // lnmf.m:88-91 leaves the loop WITHOUT trimming: cost keeps maxiter entries, zeros after the stop
+    const int nc = s->lnmf ? s->maxiter : s->pinned[1];
     if (n_cost) *n_cost = nc;
     if (cost_out && nc > 0) {
       cudaError_t e = cudaMemcpy(cost_out, s->cost, nc * sizeof(double), cudaMemcpyDeviceToHost);
@@ -997,11 +1015,11 @@ static double now_ms() {
   return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
-extern "C" int nmfb_nmf(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, float* H_out,
-                        double* cost_out, int* n_cost) {
+static int nmf_call(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, float* H_out, double* cost_out,
+                    int* n_cost, bool lnmf) {
   const bool trace = std::getenv("NMFB_TRACE") != nullptr;
   const double t0 = now_ms();
-  NMFB_TRY(nmfb_nmf_begin(h, K, cfg));
+  NMFB_TRY(nmf_begin_impl(h, K, cfg, lnmf));
   const double t1 = now_ms();
   NmfSession* s = h->sess;
   int rc = run_chunked(h, s->maxiter, s->stop, [&](int i) {
@@ -1024,4 +1042,16 @@ extern "C" int nmfb_nmf(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_
     fprintf(stderr, "[nmfb] nmf: setup %.1f ms, enqueue %.1f ms, drain %.1f ms, finish %.1f ms\n", t1 - t0, t2 - t1,
             t3 - t2, now_ms() - t3);
   return rc;
+}
+
+extern "C" int nmfb_nmf(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, float* H_out,
+                        double* cost_out, int* n_cost) {
+  return nmf_call(h, K, cfg, W_out, H_out, cost_out, n_cost, false);
+}
+
+// lnmf.m:1 - local NMF: KL-type multiplicative updates with unit-sum bases (lnmf.m:63,75) and the
+// square-root H step (lnmf.m:81), on the fused KL kernels.
+extern "C" int nmfb_lnmf(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, float* H_out,
+                         double* cost_out, int* n_cost) {
+  return nmf_call(h, K, cfg, W_out, H_out, cost_out, n_cost, true);
 }

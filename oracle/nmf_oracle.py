@@ -441,6 +441,50 @@ def cnmf(V, num_basis_elems, context_len, config=None, rng=None):
 
 
 # --------------------------------------------------------------------------
+# lnmf.m:47-93 (SURVEY section 8f item 4)
+# --------------------------------------------------------------------------
+def lnmf(V, num_basis_elems, config=None, rng=None):
+    """[W, H, cost] = lnmf(V, num_basis_elems, config): local NMF, lnmf.m:47-93.
+
+    Quirks kept: W columns have unit SUM (lines 63, 75); the loop is left without trimming `cost`
+    (lines 88-90), so the returned vector always has maxiter entries (zeros after the stop); the
+    stop test uses <= twice."""
+    V = np.asarray(V, dtype=np.float64)
+    m, n = V.shape
+    cfg = dict(config or {})
+    rng = rng or np.random.default_rng()
+    K = int(num_basis_elems)
+    H = cfg.get("H_init")
+    H = np.fmax(rng.random((K, n)), EPS) if H is None or np.size(H) == 0 else np.array(H, dtype=np.float64)  # lnmf.m:103-105
+    W = cfg.get("W_init")
+    if W is None or np.size(W) == 0:  # lnmf.m:107-110
+        W = np.fmax(rng.random((m, K)), EPS)
+    W = np.array(W, dtype=np.float64)
+    W_fixed = bool(cfg.get("W_fixed") or False)
+    H_fixed = bool(cfg.get("H_fixed") or False)
+    maxiter = cfg.get("maxiter")
+    maxiter = 100 if maxiter is None or maxiter <= 0 else int(maxiter)  # lnmf.m:120-122
+    tol = cfg.get("tolerance")
+    tol = 1e-3 if tol is None or tol <= 0 else float(tol)  # lnmf.m:124-126
+    W = W @ np.diag(1.0 / np.sum(W, axis=0))  # lnmf.m:63
+    V_hat = reconstruct_from_decomposition(W, H)  # lnmf.m:66
+    cost = np.zeros(maxiter)
+    ones_mn = np.ones((m, n))
+    for it in range(maxiter):
+        if not W_fixed:  # lnmf.m:72-77
+            W = W * (((V / V_hat) @ H.T) / np.fmax(ones_mn @ H.T, EPS))
+            W = W @ np.diag(1.0 / np.sum(W, axis=0))
+            V_hat = reconstruct_from_decomposition(W, H)
+        if not H_fixed:  # lnmf.m:80-83
+            H = np.sqrt(H * (W.T @ (V / V_hat)))
+            V_hat = reconstruct_from_decomposition(W, H)
+        cost[it] = np.sum(np.sum(V * np.log(V / V_hat) - V + V_hat))  # lnmf.m:86
+        if it > 0 and cost[it] <= cost[it - 1] and cost[it - 1] - cost[it] <= tol:  # lnmf.m:88-90 (no trim)
+            break
+    return W, H, cost
+
+
+# --------------------------------------------------------------------------
 # nmfsc.m:57-245
 # --------------------------------------------------------------------------
 def nmfsc(V, num_basis_elems, config=None, rng=None, info=None):

@@ -33,6 +33,7 @@ CASES = {
     "cnmf_frobenius_sparse": ("cnmf", 100, 300, 6, 3, 20, dict(divergence="frobenius", W_sparsity=0.05, H_sparsity=0.1)),
     "cnmf_kl": ("cnmf", 120, 400, 6, 4, 30, dict(divergence="kl")),
     "cnmf_ab_half_1": ("cnmf", 100, 350, 5, 3, 25, dict(divergence="ab", alpha=0.5, beta=1.0, H_sparsity=0.05)),
+    "lnmf_200": ("lnmf", 200, 300, 12, 1, 40, dict()),
     "nmfsc_h07": ("nmfsc", 512, 512, 16, 1, 60, dict(H_sparsity=0.7)),
     "nmfsc_plain": ("nmfsc", 200, 300, 8, 1, 40, dict()),
 }
@@ -61,6 +62,8 @@ def run(name):
     alg, V, K, T, cfg = inputs(name)
     if alg == "nmf":
         return O.nmf(V, K, cfg)
+    if alg == "lnmf":
+        return O.lnmf(V, K, cfg)
     if alg == "cnmf":
         return O.cnmf(V, K, T, cfg)
     return O.nmfsc(V, K, cfg)

@@ -54,6 +54,8 @@ def test_against_golden(api, handle, name):
     g = np.load(os.path.join(HERE, "golden", name + ".npz"))
     if alg == "nmf":
         W, H, c = api.nmf(V, K, cfg, handle=handle)
+    elif alg == "lnmf":
+        W, H, c = api.lnmf(V, K, cfg, handle=handle)
     elif alg == "cnmf":
         W, H, c = api.cnmf(V, K, T, cfg, handle=handle)
     else:
@@ -294,6 +296,41 @@ def test_nmf_is_fixed_factor(api, handle, fixed):
     Wo, Ho, co = O.nmf(V, K, cfg)
     assert cost_err(c, co) < COST_TOL
     assert recon_err(W, H, Wo, Ho) < RECON_TOL
+
+
+# ---------------------------------------------------------------- lnmf
+@pytest.mark.parametrize("m,n,K,iters", [(300, 420, 10, 60), (1024, 768, 32, 40), (129, 1000, 128, 20)])
+def test_lnmf_vs_oracle(api, handle, m, n, K, iters):
+    """lnmf.m:63-90: unit-sum bases, square-root H step, KL cost."""
+    rng = np.random.default_rng(m + K)
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    cfg = dict(W_init=rng.random((m, K)) + 1e-3, H_init=rng.random((K, n)) + 1e-3, maxiter=iters, tolerance=1e-300)
+    W, H, c = api.lnmf(V, K, cfg, handle=handle)
+    Wo, Ho, co = O.lnmf(V, K, cfg)
+    assert cost_err(c, co) < COST_TOL
+    assert recon_err(W, H, Wo, Ho) < RECON_TOL
+    np.testing.assert_allclose(W.astype(np.float64).sum(0), 1.0, rtol=1e-5)  # lnmf.m:75
+
+
+def test_lnmf_stop_leaves_cost_untrimmed(api, handle):
+    """lnmf.m:88-90 breaks without trimming: maxiter entries, zeros after the stopping iteration."""
+    rng = np.random.default_rng(3)
+    V = np.maximum(rng.random((120, 150)), 2.0 ** -24)
+    cfg = dict(W_init=rng.random((120, 4)) + 1e-3, H_init=rng.random((4, 150)) + 1e-3, maxiter=300, tolerance=2.0)
+    W, H, c = api.lnmf(V, 4, cfg, handle=handle)
+    Wo, Ho, co = O.lnmf(V, 4, cfg)
+    assert len(c) == len(co) == 300
+    assert np.count_nonzero(c) == np.count_nonzero(co) < 300
+    k = np.count_nonzero(co)
+    assert cost_err(c[:k], co[:k]) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
+    for fixed in ("W_fixed", "H_fixed"):
+        cfg2 = dict(cfg, maxiter=15, tolerance=1e-300, **{fixed: True})
+        W, H, c = api.lnmf(V, 4, cfg2, handle=handle)
+        Wo, Ho, co = O.lnmf(V, 4, cfg2)
+        assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
+    with pytest.raises(api.NmfbError) as e:  # the fused KL kernels hold at most 128 bases
+        api.lnmf(V, 130, dict(maxiter=2), handle=handle)
+    assert e.value.code == 3
 
 
 # ---------------------------------------------------------------- nmf, multi-source cell arrays

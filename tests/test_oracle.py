@@ -169,3 +169,17 @@ def test_sklearn_cross_check_plain_mu():
     obj_sk = 0.5 * np.linalg.norm(Vn - Wsk @ model.components_) ** 2
     assert cost[-1] < cost[0] and obj_sk < cost[0]
     assert abs(np.log(obj_sk / cost[-1])) < 0.5
+
+
+def test_lnmf_oracle_invariants():
+    """lnmf.m: unit-sum bases (63, 75), KL cost non-increasing on this data, untrimmed cost (88-90)."""
+    rng = np.random.default_rng(4)
+    V = np.maximum(rng.random((40, 60)), 2.0 ** -24)
+    cfg = dict(W_init=rng.random((40, 5)) + 1e-3, H_init=rng.random((5, 60)) + 1e-3, maxiter=50, tolerance=1e-300)
+    W, H, c = O.lnmf(V, 5, cfg)
+    np.testing.assert_allclose(W.sum(0), 1.0, rtol=1e-12)
+    assert len(c) == 50 and np.all(np.diff(c) <= 1e-9 * c[:-1])
+    Vh = W @ H
+    assert abs(c[-1] - np.sum(V * np.log(V / Vh) - V + Vh)) < 1e-9 * c[-1]
+    W2, H2, c2 = O.lnmf(V, 5, dict(cfg, maxiter=400, tolerance=1e-2))
+    assert len(c2) == 400 and 1 < np.count_nonzero(c2) < 400
