@@ -91,7 +91,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   const std::string cmd(cmdbuf);
   nmfb_handle* h = handle();
 
-  if (cmd == "nmf" || cmd == "cnmf" || cmd == "nmfsc") {
+  if (cmd == "nmf" || cmd == "lnmf" || cmd == "cnmf" || cmd == "nmfsc") {
     const bool conv = cmd == "cnmf";
     const mxArray* V = prhs[1];
     const int m = static_cast<int>(mxGetM(V)), n = static_cast<int>(mxGetN(V));
@@ -102,7 +102,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     check(nmfb_set_V(h, Vf.data(), m, n));
     nmfb_config c;
     std::memset(&c, 0, sizeof(c));
-    c.divergence = cmd == "nmfsc" ? 0 : divergence_code(cfg);
+    c.divergence = (cmd == "nmfsc" || cmd == "lnmf") ? 0 : divergence_code(cfg);
     c.alpha = field(cfg, "alpha", 1);
     c.beta = field(cfg, "beta", 1);
     c.W_sparsity = field(cfg, "W_sparsity", 0);
