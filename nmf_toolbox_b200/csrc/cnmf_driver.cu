@@ -83,6 +83,14 @@ int enqueue_cost(nmfb_handle* h, CnmfState* s, int iter) {
   return check_launch(h, "cost");
 }
 
+// cnmf.m:196-199 after the per-column W step: W(:,k,:) /= |W(:,k,:)|_F / T, tf32 copy, column sums
+int enqueue_w_scale(nmfb_handle* h, CnmfState* s) {
+  NMFB_TRY(zero_async(h, s->wsum, s->KTp * sizeof(double)));
+  w_normalize_kernel<<<vec_grid(s->m, s->KT), 256, 0, h->stream>>>(s->Wm, s->Wt, s->m, s->ldw, s->K, s->T, 1, s->norm2,
+                                                                  s->wsum, nullptr, s->stop);
+  return check_launch(h, "w_normalize");
+}
+
 int enqueue_hstack(nmfb_handle* h, CnmfState* s, const int* stop) {
   hstack_kernel<<<vec_grid(s->n, s->KT), 256, 0, h->stream>>>(s->Hm, s->Hs, s->K, s->T, s->n, s->ldh, stop);
   return check_launch(h, "hstack");
@@ -110,14 +118,16 @@ int enqueue_iteration_two_weight(nmfb_handle* h, CnmfState* s, int i) {
     w.B = s->B;
     w.m = s->m;
     w.ld = s->ldw;
-    w.K = s->K;
-    w.T = s->T;
-    w.cnmf_style = 1;
+    w.K = s->KT;
+    w.T = 1;
+    w.cnmf_style = 2;
+    w.norm2_out = s->norm2;
     w.wsum = s->wsum;
     w.lambda = s->lambda_w;
     w.stop = stop;
     w.expo = s->expo;
     NMFB_TRY(launch_w_step(h, w));
+    NMFB_TRY(enqueue_w_scale(h, s));
     s->gemmS.L.args.want_cost = 0;
     NMFB_TRY(run_gemm(h, s->gemmS));  // refreshed V_hat (cnmf.m:204)
   }
@@ -148,14 +158,16 @@ int enqueue_iteration(nmfb_handle* h, CnmfState* s, int i) {
     w.B = s->B;
     w.m = m;
     w.ld = s->ldw;
-    w.K = s->K;
-    w.T = s->T;
-    w.cnmf_style = 1;
+    w.K = s->KT;  // one CTA per frame-column; the per-basis scale follows in w_normalize
+    w.T = 1;
+    w.cnmf_style = 2;
+    w.norm2_out = s->norm2;
     w.wsum = s->wsum;
     w.hs = nullptr;
     w.lambda = s->lambda_w;
     w.stop = stop;
     NMFB_TRY(launch_w_step(h, w));
+    NMFB_TRY(enqueue_w_scale(h, s));
     NMFB_TRY(run_gram(h, s->gramW, stop));
   }
   // P = Wc'V and D = (Wc'Wc) Hs, then fold over the frames and update H (cnmf.m:216-231)

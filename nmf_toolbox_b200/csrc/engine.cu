@@ -19,7 +19,9 @@ int check_launch(nmfb_handle* h, const char* what) {
 }
 
 dim3 vec_grid(int len, int nvec, int threads) {
-  int bx = (len + threads * 16 - 1) / (threads * 16);
+  // 4 elements per thread: these kernels are latency-bound streams over K x n / m x K arrays, and
+  // with few vectors (cnmf: K = 64) a coarser grid left most of the GPU idle
+  int bx = (len + threads * 4 - 1) / (threads * 4);
   bx = std::max(1, std::min(bx, 64));
   return dim3(bx, nvec, 1);
 }

@@ -321,7 +321,10 @@ struct WStepArgs {
   int m;
   long long ld;
   int K, T;        // CTA k handles columns k + K*t, t < T (T = 1: plain nmf)
-  int cnmf_style;  // normalise per basis over all frames by |.|_F / T
+  int cnmf_style;  // 1: normalise per basis over all frames by |.|_F / T (CTA = basis, loops over frames)
+                   // 2: no normalisation here: W' is stored, norm2_out[c] = |W'_c|^2 and a following
+                   //    w_normalize_kernel scales (cnmf with one CTA per frame-column: T x more CTAs)
+  double* norm2_out;
   double* wsum;    // [K*T] column sums of the new W (KL: holds the old ones on entry)
   const double* hs;  // KL: row sums of H
   float lambda;
@@ -429,7 +432,16 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
     if (tid == 0) bc[2] = acc[0];
     __syncthreads();
     norm_basis += bc[2];
-    if (!a.cnmf_style) {
+    if (a.cnmf_style == 2) {
+      if (tid == 0) a.norm2_out[c] = bc[2];
+      if (CACHED) {
+#pragma unroll
+        for (int q = 0; q < kWCache; ++q) {
+          const int i = tid + q * kWThreads;
+          if (i < a.m) a.W[off + i] = wv[q];
+        }
+      }
+    } else if (!a.cnmf_style) {
       // ---- 3 (nmf): unit L2 column, tf32 copy, column sum
       const float mul = static_cast<float>(lnmf ? 1.0 / bc[2] : 1.0 / sqrt(bc[2]));  // lnmf.m:75 / nmf.m:169
       float s3 = 0.f;
@@ -466,7 +478,7 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
     }
     __syncthreads();
   }
-  if (a.cnmf_style) {
+  if (a.cnmf_style == 1) {
     // ---- 3 (cnmf.m:196-199): W(:,k,:) /= |W(:,k,:)|_F / T
     const float div = static_cast<float>(sqrt(norm_basis) / a.T);
     for (int t = 0; t < a.T; ++t) {
