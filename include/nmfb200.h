@@ -8,6 +8,8 @@
  *   nmfb_nmf          [W,H,cost] = nmf(V, num_basis_elems, config)              nmf.m:1
  *   nmfb_cnmf         [W,H,cost] = cnmf(V, num_basis_elems, context_len, config) cnmf.m:1
  *   nmfb_nmfsc        [W,H,cost] = nmfsc(V, num_basis_elems, config)            nmfsc.m:1
+ *   nmfb_cnmfsc       [W,H,cost] = cnmfsc(V, num_basis_elems, context_len, config) cnmfsc.m:1
+ *   nmfb_lnmf         [W,H,cost] = lnmf(V, num_basis_elems, config)             lnmf.m:1
  *   nmfb_reconstruct  V_hat = ReconstructFromDecomposition(W, H)     ReconstructFromDecomposition.m:1
  *   nmfb_projfunc     [v,usediters] = projfunc(s, k1, k2, nn)                   projfunc.m:1
  *
@@ -140,6 +142,17 @@ int nmfb_cnmf(nmfb_handle* h, int K, int T, const nmfb_config* cfg, float* W_out
  * W_out, H_out factor V/max(V) (nmfsc.m:62). */
 int nmfb_nmfsc(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, float* H_out,
                double* cost_out, int* n_cost);
+
+/* [W, H, cost] = cnmfsc(V, num_basis_elems, context_len, config)  (cnmfsc.m:1).
+ * Convolutive NMF with Hoyer sparseness on H: projected-gradient H step with the reference's line
+ * search when config.H_sparsity > 0 (cnmfsc.m:166-199), multiplicative H step with row
+ * normalisation otherwise (202-209), frame-by-frame multiplicative W step (257-263).  V is rescaled
+ * by its maximum (line 72), so W, H factor V / max(V).  cost_out needs maxiter + 1 entries
+ * (cost(1) = initial objective).  config.W_sparsity > 0 returns NMFB_ERR_UNSUPPORTED: the
+ * reference's W line search (218-249) compares objectives of different models and ends by
+ * step-size underflow with the initial factors (see cnmfsc_driver.cu and DESIGN.md).  One GPU. */
+int nmfb_cnmfsc(nmfb_handle* h, int K, int T, const nmfb_config* cfg, float* W_out, float* H_out, double* cost_out,
+                int* n_cost);
 /* V_hat (m x n, host) = W*H, or sum_t W(:,:,t) * shift(H, t-1) when T > 1.
  * Independent of any V set on the handle. */
 int nmfb_reconstruct(nmfb_handle* h, const float* W, const float* H, int m, int K, int T, int n,

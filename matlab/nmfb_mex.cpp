@@ -91,8 +91,8 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   const std::string cmd(cmdbuf);
   nmfb_handle* h = handle();
 
-  if (cmd == "nmf" || cmd == "lnmf" || cmd == "cnmf" || cmd == "nmfsc") {
-    const bool conv = cmd == "cnmf";
+  if (cmd == "nmf" || cmd == "lnmf" || cmd == "cnmf" || cmd == "nmfsc" || cmd == "cnmfsc") {
+    const bool conv = cmd == "cnmf" || cmd == "cnmfsc";
     const mxArray* V = prhs[1];
     const int m = static_cast<int>(mxGetM(V)), n = static_cast<int>(mxGetN(V));
     const int K = static_cast<int>(mxGetScalar(prhs[2]));
@@ -102,7 +102,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     check(nmfb_set_V(h, Vf.data(), m, n));
     nmfb_config c;
     std::memset(&c, 0, sizeof(c));
-    c.divergence = (cmd == "nmfsc" || cmd == "lnmf") ? 0 : divergence_code(cfg);
+    c.divergence = (cmd == "nmfsc" || cmd == "cnmfsc" || cmd == "lnmf") ? 0 : divergence_code(cfg);
     c.alpha = field(cfg, "alpha", 1);
     c.beta = field(cfg, "beta", 1);
     c.W_sparsity = field(cfg, "W_sparsity", 0);
@@ -155,6 +155,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     int ncost = 0;
     if (cmd == "nmf") check(nmfb_nmf(h, K, &c, W.data(), H.data(), cost.data(), &ncost));
     else if (cmd == "lnmf") check(nmfb_lnmf(h, K, &c, W.data(), H.data(), cost.data(), &ncost));
+    else if (cmd == "cnmfsc") check(nmfb_cnmfsc(h, K, T, &c, W.data(), H.data(), cost.data(), &ncost));
     else if (conv) check(nmfb_cnmf(h, K, T, &c, W.data(), H.data(), cost.data(), &ncost));
     else check(nmfb_nmfsc(h, K, &c, W.data(), H.data(), cost.data(), &ncost));
     plhs[0] = from_single(W, m, K, T);

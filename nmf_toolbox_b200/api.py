@@ -89,6 +89,7 @@ def _bind(lib):
         "nmfb_set_V_device": ([P, P, I, I, LL], I),
         "nmfb_nmf": ([P, I, ctypes.POINTER(_Config), P, P, P, PI], I),
         "nmfb_lnmf": ([P, I, ctypes.POINTER(_Config), P, P, P, PI], I),
+        "nmfb_cnmfsc": ([P, I, I, ctypes.POINTER(_Config), P, P, P, PI], I),
         "nmfb_cnmf": ([P, I, I, ctypes.POINTER(_Config), P, P, P, PI], I),
         "nmfb_nmfsc": ([P, I, ctypes.POINTER(_Config), P, P, P, PI], I),
         "nmfb_reconstruct": ([P, P, P, I, I, I, I, P], I),
@@ -289,6 +290,17 @@ class Handle:
         del keep
         return W, H, cost[: nc.value].copy()
 
+    def cnmfsc(self, K: int, T: int, config=None):
+        m, n = self.shape
+        c, keep, maxiter = self._config(config, m, n, K, T, for_nmfsc=True)
+        W = np.empty((m, K, T), dtype=np.float32, order="F")
+        H = np.empty((K, n), dtype=np.float32, order="F")
+        cost = np.zeros(maxiter + 1, dtype=np.float64)
+        nc = ctypes.c_int(0)
+        self._check(self.lib.nmfb_cnmfsc(self._h, K, T, ctypes.byref(c), _ptr(W), _ptr(H), _ptr(cost), ctypes.byref(nc)))
+        del keep
+        return W, H, cost[: nc.value].copy()
+
     # -- stepping interface (bench.py)
     def nmf_begin(self, K: int, config=None):
         m, n = self.shape
@@ -437,6 +449,13 @@ def nmfsc(V, num_basis_elems, config=None, handle: Optional[Handle] = None):
     h = handle or default_handle()
     h.set_V(V)
     return h.nmfsc(int(num_basis_elems), config)
+
+
+def cnmfsc(V, num_basis_elems, context_len, config=None, handle: Optional[Handle] = None):
+    """``[W, H, cost] = cnmfsc(V, num_basis_elems, context_len, config)`` (cnmfsc.m:1)."""
+    h = handle or default_handle()
+    h.set_V(V)
+    return h.cnmfsc(int(num_basis_elems), int(context_len), config)
 
 
 def ReconstructFromDecomposition(W, H, handle: Optional[Handle] = None):

@@ -612,3 +612,146 @@ def nmfsc(V, num_basis_elems, config=None, rng=None, info=None):
     if info is not None:
         info.update(halvings_H=halvings_H, halvings_W=halvings_W, converged_early=False)
     return W, H, cost
+
+
+# --------------------------------------------------------------------------
+# cnmfsc.m:66-277
+# --------------------------------------------------------------------------
+def cnmfsc(V, num_basis_elems, context_len, config=None, rng=None, info=None):
+    """``[W, H, cost] = cnmfsc(V, num_basis_elems, context_len, config)`` - cnmfsc.m:1, loop 152-274.
+
+    Literal, including the reference's quirks: the initial sparseness projection is applied to W
+    while the iterations start from the unprojected W0 (lines 88-111); inside the W line search the
+    trial reconstruction is ``ReconstructFromDecomposition(Wnew, H)`` with the 2-D frame ``Wnew``
+    (line 227: a plain product with the unshifted H), and that V_hat is what the next frame sees;
+    the multiplicative W branch updates V_hat incrementally with a clamp at 0 (line 262)."""
+    V = np.asarray(V, dtype=np.float64)
+    if V.min() < 0:  # cnmfsc.m:67-69
+        raise ReferenceError_("Negative values in data!")
+    V = V / V.max()  # cnmfsc.m:72
+    m, n = V.shape
+    K, T = int(num_basis_elems), int(context_len)
+    cfg = dict(config or {})
+    rng = rng or np.random.default_rng()
+    if cfg.get("W_init") is None:  # cnmfsc.m:83-85
+        cfg["W_init"] = rng.random((m, K, T))
+    if cfg.get("H_init") is None:  # cnmfsc.m:88-91
+        h = rng.random((K, n))
+        cfg["H_init"] = np.diag(1.0 / np.sqrt(np.sum(h ** 2, axis=1))) @ h
+    W0 = np.array(cfg["W_init"], dtype=np.float64).reshape(m, K, T)  # cnmfsc.m:93
+    W = W0.copy()  # cnmfsc.m:94
+    H = np.array(cfg["H_init"], dtype=np.float64)  # cnmfsc.m:95
+    L1a = L1s = None
+    if cfg.get("W_sparsity") is None:  # cnmfsc.m:98-99
+        cfg["W_sparsity"] = 0
+    elif cfg["W_sparsity"] > 0:  # cnmfsc.m:100-110 (projects W, not W0)
+        if cfg["W_sparsity"] > 1:
+            cfg["W_sparsity"] = 1
+        L1a = np.sqrt(m) - (np.sqrt(m) - 1) * cfg["W_sparsity"]
+        for t in range(T):
+            for k in range(K):
+                W[:, k, t] = projfunc(W[:, k, t], L1a, 1, 1)[0]
+    if cfg.get("H_sparsity") is None:  # cnmfsc.m:114-115
+        cfg["H_sparsity"] = 0
+    elif cfg["H_sparsity"] > 0:  # cnmfsc.m:116-124
+        if cfg["H_sparsity"] > 1:
+            cfg["H_sparsity"] = 1
+        L1s = np.sqrt(n) - (np.sqrt(n) - 1) * cfg["H_sparsity"]
+        for k in range(K):
+            H[k, :] = projfunc(H[k, :], L1s, 1, 1)[0]
+    W_fixed = bool(cfg.get("W_fixed") or False)  # cnmfsc.m:127-129
+    H_fixed = bool(cfg.get("H_fixed") or False)  # cnmfsc.m:132-134
+    maxiter = cfg.get("maxiter")
+    maxiter = 100 if maxiter is None or maxiter <= 0 else int(maxiter)  # cnmfsc.m:137-139
+    tolerance = cfg.get("tolerance")
+    tolerance = 1e-3 if tolerance is None or tolerance <= 0 else float(tolerance)  # cnmfsc.m:142-144
+
+    def shift_left(X, t):  # [X(:, t:n) zeros(m, t-1)] with t 1-based
+        out = np.zeros_like(X)
+        out[:, : n - (t - 1)] = X[:, t - 1:]
+        return out
+
+    def shift_right(X, t):  # [zeros(K, t-1) X(:, 1:n-t+1)]
+        out = np.zeros_like(X)
+        out[:, t - 1:] = X[:, : n - (t - 1)]
+        return out
+
+    stepsizeW = np.ones(T)  # cnmfsc.m:147
+    stepsizeH = 1.0  # cnmfsc.m:148
+    cost = np.zeros(maxiter + 1)  # cnmfsc.m:151
+    V_hat = reconstruct_from_decomposition(W, H)  # cnmfsc.m:152 (the PROJECTED W, while the loop starts from W0)
+    cost[0] = 0.5 * np.sum(np.sum((V - V_hat) ** 2))  # cnmfsc.m:153
+    trials_H, trials_W = [], []
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for it in range(1, maxiter + 1):  # cnmfsc.m:155
+            if not H_fixed:  # cnmfsc.m:157
+                neg = np.zeros((K, n))
+                pos = np.zeros((K, n))
+                for t in range(1, T + 1):  # cnmfsc.m:160-165
+                    neg = neg + W0[:, :, t - 1].T @ shift_left(V, t)
+                    pos = pos + W0[:, :, t - 1].T @ shift_left(V_hat, t)
+                if cfg["H_sparsity"] > 0:  # cnmfsc.m:166
+                    dH = pos - neg  # cnmfsc.m:168
+                    begobj = cost[it - 1]  # cnmfsc.m:169
+                    nt = 0
+                    while True:  # cnmfsc.m:172
+                        Hnew = H - stepsizeH * dH  # cnmfsc.m:174
+                        for k in range(K):  # cnmfsc.m:175-177
+                            Hnew[k, :] = projfunc(Hnew[k, :], L1s, 1, 1)[0]
+                        V_hat = reconstruct_from_decomposition(W0, Hnew)  # cnmfsc.m:180
+                        newobj = 0.5 * np.sum(np.sum((V - V_hat) ** 2))  # cnmfsc.m:181
+                        nt += 1
+                        if newobj <= begobj:  # cnmfsc.m:184-186
+                            break
+                        stepsizeH = stepsizeH / 2  # cnmfsc.m:189
+                        if stepsizeH < 1e-200:  # cnmfsc.m:190-194
+                            return W, H, cost[:it]
+                    trials_H.append(nt)
+                    stepsizeH = 1.2 * stepsizeH  # cnmfsc.m:198
+                    H = Hnew  # cnmfsc.m:199
+                else:
+                    H = H * (neg / (pos + EPS))  # cnmfsc.m:202
+                    norms = np.sqrt(np.sum(H ** 2, axis=1))  # cnmfsc.m:205
+                    H = np.diag(1.0 / norms) @ H  # cnmfsc.m:206
+                    for t in range(T):  # cnmfsc.m:207-209
+                        W0[:, :, t] = W0[:, :, t] @ np.diag(norms)
+            if not W_fixed:  # cnmfsc.m:214
+                V_hat = reconstruct_from_decomposition(W0, H)  # cnmfsc.m:215
+                if cfg["W_sparsity"] > 0:  # cnmfsc.m:216
+                    for t in range(1, T + 1):  # cnmfsc.m:217
+                        begobj = 0.5 * np.sum(np.sum((V - V_hat) ** 2))  # cnmfsc.m:218
+                        H_shifted = shift_right(H, t)  # cnmfsc.m:221
+                        dW = V_hat @ H_shifted.T - V @ H_shifted.T  # cnmfsc.m:222-224
+                        nt = 0
+                        while True:  # cnmfsc.m:227
+                            Wnew = W0[:, :, t - 1] - stepsizeW[t - 1] * dW  # cnmfsc.m:229
+                            for k in range(K):  # cnmfsc.m:230-232
+                                Wnew[:, k] = projfunc(Wnew[:, k], L1a, 1, 1)[0]
+                            V_hat = reconstruct_from_decomposition(Wnew, H)  # cnmfsc.m:235 (2-D Wnew: plain product)
+                            newobj = 0.5 * np.sum(np.sum((V - V_hat) ** 2))  # cnmfsc.m:236
+                            nt += 1
+                            if newobj <= begobj:  # cnmfsc.m:239-241
+                                break
+                            stepsizeW[t - 1] = stepsizeW[t - 1] / 2  # cnmfsc.m:244
+                            if stepsizeW[t - 1] < 1e-200:  # cnmfsc.m:245-249
+                                return W, H, cost[:it]
+                        trials_W.append(nt)
+                        stepsizeW[t - 1] = 1.2 * stepsizeW[t - 1]  # cnmfsc.m:252
+                        W[:, :, t - 1] = Wnew  # cnmfsc.m:253
+                else:
+                    for t in range(1, T + 1):  # cnmfsc.m:257-263
+                        H_shifted = shift_right(H, t)
+                        neg = V @ H_shifted.T
+                        pos = V_hat @ H_shifted.T
+                        W[:, :, t - 1] = W0[:, :, t - 1] * (neg / np.fmax(pos, EPS))
+                        V_hat = np.fmax(V_hat + (W[:, :, t - 1] - W0[:, :, t - 1]) @ H_shifted, 0)
+            W0 = W.copy()  # cnmfsc.m:266
+            V_hat = reconstruct_from_decomposition(W0, H)  # cnmfsc.m:269
+            cost[it] = 0.5 * np.sum(np.sum((V - V_hat) ** 2))  # cnmfsc.m:270
+            if it > 1 and cost[it] < cost[it - 1] and cost[it - 1] - cost[it] < tolerance:  # cnmfsc.m:273-276
+                cost = cost[: it + 1]
+                break
+    if info is not None:
+        info["trials_H"] = trials_H
+        info["trials_W"] = trials_W
+    return W, H, cost

@@ -34,6 +34,8 @@ CASES = {
     "cnmf_kl": ("cnmf", 120, 400, 6, 4, 30, dict(divergence="kl")),
     "cnmf_ab_half_1": ("cnmf", 100, 350, 5, 3, 25, dict(divergence="ab", alpha=0.5, beta=1.0, H_sparsity=0.05)),
     "lnmf_200": ("lnmf", 200, 300, 12, 1, 40, dict()),
+    "cnmfsc_h06": ("cnmfsc", 129, 500, 6, 4, 30, dict(H_sparsity=0.6)),
+    "cnmfsc_plain": ("cnmfsc", 100, 360, 5, 3, 30, dict()),
     "nmfsc_h07": ("nmfsc", 512, 512, 16, 1, 60, dict(H_sparsity=0.7)),
     "nmfsc_plain": ("nmfsc", 200, 300, 8, 1, 40, dict()),
 }
@@ -46,12 +48,14 @@ def inputs(name):
     V = np.maximum(rng.random((m, n)), 2.0 ** -24)
     if alg == "cnmf":
         W0 = rng.random((m, K, T))
+    elif alg == "cnmfsc":
+        W0 = 0.3 * rng.random((m, K, T))
     elif alg == "nmfsc":
         W0 = rng.random((m, K))
     else:
         W0 = np.maximum(rng.random((m, K)), O.EPS)
     H0 = np.maximum(rng.random((K, n)), O.EPS)
-    if alg == "nmfsc":
+    if alg in ("nmfsc", "cnmfsc"):
         V = V * 3.0
         H0 = H0 / np.sqrt((H0 ** 2).sum(1, keepdims=True))
     cfg = dict(extra, W_init=W0, H_init=H0, maxiter=iters, tolerance=1e-300)
@@ -64,6 +68,8 @@ def run(name):
         return O.nmf(V, K, cfg)
     if alg == "lnmf":
         return O.lnmf(V, K, cfg)
+    if alg == "cnmfsc":
+        return O.cnmfsc(V, K, T, cfg)
     if alg == "cnmf":
         return O.cnmf(V, K, T, cfg)
     return O.nmfsc(V, K, cfg)

@@ -58,6 +58,8 @@ def test_against_golden(api, handle, name):
         W, H, c = api.lnmf(V, K, cfg, handle=handle)
     elif alg == "cnmf":
         W, H, c = api.cnmf(V, K, T, cfg, handle=handle)
+    elif alg == "cnmfsc":
+        W, H, c = api.cnmfsc(V, K, T, cfg, handle=handle)
     else:
         W, H, c = api.nmfsc(V, K, cfg, handle=handle)
     assert cost_err(c, g["cost"]) < COST_TOL
@@ -296,6 +298,45 @@ def test_nmf_is_fixed_factor(api, handle, fixed):
     Wo, Ho, co = O.nmf(V, K, cfg)
     assert cost_err(c, co) < COST_TOL
     assert recon_err(W, H, Wo, Ho) < RECON_TOL
+
+
+# ---------------------------------------------------------------- cnmfsc
+@pytest.mark.parametrize("m,n,K,T,sH,iters", [(129, 500, 6, 4, 0.6, 30), (200, 700, 16, 8, 0.7, 20), (120, 400, 5, 3, 0.0, 40),
+                                               (300, 640, 40, 5, 0.5, 12), (64, 256, 4, 1, 0.4, 25)])
+def test_cnmfsc_vs_oracle(api, handle, m, n, K, T, sH, iters):
+    """cnmfsc.m:155-276 with W_sparsity = 0: projected-gradient / multiplicative H step, frame-by-frame W step."""
+    rng = np.random.default_rng(m + T)
+    V = rng.random((m, n)) * 3.0
+    H0 = rng.random((K, n))
+    H0 /= np.sqrt((H0 ** 2).sum(1, keepdims=True))
+    cfg = dict(W_init=0.3 * rng.random((m, K, T)), H_init=H0, H_sparsity=sH, maxiter=iters, tolerance=1e-300)
+    W, H, c = api.cnmfsc(V, K, T, cfg, handle=handle)
+    Wo, Ho, co = O.cnmfsc(V, K, T, cfg)
+    assert W.shape == (m, K, T) and len(c) == len(co) == iters + 1
+    assert cost_err(c, co) < COST_TOL
+    assert recon_err(W, H, Wo, Ho) < RECON_TOL
+    if sH > 0:
+        k1 = np.sqrt(n) - (np.sqrt(n) - 1) * sH
+        np.testing.assert_allclose(np.abs(H.astype(np.float64)).sum(1), k1, rtol=1e-4)
+
+
+def test_cnmfsc_fixed_factors_and_errors(api, handle):
+    rng = np.random.default_rng(77)
+    m, n, K, T = 100, 300, 5, 3
+    V = rng.random((m, n))
+    base = dict(W_init=0.3 * rng.random((m, K, T)), H_init=0.3 * rng.random((K, n)), maxiter=12, tolerance=1e-300)
+    for extra in (dict(W_fixed=True), dict(W_fixed=True, H_sparsity=0.5), dict(H_fixed=True), dict(W_fixed=True, H_fixed=True)):
+        cfg = dict(base, **extra)
+        W, H, c = api.cnmfsc(V, K, T, cfg, handle=handle)
+        Wo, Ho, co = O.cnmfsc(V, K, T, cfg)
+        assert len(c) == len(co), extra
+        assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL, extra
+    with pytest.raises(api.NmfbError) as e:  # cnmfsc.m:67-69
+        api.cnmfsc(-V, K, T, dict(maxiter=2), handle=handle)
+    assert e.value.code == 6
+    with pytest.raises(api.NmfbError) as e:  # documented gap: the reference's W line search is degenerate
+        api.cnmfsc(V, K, T, dict(W_sparsity=0.5, maxiter=2), handle=handle)
+    assert e.value.code == 3
 
 
 # ---------------------------------------------------------------- lnmf

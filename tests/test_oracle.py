@@ -183,3 +183,25 @@ def test_lnmf_oracle_invariants():
     assert abs(c[-1] - np.sum(V * np.log(V / Vh) - V + Vh)) < 1e-9 * c[-1]
     W2, H2, c2 = O.lnmf(V, 5, dict(cfg, maxiter=400, tolerance=1e-2))
     assert len(c2) == 400 and 1 < np.count_nonzero(c2) < 400
+
+
+def test_cnmfsc_oracle_behaviour():
+    """cnmfsc.m: T == 1 with no sparseness is nmfsc's multiplicative branch; the H line search decreases the
+    cost; with W_sparsity > 0 the W line search compares the full model (line 218) with a single-frame trial
+    (line 235) and the function returns by step-size underflow with the cost trimmed (lines 245-249)."""
+    rng = np.random.default_rng(8)
+    m, n, K, T = 30, 90, 3, 3
+    V = rng.random((m, n))
+    W0, H0 = 0.2 * rng.random((m, K, T)), 0.2 * rng.random((K, n))
+    W1, H1, c1 = O.cnmfsc(V, K, 1, dict(W_init=W0[:, :, :1], H_init=H0, maxiter=8, tolerance=1e-300))
+    W2, H2, c2 = O.nmfsc(V, K, dict(W_init=W0[:, :, 0], H_init=H0, maxiter=8, tolerance=1e-300))
+    np.testing.assert_allclose(c1, c2, rtol=1e-9)
+    np.testing.assert_allclose(W1[:, :, 0], W2, rtol=1e-8)
+    info = {}
+    W, H, c = O.cnmfsc(V, K, T, dict(W_init=W0, H_init=H0, H_sparsity=0.5, maxiter=12, tolerance=1e-300), info=info)
+    assert len(c) == 13 and np.all(np.diff(c) <= 0) and len(info["trials_H"]) == 12
+    k1 = np.sqrt(n) - (np.sqrt(n) - 1) * 0.5
+    np.testing.assert_allclose(np.abs(H).sum(1), k1, rtol=1e-9)  # rows keep the requested L1 at unit L2
+    np.testing.assert_allclose((H ** 2).sum(1), 1.0, rtol=1e-9)
+    W, H, c = O.cnmfsc(V, K, T, dict(W_init=W0, H_init=H0, W_sparsity=0.5, maxiter=12, tolerance=1e-300))
+    assert len(c) <= 2  # "Algorithm converged" (step size below 1e-200) in the first or second iteration
