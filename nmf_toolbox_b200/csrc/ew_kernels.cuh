@@ -229,78 +229,12 @@ __global__ void split_reduce_kernel(const float* __restrict__ parts, int splits,
   }
 }
 
-// ---------------------------------------------------------------- W update
-// ab[c] += <W_c, A_c>, ab[Kp + c] += <W_c, B_c>      (the diag(diag(.)) terms, nmf.m:149-153)
-__global__ void w_dots_kernel(const float* __restrict__ W, const float* __restrict__ A,
-                              const float* __restrict__ B, int m, long long ld, int Kp, double* ab,
-                              const int* stop) {
-  NMFB_STOP_GUARD(stop);
-  __shared__ double sh[64];
-  const int c = blockIdx.y;
-  const long long off = static_cast<long long>(c) * ld;
-  double acc[2] = {0.0, 0.0};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-    const float w = W[off + i];
-    acc[0] += static_cast<double>(w) * A[off + i];
-    if (B) acc[1] += static_cast<double>(w) * B[off + i];
-  }
-  block_sum<2>(acc, sh);
-  if (threadIdx.x == 0) {
-    atomicAdd(ab + c, acc[0]);
-    if (B) atomicAdd(ab + Kp + c, acc[1]);
-  }
-}
-
 // Per-column coefficients of the generic W step
 //   W' = W .* (A + W*p_c) ./ max(Bterm + W*q_c + lambda, eps)
 // Euclidean (nmf.m:149-150): p = <W_c,B_c>, q = <W_c,A_c>, Bterm = B
 // KL        (nmf.m:152-153): p = hs_c*ws_c, q = <W_c,R_c>, Bterm = hs_c
 // LNMF      (lnmf.m:74-75):  W' = W .* R ./ max(hs_c, eps), then unit column SUM instead of unit L2
 enum { WSTEP_EUCLID = 0, WSTEP_KL = 1, WSTEP_PLAIN = 2, WSTEP_LNMF = 3 };
-__global__ void w_coef_kernel(int mode, int Kp, const double* ab, const double* hs, const double* ws,
-                              float* p, float* q, float* bvec, const int* stop) {
-  NMFB_STOP_GUARD(stop);
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Kp) return;
-  if (mode == WSTEP_EUCLID) {
-    p[c] = static_cast<float>(ab[Kp + c]);
-    q[c] = static_cast<float>(ab[c]);
-    bvec[c] = 0.f;
-  } else if (mode == WSTEP_KL) {
-    p[c] = static_cast<float>(hs[c] * ws[c]);
-    q[c] = static_cast<float>(ab[c]);
-    bvec[c] = static_cast<float>(hs[c]);
-  } else {
-    p[c] = 0.f;
-    q[c] = 0.f;
-    bvec[c] = 0.f;
-  }
-}
-
-// In place on W; norm2[c] += sum W'^2.  B may be null (then Bterm = bvec[c]).
-__global__ void w_update_kernel(float* __restrict__ W, const float* __restrict__ A,
-                                const float* __restrict__ B, int m, long long ld,
-                                const float* __restrict__ p, const float* __restrict__ q,
-                                const float* __restrict__ bvec, float lambda, double* norm2,
-                                const int* stop) {
-  NMFB_STOP_GUARD(stop);
-  __shared__ double sh[32];
-  const int c = blockIdx.y;
-  const long long off = static_cast<long long>(c) * ld;
-  const float pc = p[c], qc = q[c], bc = bvec[c];
-  double acc[1] = {0.0};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-    const float w = W[off + i];
-    const float neg = A[off + i] + w * pc;
-    const float pos = (B ? B[off + i] : bc) + w * qc;
-    const float wn = w * (neg / fmaxf(pos + lambda, NMFB_EPS));
-    W[off + i] = wn;
-    acc[0] += static_cast<double>(wn) * wn;
-  }
-  block_sum<1>(acc, sh);
-  if (threadIdx.x == 0 && norm2) atomicAdd(norm2 + c, acc[0]);
-}
-
 // The whole W step of nmf.m:149-169 / cnmf.m:187-199 in ONE launch, one CTA per basis vector:
 // everything the step needs is local to a column of W (cnmf: to the T frame-columns of one
 // basis), so the three dependent reductions are block-level and the column stays in registers:

@@ -445,17 +445,6 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     NMFB_TRY(plan_fused(h, &s->gemmH, EPI_HUPDATE, Xvt, Yw, m, &Xh, &Ygw, Kp, n, Kp, Kp, stop));
     }
     if (s->gate_h) s->gemmH.L.args.gate = s->gates + 1;
-    if (const char* env = std::getenv("NMFB_EXPERIMENT_HSTORE")) {  // timing experiment only: results are wrong
-      if (env[0] == '1') {
-        float *t0 = nullptr, *t1 = nullptr;
-        NMFB_TRY(ar->alloc(h, &t0, static_cast<size_t>(Kp) * s->ldh));
-        NMFB_TRY(ar->alloc(h, &t1, static_cast<size_t>(Kp) * s->ldh));
-        s->gemmH.epi = EPI_STORE;
-        s->gemmH.L.args.out0 = t0;
-        s->gemmH.L.args.out1 = t1;
-        s->gemmH.L.args.ldo = s->ldh;
-      }
-    }
     GemmArgs& a = s->gemmH.L.args;
     if (!s->h_split) {
       a.Hm = s->Hm;
