@@ -45,16 +45,43 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def _flatten(obj, prefix=""):
+    if isinstance(obj, dict):
+        for k, v in obj.items():
+            yield from _flatten(v, f"{prefix}.{k}".lower() if prefix else str(k).lower())
+    elif isinstance(obj, (int, float)) and not isinstance(obj, bool):
+        yield prefix, float(obj)
+
+
 def measured_peaks():
-    """(tf32 TFLOP/s peak, hbm GB/s, source string).  tf32 runs at half the bf16 tensor rate."""
+    """(tf32 TFLOP/s peak, hbm GB/s, source string).  tf32 runs at half the bf16 tensor rate.
+
+    MEASURED_PEAKS.json is written by the driver; its key names are not known here, so the numbers are
+    found by pattern: a dense bf16 throughput (TFLOP/s; a value above 10000 is taken as GFLOP/s) and an
+    HBM / copy bandwidth (GB/s; a value below 100 is taken as TB/s).  The step is timed inside a long
+    run, so a "sustained" figure is preferred over a "burst" one when both exist."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    fallback = (1590.0 / 2.0, 6650.0, "fallback 1.59 PFLOP/s bf16 / 2 (tf32 = half the bf16 rate), of fallback")
     try:
         with open(path) as f:
-            p = json.load(f)
-        bf16 = float(p.get("bf16_tflops_sustained") or p.get("bf16_tflops"))
-        return bf16 / 2.0, float(p.get("hbm_gbs")), "MEASURED_PEAKS.json bf16_tflops_sustained/2 (tf32 = half the bf16 rate), of measured"
+            flat = list(_flatten(json.load(f)))
     except Exception:
-        return 1590.0 / 2.0, 6650.0, "fallback 1.59 PFLOP/s bf16 / 2 (tf32 = half the bf16 rate), of fallback"
+        return fallback
+
+    def pick(words):
+        cand = [(k, v) for k, v in flat if any(w in k for w in words) and v > 0]
+        if not cand:
+            return None
+        cand.sort(key=lambda kv: (0 if "sustain" in kv[0] else 1 if "burst" not in kv[0] else 2))
+        return cand[0]
+
+    t = pick(("bf16", "tensor", "tflop"))
+    b = pick(("hbm", "copy", "bandwidth", "gbs", "gb_s", "gb/s"))
+    if t is None or b is None:
+        return fallback
+    tf = t[1] / 1000.0 if t[1] > 10000 else t[1]
+    bw = b[1] * 1000.0 if b[1] < 100 else b[1]
+    return tf / 2.0, bw, f"MEASURED_PEAKS.json {t[0]} / 2 (tf32 = half the bf16 rate) and {b[0]}, of measured"
 
 
 class ClockSampler:
