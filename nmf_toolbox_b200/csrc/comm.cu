@@ -95,7 +95,7 @@ __device__ __forceinline__ void p2p_block_barrier(const PeerTable& t, size_t fla
     const int* mine = reinterpret_cast<const int*>(t.base[t.rank] + row) + q;
     long long t0 = clock64();
     while (ld_acquire_sys(mine) - epoch < 0) {
-      if (clock64() - t0 > 8000000000LL) {
+      if (clock64() - t0 > 30000000000LL) {
         printf("nmfb: peer barrier timeout (rank %d block %d waiting for rank %d, epoch %d)\n", t.rank, blockIdx.x, q,
                epoch);
         __trap();
