@@ -49,3 +49,47 @@ def test_north_star_shape_properties():
         total += float(((Vb - Sb) ** 2).sum())
     direct = 0.5 * total
     assert abs(cost[-1] - direct) / direct < 1e-4, (cost[-1], direct)
+
+
+@pytest.mark.parametrize("div,alpha,beta", [("kl", 1, 1), ("is", 1, 1), ("ab", 0.5, 0.5), ("ab", 2.0, 1.0)])
+def test_large_divergences_cost_matches_explicit_formula(div, alpha, beta):
+    """8192 x 8192, K = 128 (BASELINE.json configs[2] per-GPU shard shape): the cost the engine sums in its
+    epilogues must equal the divergence of the returned factors evaluated independently in float64
+    (nmf.m:209-214), the cost must not increase, and W keeps unit columns."""
+    import torch
+    from nmf_toolbox_b200 import api
+
+    m = n = 8192
+    K = 128
+    iters = 6
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(3)
+    Vd = torch.rand((n, m), device=dev, generator=g).clamp_(min=2.0 ** -10)  # column-major m x n
+    rng = np.random.default_rng(2)
+    W0 = np.asfortranarray(rng.random((m, K), dtype=np.float32) + 1e-3)
+    H0 = np.asfortranarray(rng.random((K, n), dtype=np.float32) + 1e-3)
+    h = api.Handle(0)
+    h.set_V_device(Vd.data_ptr(), m, n, m)
+    h.nmf_begin(K, dict(divergence=div, alpha=alpha, beta=beta, W_init=W0, H_init=H0, maxiter=iters, tolerance=1e-300))
+    h.nmf_step(iters)
+    h.nmf_sync()
+    W, H, cost = h.nmf_end()
+    h.close()
+    assert len(cost) == iters and np.all(np.isfinite(cost))
+    assert np.all(np.diff(cost) <= 1e-7 * np.abs(cost[:-1])), "cost must not increase"
+    Wd = torch.from_numpy(np.ascontiguousarray(W.T)).to(dev).double()  # [K][m]
+    Hd = torch.from_numpy(np.ascontiguousarray(H)).to(dev).double()    # [K][n]
+    assert torch.allclose((Wd ** 2).sum(1), torch.ones(K, device=dev, dtype=torch.float64), rtol=1e-5)
+    total = 0.0
+    for j0 in range(0, n, 1024):
+        Vb = Vd[j0:j0 + 1024].double()            # [cols][m] = V[:, j0:j1]'
+        Sb = Hd[:, j0:j0 + 1024].T @ Wd           # V_hat block, same orientation
+        if div == "kl":
+            t = Vb * torch.log(Vb / Sb) - Vb + Sb
+        elif div == "is":
+            t = torch.log(Sb / Vb) + Vb / Sb - 1
+        else:
+            a, b = alpha, beta
+            t = (-1.0 / (a * b)) * (Vb ** a * Sb ** b - (a * Vb ** (a + b) + b * Sb ** (a + b) + b) / (a + b))
+        total += float(t.sum())
+    assert abs(cost[-1] - total) / abs(total) < 1e-4, (cost[-1], total)
