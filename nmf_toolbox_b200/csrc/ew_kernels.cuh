@@ -688,13 +688,15 @@ __global__ void fold_update_kernel(const float* __restrict__ P, const float* __r
   const bool powered = expo != 0.f && expo != 1.f;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     float neg = 0.f, pos = 0.f;
+    // branch-free body (clamped index + select) so that the 2T loads of a thread are issued together
+#pragma unroll 4
     for (int t = 0; t < T; ++t) {
-      if (j + t < n) {
-        const long long o = static_cast<long long>(k + K * t) * ld + j + t;
-        neg += P[o];
-        if (!pos_unshifted) pos += D[o];
-      }
-      if (pos_unshifted) pos += D[static_cast<long long>(k + K * t) * ld + j];
+      const bool ok = j + t < n;
+      const long long row = static_cast<long long>(k + K * t) * ld;
+      const float p = P[row + (ok ? j + t : j)];
+      const float d = D[row + ((ok && !pos_unshifted) ? j + t : j)];
+      neg += ok ? p : 0.f;
+      pos += (ok || pos_unshifted) ? d : 0.f;
     }
     if (powered) {
       neg = powf(neg, expo);
