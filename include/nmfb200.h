@@ -148,9 +148,10 @@ int nmfb_nmfsc(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, floa
  * search when config.H_sparsity > 0 (cnmfsc.m:166-199), multiplicative H step with row
  * normalisation otherwise (202-209), frame-by-frame multiplicative W step (257-263).  V is rescaled
  * by its maximum (line 72), so W, H factor V / max(V).  cost_out needs maxiter + 1 entries
- * (cost(1) = initial objective).  config.W_sparsity > 0 returns NMFB_ERR_UNSUPPORTED: the
- * reference's W line search (218-249) compares objectives of different models and ends by
- * step-size underflow with the initial factors (see cnmfsc_driver.cu and DESIGN.md).  One GPU. */
+ * (cost(1) = initial objective).  config.W_sparsity > 0 follows the reference literally, quirks
+ * included (cnmfsc.m:93-111, 218, 235): the W line search reconstructs its trial from one frame
+ * alone and on ordinary data ends by step-size underflow with the cost trimmed (lines 245-249).
+ * One GPU. */
 int nmfb_cnmfsc(nmfb_handle* h, int K, int T, const nmfb_config* cfg, float* W_out, float* H_out, double* cost_out,
                 int* n_cost);
 /* V_hat (m x n, host) = W*H, or sum_t W(:,:,t) * shift(H, t-1) when T > 1.

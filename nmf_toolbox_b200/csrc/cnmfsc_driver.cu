@@ -16,12 +16,14 @@
 // All contractions are split-tf32 products (three operand segments, short accumulation chunks) for the
 // reason given in nmfsc_driver.cu: the line search compares objectives that differ by parts in 1e5.
 //
-// W_sparsity > 0 is NOT built (NMFB_ERR_UNSUPPORTED).  The reference's W line search compares the
-// objective of the full model (cnmfsc.m:218) with that of a trial reconstructed from the single frame
-// alone (line 235: ReconstructFromDecomposition(Wnew, H) with a 2-D Wnew is Wnew*H), and it starts
-// from the unprojected W0 while the projected W is what gets returned (lines 93-111); on ordinary data
-// the trial never wins and the function returns after ~665 halvings with the initial factors
-// (the literal CPU restatement used by the test-suite reproduces this).
+// W_sparsity > 0 (cnmfsc.m:100-110, 216-254) is reproduced literally, quirks included: the initial
+// projection is applied to W while the iterations start from the unprojected W0 (W0 = W only at the end
+// of an iteration, line 266), so the first cost and the first H gradient see V_hat = RFD(W, H) with
+// the projected W (a cross Gram matrix W0c' Wc on the device); and the W line search reconstructs its
+// trial from the single frame alone (line 235: RFD(Wnew, H) with a 2-D Wnew is Wnew*H, unshifted),
+// compares that with the objective it inherited (line 218) and hands this V_hat to the next frame.
+// On ordinary data the trial cannot win and the function returns by step-size underflow
+// ("Algorithm converged", lines 245-249) after ~665 halvings with the cost trimmed.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -72,6 +74,13 @@ struct State {
   std::vector<GemmOp> gemmBt;
   ResidOp rsCur, rsTrial;
   bool fused_resid = false;
+  // W_sparsity > 0: the returned W (projected at the start), its head/tail, the frame trial, the cross Gram matrix
+  float *Wret = nullptr, *Wrt = nullptr, *Wrl = nullptr, *Wnew = nullptr, *Wnt = nullptr, *Wnl = nullptr;
+  float *Cx = nullptr, *Cxt = nullptr, *Cxl = nullptr;
+  GemmOp gemmC, gemmD1, residInit, residW;
+  std::vector<GemmOp> gemmPosT;
+  ResidOp rsInit, rsW;
+  bool fused_w = false;
 };
 
 int objective(nmfb_handle* h, State* s, const GemmOp& op, const ResidOp& rs, double* out) {
@@ -122,10 +131,9 @@ int run(nmfb_handle* h, State* s, int K, int T, const nmfb_config* cfg_in, float
   if (!(cfg.tolerance > 0)) cfg.tolerance = 1e-3;  // cnmfsc.m:142-144
   double sH = cfg.H_sparsity;
   if (sH > 1) sH = 1;  // cnmfsc.m:117-119
-  if (cfg.W_sparsity > 0)
-    return h->fail(NMFB_ERR_UNSUPPORTED,
-                   "cnmfsc: W_sparsity > 0 is not built (the reference's W line search, cnmfsc.m:218-249, compares "
-                   "objectives of different models and ends by step-size underflow); use W_sparsity = 0");
+  double sW = cfg.W_sparsity;
+  if (sW > 1) sW = 1;  // cnmfsc.m:101-103
+  const bool spW = sW > 0;
   const bool W_fixed = cfg.W_fixed != 0, H_fixed = cfg.H_fixed != 0;
   const int m = h->m, n = h->n;
   s->K = K;
@@ -157,6 +165,17 @@ int run(nmfb_handle* h, State* s, int K, int T, const nmfb_config* cfg_in, float
   NMFB_TRY(ar->alloc(h, &s->Wt, cw));
   NMFB_TRY(ar->alloc(h, &s->Wl, cw));
   if (W_fixed) NMFB_TRY(ar->alloc(h, &s->Wsave, cw));
+  if (spW) {
+    NMFB_TRY(ar->alloc(h, &s->Wret, cw));
+    NMFB_TRY(ar->alloc(h, &s->Wrt, cw));
+    NMFB_TRY(ar->alloc(h, &s->Wrl, cw));
+    NMFB_TRY(ar->alloc(h, &s->Wnew, static_cast<size_t>(Kp) * ldw));
+    NMFB_TRY(ar->alloc(h, &s->Wnt, static_cast<size_t>(Kp) * ldw));
+    NMFB_TRY(ar->alloc(h, &s->Wnl, static_cast<size_t>(Kp) * ldw));
+    NMFB_TRY(ar->alloc(h, &s->Cx, static_cast<size_t>(KTp) * KTp));
+    NMFB_TRY(ar->alloc(h, &s->Cxt, static_cast<size_t>(KTp) * KTp));
+    NMFB_TRY(ar->alloc(h, &s->Cxl, static_cast<size_t>(KTp) * KTp));
+  }
   NMFB_TRY(ar->alloc(h, &s->A, cw));
   NMFB_TRY(ar->alloc(h, &s->Bt, static_cast<size_t>(Kp) * ldw));
   NMFB_TRY(ar->alloc(h, &s->Hm, ch));
@@ -205,7 +224,19 @@ int run(nmfb_handle* h, State* s, int K, int T, const nmfb_config* cfg_in, float
     L1s = std::sqrt(static_cast<double>(n)) - (std::sqrt(static_cast<double>(n)) - 1) * sH;
     NMFB_TRY(project_rows(h, s, s->Hm, L1s));
   }
-  if (W_fixed) NMFB_CUDA(h, cudaMemcpyAsync(s->Wsave, s->Wm, cw * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  double L1a = 0;
+  if (spW) {  // cnmfsc.m:100-110: W is projected, W0 is not
+    if (m > kProjThreads * 32 * kProjMaskWords)
+      return h->fail(NMFB_ERR_UNSUPPORTED, "cnmfsc: projfunc vectors longer than %d are not supported",
+                     kProjThreads * 32 * kProjMaskWords);
+    L1a = std::sqrt(static_cast<double>(m)) - (std::sqrt(static_cast<double>(m)) - 1) * sW;
+    NMFB_CUDA(h, cudaMemcpyAsync(s->Wret, s->Wm, cw * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    projfunc_kernel<<<KT, kProjThreads, 0, h->stream>>>(s->Wret, m, ldw, L1a, 1.0, 1, nullptr, s->fail);
+    NMFB_TRY(check_launch(h, "projfunc(W init)"));
+    NMFB_TRY(split_to(h, s->Wret, s->Wrt, s->Wrl, KT, m, ldw));
+  }
+  if (W_fixed)  // the W that "W0 = W" (cnmfsc.m:266) restores at the end of every iteration
+    NMFB_CUDA(h, cudaMemcpyAsync(s->Wsave, spW ? s->Wret : s->Wm, cw * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
   NMFB_TRY(split_to(h, s->Wm, s->Wt, s->Wl, KT, m, ldw));
   NMFB_TRY(stack_split(h, s, s->Hm, s->Hs, s->Hst, s->Hsl));
 
@@ -255,11 +286,11 @@ int run(nmfb_handle* h, State* s, int K, int T, const nmfb_config* cfg_in, float
     }
     for (GemmOp* op : {&s->gemmN, &s->gemmD, &s->gemmA}) op->L.args.chunk_kb = kChunk;
     // objective 0.5*|V - Wc*Hs|^2 for the current and the trial stack
-    auto plan_obj = [&](GemmOp* op, const float* Hhi, const float* Hlo) {
-      MatRef Xh{s->Wt, m, KTp, ldw, true}, Xl{s->Wl, m, KTp, ldw, true};
-      MatRef Yh{Hhi, n, KTp, ldh, true}, Yl{Hlo, n, KTp, ldh, true};
+    auto plan_obj = [&](GemmOp* op, const float* Whi, const float* Wlo, int Kdim, const float* Hhi, const float* Hlo) {
+      MatRef Xh{Whi, m, Kdim, ldw, true}, Xl{Wlo, m, Kdim, ldw, true};
+      MatRef Yh{Hhi, n, Kdim, ldh, true}, Yl{Hlo, n, Kdim, ldh, true};
       ExtraSegs e = three(Xh, Xl, Yh, Yl);
-      NMFB_TRY(plan_fused(h, op, EPI_RESID, Xh, Yh, KTp, nullptr, nullptr, 0, m, round_up(n, 64), n, nullptr, &e));
+      NMFB_TRY(plan_fused(h, op, EPI_RESID, Xh, Yh, Kdim, nullptr, nullptr, 0, m, round_up(n, 64), n, nullptr, &e));
       op->L.args.Vsrc = h->Vwork;
       op->L.args.ldv = h->ldv;
       op->L.args.scal = s->scal;
@@ -273,21 +304,67 @@ int run(nmfb_handle* h, State* s, int K, int T, const nmfb_config* cfg_in, float
       NMFB_TRY(nmfb::plan_resid(h, &s->rsCur, s->Wt, s->Wl, ldw, s->Hst, s->Hsl, ldh, h->Vwork, h->ldv, m, n, KTp, s->scal));
       NMFB_TRY(nmfb::plan_resid(h, &s->rsTrial, s->Wt, s->Wl, ldw, s->Hnt, s->Hnl, ldh, h->Vwork, h->ldv, m, n, KTp, s->scal));
     } else {
-      NMFB_TRY(plan_obj(&s->residCur, s->Hst, s->Hsl));
-      NMFB_TRY(plan_obj(&s->residTrial, s->Hnt, s->Hnl));
+      NMFB_TRY(plan_obj(&s->residCur, s->Wt, s->Wl, KTp, s->Hst, s->Hsl));
+      NMFB_TRY(plan_obj(&s->residTrial, s->Wt, s->Wl, KTp, s->Hnt, s->Hnl));
+    }
+    if (spW) {
+      // initial cost with the projected W (cnmfsc.m:152-153)
+      if (s->fused_resid) NMFB_TRY(nmfb::plan_resid(h, &s->rsInit, s->Wrt, s->Wrl, ldw, s->Hst, s->Hsl, ldh, h->Vwork, h->ldv, m, n, KTp, s->scal));
+      else NMFB_TRY(plan_obj(&s->residInit, s->Wrt, s->Wrl, KTp, s->Hst, s->Hsl));
+      // frame trial: 0.5*|V - Wnew*H|^2 with the unshifted H = the first K rows of the stack (line 235);
+      // rows K..Kp of the stack meet the zero padding columns of Wnew
+      s->fused_w = Kp <= kKlMaxKp && std::getenv("NMFB_RESID_UNFUSED") == nullptr;
+      if (s->fused_w) NMFB_TRY(nmfb::plan_resid(h, &s->rsW, s->Wnt, s->Wnl, ldw, s->Hst, s->Hsl, ldh, h->Vwork, h->ldv, m, n, Kp, s->scal));
+      else NMFB_TRY(plan_obj(&s->residW, s->Wnt, s->Wnl, Kp, s->Hst, s->Hsl));
+      // cross Gram C[c][c'] = sum_i W0[i][c] W[i][c'] for the first H gradient: W0c' V_hat = C Hs
+      MatRef Xr_hi{s->Wrt, m, KTp, ldw, false}, Xr_lo{s->Wrl, m, KTp, ldw, false};
+      MatRef Y0_hi{s->Wt, m, KTp, ldw, false}, Y0_lo{s->Wl, m, KTp, ldw, false};
+      ExtraSegs eC = three(Xr_hi, Xr_lo, Y0_hi, Y0_lo);
+      NMFB_TRY(plan_store(h, ar, &s->gemmC, Xr_hi, Y0_hi, m, nullptr, nullptr, 0, KTp, KTp, s->Cx, nullptr, KTp, true,
+                          nullptr, &eC));
+      MatRef Hm_hi{s->Hst, n, KTp, ldh, true}, Hm_lo{s->Hsl, n, KTp, ldh, true};
+      MatRef C_hi{s->Cxt, KTp, KTp, KTp, false}, C_lo{s->Cxl, KTp, KTp, KTp, false};
+      ExtraSegs eD1 = three(Hm_hi, Hm_lo, C_hi, C_lo);
+      NMFB_TRY(plan_store(h, ar, &s->gemmD1, Hm_hi, C_hi, KTp, nullptr, nullptr, 0, n, KTp, s->D, nullptr, ldh, false,
+                          nullptr, &eD1));
+      // pos_t for t >= 1: (Wnew_{t-1} H) Hs_t' = Wnew_{t-1} * G[0:K, frame t]  (G symmetric: rows of frame t, first K entries)
+      MatRef Xn_hi{s->Wnt, m, Kp, ldw, true}, Xn_lo{s->Wnl, m, Kp, ldw, true};
+      s->gemmPosT.resize(T);
+      for (int t = 1; t < T; ++t) {
+        const size_t off = static_cast<size_t>(t) * K * KTp;
+        MatRef Gt_hi{s->gramH.gtf + off, Kp, K, KTp, false}, Gt_lo{s->gramH.glo + off, Kp, K, KTp, false};
+        ExtraSegs eP = three(Xn_hi, Xn_lo, Gt_hi, Gt_lo);
+        NMFB_TRY(plan_store(h, ar, &s->gemmPosT[t], Xn_hi, Gt_hi, Kp, nullptr, nullptr, 0, m, Kp, s->Bt, nullptr, ldw,
+                            false, nullptr, &eP));
+        s->gemmPosT[t].L.args.chunk_kb = kChunk;
+      }
+      for (GemmOp* op : {&s->gemmC, &s->gemmD1}) op->L.args.chunk_kb = kChunk;
     }
   }
 
   std::vector<double> cost(static_cast<size_t>(cfg.maxiter) + 1, 0.0);  // cnmfsc.m:151
-  NMFB_TRY(objective(h, s, s->residCur, s->rsCur, &cost[0]));           // cnmfsc.m:152-153 (W == W0 here)
+  if (spW) {  // cnmfsc.m:152-153: V_hat = RFD(W, H) with the projected W
+    const bool keep = s->fused_resid;
+    NMFB_TRY(objective(h, s, s->residInit, s->rsInit, &cost[0]));
+    s->fused_resid = keep;
+  } else {
+    NMFB_TRY(objective(h, s, s->residCur, s->rsCur, &cost[0]));  // W == W0 here
+  }
+  std::vector<double> stepW(static_cast<size_t>(T), 1.0);  // cnmfsc.m:147
   double stepH = 1.0;                                                    // cnmfsc.m:148
   int ncost = cfg.maxiter + 1;
   bool done = false;
   for (int it = 1; it <= cfg.maxiter && !done; ++it) {
     if (!H_fixed) {
-      NMFB_TRY(run_gram(h, s->gramW, nullptr));
       NMFB_TRY(run_gemm(h, s->gemmN));
-      NMFB_TRY(run_gemm(h, s->gemmD));
+      if (spW && it == 1) {  // V_hat still is RFD(W, H) with the projected W (cnmfsc.m:152,164)
+        NMFB_TRY(run_gemm(h, s->gemmC));
+        NMFB_TRY(split_to(h, s->Cx, s->Cxt, s->Cxl, KTp, KTp, KTp));
+        NMFB_TRY(run_gemm(h, s->gemmD1));
+      } else {
+        NMFB_TRY(run_gram(h, s->gramW, nullptr));
+        NMFB_TRY(run_gemm(h, s->gemmD));
+      }
       fold_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->P, s->Nf, K, T, n, ldh);
       NMFB_TRY(check_launch(h, "fold(N)"));
       fold_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->D, s->Df, K, T, n, ldh);
@@ -329,7 +406,46 @@ int run(nmfb_handle* h, State* s, int K, int T, const nmfb_config* cfg_in, float
         NMFB_TRY(stack_split(h, s, s->Hm, s->Hs, s->Hst, s->Hsl));
       }
     }
-    if (!W_fixed) {  // cnmfsc.m:257-263
+    if (!W_fixed && spW) {  // cnmfsc.m:216-254
+      NMFB_TRY(run_gram(h, s->gramH, nullptr));
+      NMFB_TRY(run_gemm(h, s->gemmA));
+      double begobj;
+      NMFB_TRY(objective(h, s, s->residCur, s->rsCur, &begobj));  // cnmfsc.m:215,218 (frame 1: the full model)
+      for (int t = 0; t < T && !done; ++t) {
+        const size_t off = static_cast<size_t>(t) * K * ldw;
+        // pos = V_hat Hs_t' with the V_hat left by the previous frame's accepted trial (line 222)
+        NMFB_TRY(run_gemm(h, t == 0 ? s->gemmBt[0] : s->gemmPosT[t]));
+        double newobj = 0.0;
+        while (true) {
+          grad_step_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm + off, s->Bt, s->A + off, s->Wnew, K, m, ldw,
+                                                                  stepW[t]);  // cnmfsc.m:229
+          NMFB_TRY(check_launch(h, "grad_step(W)"));
+          projfunc_kernel<<<K, kProjThreads, 0, h->stream>>>(s->Wnew, m, ldw, L1a, 1.0, 1, nullptr, s->fail);  // 230-232
+          NMFB_TRY(check_launch(h, "projfunc(W)"));
+          NMFB_TRY(split_to(h, s->Wnew, s->Wnt, s->Wnl, K, m, ldw));
+          const bool keep = s->fused_resid;
+          s->fused_resid = s->fused_w;
+          int rc = objective(h, s, s->residW, s->rsW, &newobj);  // cnmfsc.m:235-236
+          s->fused_resid = keep;
+          NMFB_TRY(rc);
+          if (newobj <= begobj) break;  // cnmfsc.m:239-241
+          stepW[t] /= 2;                // cnmfsc.m:244
+          if (stepW[t] < 1e-200) {      // cnmfsc.m:245-249
+            ncost = it;
+            done = true;
+            break;
+          }
+        }
+        if (done) break;
+        stepW[t] *= 1.2;  // cnmfsc.m:252
+        NMFB_CUDA(h, cudaMemcpyAsync(s->Wret + off, s->Wnew, static_cast<size_t>(K) * ldw * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, h->stream));  // cnmfsc.m:253
+        begobj = newobj;  // line 218 of the next frame sees the V_hat of this trial
+      }
+      if (done) break;
+      NMFB_CUDA(h, cudaMemcpyAsync(s->Wm, s->Wret, cw * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));  // 266
+      NMFB_TRY(split_to(h, s->Wm, s->Wt, s->Wl, KT, m, ldw));
+    } else if (!W_fixed) {  // cnmfsc.m:257-263
       NMFB_TRY(run_gram(h, s->gramH, nullptr));
       NMFB_TRY(run_gemm(h, s->gemmA));
       for (int t = 0; t < T; ++t) {
@@ -339,9 +455,10 @@ int run(nmfb_handle* h, State* s, int K, int T, const nmfb_config* cfg_in, float
         NMFB_TRY(check_launch(h, "mu_step(W)"));
         NMFB_TRY(split_to(h, s->Wm + off, s->Wt + off, s->Wl + off, K, m, ldw));
       }
-    } else if (!H_fixed && !(sH > 0)) {
-      // cnmfsc.m:266 with W never updated: "W0 = W" discards the scaling of lines 207-209 BEFORE the
-      // cost of this iteration is taken (H stays normalised) - a quirk of the reference, kept
+    } else if (spW || (!H_fixed && !(sH > 0))) {
+      // cnmfsc.m:266 with W never updated: "W0 = W" replaces the unprojected W0 of the first iteration
+      // and discards the scaling of lines 207-209 BEFORE the cost of this iteration is taken (H stays
+      // normalised) - quirks of the reference, kept
       NMFB_CUDA(h, cudaMemcpyAsync(s->Wm, s->Wsave, cw * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
       NMFB_TRY(split_to(h, s->Wm, s->Wt, s->Wl, KT, m, ldw));
     }
@@ -353,7 +470,8 @@ int run(nmfb_handle* h, State* s, int K, int T, const nmfb_config* cfg_in, float
   }
   if (n_cost) *n_cost = ncost;
   if (cost_out) std::memcpy(cost_out, cost.data(), static_cast<size_t>(ncost) * sizeof(double));
-  if (W_out) NMFB_TRY(download_colmajor(h, s->Wm, ldw, m, KT, W_out));
+  // the function returns W, which differs from W0 when it stops inside an iteration (cnmfsc.m:93-94,253,266)
+  if (W_out) NMFB_TRY(download_colmajor(h, (spW && !W_fixed) ? s->Wret : (W_fixed ? s->Wsave : s->Wm), ldw, m, KT, W_out));
   if (H_out) NMFB_TRY(download_H(h, s->Hm, ldh, K, n, H_out));
   return NMFB_OK;
 }

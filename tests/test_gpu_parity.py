@@ -334,9 +334,25 @@ def test_cnmfsc_fixed_factors_and_errors(api, handle):
     with pytest.raises(api.NmfbError) as e:  # cnmfsc.m:67-69
         api.cnmfsc(-V, K, T, dict(maxiter=2), handle=handle)
     assert e.value.code == 6
-    with pytest.raises(api.NmfbError) as e:  # documented gap: the reference's W line search is degenerate
-        api.cnmfsc(V, K, T, dict(W_sparsity=0.5, maxiter=2), handle=handle)
-    assert e.value.code == 3
+
+
+@pytest.mark.parametrize("extra", [dict(W_sparsity=0.5), dict(W_sparsity=0.5, H_sparsity=0.6), dict(W_sparsity=0.4, W_fixed=True),
+                                   dict(W_sparsity=0.4, W_fixed=True, H_sparsity=0.5), dict(W_sparsity=0.6, H_fixed=True)])
+@pytest.mark.parametrize("scale", [1.0, 0.2])
+def test_cnmfsc_w_sparsity_literal(api, handle, extra, scale):
+    """cnmfsc.m:100-110, 216-254 with W_sparsity > 0, quirks included: W is projected but the loop starts from the
+    unprojected W0; the W line search reconstructs its trial from one frame alone (line 235) and usually ends by
+    step-size underflow with the cost trimmed (lines 245-249).  Same stopping point, same cost entries, same factors."""
+    rng = np.random.default_rng(5)
+    m, n, K, T = 60, 150, 4, 3
+    V = rng.random((m, n))
+    cfg = dict(W_init=scale * rng.random((m, K, T)), H_init=scale * rng.random((K, n)), maxiter=8, tolerance=1e-300, **extra)
+    W, H, c = api.cnmfsc(V, K, T, cfg, handle=handle)
+    Wo, Ho, co = O.cnmfsc(V, K, T, cfg)
+    assert len(c) == len(co), (len(c), len(co))
+    assert cost_err(c, co) < COST_TOL
+    assert np.linalg.norm(W - Wo) / np.linalg.norm(Wo) < 2e-3
+    assert np.linalg.norm(H - Ho) / np.linalg.norm(Ho) < 2e-3
 
 
 # ---------------------------------------------------------------- lnmf

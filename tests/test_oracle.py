@@ -205,3 +205,6 @@ def test_cnmfsc_oracle_behaviour():
     np.testing.assert_allclose((H ** 2).sum(1), 1.0, rtol=1e-9)
     W, H, c = O.cnmfsc(V, K, T, dict(W_init=W0, H_init=H0, W_sparsity=0.5, maxiter=12, tolerance=1e-300))
     assert len(c) <= 2  # "Algorithm converged" (step size below 1e-200) in the first or second iteration
+    # with W held fixed the projected W replaces the unprojected W0 at the end of the first iteration (line 266)
+    W, H, c = O.cnmfsc(V, K, T, dict(W_init=W0, H_init=H0, W_sparsity=0.5, W_fixed=True, maxiter=6, tolerance=1e-300))
+    assert len(c) == 7 and abs((W ** 2).sum(0) - 1).max() < 1e-9
