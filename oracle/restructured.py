@@ -10,6 +10,9 @@ NumPy float64.  It exists to pin the literal restatement (both must agree to
 * CNMF as ONE nmf-style update on the stacked (Wc, Hs) pair + a fold (cnmf.m:187-231)
 * column sharding over ``shards`` virtual ranks with one packed reduction per
   iteration - only summation order differs from 1 rank.
+* IS / AB (and cnmf's KL / IS / AB) in "two-weight" form: A = Qn H', B = Qp H' and the
+  Euclidean-shaped W step; per-basis lambda / fixed vectors == the per-source cell loops
+* cnmfsc's W gradients through the Gram matrix of the shifted stack
 
 Only ``tests/`` may import this module.
 """
@@ -164,3 +167,117 @@ def cnmf_stacked(V, K, T, config):
             break
     W3 = np.stack([Wc[:, t * K:(t + 1) * K] for t in range(T)], axis=2)
     return W3, H, cost
+
+
+# --------------------------------------------------------------------------
+# IS / AB divergences ("two-weight" form of nmf_driver.cu::plan_two_weight and
+# cnmf_driver.cu): both gradients are contractions with element-wise weights.
+# --------------------------------------------------------------------------
+def _weights(V, V_hat, div, alpha, beta):
+    """Qn, Qp, outer exponent (nmf.m:154-164, 185-195)."""
+    if div in ("is_divergence", "is"):
+        return V / V_hat ** 2, 1.0 / V_hat, 1.0
+    if div in ("kl_divergence", "kl"):  # cnmf.m:141-143 reaches KL as alpha = 1, beta = 0
+        alpha, beta = 1.0, 0.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if alpha == 0:  # dual (nmf.m:124-128)
+            return V ** (alpha - 1) * V_hat ** beta, V ** (alpha + beta - 1), 1.0 / beta
+        return V ** alpha * V_hat ** (beta - 1), V_hat ** (alpha + beta - 1), 1.0 / alpha
+
+
+def nmf_two_weight(V, K, config, lam_w=None, lam_h=None, fix_w=None, fix_h=None):
+    """nmf.m for 'is' / 'ab' (single source, or concatenated sources with per-basis vectors) the way
+    the device computes it: A = Qn H', B = Qp H', neg = A + W diag(<W_k, B_k>), pos = B + W diag(<W_k, A_k>)
+    (the Euclidean-shaped W step), N = W' Qn, D = W' Qp.  Returns W, H, cost."""
+    V = np.asarray(V, dtype=np.float64)
+    div = config["divergence"]
+    alpha, beta = float(config.get("alpha", 1)), float(config.get("beta", 1))
+    maxiter = int(config.get("maxiter", 100))
+    W = np.array(config["W_init"], dtype=np.float64)
+    H = np.array(config["H_init"], dtype=np.float64)
+    lam_w = np.full(K, max(float(config.get("W_sparsity", 0) or 0), 0.0)) if lam_w is None else np.asarray(lam_w, float)
+    lam_h = np.full(K, max(float(config.get("H_sparsity", 0) or 0), 0.0)) if lam_h is None else np.asarray(lam_h, float)
+    fix_w = np.zeros(K, bool) if fix_w is None else np.asarray(fix_w, bool)
+    fix_h = np.zeros(K, bool) if fix_h is None else np.asarray(fix_h, bool)
+    W = W / np.sqrt((W ** 2).sum(0))  # nmf.m:132
+    cost = np.zeros(maxiter)
+    for it in range(maxiter):
+        Qn, Qp, expo = _weights(V, W @ H, div, alpha, beta)
+        A, B = Qn @ H.T, Qp @ H.T
+        a, b = (W * A).sum(0), (W * B).sum(0)
+        neg, pos = (A + W * b) ** expo, (B + W * a) ** expo
+        Wn = W * (neg / np.fmax(pos + lam_w, EPS))
+        Wn = Wn / np.sqrt((Wn ** 2).sum(0))
+        W = np.where(fix_w, W, Wn)
+        Qn, Qp, expo = _weights(V, W @ H, div, alpha, beta)
+        N, D = (W.T @ Qn) ** expo, (W.T @ Qp) ** expo
+        Hn = H * (N / np.fmax(D + lam_h[:, None], EPS))
+        H = np.where(fix_h[:, None], H, Hn)
+        V_hat = W @ H
+        if div in ("is_divergence", "is"):
+            c = np.sum(np.log(V_hat / V) + V / V_hat - 1)
+        else:
+            c = (np.float64(-1.0) / np.float64(alpha * beta)) * np.sum(
+                V ** alpha * V_hat ** beta
+                - (alpha * V ** (alpha + beta) + beta * V_hat ** (alpha + beta) + beta) / np.float64(alpha + beta))
+        cost[it] = c + np.sum(lam_w * np.abs(W).sum(0)) + np.sum(lam_h * np.abs(H).sum(1))
+    return W, H, cost
+
+
+def cnmf_two_weight(V, K, T, config):
+    """cnmf.m for 'kl' / 'is' / 'ab' in stacked two-weight form (cnmf_driver.cu): A = Qn Hs', B = Qp Hs',
+    per-column Euclidean-shaped W step, per-basis normalisation, fold(Wc' Qn), fold(Wc' Qp) with the
+    unshifted V_pos of the KL branch (cnmf.m:221-222)."""
+    V = np.asarray(V, dtype=np.float64)
+    m, n = V.shape
+    div = config["divergence"]
+    alpha, beta = float(config.get("alpha", 1)), float(config.get("beta", 1))
+    lamW = max(float(config.get("W_sparsity", 0) or 0), 0.0)
+    lamH = max(float(config.get("H_sparsity", 0) or 0), 0.0)
+    maxiter = int(config.get("maxiter", 100))
+    W3 = np.array(config["W_init"], dtype=np.float64).reshape(m, K, T)
+    H = np.array(config["H_init"], dtype=np.float64)
+    nrm = np.sqrt((W3 ** 2).sum(axis=(0, 2))) / T  # cnmf.m:157-166
+    W3 = W3 / nrm[None, :, None]
+    H = H * nrm[:, None]
+    Wc = np.concatenate([W3[:, :, t] for t in range(T)], axis=1)  # column k + K*t
+    kl = div in ("kl_divergence", "kl")
+    cost = np.zeros(maxiter)
+    for it in range(maxiter):
+        Hs = _stack_shift(H, T)
+        Qn, Qp, expo = _weights(V, Wc @ Hs, div, alpha, beta)
+        A, B = Qn @ Hs.T, Qp @ Hs.T
+        a, b = (Wc * A).sum(0), (Wc * B).sum(0)
+        Wc = Wc * ((A + Wc * b) ** expo / np.fmax((B + Wc * a) ** expo + lamW, EPS))
+        sq = (Wc ** 2).sum(0).reshape(T, K).sum(0)  # per basis over all frames
+        Wc = Wc / np.tile(np.sqrt(sq) / T, T)
+        Qn, Qp, expo = _weights(V, Wc @ Hs, div, alpha, beta)
+        neg = _fold(Wc.T @ Qn, K, T)
+        P = Wc.T @ (Qp if not np.isscalar(Qp) else np.full_like(V, Qp))
+        pos = P.reshape(T, K, n).sum(0) if kl else _fold(P, K, T)
+        H = H * (neg ** expo / np.fmax(pos ** expo + lamH, EPS))
+        V_hat = Wc @ _stack_shift(H, T)
+        if kl:
+            c = np.sum(V * np.log(V / V_hat) - V + V_hat)
+        elif div in ("is_divergence", "is"):
+            c = np.sum(np.log(V_hat / V) + V / V_hat - 1)
+        else:
+            c = (np.float64(-1.0) / np.float64(alpha * beta)) * np.sum(
+                V ** alpha * V_hat ** beta
+                - (alpha * V ** (alpha + beta) + beta * V_hat ** (alpha + beta) + beta) / np.float64(alpha + beta))
+        cost[it] = c + lamW * np.abs(Wc).sum() + lamH * np.abs(H).sum()
+    W3 = np.stack([Wc[:, t * K:(t + 1) * K] for t in range(T)], axis=2)
+    return W3, H, cost
+
+
+def cnmfsc_w_gradients(V, W0c, Wprev, H, K, T, t):
+    """The two W gradients of cnmfsc.m the way cnmfsc_driver.cu forms them, for frame t (0-based):
+    multiplicative branch (lines 257-263)  pos_t = Wc_current (Hs Hs')[:, frame t];
+    sparse branch, t >= 1 (lines 218-224 after the trial of line 235)  pos_t = Wprev (H Hs_t') taken from the
+    rows of frame t and the first K columns of the symmetric Gram matrix."""
+    Hs = _stack_shift(H, T)
+    G = Hs @ Hs.T
+    neg = (V @ Hs.T)[:, t * K:(t + 1) * K]
+    pos_mu = W0c @ G[:, t * K:(t + 1) * K]
+    pos_sparse = Wprev @ G[t * K:(t + 1) * K, :K].T if Wprev is not None else None
+    return neg, pos_mu, pos_sparse

@@ -208,3 +208,73 @@ def test_cnmfsc_oracle_behaviour():
     # with W held fixed the projected W replaces the unprojected W0 at the end of the first iteration (line 266)
     W, H, c = O.cnmfsc(V, K, T, dict(W_init=W0, H_init=H0, W_sparsity=0.5, W_fixed=True, maxiter=6, tolerance=1e-300))
     assert len(c) == 7 and abs((W ** 2).sum(0) - 1).max() < 1e-9
+
+
+@pytest.mark.parametrize("div,alpha,beta", [("is", 1, 1), ("ab", 0.5, 0.5), ("ab", 2, 1), ("ab", 1.5, -0.5), ("ab", 0, 1)])
+def test_two_weight_form_matches_literal_nmf(div, alpha, beta):
+    """The device algebra of the IS / AB path (A = Qn H', B = Qp H', Euclidean-shaped W step) is the literal
+    nmf.m:154-164,185-195 - checked here on the CPU, incl. the dual updates and sparsity."""
+    rng = np.random.default_rng(12)
+    m, n, K = 30, 44, 4
+    V = 0.5 + rng.random((m, n))
+    cfg = dict(divergence=div, alpha=alpha, beta=beta, W_init=rng.random((m, K)) + 0.1, H_init=rng.random((K, n)) + 0.1,
+               maxiter=2 if alpha == 0 else 6, tolerance=1e-300, W_sparsity=0.05, H_sparsity=0.02)
+    with np.errstate(all="ignore"):
+        W, H, c = O.nmf(V, K, cfg)
+        W2, H2, c2 = R.nmf_two_weight(V, K, cfg)
+    np.testing.assert_allclose(W2, W, rtol=1e-9)
+    np.testing.assert_allclose(H2, H, rtol=1e-9)
+    fin = np.isfinite(c)
+    assert np.array_equal(fin, np.isfinite(c2))
+    np.testing.assert_allclose(c2[fin], c[fin], rtol=1e-10)
+
+
+def test_per_basis_vectors_equal_per_source_loops():
+    """Concatenated sources with per-basis lambda / fixed flags == the reference's per-source cell loops."""
+    rng = np.random.default_rng(13)
+    m, n, sizes = 24, 40, [2, 3, 2]
+    V = 0.2 + rng.random((m, n))
+    W0 = [rng.random((m, k)) + 0.1 for k in sizes]
+    H0 = [rng.random((k, n)) + 0.1 for k in sizes]
+    lw, lh = [0.0, 0.2, 0.05], [0.3, 0.0, 0.1]
+    cfg = dict(divergence="is", W_init=W0, H_init=H0, maxiter=5, tolerance=1e-300, W_sparsity=lw, H_sparsity=lh,
+               W_fixed=[True, False, False], H_fixed=[False, False, True])
+    W, H, c = O.nmf(V, sizes, cfg)
+    cat = dict(cfg, W_init=np.concatenate(W0, 1), H_init=np.concatenate(H0, 0))
+    W2, H2, c2 = R.nmf_two_weight(V, sum(sizes), cat, lam_w=np.repeat(lw, sizes), lam_h=np.repeat(lh, sizes),
+                                  fix_w=np.repeat([True, False, False], sizes), fix_h=np.repeat([False, False, True], sizes))
+    np.testing.assert_allclose(W2, np.concatenate(W, 1), rtol=1e-9)
+    np.testing.assert_allclose(H2, np.concatenate(H, 0), rtol=1e-9)
+    np.testing.assert_allclose(c2, c, rtol=1e-10)
+
+
+@pytest.mark.parametrize("div,alpha,beta", [("kl", 1, 1), ("is", 1, 1), ("ab", 0.5, 1.0), ("ab", 2, 1)])
+def test_stacked_two_weight_cnmf_matches_literal(div, alpha, beta):
+    rng = np.random.default_rng(14)
+    m, n, K, T = 20, 60, 3, 3
+    V = 0.2 + rng.random((m, n))
+    cfg = dict(divergence=div, alpha=alpha, beta=beta, W_init=rng.random((m, K, T)) + 0.1, H_init=rng.random((K, n)) + 0.1,
+               maxiter=5, tolerance=1e-300, W_sparsity=0.03, H_sparsity=0.05)
+    W, H, c = O.cnmf(V, K, T, cfg)
+    W2, H2, c2 = R.cnmf_two_weight(V, K, T, cfg)
+    np.testing.assert_allclose(W2, W, rtol=1e-9)
+    np.testing.assert_allclose(H2, H, rtol=1e-9)
+    np.testing.assert_allclose(c2, c, rtol=1e-10)
+
+
+def test_cnmfsc_gram_forms_of_the_w_gradients():
+    """pos_t of cnmfsc.m:222,260 through the Gram matrix of the shifted stack, as the device forms it."""
+    rng = np.random.default_rng(15)
+    m, n, K, T = 18, 50, 3, 4
+    V, H = rng.random((m, n)), rng.random((K, n))
+    W3 = rng.random((m, K, T))
+    Wc = np.concatenate([W3[:, :, t] for t in range(T)], axis=1)
+    V_hat = O.reconstruct_from_decomposition(W3, H)
+    Wprev = rng.random((m, K))
+    for t in range(T):
+        Hsh = np.zeros_like(H)
+        Hsh[:, t:] = H[:, : n - t]
+        neg, pos_mu, pos_sparse = R.cnmfsc_w_gradients(V, Wc, Wprev, H, K, T, t)
+        np.testing.assert_allclose(neg, V @ Hsh.T, rtol=1e-12)
+        np.testing.assert_allclose(pos_mu, V_hat @ Hsh.T, rtol=1e-11)
+        np.testing.assert_allclose(pos_sparse, (Wprev @ H) @ Hsh.T, rtol=1e-11)  # V_hat = RFD(Wnew, H), line 235
