@@ -118,3 +118,29 @@ def test_shard_bounds_cover_and_partition():
         assert max(sizes) - min(sizes) <= 1
     lay = pack_layout(8192, 128)  # config 3: 8192*128 + 128^2 floats ~ 4.26 MB
     assert lay["total"] == 8192 * 128 + 128 * 128 and lay["G_H"][0] == 8192 * 128
+
+
+def test_header_is_valid_c99_and_matches_the_python_struct(tmp_path):
+    """include/nmfb200.h is the drop-in boundary: it must compile as plain C (the MEX gateway and any C
+    caller include it) and nmfb_config must have the layout api._Config marshals."""
+    import shutil
+    import subprocess
+
+    from nmf_toolbox_b200 import api
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text(
+        '#include <stddef.h>\n#include <stdio.h>\n#include "nmfb200.h"\n'
+        "int main(void) { nmfb_config c = {0}; (void)c;\n"
+        '  printf("%zu %zu %zu %zu %zu\\n", sizeof(nmfb_config), offsetof(nmfb_config, W_init), offsetof(nmfb_config, maxiter),\n'
+        "         offsetof(nmfb_config, cost_mode), offsetof(nmfb_config, W_sparsity_k)); return 0; }\n")
+    exe = tmp_path / "t"
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    C = api._Config
+    assert [int(x) for x in out] == [ctypes.sizeof(C), C.W_init.offset, C.maxiter.offset, C.cost_mode.offset,
+                                     C.W_sparsity_k.offset]
