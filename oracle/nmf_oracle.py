@@ -2,7 +2,7 @@
 
 Literal, line-by-line NumPy float64 restatement of the reference's MATLAB hot
 path (colinvaz/nmf-toolbox): ``nmf.m``, ``cnmf.m``, ``nmfsc.m``, ``projfunc.m``
-and ``ReconstructFromDecomposition.m``.  It deliberately keeps the reference's
+and ``ReconstructFromDecomposition.m``, plus ``cnmfsc.m`` and ``lnmf.m``.  It deliberately keeps the reference's
 exact operation sequence - the dense ``ones(n, m)`` products, the
 ``diag(diag(...))`` terms, the per-frame loops, the redundant GEMMs - so that it
 is a readable statement of WHAT the reference computes, not a fast one.
@@ -38,6 +38,8 @@ __all__ = [
     "nmf",
     "cnmf",
     "nmfsc",
+    "cnmfsc",
+    "lnmf",
 ]
 
 
