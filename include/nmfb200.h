@@ -176,10 +176,24 @@ int nmfb_nmf_end(nmfb_handle* h, float* W_out, float* H_out, double* cost_out, i
  * launch of the two large contractions of the Euclidean nmf iteration). */
 int nmfb_profile_enable(nmfb_handle* h, int on);
 int nmfb_profile_get(nmfb_handle* h, double* ms_w_gemm, double* ms_h_gemm, int* count);
-/* ms_out[5]: W-step GEMM, H-step GEMM, gram(H)+cost, element-wise W step, gram(W) (averages). */
+/* ms_out[5], averages per launch group.  nmf euclidean: W-step GEMM, H-step GEMM, gram(H)+cost,
+ * element-wise W step, gram(W).  nmf KL: [0] fused W half, [1] fused H half.  cnmf: [0] A/B GEMM,
+ * [1] P/D GEMM (+ slab sum), [2] fold + H update.  nmfsc: [0] gradient GEMMs of the H step, [1] one
+ * objective evaluation, [2] step + projfunc + split of one trial, [3] W step. */
 int nmfb_profile_get_all(nmfb_handle* h, double* ms_out);
+/* Iterations executed by, and device time (CUDA events on the handle's stream, ms) of, the iteration
+ * loop of the last nmfb_nmf / nmfb_lnmf / nmfb_cnmf / nmfb_nmfsc / nmfb_cnmfsc call on this handle:
+ * setup, uploads and downloads excluded (bench.py's resident timing of the one-call algorithms). */
+int nmfb_last_loop(nmfb_handle* h, int* iters, double* device_ms);
+/* nmfb_nmfsc: how often the line searches of the last call halved their step (nmfsc.m:169, 220):
+ * out[2*i] for the H search, out[2*i+1] for the W search of iteration i.  Returns the number of
+ * entries available (2 x executed iterations); at most `capacity` are written. */
+int nmfb_last_halvings(nmfb_handle* h, int* out, int capacity);
 /* Number of kernel launches issued by the handle since creation. */
 long long nmfb_launch_count(const nmfb_handle* h);
+/* Number of cudaMalloc calls the handle has made (allocations that missed its block cache): constant
+ * across repeated calls of the same shape, i.e. a steady-state call allocates nothing. */
+long long nmfb_malloc_count(const nmfb_handle* h);
 
 /* ---- multi-GPU ---------------------------------------------------------- */
 #define NMFB_UNIQUE_ID_BYTES 128

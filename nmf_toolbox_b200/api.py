@@ -99,6 +99,9 @@ def _bind(lib):
         "nmfb_nmf_sync": ([P, PI, ctypes.POINTER(D)], I),
         "nmfb_nmf_end": ([P, P, P, P, PI], I),
         "nmfb_launch_count": ([P], LL),
+        "nmfb_malloc_count": ([P], LL),
+        "nmfb_last_loop": ([P, PI, ctypes.POINTER(D)], I),
+        "nmfb_last_halvings": ([P, PI, I], I),
         "nmfb_profile_enable": ([P, I], I),
         "nmfb_profile_get": ([P, ctypes.POINTER(D), ctypes.POINTER(D), PI], I),
         "nmfb_profile_get_all": ([P, ctypes.POINTER(D)], I),
@@ -183,6 +186,24 @@ class Handle:
 
     def launch_count(self) -> int:
         return int(self.lib.nmfb_launch_count(self._h))
+
+    def last_loop(self):
+        """(iterations executed, device ms) of the iteration loop of the last one-call algorithm run."""
+        it, ms = ctypes.c_int(0), ctypes.c_double(0)
+        self._check(self.lib.nmfb_last_loop(self._h, ctypes.byref(it), ctypes.byref(ms)))
+        return it.value, ms.value
+
+    def last_halvings(self):
+        """nmfsc: (halvings of the H search, halvings of the W search) per iteration of the last call."""
+        n = self.lib.nmfb_last_halvings(self._h, None, 0)
+        buf = (ctypes.c_int * max(n, 1))()
+        self.lib.nmfb_last_halvings(self._h, buf, n)
+        a = np.asarray(buf[:n], dtype=np.int32).reshape(-1, 2)
+        return a[:, 0].copy(), a[:, 1].copy()
+
+    def malloc_count(self) -> int:
+        """cudaMalloc calls made by the handle so far (steady-state calls of one shape add none)."""
+        return int(self.lib.nmfb_malloc_count(self._h))
 
     def profile_enable(self, on: bool = True):
         self._check(self.lib.nmfb_profile_enable(self._h, int(on)))

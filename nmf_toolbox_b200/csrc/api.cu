@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 
 #include "comm.cuh"
@@ -22,6 +23,19 @@ extern "C" const char* nmfb_last_error(const nmfb_handle* h) {
 }
 
 extern "C" long long nmfb_launch_count(const nmfb_handle* h) { return h ? h->launches : 0; }
+extern "C" int nmfb_last_loop(nmfb_handle* h, int* iters, double* device_ms) {
+  if (!h) return NMFB_ERR_INVALID_ARGUMENT;
+  if (iters) *iters = h->loop_iters;
+  if (device_ms) *device_ms = h->loop_ms;
+  return NMFB_OK;
+}
+extern "C" int nmfb_last_halvings(nmfb_handle* h, int* out, int capacity) {
+  if (!h) return 0;
+  const int n = static_cast<int>(h->halvings.size());
+  for (int i = 0; i < n && i < capacity && out; ++i) out[i] = h->halvings[i];
+  return n;
+}
+extern "C" long long nmfb_malloc_count(const nmfb_handle* h) { return h ? h->mallocs : 0; }
 
 extern "C" int nmfb_create(nmfb_handle** out, int device) {
   if (!out) return NMFB_ERR_INVALID_ARGUMENT;
@@ -63,7 +77,7 @@ extern "C" int nmfb_create(nmfb_handle** out, int device) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
-  if (e == cudaSuccess) e = cudaMallocHost(&h->pinned, 8 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMallocHost(&h->pinned, 64 * sizeof(int));
   if (e != cudaSuccess) {
     g_create_error = std::string("handle creation failed: ") + cudaGetErrorString(e);
     delete h;
@@ -80,8 +94,8 @@ extern "C" void nmfb_destroy(nmfb_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->stream2) cudaStreamSynchronize(h->stream2);
   if (h->comm) comm_destroy(h);
-  if (h->Vown) cudaFree(h->Vown);
-  if (h->Vwork) cudaFree(h->Vwork);
+  if (h->Vown) dev_free(h, h->Vown, h->Vown_bytes);
+  if (h->Vwork) dev_free(h, h->Vwork, h->Vwork_bytes);
   h->pool.trim();
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -114,12 +128,16 @@ extern "C" int nmfb_set_V(nmfb_handle* h, const float* V_host, int m, int n) {
   if (!h) return NMFB_ERR_INVALID_ARGUMENT;
   if (!V_host || m <= 0 || n <= 0) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "set_V: bad arguments");
   cudaSetDevice(h->device);
+  const bool trace = std::getenv("NMFB_TRACE") != nullptr;
+  timespec ts0, ts1, ts2;
+  clock_gettime(CLOCK_MONOTONIC, &ts0);
   nmf_session_release(h);
   drop_V(h);
   const long long ld = round_up(m, 4);
   const size_t bytes = static_cast<size_t>(n) * ld * sizeof(float);
   void* vp = nullptr;
   NMFB_CUDA(h, dev_alloc(h, &vp, bytes));
+  clock_gettime(CLOCK_MONOTONIC, &ts1);
   h->Vown = static_cast<float*>(vp);
   h->Vown_bytes = bytes;
   if (ld != m) NMFB_CUDA(h, cudaMemsetAsync(h->Vown, 0, bytes, h->stream));
@@ -129,6 +147,12 @@ extern "C" int nmfb_set_V(nmfb_handle* h, const float* V_host, int m, int n) {
   h->ldv = ld;
   NMFB_TRY(upload_colmajor(h, V_host, m, n, h->Vown, ld));
   NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (trace) {
+    clock_gettime(CLOCK_MONOTONIC, &ts2);
+    auto ms = [](const timespec& a, const timespec& b) { return (b.tv_sec - a.tv_sec) * 1e3 + (b.tv_nsec - a.tv_nsec) * 1e-6; };
+    fprintf(stderr, "[nmfb] set_V: release+alloc %.1f ms, upload of %.0f MiB %.1f ms (%.1f GB/s), %lld cudaMalloc so far\n",
+            ms(ts0, ts1), bytes / 1048576.0, ms(ts1, ts2), bytes / 1e6 / ms(ts1, ts2), h->mallocs);
+  }
   return NMFB_OK;
 }
 

@@ -149,7 +149,9 @@ int enqueue_iteration(nmfb_handle* h, CnmfState* s, int i) {
   }
   if (i > 0) NMFB_TRY(enqueue_cost(h, s, i - 1));
   if (!s->W_fixed) {
+    NMFB_TRY(prof_mark(h, 0));
     NMFB_TRY(run_gemm(h, s->gemmA));  // A = V Hs', B = Wc (Hs Hs')
+    NMFB_TRY(prof_mark(h, 0));
     WStepArgs w{};  // dots, multiplicative step and per-basis normalisation in one launch (CTA per basis)
     w.mode = WSTEP_EUCLID;
     w.W = s->Wm;
@@ -171,11 +173,15 @@ int enqueue_iteration(nmfb_handle* h, CnmfState* s, int i) {
     NMFB_TRY(run_gram(h, s->gramW, stop));
   }
   // P = Wc'V and D = (Wc'Wc) Hs, then fold over the frames and update H (cnmf.m:216-231)
+  NMFB_TRY(prof_mark(h, 1));
   NMFB_TRY(run_gemm(h, s->gemmP));
+  NMFB_TRY(prof_mark(h, 1));
+  NMFB_TRY(prof_mark(h, 2));
   fold_update_kernel<<<vec_grid(s->n, s->K), 256, 0, h->stream>>>(s->P, s->D, s->Hm, s->K, s->T, s->n, s->ldh,
                                                                   s->lambda_h, s->H_fixed ? 1 : 0, s->scal,
                                                                   stop);
-  return check_launch(h, "fold_update");
+  NMFB_TRY(check_launch(h, "fold_update"));
+  return prof_mark(h, 2);
 }
 
 int cnmf_finish(nmfb_handle* h, CnmfState* s, float* W_out, float* H_out, double* cost_out, int* n_cost) {
@@ -183,6 +189,7 @@ int cnmf_finish(nmfb_handle* h, CnmfState* s, float* W_out, float* H_out, double
   NMFB_CUDA(h, cudaMemcpyAsync(flags, s->stop, sizeof(flags), cudaMemcpyDeviceToHost, h->stream));
   NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
   const int nc = flags[1];
+  h->loop_iters = nc;  // executed iterations (launches queued behind the stop flag were no-ops)
   if (n_cost) *n_cost = nc;
   if (cost_out && nc > 0)
     NMFB_CUDA(h, cudaMemcpy(cost_out, s->cost, nc * sizeof(double), cudaMemcpyDeviceToHost));
@@ -335,7 +342,9 @@ int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_
     const bool split_h = tiles_h * 2 <= h->num_sms;
     NMFB_TRY(plan_store(h, ar, &s->gemmPn, Xnt, Yw, m, nullptr, nullptr, 0, n, KTp, s->P, nullptr, s->ldh, split_h, stop));
     NMFB_TRY(plan_store(h, ar, &s->gemmPd, Xpt, Yw, m, nullptr, nullptr, 0, n, KTp, s->D, nullptr, s->ldh, split_h, stop));
+    loop_begin(h);
     NMFB_TRY(run_chunked(h, s->maxiter, s->stop, [&](int i) { return enqueue_iteration(h, s, i); }));
+    loop_end(h, s->maxiter);
     NMFB_TRY(enqueue_hstack(h, s, stop));
     s->gemmS.L.args.want_cost = 1;
     NMFB_TRY(run_gemm(h, s->gemmS));
@@ -363,7 +372,9 @@ int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_
   if (s->W_fixed) NMFB_TRY(run_gram(h, s->gramW, nullptr));
   // sum(H) for the sparsity term when H is never updated is accumulated by fold_update (freeze)
 
+  loop_begin(h);
   NMFB_TRY(run_chunked(h, s->maxiter, s->stop, [&](int i) { return enqueue_iteration(h, s, i); }));
+  loop_end(h, s->maxiter);
   // cost of the last executed iteration needs Hs Hs' of the final H
   NMFB_TRY(enqueue_hstack(h, s, stop));
   NMFB_TRY(run_gram(h, s->gramH, stop));

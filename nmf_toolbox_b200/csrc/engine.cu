@@ -198,10 +198,16 @@ int compute_v_stats(nmfb_handle* h, bool want_log, VStats* out, double** dev_sta
 int prepare_v_work(nmfb_handle* h, bool divide_by_max, bool round, double* sumsq_dev,
                    const unsigned int* maxbits_dev) {
   const size_t bytes = static_cast<size_t>(h->n) * h->ldv * sizeof(float);
-  if (h->Vwork == nullptr || h->Vwork_bytes < bytes) {
-    if (h->Vwork) cudaFree(h->Vwork);
+  if (h->Vwork == nullptr || h->Vwork_bytes != bytes) {  // through the block pool: trimmed and retried on failure
+    if (h->Vwork) {
+      cudaStreamSynchronize(h->stream);
+      dev_free(h, h->Vwork, h->Vwork_bytes);
+    }
     h->Vwork = nullptr;
-    NMFB_CUDA(h, cudaMalloc(&h->Vwork, bytes));
+    h->Vwork_bytes = 0;
+    void* p = nullptr;
+    NMFB_CUDA(h, dev_alloc(h, &p, bytes));
+    h->Vwork = static_cast<float*>(p);
     h->Vwork_bytes = bytes;
   }
   const int blocks = std::min(h->n, h->num_sms * 8);
@@ -237,7 +243,12 @@ int upload_H(nmfb_handle* h, Arena* ar, const float* host, int K, int n, float* 
 }
 int download_H(nmfb_handle* h, const float* Hm, long long ldh, int K, int n, float* host) {
   float* tmp = nullptr;
-  NMFB_CUDA(h, cudaMalloc(&tmp, static_cast<size_t>(n) * K * sizeof(float)));
+  const size_t tmp_bytes = (static_cast<size_t>(n) * K * sizeof(float) + 255) / 256 * 256;
+  {
+    void* p = nullptr;
+    NMFB_CUDA(h, dev_alloc(h, &p, tmp_bytes));
+    tmp = static_cast<float*>(p);
+  }
   dim3 grid((K + 31) / 32, (n + 31) / 32);
   // dst[r = j][c = k] = src[c = k][r = j]
   transpose_kernel<<<grid, dim3(32, 8), 0, h->stream>>>(Hm, ldh, tmp, K, n, K);
@@ -248,7 +259,8 @@ int download_H(nmfb_handle* h, const float* Hm, long long ldh, int K, int n, flo
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) rc = h->fail(NMFB_ERR_CUDA, "download H: %s", cudaGetErrorString(e));
   }
-  cudaFree(tmp);
+  cudaStreamSynchronize(h->stream);  // (also on the error paths) nothing may still write the block
+  dev_free(h, tmp, tmp_bytes);
   return rc;
 }
 

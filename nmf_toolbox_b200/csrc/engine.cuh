@@ -73,6 +73,7 @@ struct nmfb_handle {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   long long launches = 0;
+  long long mallocs = 0;  // cudaMalloc calls that missed the block pool (nmfb_malloc_count)
 
   // V as given (uploaded copy or adopted device pointer)
   const float* Vraw = nullptr;
@@ -81,7 +82,7 @@ struct nmfb_handle {
   BlockPool pool;
   // pinned host scratch, allocated once per handle (cudaMallocHost / cudaFreeHost synchronise the
   // device and took up to 0.8 s when issued per call next to a large pinned user buffer):
-  // [0..1] session stop flag / cost count, [2..3] run_chunked flags
+  // (64 ints) [0..1] session stop flag / cost count, [2..3] run_chunked flags, [8..15] line-search state (nmfsc)
   int* pinned = nullptr;
   int m = 0, n = 0;
   long long ldv = 0;
@@ -92,6 +93,10 @@ struct nmfb_handle {
   nmfb::Comm* comm = nullptr;
   NmfSession* sess = nullptr;
 
+  // device time of the iteration loop of the last one-call entry point (nmfb_last_loop)
+  double loop_ms = 0.0;
+  int loop_iters = 0;
+  std::vector<int> halvings;  // nmfsc: rejected line-search trials (H, W) per iteration of the last call
   // optional per-kernel timing of the two large contractions (bench.py roofline)
   bool profile = false;
   // [0] W-step GEMM, [1] H-step GEMM, [2] gram(H)+cost, [3] element-wise W step, [4] gram(W)
@@ -128,6 +133,7 @@ namespace nmfb {
 inline cudaError_t dev_alloc(nmfb_handle* h, void** p, size_t bytes) {
   *p = h->pool.take(bytes);
   if (*p) return cudaSuccess;
+  ++h->mallocs;
   cudaError_t e = cudaMalloc(p, bytes);
   if (e != cudaSuccess && h->pool.held > 0) {
     cudaGetLastError();
@@ -263,6 +269,30 @@ int run_gram_cost(nmfb_handle* h, const GramOp& op, unsigned int* ticket, const 
 // After an all-reduce of a Gram matrix (multi-GPU): tf32 copy, <G_W,G_H>, cost and stop test in one kernel.
 int run_gram_post_allreduce(nmfb_handle* h, const GramOp& op, unsigned int* ticket, const CostArgs& c,
                             bool with_cost);
+
+// CUDA-event pair around a group of launches when profiling is on (nmfb_profile_enable); slot meanings
+// per algorithm are listed at nmfb_profile_get_all in include/nmfb200.h
+inline int prof_mark(nmfb_handle* h, int which) {
+  if (!h->profile) return NMFB_OK;
+  cudaEvent_t e;
+  NMFB_CUDA(h, cudaEventCreate(&e));
+  h->prof_ev[which].push_back(e);
+  NMFB_CUDA(h, cudaEventRecord(e, h->stream));
+  return NMFB_OK;
+}
+// Brackets of the iteration loop of a one-call entry point (device time for nmfb_last_loop)
+inline void loop_begin(nmfb_handle* h) {
+  h->loop_ms = 0.0;
+  h->loop_iters = 0;
+  cudaEventRecord(h->ev0, h->stream);
+}
+inline void loop_end(nmfb_handle* h, int iters) {  // the stream must be idle (synchronised) when this returns
+  cudaEventRecord(h->ev1, h->stream);
+  cudaEventSynchronize(h->ev1);
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->loop_ms = ms;
+  h->loop_iters = iters;
+}
 
 // Queue `maxiter` iterations in chunks.  The stop flag written by the cost
 // kernel turns everything queued behind a converged iteration into no-ops, so

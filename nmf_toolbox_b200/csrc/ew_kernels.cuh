@@ -137,7 +137,9 @@ __global__ void round_copy_kernel(const float* __restrict__ src, float* __restri
 
 // hi = tf32(x), lo = tf32(x - hi): x = hi + lo to ~2^-22 relative ("3xTF32" operand split)
 __global__ void split_copy_kernel(const float* __restrict__ src, float* __restrict__ hi,
-                                  float* __restrict__ lo, int nvec, int len, long long ld) {
+                                  float* __restrict__ lo, int nvec, int len, long long ld,
+                                  const int* skip = nullptr) {
+  NMFB_STOP_GUARD(skip);
   for (int c = blockIdx.y; c < nvec; c += gridDim.y)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
       const float x = src[c * ld + i];
@@ -731,7 +733,8 @@ __global__ void grad_step_kernel(const float* __restrict__ X, const float* __res
 }
 // plain multiplicative step X <- X .* N ./ max(D, eps)   (nmfsc.m:182,232)
 __global__ void mu_step_kernel(float* __restrict__ X, const float* __restrict__ N,
-                               const float* __restrict__ D, int len, long long ld) {
+                               const float* __restrict__ D, int len, long long ld, const int* skip = nullptr) {
+  NMFB_STOP_GUARD(skip);
   const int c = blockIdx.y;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
     const long long o = static_cast<long long>(c) * ld + i;
@@ -740,7 +743,8 @@ __global__ void mu_step_kernel(float* __restrict__ X, const float* __restrict__ 
 }
 // nmfsc.m:185-187: H rows -> unit L2, W columns scaled by the norms.  sq[c] = sum H_c^2.
 __global__ void renorm_pair_kernel(float* __restrict__ H, int n, long long ldh, float* __restrict__ W,
-                                   int m, long long ldw, const double* sq) {
+                                   int m, long long ldw, const double* sq, const int* skip = nullptr) {
+  NMFB_STOP_GUARD(skip);
   const int c = blockIdx.y;
   const float nrm = static_cast<float>(sqrt(sq[c]));
   const float inv = 1.f / nrm;
@@ -754,13 +758,29 @@ __global__ void renorm_pair_kernel(float* __restrict__ H, int n, long long ldh, 
 // vector kept in global memory (L1/L2 resident), zero-set kept as per-thread bit masks.
 constexpr int kProjThreads = 512;
 constexpr int kProjMaskWords = 8;  // supports len <= 512 * 32 * 8 = 131072
+// Optional fusion of what surrounds the projection in a line-search trial of nmfsc.m / cnmfsc.m:
+//   before: the projected-gradient step X = src - step * (Dp - Dn) (nmfsc.m:154 / 205), formed in the
+//           first sweep with the step size read from device memory (the line search lives on the device);
+//   after : the tf32 head / tail split of the projected vector (operands of the split-tf32 contractions).
+struct ProjFuse {
+  const float* src = nullptr;
+  const float* Dp = nullptr;
+  const float* Dn = nullptr;
+  const double* step = nullptr;
+  float* hi = nullptr;
+  float* lo = nullptr;
+  const int* skip = nullptr;  // device flag: non-zero = this launch is a no-op
+};
 __global__ void __launch_bounds__(kProjThreads)
 projfunc_kernel(float* __restrict__ X, int len, long long ld, double k1, double k2, int nn,
-                int* iters_out, int* fail_flag) {
+                int* iters_out, int* fail_flag, ProjFuse f = ProjFuse()) {
+  NMFB_STOP_GUARD(f.skip);
   __shared__ double sh[32 * 3];
   __shared__ double bc[4];
-  float* v = X + static_cast<long long>(blockIdx.x) * ld;
+  const long long voff = static_cast<long long>(blockIdx.x) * ld;
+  float* v = X + voff;
   const int tid = threadIdx.x;
+  const float stepf = f.step != nullptr ? static_cast<float>(*f.step) : 0.f;
   uint32_t zmask[kProjMaskWords];
   uint32_t negmask[kProjMaskWords];  // signs when nn == 0
 #pragma unroll
@@ -769,7 +789,13 @@ projfunc_kernel(float* __restrict__ X, int len, long long ld, double k1, double 
   // projfunc.m:16-22: v = s + (k1 - sum(s)) / N
   double acc[3] = {0.0, 0.0, 0.0};
   for (int e = tid, q = 0; e < len; e += kProjThreads, ++q) {
-    float s = v[e];
+    float s;
+    if (f.src != nullptr) {
+      s = f.src[voff + e] - stepf * (f.Dp[voff + e] - f.Dn[voff + e]);
+      v[e] = s;
+    } else {
+      s = v[e];
+    }
     if (!nn && s < 0.f) {
       negmask[q >> 5] |= 1u << (q & 31);
       s = -s;
@@ -851,7 +877,136 @@ projfunc_kernel(float* __restrict__ X, int len, long long ld, double k1, double 
     for (int e = tid, q = 0; e < len; e += kProjThreads, ++q)
       if ((negmask[q >> 5] >> (q & 31)) & 1u) v[e] = -v[e];
   }
+  if (f.hi != nullptr) {  // every thread re-reads only elements it wrote itself
+    for (int e = tid; e < len; e += kProjThreads) {
+      const float x = v[e];
+      const float hi = tf32_rn(x);
+      f.hi[voff + e] = hi;
+      f.lo[voff + e] = tf32_rn(x - hi);
+    }
+  }
   if (tid == 0 && iters_out) iters_out[blockIdx.x] = iters;
+}
+
+// ---------------------------------------------------------------- device-side line search (nmfsc.m:146-179,196-229)
+// The accept / halve decisions of the projected-gradient line searches are taken on the device.  The
+// host queues a fixed PATTERN of kernels per iteration, every kernel guarded by the skip word of its
+// phase, and the small kernels below move the phase on:
+//   phase 0  H gradient (G_W, N = W'V, D = G_W H)           -> 1 (H_sparsity > 0) or 2 (multiplicative H step)
+//   phase 1  one H trial: step + projfunc + split, objective  -> stays (halved) or 2 (accepted)
+//   phase 2  commit H; W gradient (G_H, A = VH', B = W G_H)  -> 3 (W_sparsity > 0) or 4 (multiplicative W step)
+//   phase 3  one W trial                                      -> stays or 4
+//   phase 4  commit W; cost(iter+1) and stop test            -> 0, or everything off (done)
+// A pattern holds a fixed number of trial slots; a search that needs more simply continues in the
+// trial slots of the next pattern (all other phases of that pattern are no-ops), so the host never
+// waits for a decision and the sequence of accepted / halved steps is exactly the reference's.
+struct LsState {
+  double stepH, stepW;  // nmfsc.m:133-134
+  double begobj;        // objective the running line search must not exceed (nmfsc.m:149,197)
+  int skip[5];          // per phase: 1 = kernels of that phase do nothing
+  int iter;             // completed iterations
+  int ncost;            // valid entries of cost[]
+  int done;             // loop over: converged, step-size underflow, maxiter reached or failure
+  int failed;           // projfunc produced non-finite values
+  int trials;           // line-search trials evaluated so far (diagnostic)
+  int maxiter;
+  double tolerance;
+  int* halvings;        // [2 * maxiter]: rejected trials of the H / W search of every iteration (diagnostic)
+};
+enum { LS_INIT = 0, LS_TO_HTRIAL, LS_H_TO_WGRAD, LS_TO_WTRIAL, LS_W_TO_COST };
+// single-thread transitions that do not decide anything
+__global__ void ls_advance_kernel(LsState* st, int what, double* scal, double* cost, const int* fail) {
+  if (what == LS_INIT) {  // nmfsc.m:138-139: cost(1) = objective of the initial factors
+    cost[0] = 0.5 * scal[0];
+    scal[0] = scal[1] = 0.0;
+    st->ncost = 1;
+    if (fail != nullptr && *fail != 0) {
+      st->failed = st->done = 1;
+      for (int g = 0; g < 5; ++g) st->skip[g] = 1;
+    }
+    return;
+  }
+  if (st->done) return;
+  if (what == LS_TO_HTRIAL) {  // phase 0 -> 1
+    if (st->skip[0]) return;
+    st->begobj = cost[st->iter];  // nmfsc.m:149
+    st->skip[0] = 1;
+    st->skip[1] = 0;
+  } else if (what == LS_H_TO_WGRAD) {  // phase 0 -> 2 (no H line search)
+    if (st->skip[0]) return;
+    st->skip[0] = 1;
+    st->skip[2] = 0;
+  } else if (what == LS_TO_WTRIAL) {  // phase 2 -> 3: begobj = objective with the new H (nmfsc.m:193,197)
+    if (st->skip[2]) return;
+    st->begobj = 0.5 * scal[0];
+    scal[0] = scal[1] = 0.0;
+    st->skip[2] = 1;
+    st->skip[3] = 0;
+  } else if (what == LS_W_TO_COST) {  // phase 2 -> 4 (no W line search)
+    if (st->skip[2]) return;
+    st->skip[2] = 1;
+    st->skip[4] = 0;
+  }
+}
+// end of a trial slot: accept (nmfsc.m:164-166,178 / 215-217,228) or halve (169-174 / 220-225)
+__global__ void ls_decide_kernel(LsState* st, int for_w, double* scal, const int* fail) {
+  const int ph = for_w ? 3 : 1;
+  if (st->done || st->skip[ph]) return;
+  const double newobj = 0.5 * scal[0];
+  scal[0] = scal[1] = 0.0;
+  ++st->trials;
+  double& step = for_w ? st->stepW : st->stepH;
+  if (fail != nullptr && *fail != 0) {
+    st->failed = st->done = 1;
+  } else if (newobj <= st->begobj) {
+    step *= 1.2;
+    st->skip[ph] = 1;
+    st->skip[ph + 1] = 0;
+    return;
+  } else {
+    step /= 2;
+    if (st->halvings != nullptr && st->iter < st->maxiter) ++st->halvings[2 * st->iter + (for_w ? 1 : 0)];
+    if (!(step < 1e-200)) return;
+    st->ncost = st->iter + 1;  // 'Algorithm converged': cost = cost(1:iter) (nmfsc.m:170-174,221-225)
+    st->done = 1;
+  }
+  for (int g = 0; g < 5; ++g) st->skip[g] = 1;
+}
+// end of an iteration: cost(iter+1) and the stop test (nmfsc.m:237-244)
+__global__ void ls_cost_kernel(LsState* st, double* scal, double* cost) {
+  if (st->done || st->skip[4]) return;
+  const int it = st->iter + 1;  // 1-based iteration that just finished
+  const double c = 0.5 * scal[0];
+  scal[0] = scal[1] = 0.0;
+  cost[it] = c;
+  st->iter = it;
+  st->ncost = it + 1;
+  st->skip[4] = 1;
+  const bool conv = it > 1 && c < cost[it - 1] && cost[it - 1] - c < st->tolerance;  // nmfsc.m:241-244
+  if (conv || it >= st->maxiter) {
+    st->done = 1;
+    for (int g = 0; g < 5; ++g) st->skip[g] = 1;
+  } else {
+    st->skip[0] = 0;
+  }
+}
+// accepted trial -> current factor (master, tf32 head, tf32 tail) in one launch
+__global__ void copy3_kernel(const float* __restrict__ a0, float* __restrict__ b0, const float* __restrict__ a1,
+                             float* __restrict__ b1, const float* __restrict__ a2, float* __restrict__ b2,
+                             long long count4, const int* skip) {
+  NMFB_STOP_GUARD(skip);
+  const float4* s0 = reinterpret_cast<const float4*>(a0);
+  const float4* s1 = reinterpret_cast<const float4*>(a1);
+  const float4* s2 = reinterpret_cast<const float4*>(a2);
+  float4* d0 = reinterpret_cast<float4*>(b0);
+  float4* d1 = reinterpret_cast<float4*>(b1);
+  float4* d2 = reinterpret_cast<float4*>(b2);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    d0[i] = s0[i];
+    d1[i] = s1[i];
+    d2[i] = s2[i];
+  }
 }
 
 }  // namespace nmfb

@@ -201,6 +201,17 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
                      cfg.divergence);
   }
   const int m = h->m, n = h->n;
+  const bool trace = std::getenv("NMFB_TRACE") != nullptr;
+  timespec tr0;
+  clock_gettime(CLOCK_MONOTONIC, &tr0);
+  auto lap = [&](const char* what) {  // NMFB_TRACE=1: where the setup time of a call goes (synchronises)
+    if (!trace) return;
+    cudaStreamSynchronize(h->stream);
+    timespec t1;
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    fprintf(stderr, "[nmfb] nmf setup: %s %.1f ms\n", what, (t1.tv_sec - tr0.tv_sec) * 1e3 + (t1.tv_nsec - tr0.tv_nsec) * 1e-6);
+    tr0 = t1;
+  };
   s->K = K;
   s->Kp = round_up(K, 32);
   s->m = m;
@@ -300,6 +311,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   s->pinned = h->pinned;
   s->pinned[0] = s->pinned[1] = 0;
 
+  lap("device blocks for the factors");
   // ---- initial factors (nmf.m:130-134; defaults nmf.m:277,298)
   {
     std::vector<float> tmp;
@@ -334,6 +346,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   vec_sums_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, K, n, s->ldh, s->hs, nullptr, nullptr);
   NMFB_TRY(check_launch(h, "vec_sums(H init)"));
 
+  lap("upload + normalise W_init, H_init");
   // ---- V
   if (tw) {
     // the weights are formed from the fp32 V in the epilogue of V_hat = W H; nothing to prepare
@@ -351,6 +364,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     s->Vmma = h->Vwork;
   }
 
+  lap("V statistics / tf32 working copy");
   // ---- plan the contractions
   const int* stop = s->stop;
   const bool multi = comm_size(h->comm) > 1;
@@ -368,8 +382,13 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
                  !(env && env[0] == '0') && m > kTileM && ctasA + 8 <= h->num_sms;
     const bool can_side = !s->direct_cost && !s->W_fixed && !s->H_fixed && !(env && env[0] == '0') && m > kTileM &&
                           ctasA + 8 <= h->num_sms;
-    // the split-K H step is planned with a reduced SM budget when it runs beside gram(W) (see below)
-    s->gate_h = (s->overlap && !s->h_split && ctasH + 8 <= h->num_sms) || (can_side && s->h_split);
+    // The H-step contraction may only wait at the gate for gram(W) when its whole grid is resident with
+    // SMs to spare: gram(W) (<= 20 CTAs with large dynamic shared memory) needs free SMs to run on, and
+    // a grid of more CTAs than SMs spinning at the gate would never let it start (deadlock).  The fused
+    // kernel launches ctasH CTAs; the split-K variant is planned below with num_sms - 20 as its budget,
+    // which it can only honour when the unsplit grid already fits (choose_splits never goes below 1).
+    const bool h_grid_fits = s->h_split ? ctasH + 20 <= h->num_sms : ctasH + 8 <= h->num_sms;
+    s->gate_h = ((s->overlap && !s->h_split) || (can_side && s->h_split)) && h_grid_fits;
     s->side_gh = multi && can_side;
   }
   NMFB_TRY(plan_gram(h, ar, &s->gramW, s->Wt, Kp, m, s->ldw, stop, nullptr, 0, s->gate_h ? 20 : 0));
@@ -444,7 +463,12 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     } else {
     NMFB_TRY(plan_fused(h, &s->gemmH, EPI_HUPDATE, Xvt, Yw, m, &Xh, &Ygw, Kp, n, Kp, Kp, stop));
     }
-    if (s->gate_h) s->gemmH.L.args.gate = s->gates + 1;
+    if (s->gate_h) {
+      const dim3 g = s->gemmH.L.grid;
+      if (static_cast<int>(g.x * g.y * g.z) + 8 > h->num_sms)  // cannot happen with the guard above
+        return h->fail(NMFB_ERR_CUDA, "internal: gated H-step grid of %u CTAs leaves no SM for gram(W)", g.x * g.y * g.z);
+      s->gemmH.L.args.gate = s->gates + 1;
+    }
     GemmArgs& a = s->gemmH.L.args;
     if (!s->h_split) {
       a.Hm = s->Hm;
@@ -542,6 +566,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   D2FArgs da{s->wsum, s->wsf, Kp};
   d2f_kernel<<<(Kp + 127) / 128, 128, 0, h->stream>>>(da, nullptr);
   NMFB_TRY(check_launch(h, "d2f(ws)"));
+  lap("plans, tensor maps, row-major copy of V");
   return NMFB_OK;
 }
 
@@ -632,15 +657,6 @@ static void fill_cost_args(NmfSession* s, CostArgs* c, int iter, int mode) {
   c->stop = s->stop;
 }
 
-// CUDA-event pair around a group of launches when profiling is on
-static int prof_mark(nmfb_handle* h, int which) {
-  if (!h->profile) return NMFB_OK;
-  cudaEvent_t e;
-  NMFB_CUDA(h, cudaEventCreate(&e));
-  h->prof_ev[which].push_back(e);
-  NMFB_CUDA(h, cudaEventRecord(e, h->stream));
-  return NMFB_OK;
-}
 static int run_timed(nmfb_handle* h, const GemmOp& op, int which) {
   NMFB_TRY(prof_mark(h, which));
   NMFB_TRY(run_gemm(h, op));
@@ -662,15 +678,30 @@ extern "C" int nmfb_profile_get_all(nmfb_handle* h, double* ms_out /* [5] */) {
   if (!h || !ms_out) return NMFB_ERR_INVALID_ARGUMENT;
   NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
   for (int w = 0; w < 5; ++w) {
-    double tot = 0.0;
-    int c = 0;
+    // Launch groups whose kernels were switched off by a device-side guard (stop flag, line-search
+    // phase) return in a few microseconds; they are not launches of the kernel being measured, so
+    // samples below 30 % of the 90th percentile are left out of the average.
+    std::vector<float> v;
+    float mx = 0.f;
     for (size_t i = 0; i + 1 < h->prof_ev[w].size(); i += 2) {
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, h->prof_ev[w][i], h->prof_ev[w][i + 1]) == cudaSuccess) {
+        v.push_back(ms);
+        mx = std::max(mx, ms);
+      }
+    }
+    if (!v.empty()) {  // reference = 90th percentile (one slow outlier must not hide the real launches)
+      std::vector<float> sorted(v);
+      std::sort(sorted.begin(), sorted.end());
+      mx = sorted[(sorted.size() - 1) * 9 / 10];
+    }
+    double tot = 0.0;
+    int c = 0;
+    for (float ms : v)
+      if (ms >= 0.3f * mx) {
         tot += ms;
         ++c;
       }
-    }
     ms_out[w] = c ? tot / c : 0.0;
   }
   return NMFB_OK;
@@ -843,7 +874,9 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
       // R = (V ./ (W H)) H' (+ the cost sums of the previous iteration) in one fused kernel
       if (!s->W_fixed || i > 0) {
         s->klW.args.want_cost = i > 0 ? 1 : 0;
+        NMFB_TRY(prof_mark(h, 0));
         NMFB_TRY(run_kl(h, s->klW));
+        NMFB_TRY(prof_mark(h, 0));
         if (!s->W_fixed) {
           const long long cnt = s->klW.args.slab;
           split_reduce_kernel<<<static_cast<int>(std::min<long long>((cnt + 255) / 256, 2048)), 256, 0, h->stream>>>(
@@ -870,7 +903,9 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
     }
     if (s->kl_fused) {
       // N' = (V ./ (W H))' W with the refreshed V_hat, then the H update on the summed slabs
+      NMFB_TRY(prof_mark(h, 1));
       NMFB_TRY(run_kl(h, s->klH));
+      NMFB_TRY(prof_mark(h, 1));
       kl_h_finish_kernel<<<dim3(std::max(1, std::min(64, (n + 1023) / 1024)), K), 256, 0, h->stream>>>(s->klH.parts, s->klH.splits, s->klH.args.slab,
                                                                 s->klH.args.ldo, s->Hm, s->Ht, s->ldh, s->wsf,
                                                                 s->lambda_h, n, s->H_fixed ? 1 : 0, s->scal, stop,
@@ -973,10 +1008,18 @@ extern "C" int nmfb_nmf_sync(nmfb_handle* h, int* iters_done, double* device_ms)
   return NMFB_OK;
 }
 
+static double now_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 extern "C" int nmfb_nmf_end(nmfb_handle* h, float* W_out, float* H_out, double* cost_out, int* n_cost) {
   if (!h || !h->sess) return NMFB_ERR_INVALID_ARGUMENT;
   NmfSession* s = h->sess;
   cudaSetDevice(h->device);
+  const bool trace = std::getenv("NMFB_TRACE") != nullptr;
+  const double t0 = now_ms();
   int rc = enqueue_final_cost(h, s);
   if (rc == NMFB_OK) {
     cudaError_t e = cudaMemcpyAsync(s->pinned, s->stop, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
@@ -992,16 +1035,16 @@ extern "C" int nmfb_nmf_end(nmfb_handle* h, float* W_out, float* H_out, double* 
       if (e != cudaSuccess) rc = h->fail(NMFB_ERR_CUDA, "cost download: %s", cudaGetErrorString(e));
     }
   }
+  const double t1 = now_ms();
   if (rc == NMFB_OK && W_out) rc = download_colmajor(h, s->Wm, s->ldw, s->m, s->K, W_out);
+  const double t2 = now_ms();
   if (rc == NMFB_OK && H_out) rc = download_H(h, s->Hm, s->ldh, s->K, s->n, H_out);
+  const double t3 = now_ms();
   nmf_session_release(h);
+  if (trace)
+    fprintf(stderr, "[nmfb] nmf_end: final cost + trace %.1f ms, W download %.1f ms, H download %.1f ms, release %.1f ms, "
+                    "%lld cudaMalloc so far\n", t1 - t0, t2 - t1, t3 - t2, now_ms() - t3, h->mallocs);
   return rc;
-}
-
-static double now_ms() {
-  timespec ts;
-  clock_gettime(CLOCK_MONOTONIC, &ts);
-  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
 static int nmf_call(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, float* H_out, double* cost_out,
@@ -1011,6 +1054,7 @@ static int nmf_call(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out,
   NMFB_TRY(nmf_begin_impl(h, K, cfg, lnmf));
   const double t1 = now_ms();
   NmfSession* s = h->sess;
+  loop_begin(h);
   int rc = run_chunked(h, s->maxiter, s->stop, [&](int i) {
     int r = enqueue_iteration(h, s, i);
     if (r == NMFB_OK) ++s->iters_enqueued;
@@ -1025,8 +1069,11 @@ static int nmf_call(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out,
   // a pathological slow path of cudaMalloc / pageable copies issued under a deep launch queue
   cudaStreamSynchronize(h->stream);
   cudaStreamSynchronize(h->stream2);
+  loop_end(h, s->iters_enqueued);
   const double t3 = now_ms();
-  rc = nmfb_nmf_end(h, W_out, H_out, cost_out, n_cost);
+  int nc_local = 0;
+  rc = nmfb_nmf_end(h, W_out, H_out, cost_out, n_cost ? n_cost : &nc_local);
+  h->loop_iters = lnmf ? h->loop_iters : (n_cost ? *n_cost : nc_local);  // executed (not merely queued) iterations
   if (trace)
     fprintf(stderr, "[nmfb] nmf: setup %.1f ms, enqueue %.1f ms, drain %.1f ms, finish %.1f ms\n", t1 - t0, t2 - t1,
             t3 - t2, now_ms() - t3);

@@ -8,6 +8,9 @@
 // search is the reference's (newobj <= begobj) on those values.  An
 // unconstrained factor takes the plain multiplicative step (182-188 / 232).
 //
+// The line searches run on the device (ew_kernels.cuh, "device-side line search"): the host queues a
+// fixed pattern of phase-guarded kernels per iteration and never waits for an accept / halve decision.
+//
 // Precision.  The projected-gradient step subtracts two nearly equal products
 // (dH = W'V_hat - W'V) and the line search compares objectives that differ by
 // parts in 1e5, so plain tf32 contractions (relative error ~1e-4 per operand)
@@ -37,43 +40,50 @@ struct State {
   float *Wm, *Wt, *Wl, *Hm, *Ht, *Hl, *Wnew, *Wnt, *Wnl, *Hnew, *Hnt, *Hnl;
   float *Vhi, *Vlo;
   float *N, *D, *A, *B;
-  double *scal, *sq;
+  double *scal, *sq, *cost;
   int* fail;
+  LsState* ls;
   GramOp gramW, gramH;
   GemmOp gemmN, gemmD, gemmA, gemmB, residCur, residH, residW;
   ResidOp rsCur, rsH, rsW;  // streaming objective kernel (resid_fused.cuh), K <= 128
   bool fused_resid = false;
 };
 
-int objective(nmfb_handle* h, State* s, const GemmOp& op, const ResidOp& rs, double* out) {
-  NMFB_CUDA(h, cudaMemsetAsync(s->scal, 0, 2 * sizeof(double), h->stream));
-  if (s->fused_resid) NMFB_TRY(run_resid(h, rs));
-  else NMFB_TRY(run_gemm(h, op));
-  double v[2];
-  int failed = 0;
-  NMFB_CUDA(h, cudaMemcpyAsync(v, s->scal, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
-  NMFB_CUDA(h, cudaMemcpyAsync(&failed, s->fail, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (failed) return h->fail(NMFB_ERR_PROJFUNC, "projfunc diverged (non-finite values)");
-  *out = 0.5 * v[0];  // nmfsc.m:139,161,212,238
-  return NMFB_OK;
+// objective 0.5*|V - W*H|^2 into scal[0] (x2), guarded by the phase word `skip`
+int objective(nmfb_handle* h, State* s, GemmOp& op, ResidOp& rs, const int* skip) {
+  NMFB_TRY(prof_mark(h, 1));
+  if (s->fused_resid) {
+    rs.args.skip = skip;
+    NMFB_TRY(run_resid(h, rs));
+  } else {
+    op.L.args.stop = skip;
+    NMFB_TRY(run_gemm(h, op));
+  }
+  return prof_mark(h, 1);
 }
 
-int split_to(nmfb_handle* h, const float* src, float* hi, float* lo, int nvec, int len, long long ld) {
+int split_to(nmfb_handle* h, const float* src, float* hi, float* lo, int nvec, int len, long long ld,
+             const int* skip = nullptr) {
   dim3 grid = vec_grid(len, nvec);
   grid.y = std::min<unsigned>(grid.y, 8192u);
-  split_copy_kernel<<<grid, 256, 0, h->stream>>>(src, hi, lo, nvec, len, ld);
+  split_copy_kernel<<<grid, 256, 0, h->stream>>>(src, hi, lo, nvec, len, ld, skip);
   return check_launch(h, "split_copy");
 }
 
 constexpr int kChunk = 2;  // k-blocks per TMEM accumulation chunk (8 MMA steps)
 
-int project(nmfb_handle* h, State* s, float* X, int nvec, int len, long long ld, double k1) {
+int project(nmfb_handle* h, State* s, float* X, int nvec, int len, long long ld, double k1,
+            const ProjFuse& f = ProjFuse()) {
   if (len > kProjThreads * 32 * kProjMaskWords)
     return h->fail(NMFB_ERR_UNSUPPORTED, "nmfsc: projfunc vectors longer than %d are not supported",
                    kProjThreads * 32 * kProjMaskWords);
-  projfunc_kernel<<<nvec, kProjThreads, 0, h->stream>>>(X, len, ld, k1, 1.0, 1, nullptr, s->fail);
+  projfunc_kernel<<<nvec, kProjThreads, 0, h->stream>>>(X, len, ld, k1, 1.0, 1, nullptr, s->fail, f);
   return check_launch(h, "projfunc");
+}
+
+int advance(nmfb_handle* h, State* s, int what) {
+  ls_advance_kernel<<<1, 1, 0, h->stream>>>(s->ls, what, s->scal, s->cost, s->fail);
+  return check_launch(h, "ls_advance");
 }
 
 int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out, float* H_out,
@@ -131,6 +141,24 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
   NMFB_TRY(ar->alloc(h, &s->scal, 2));
   NMFB_TRY(ar->alloc(h, &s->sq, Kp));
   NMFB_TRY(ar->alloc(h, &s->fail, 1));
+  NMFB_TRY(ar->alloc(h, &s->cost, static_cast<size_t>(cfg.maxiter) + 1));  // nmfsc.m:137
+  NMFB_TRY(ar->alloc(h, &s->ls, 1));
+  {
+    LsState init{};
+    init.stepH = init.stepW = 1.0;  // nmfsc.m:133-134
+    init.skip[0] = 0;
+    init.skip[1] = init.skip[2] = init.skip[3] = init.skip[4] = 1;
+    init.maxiter = cfg.maxiter;
+    init.tolerance = cfg.tolerance;
+    NMFB_TRY(ar->alloc(h, &init.halvings, 2 * static_cast<size_t>(cfg.maxiter)));
+    NMFB_CUDA(h, cudaMemcpyAsync(s->ls, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  const int* sk0 = &s->ls->skip[0];
+  const int* sk1 = &s->ls->skip[1];
+  const int* sk2 = &s->ls->skip[2];
+  const int* sk3 = &s->ls->skip[3];
+  const int* sk4 = &s->ls->skip[4];
 
   {  // nmfsc.m:73-84
     std::vector<float> tmp;
@@ -170,8 +198,8 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
   NMFB_TRY(split_to(h, s->Hm, s->Ht, s->Hl, K, n, ldh));
 
   // ---- contractions
-  NMFB_TRY(plan_gram(h, ar, &s->gramW, s->Wt, Kp, m, ldw, nullptr, s->Wl, kChunk));
-  NMFB_TRY(plan_gram(h, ar, &s->gramH, s->Ht, Kp, n, ldh, nullptr, s->Hl, kChunk));
+  NMFB_TRY(plan_gram(h, ar, &s->gramW, s->Wt, Kp, m, ldw, sk0, s->Wl, kChunk));
+  NMFB_TRY(plan_gram(h, ar, &s->gramH, s->Ht, Kp, n, ldh, sk2, s->Hl, kChunk));
   {
     auto three = [](const MatRef& Xhi, const MatRef& Xlo, const MatRef& Yhi, const MatRef& Ylo) {
       ExtraSegs e;  // acc = Xhi*Yhi' (segment 0) + Xlo*Yhi' + Xhi*Ylo'
@@ -188,26 +216,26 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
     ExtraSegs eN = three(Vk_hi, Vk_lo, Wk_hi, Wk_lo);
     const int tiles_h = (n + kTileM - 1) / kTileM * ((Kp + kMaxN - 1) / kMaxN);
     NMFB_TRY(plan_store(h, ar, &s->gemmN, Vk_hi, Wk_hi, m, nullptr, nullptr, 0, n, Kp, s->N, nullptr, ldh,
-                        tiles_h * 2 <= h->num_sms, nullptr, &eN));
+                        tiles_h * 2 <= h->num_sms, sk0, &eN));
     // D = W'V_hat = (W'W) H (nmfsc.m:145): rows j (H is MN-major there), contraction over k
     MatRef Hm_hi{s->Ht, n, Kp, ldh, true}, Hm_lo{s->Hl, n, Kp, ldh, true};
     MatRef Gw_hi{s->gramW.gtf, Kp, Kp, Kp, false}, Gw_lo{s->gramW.glo, Kp, Kp, Kp, false};
     ExtraSegs eD = three(Hm_hi, Hm_lo, Gw_hi, Gw_lo);
     NMFB_TRY(plan_store(h, ar, &s->gemmD, Hm_hi, Gw_hi, Kp, nullptr, nullptr, 0, n, Kp, s->D, nullptr, ldh,
-                        false, nullptr, &eD));
+                        false, sk0, &eD));
     // A = V H' (nmfsc.m:194): rows i of V (MN-major), contraction over j
     MatRef Vm_hi{s->Vhi, m, n, h->ldv, true}, Vm_lo{s->Vlo, m, n, h->ldv, true};
     MatRef Hk_hi{s->Ht, n, Kp, ldh, false}, Hk_lo{s->Hl, n, Kp, ldh, false};
     ExtraSegs eA = three(Vm_hi, Vm_lo, Hk_hi, Hk_lo);
     const int tiles_w = (m + kTileM - 1) / kTileM * ((Kp + kMaxN - 1) / kMaxN);
     NMFB_TRY(plan_store(h, ar, &s->gemmA, Vm_hi, Hk_hi, n, nullptr, nullptr, 0, m, Kp, s->A, nullptr, ldw,
-                        tiles_w * 2 <= h->num_sms, nullptr, &eA));
+                        tiles_w * 2 <= h->num_sms, sk2, &eA));
     // B = V_hat H' = W (H H') (nmfsc.m:195)
     MatRef Wm_hi{s->Wt, m, Kp, ldw, true}, Wm_lo{s->Wl, m, Kp, ldw, true};
     MatRef Gh_hi{s->gramH.gtf, Kp, Kp, Kp, false}, Gh_lo{s->gramH.glo, Kp, Kp, Kp, false};
     ExtraSegs eB = three(Wm_hi, Wm_lo, Gh_hi, Gh_lo);
     NMFB_TRY(plan_store(h, ar, &s->gemmB, Wm_hi, Gh_hi, Kp, nullptr, nullptr, 0, m, Kp, s->B, nullptr, ldw,
-                        false, nullptr, &eB));
+                        false, sk2, &eB));
     for (GemmOp* op : {&s->gemmN, &s->gemmD, &s->gemmA, &s->gemmB}) op->L.args.chunk_kb = kChunk;
     // objective 0.5*|V - W*H|^2 of (W, H) pairs given as head/tail
     auto plan_resid = [&](GemmOp* op, const float* Whi, const float* Wlo, const float* Hhi, const float* Hlo) {
@@ -236,117 +264,145 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
   }
 
   const bool trace = std::getenv("NMFB_TRACE") != nullptr;
-  double tr[6] = {0, 0, 0, 0, 0, 0};
-  int ntrials = 0;
-  auto now = [] {
-    timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  const bool searchH = sH > 0 && !H_fixed, searchW = sW > 0 && !W_fixed;
+  int slots = 2;  // line-search trial slots per pattern (a longer search continues in the next pattern)
+  if (const char* e = std::getenv("NMFB_LS_SLOTS")) slots = std::max(1, std::atoi(e));
+  const long long ch4 = static_cast<long long>(ch / 4), cw4 = static_cast<long long>(cw / 4);
+  const int copy_blocks = h->num_sms * 4;
+
+  // one trial slot of a line search (nmfsc.m:152-175 / 203-226): step + projfunc + split, objective, decision
+  auto trial = [&](bool for_w) -> int {
+    ProjFuse f;
+    f.src = for_w ? s->Wm : s->Hm;
+    f.Dp = for_w ? s->B : s->D;
+    f.Dn = for_w ? s->A : s->N;
+    f.step = for_w ? &s->ls->stepW : &s->ls->stepH;
+    f.hi = for_w ? s->Wnt : s->Hnt;
+    f.lo = for_w ? s->Wnl : s->Hnl;
+    f.skip = for_w ? sk3 : sk1;
+    NMFB_TRY(prof_mark(h, 2));
+    if (for_w) NMFB_TRY(project(h, s, s->Wnew, K, m, ldw, L1a, f));  // nmfsc.m:205-208
+    else NMFB_TRY(project(h, s, s->Hnew, K, n, ldh, L1s, f));        // nmfsc.m:154-157
+    NMFB_TRY(prof_mark(h, 2));
+    if (for_w) NMFB_TRY(objective(h, s, s->residW, s->rsW, sk3));    // nmfsc.m:211-212
+    else NMFB_TRY(objective(h, s, s->residH, s->rsH, sk1));          // nmfsc.m:160-161
+    ls_decide_kernel<<<1, 1, 0, h->stream>>>(s->ls, for_w ? 1 : 0, s->scal, s->fail);
+    return check_launch(h, "ls_decide");
   };
-  auto lap = [&](int slot, double& t0) {
-    if (!trace) return;
-    cudaStreamSynchronize(h->stream);
-    const double t1 = now();
-    tr[slot] += t1 - t0;
-    t0 = t1;
-  };
-  std::vector<double> cost(static_cast<size_t>(cfg.maxiter) + 1, 0.0);  // nmfsc.m:137
-  NMFB_TRY(objective(h, s, s->residCur, s->rsCur, &cost[0]));                      // nmfsc.m:138-139
-  double stepW = 1.0, stepH = 1.0;                                       // nmfsc.m:133-134
-  int ncost = cfg.maxiter + 1;
-  bool done = false;
-  for (int it = 1; it <= cfg.maxiter && !done; ++it) {
-    double tl = now();
+  // the kernels of one iteration (H first, then W: nmfsc.m:143-244), every one guarded by its phase
+  auto pattern = [&]() -> int {
+    // ---- phase 0: H gradient
     if (!H_fixed) {
-      NMFB_TRY(run_gram(h, s->gramW, nullptr));
+      NMFB_TRY(prof_mark(h, 0));
+      NMFB_TRY(run_gram(h, s->gramW, sk0));
       NMFB_TRY(run_gemm(h, s->gemmN));  // N = W'V (144)
       NMFB_TRY(run_gemm(h, s->gemmD));  // D = W'V_hat = (W'W)H (145)
-      lap(0, tl);
-      if (sH > 0) {
-        const double begobj = cost[it - 1];  // nmfsc.m:149
-        while (true) {
-          grad_step_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, s->D, s->N, s->Hnew, K, n, ldh, stepH);
-          NMFB_TRY(check_launch(h, "grad_step(H)"));
-          NMFB_TRY(project(h, s, s->Hnew, K, n, ldh, L1s));  // nmfsc.m:155-157
-          NMFB_TRY(split_to(h, s->Hnew, s->Hnt, s->Hnl, K, n, ldh));
-          lap(1, tl);
-          ++ntrials;
-          double newobj;
-          NMFB_TRY(objective(h, s, s->residH, s->rsH, &newobj));  // nmfsc.m:160-161
-          lap(2, tl);
-          if (newobj <= begobj) break;                    // nmfsc.m:164-166
-          stepH /= 2;                                     // nmfsc.m:169
-          if (stepH < 1e-200) {                           // nmfsc.m:170-174
-            ncost = it;
-            done = true;
-            break;
-          }
-        }
-        if (done) break;
-        stepH *= 1.2;  // nmfsc.m:178
-        NMFB_CUDA(h, cudaMemcpyAsync(s->Hm, s->Hnew, ch * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-        NMFB_CUDA(h, cudaMemcpyAsync(s->Ht, s->Hnt, ch * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-        NMFB_CUDA(h, cudaMemcpyAsync(s->Hl, s->Hnl, ch * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+      NMFB_TRY(prof_mark(h, 0));
+      if (searchH) {
+        NMFB_TRY(advance(h, s, LS_TO_HTRIAL));
       } else {  // nmfsc.m:182-187
-        mu_step_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, s->N, s->D, n, ldh);
+        mu_step_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, s->N, s->D, n, ldh, sk0);
         NMFB_TRY(check_launch(h, "mu_step(H)"));
-        NMFB_CUDA(h, cudaMemsetAsync(s->sq, 0, Kp * sizeof(double), h->stream));
-        vec_sums_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, K, n, ldh, nullptr, s->sq, nullptr);
+        NMFB_CUDA(h, cudaMemsetAsync(s->sq, 0, Kp * sizeof(double), h->stream));  // scratch of this phase only
+        vec_sums_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, K, n, ldh, nullptr, s->sq, sk0);
         NMFB_TRY(check_launch(h, "vec_sums(H)"));
-        renorm_pair_kernel<<<vec_grid(std::max(m, n), K), 256, 0, h->stream>>>(s->Hm, n, ldh, s->Wm, m, ldw, s->sq);
+        renorm_pair_kernel<<<vec_grid(std::max(m, n), K), 256, 0, h->stream>>>(s->Hm, n, ldh, s->Wm, m, ldw, s->sq, sk0);
         NMFB_TRY(check_launch(h, "renorm_pair"));
-        NMFB_TRY(split_to(h, s->Hm, s->Ht, s->Hl, K, n, ldh));
-        NMFB_TRY(split_to(h, s->Wm, s->Wt, s->Wl, K, m, ldw));
+        NMFB_TRY(split_to(h, s->Hm, s->Ht, s->Hl, K, n, ldh, sk0));
+        NMFB_TRY(split_to(h, s->Wm, s->Wt, s->Wl, K, m, ldw, sk0));
+        NMFB_TRY(advance(h, s, LS_H_TO_WGRAD));
       }
+    } else {
+      NMFB_TRY(advance(h, s, LS_H_TO_WGRAD));
     }
-    lap(3, tl);
+    // ---- phase 1: H line search
+    if (searchH)
+      for (int t = 0; t < slots; ++t) NMFB_TRY(trial(false));
+    // ---- phase 2: commit H (nmfsc.m:179), W gradient
+    if (searchH) {
+      copy3_kernel<<<copy_blocks, 256, 0, h->stream>>>(s->Hnew, s->Hm, s->Hnt, s->Ht, s->Hnl, s->Hl, ch4, sk2);
+      NMFB_TRY(check_launch(h, "copy3(H)"));
+    }
     if (!W_fixed) {
-      NMFB_TRY(run_gram(h, s->gramH, nullptr));
+      NMFB_TRY(prof_mark(h, 3));
+      NMFB_TRY(run_gram(h, s->gramH, sk2));
       NMFB_TRY(run_gemm(h, s->gemmA));  // A = V H' (194)
       NMFB_TRY(run_gemm(h, s->gemmB));  // B = V_hat H' = W (H H') (195)
-      if (sW > 0) {
-        double begobj;
-        NMFB_TRY(objective(h, s, s->residCur, s->rsCur, &begobj));  // nmfsc.m:193,197
-        while (true) {
-          grad_step_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, s->B, s->A, s->Wnew, K, m, ldw, stepW);
-          NMFB_TRY(check_launch(h, "grad_step(W)"));
-          NMFB_TRY(project(h, s, s->Wnew, K, m, ldw, L1a));  // nmfsc.m:206-208
-          NMFB_TRY(split_to(h, s->Wnew, s->Wnt, s->Wnl, K, m, ldw));
-          double newobj;
-          NMFB_TRY(objective(h, s, s->residW, s->rsW, &newobj));  // nmfsc.m:211-212
-          if (newobj <= begobj) break;
-          stepW /= 2;
-          if (stepW < 1e-200) {  // nmfsc.m:221-225
-            ncost = it;
-            done = true;
-            break;
-          }
-        }
-        if (done) break;
-        stepW *= 1.2;
-        NMFB_CUDA(h, cudaMemcpyAsync(s->Wm, s->Wnew, cw * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-        NMFB_CUDA(h, cudaMemcpyAsync(s->Wt, s->Wnt, cw * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-        NMFB_CUDA(h, cudaMemcpyAsync(s->Wl, s->Wnl, cw * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+      if (searchW) {
+        NMFB_TRY(objective(h, s, s->residCur, s->rsCur, sk2));  // nmfsc.m:193,197
+        NMFB_TRY(advance(h, s, LS_TO_WTRIAL));
       } else {  // nmfsc.m:232
-        mu_step_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, s->A, s->B, m, ldw);
+        mu_step_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, s->A, s->B, m, ldw, sk2);
         NMFB_TRY(check_launch(h, "mu_step(W)"));
-        NMFB_TRY(split_to(h, s->Wm, s->Wt, s->Wl, K, m, ldw));
+        NMFB_TRY(split_to(h, s->Wm, s->Wt, s->Wl, K, m, ldw, sk2));
+        NMFB_TRY(advance(h, s, LS_W_TO_COST));
       }
+      NMFB_TRY(prof_mark(h, 3));
+    } else {
+      NMFB_TRY(advance(h, s, LS_W_TO_COST));
     }
-    lap(4, tl);
-    NMFB_TRY(objective(h, s, s->residCur, s->rsCur, &cost[it]));  // nmfsc.m:237-238
-    lap(5, tl);
-    if (it > 1 && cost[it] < cost[it - 1] && cost[it - 1] - cost[it] < cfg.tolerance) {  // 241-244
-      ncost = it + 1;
-      done = true;
+    // ---- phase 3: W line search
+    if (searchW)
+      for (int t = 0; t < slots; ++t) NMFB_TRY(trial(true));
+    // ---- phase 4: commit W (nmfsc.m:229), cost(iter+1) and stop test (237-244)
+    if (searchW) {
+      copy3_kernel<<<copy_blocks, 256, 0, h->stream>>>(s->Wnew, s->Wm, s->Wnt, s->Wt, s->Wnl, s->Wl, cw4, sk4);
+      NMFB_TRY(check_launch(h, "copy3(W)"));
     }
+    NMFB_TRY(objective(h, s, s->residCur, s->rsCur, sk4));
+    ls_cost_kernel<<<1, 1, 0, h->stream>>>(s->ls, s->scal, s->cost);
+    return check_launch(h, "ls_cost");
+  };
+
+  NMFB_CUDA(h, cudaMemsetAsync(s->scal, 0, 2 * sizeof(double), h->stream));
+  NMFB_TRY(objective(h, s, s->residCur, s->rsCur, nullptr));  // nmfsc.m:138-139
+  NMFB_TRY(advance(h, s, LS_INIT));
+  loop_begin(h);
+  // Queue patterns in chunks; the host looks at {iter, ncost, done, failed} of the chunk before the one
+  // it has just queued, so it never waits for the device while work is outstanding.
+  constexpr int kChunkPatterns = 8;
+  int* pin = h->pinned + 8;  // two slots of four ints
+  cudaEvent_t evs[2] = {nullptr, nullptr};
+  for (int b = 0; b < 2; ++b)
+    if (cudaEventCreateWithFlags(&evs[b], cudaEventDisableTiming) != cudaSuccess)
+      return h->fail(NMFB_ERR_CUDA, "cudaEventCreate failed");
+  int rc = NMFB_OK, c = 0, queued = 0;
+  std::memset(pin, 0, 8 * sizeof(int));
+  // a search may halve ~665 times before the step underflows (nmfsc.m:170): generous bound, never reached
+  const long long max_patterns = (static_cast<long long>(cfg.maxiter) + 2) * 700;
+  while (rc == NMFB_OK) {
+    for (int p = 0; p < kChunkPatterns && rc == NMFB_OK; ++p, ++queued) rc = pattern();
+    if (rc != NMFB_OK) break;
+    if (queued > max_patterns) {
+      rc = h->fail(NMFB_ERR_CUDA, "internal: nmfsc iteration loop did not finish after %d kernel patterns", queued);
+      break;
+    }
+    if (c > 0) {
+      cudaEventSynchronize(evs[(c - 1) & 1]);
+      if (pin[((c - 1) & 1) * 4 + 2] != 0) break;  // done
+    }
+    cudaMemcpyAsync(pin + (c & 1) * 4, &s->ls->iter, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    cudaEventRecord(evs[c & 1], h->stream);
+    ++c;
   }
+  for (int b = 0; b < 2; ++b) cudaEventDestroy(evs[b]);
+  cudaStreamSynchronize(h->stream);
+  NMFB_TRY(rc);
+  LsState fin;
+  NMFB_CUDA(h, cudaMemcpy(&fin, s->ls, sizeof(fin), cudaMemcpyDeviceToHost));
+  loop_end(h, fin.iter);
+  if (fin.failed) return h->fail(NMFB_ERR_PROJFUNC, "projfunc diverged (non-finite values)");
   if (trace)
-    fprintf(stderr, "[nmfb] nmfsc per-phase ms over the run: gradient GEMMs %.2f, trial prep (step+projfunc+split) %.2f, "
-                    "trial objective %.2f (%d trials), copies %.2f, W step %.2f, final objective %.2f\n",
-            tr[0], tr[1], tr[2], ntrials, tr[3], tr[4], tr[5]);
+    fprintf(stderr, "[nmfb] nmfsc: %d iterations, %d line-search trials, %d patterns queued, loop %.2f ms "
+                    "(%.1f us per iteration), final steps H %.3g W %.3g\n",
+            fin.iter, fin.trials, queued, h->loop_ms, fin.iter ? 1e3 * h->loop_ms / fin.iter : 0.0, fin.stepH, fin.stepW);
+  h->halvings.assign(2 * static_cast<size_t>(fin.iter), 0);
+  if (fin.iter > 0)
+    NMFB_CUDA(h, cudaMemcpy(h->halvings.data(), fin.halvings, h->halvings.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  const int ncost = fin.ncost;
   if (n_cost) *n_cost = ncost;
-  if (cost_out) std::memcpy(cost_out, cost.data(), static_cast<size_t>(ncost) * sizeof(double));
+  if (cost_out && ncost > 0)
+    NMFB_CUDA(h, cudaMemcpy(cost_out, s->cost, static_cast<size_t>(ncost) * sizeof(double), cudaMemcpyDeviceToHost));
   if (W_out) NMFB_TRY(download_colmajor(h, s->Wm, ldw, m, K, W_out));
   if (H_out) NMFB_TRY(download_H(h, s->Hm, ldh, K, n, H_out));
   return NMFB_OK;

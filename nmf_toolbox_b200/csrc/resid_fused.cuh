@@ -23,6 +23,7 @@ struct ResidArgs {
   int rows, cols, Kp;
   int tiles_per_split;
   double* scal;  // scal[0] += sum (V - S)^2
+  const int* skip;  // device flag: non-zero = do nothing (phase guard of the device-side line search)
 };
 
 __global__ void __launch_bounds__(64 + kKlEpiWarps * 32, 1)
@@ -39,6 +40,7 @@ resid_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_const
   __shared__ uint32_t tmem_slot;
   __shared__ double red[kKlEpiWarps];
 
+  if (a.skip != nullptr && *a.skip != 0) return;  // uniform across the grid
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();

@@ -184,6 +184,37 @@ def test_nmf_stop_rule_and_trim(api, handle):
     assert 2 <= len(c) <= 100 and np.all(np.isfinite(c))
 
 
+def test_nmf_stop_rule_default_cost_mode(api, handle):
+    """The default Euclidean cost is the Gram / trace identity evaluated from tf32 products (relative accuracy
+    ~1e-5, include/nmfb200.h): the stop test of nmf.m:221-224 fires within one iteration of the reference's as
+    long as the tolerance is resolvable at that accuracy, and the cost entries agree up to there."""
+    alg, V, K, T, cfg = inputs("nmf_euclid_512")
+    _, _, full = O.nmf(V, K, cfg)
+    d = -np.diff(full)
+    tol = float(np.sort(d)[len(d) // 2]) * 1.0001
+    assert tol > 1e-5 * full[-1]
+    _, _, co = O.nmf(V, K, dict(cfg, tolerance=tol))
+    W, H, c = api.nmf(V, K, dict(cfg, tolerance=tol), handle=handle)
+    assert 2 <= len(co) < 50 and abs(len(c) - len(co)) <= 1
+    k = min(len(c), len(co))
+    assert cost_err(c[:k], co[:k]) < COST_TOL
+
+
+def test_nmf_per_source_settings_many_columns(api, handle):
+    """Per-source settings force the split-K H step; with many column tiles its grid exceeds the SM count and
+    must NOT wait at the device-side gate for gram(W) (which would need a free SM: deadlock)."""
+    m, n, sizes = 512, 40000, [8, 8]
+    rng = np.random.default_rng(12)
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    cfg = dict(divergence="euclidean", W_init=[rng.random((m, k)) + 1e-3 for k in sizes],
+               H_init=[rng.random((k, n)) + 1e-3 for k in sizes], W_sparsity=[0.0, 0.1], H_sparsity=[0.2, 0.0],
+               H_fixed=[False, True], maxiter=6, tolerance=1e-300)
+    W, H, c = api.nmf(V, sizes, cfg, handle=handle)
+    Wo, Ho, co = O.nmf(V, sizes, cfg)
+    assert cost_err(c, co) < COST_TOL
+    assert recon_err(np.concatenate(W, 1), np.concatenate(H, 0), np.concatenate(Wo, 1), np.concatenate(Ho, 0)) < RECON_TOL
+
+
 @pytest.mark.parametrize("div", ["euclidean", "kl"])
 def test_nmf_exact_fixed_point(api, handle, div):
     """V = W0*H0 with unit-L2 columns: factors do not move (to tf32 rounding), cost ~ 0."""
@@ -475,13 +506,63 @@ def test_nmfsc_vs_oracle(api, handle, sW, sH, iters):
     H0 /= np.sqrt((H0 ** 2).sum(1, keepdims=True))
     cfg = dict(W_init=rng.random((m, K)), H_init=H0, W_sparsity=sW, H_sparsity=sH, maxiter=iters, tolerance=1e-300)
     W, H, c = api.nmfsc(V, K, cfg, handle=handle)
-    Wo, Ho, co = O.nmfsc(V, K, cfg)
+    info = {}
+    Wo, Ho, co = O.nmfsc(V, K, cfg, info=info)
     assert cost_err(c, co) < COST_TOL
+    # the line searches run on the device (no host decision): same accept / halve sequence as the reference
+    hH, hW = handle.last_halvings()
+    if sH:
+        assert hH.tolist() == list(info["halvings_H"])
+    if sW:
+        assert hW.tolist() == list(info["halvings_W"])
     if sH:
         Hd = H.astype(np.float64)
         l1, l2 = np.abs(Hd).sum(1), np.sqrt((Hd ** 2).sum(1))
         np.testing.assert_allclose((np.sqrt(n) - l1 / l2) / (np.sqrt(n) - 1), sH, atol=1e-4)  # rows keep sparseness
         np.testing.assert_allclose(l2, 1.0, atol=1e-4)
+
+
+@pytest.mark.parametrize("slots", ["1", "3"])
+def test_nmfsc_line_search_slots(api, handle, slots, monkeypatch):
+    """The number of trial slots queued per iteration only changes how far a long search spills into the
+    following kernel patterns, never the result (first iterations need up to ~10 halvings)."""
+    monkeypatch.setenv("NMFB_LS_SLOTS", slots)
+    rng = np.random.default_rng(5)
+    m, n, K = 300, 400, 12
+    V = rng.random((m, n)) * 2.0
+    H0 = rng.random((K, n))
+    H0 /= np.sqrt((H0 ** 2).sum(1, keepdims=True))
+    cfg = dict(W_init=rng.random((m, K)), H_init=H0, W_sparsity=0.4, H_sparsity=0.6, maxiter=25, tolerance=1e-300)
+    W, H, c = api.nmfsc(V, K, cfg, handle=handle)
+    info = {}
+    Wo, Ho, co = O.nmfsc(V, K, cfg, info=info)
+    assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
+    hH, hW = handle.last_halvings()
+    assert hH.tolist() == list(info["halvings_H"]) and hW.tolist() == list(info["halvings_W"])
+
+
+def test_nmfsc_stop_rule_and_fixed_factors(api, handle):
+    """nmfsc.m:241-244 on the device: the loop ends at the reference's iteration, cost keeps iter+1 entries;
+    W_fixed / H_fixed skip the corresponding half (nmfsc.m:143,192)."""
+    rng = np.random.default_rng(8)
+    m, n, K = 256, 320, 8
+    V = rng.random((m, n)) * 2.0
+    H0 = rng.random((K, n))
+    H0 /= np.sqrt((H0 ** 2).sum(1, keepdims=True))
+    cfg = dict(W_init=rng.random((m, K)), H_init=H0, H_sparsity=0.5, maxiter=60, tolerance=1e-300)
+    _, _, full = O.nmfsc(V, K, cfg)
+    d = -np.diff(full)[1:]
+    tol = float(np.sort(d)[len(d) // 2]) * 1.0001
+    Wo, Ho, co = O.nmfsc(V, K, dict(cfg, tolerance=tol))
+    W, H, c = api.nmfsc(V, K, dict(cfg, tolerance=tol), handle=handle)
+    assert 3 <= len(co) < 61 and abs(len(c) - len(co)) <= 1
+    k = min(len(c), len(co))
+    assert cost_err(c[:k], co[:k]) < COST_TOL
+    for fixed in ("W_fixed", "H_fixed"):
+        cfg2 = dict(cfg, maxiter=12, **{fixed: True})
+        W, H, c = api.nmfsc(V, K, cfg2, handle=handle)
+        Wo, Ho, co = O.nmfsc(V, K, cfg2)
+        assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
 
 
 @pytest.mark.parametrize("N,sp", [(100, 0.7), (4096, 0.7), (1000, 0.3), (5000, 0.95), (20000, 0.5), (33, 0.9)])
