@@ -54,12 +54,38 @@ static std::vector<float> to_single(const mxArray* a) {
   return out;
 }
 
+// Scalar config field.  A one-element cell is a single-source setting (nmf.m:312-359); cells with several
+// sources are resolved by the .m wrappers (matlab/nmf.m, matlab/cnmf.m) before the gateway is called and are
+// rejected here rather than silently reduced to their first element.
 static double field(const mxArray* cfg, const char* name, double dflt) {
   if (!cfg || !mxIsStruct(cfg)) return dflt;
   const mxArray* f = mxGetField(cfg, 0, name);
   if (!f || mxIsEmpty(f)) return dflt;
-  if (mxIsCell(f)) f = mxGetCell(f, 0);  // single-source cell (nmf.m:312-359)
+  if (mxIsCell(f)) {
+    if (mxGetNumberOfElements(f) != 1)
+      mexErrMsgIdAndTxt("nmfb:invalidArgument", "config.%s: multi-source cell arrays must go through nmf.m / cnmf.m", name);
+    f = mxGetCell(f, 0);
+  }
+  if (!f || mxIsEmpty(f) || mxGetNumberOfElements(f) != 1)
+    mexErrMsgIdAndTxt("nmfb:invalidArgument", "config.%s must be a scalar", name);
   return mxGetScalar(f);
+}
+
+// Initial factor: single-source cell unwrapped, element count checked against what the engine will read.
+static const mxArray* init_field(const mxArray* cfg, const char* name, size_t expect) {
+  if (!cfg || !mxIsStruct(cfg)) return nullptr;
+  const mxArray* f = mxGetField(cfg, 0, name);
+  if (!f || mxIsEmpty(f)) return nullptr;
+  if (mxIsCell(f)) {
+    if (mxGetNumberOfElements(f) != 1)
+      mexErrMsgIdAndTxt("nmfb:invalidArgument", "config.%s: multi-source cell arrays must go through nmf.m / cnmf.m", name);
+    f = mxGetCell(f, 0);
+    if (!f || mxIsEmpty(f)) return nullptr;
+  }
+  if (mxGetNumberOfElements(f) != expect)
+    mexErrMsgIdAndTxt("nmfb:invalidArgument", "config.%s has %llu elements, expected %llu", name,
+                      static_cast<unsigned long long>(mxGetNumberOfElements(f)), static_cast<unsigned long long>(expect));
+  return f;
 }
 
 static int divergence_code(const mxArray* cfg) {
@@ -95,8 +121,14 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     const bool conv = cmd == "cnmf" || cmd == "cnmfsc";
     const mxArray* V = prhs[1];
     const int m = static_cast<int>(mxGetM(V)), n = static_cast<int>(mxGetN(V));
-    const int K = static_cast<int>(mxGetScalar(prhs[2]));
+    if (nrhs < (conv ? 4 : 3)) mexErrMsgIdAndTxt("nmfb:usage", "%s: too few arguments", cmd.c_str());
+    if (mxIsCell(prhs[2]) && mxGetNumberOfElements(prhs[2]) != 1)
+      mexErrMsgIdAndTxt("nmfb:invalidArgument", "num_basis_elems: multi-source cell arrays must go through nmf.m / cnmf.m");
+    const mxArray* Karg = mxIsCell(prhs[2]) ? mxGetCell(prhs[2], 0) : prhs[2];
+    if (!Karg || mxGetNumberOfElements(Karg) != 1) mexErrMsgIdAndTxt("nmfb:invalidArgument", "num_basis_elems must be a scalar");
+    const int K = static_cast<int>(mxGetScalar(Karg));
     const int T = conv ? static_cast<int>(mxGetScalar(prhs[3])) : 1;
+    if (K <= 0 || T <= 0 || m <= 0 || n <= 0) mexErrMsgIdAndTxt("nmfb:invalidArgument", "sizes must be positive");
     const mxArray* cfg = nrhs > (conv ? 4 : 3) ? prhs[conv ? 4 : 3] : nullptr;
     std::vector<float> Vf = to_single(V), W0, H0;
     check(nmfb_set_V(h, Vf.data(), m, n));
@@ -111,13 +143,11 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     c.H_fixed = field(cfg, "H_fixed", 0) != 0;
     c.maxiter = static_cast<int>(field(cfg, "maxiter", 0));
     c.tolerance = field(cfg, "tolerance", 0);
-    if (cfg && mxIsStruct(cfg)) {
-      const mxArray* w = mxGetField(cfg, 0, "W_init");
-      const mxArray* hh = mxGetField(cfg, 0, "H_init");
-      if (w && mxIsCell(w)) w = mxGetCell(w, 0);
-      if (hh && mxIsCell(hh)) hh = mxGetCell(hh, 0);
-      if (w && !mxIsEmpty(w)) { W0 = to_single(w); c.W_init = W0.data(); }
-      if (hh && !mxIsEmpty(hh)) { H0 = to_single(hh); c.H_init = H0.data(); }
+    {  // wrong-shaped initial factors would make the engine read past the host arrays
+      const mxArray* w = init_field(cfg, "W_init", static_cast<size_t>(m) * K * T);
+      const mxArray* hh = init_field(cfg, "H_init", static_cast<size_t>(K) * n);
+      if (w) { W0 = to_single(w); c.W_init = W0.data(); }
+      if (hh) { H0 = to_single(hh); c.H_init = H0.data(); }
     }
     // per-basis vectors (what nmf.m's per-source cell settings become after concatenating the
     // sources, see matlab/nmf.m): numeric vectors with one entry per basis column

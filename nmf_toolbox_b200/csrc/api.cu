@@ -246,7 +246,7 @@ extern "C" int nmfb_projfunc(nmfb_handle* h, const float* s, int N, int count, d
   NMFB_TRY(ar.alloc(h, &it, count));
   NMFB_TRY(ar.alloc(h, &fail, 1));
   NMFB_CUDA(h, cudaMemcpyAsync(X, s, total * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  projfunc_kernel<<<count, kProjThreads, 0, h->stream>>>(X, N, N, k1, k2, nn, it, fail);
+  launch_projfunc(h->stream, count, X, N, N, k1, k2, nn, it, fail);
   NMFB_TRY(check_launch(h, "projfunc"));
   int failed = 0;
   NMFB_CUDA(h, cudaMemcpyAsync(v_out, X, total * sizeof(float), cudaMemcpyDeviceToHost, h->stream));

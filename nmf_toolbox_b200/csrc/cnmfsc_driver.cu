@@ -115,7 +115,7 @@ int project_rows(nmfb_handle* h, State* s, float* X, double k1) {
   if (s->n > kProjThreads * 32 * kProjMaskWords)
     return h->fail(NMFB_ERR_UNSUPPORTED, "cnmfsc: projfunc vectors longer than %d are not supported",
                    kProjThreads * 32 * kProjMaskWords);
-  projfunc_kernel<<<s->K, kProjThreads, 0, h->stream>>>(X, s->n, s->ldh, k1, 1.0, 1, nullptr, s->fail);
+  launch_projfunc(h->stream, s->K, X, s->n, s->ldh, k1, 1.0, 1, nullptr, s->fail);
   return check_launch(h, "projfunc");
 }
 
@@ -231,7 +231,7 @@ int run(nmfb_handle* h, State* s, int K, int T, const nmfb_config* cfg_in, float
                      kProjThreads * 32 * kProjMaskWords);
     L1a = std::sqrt(static_cast<double>(m)) - (std::sqrt(static_cast<double>(m)) - 1) * sW;
     NMFB_CUDA(h, cudaMemcpyAsync(s->Wret, s->Wm, cw * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-    projfunc_kernel<<<KT, kProjThreads, 0, h->stream>>>(s->Wret, m, ldw, L1a, 1.0, 1, nullptr, s->fail);
+    launch_projfunc(h->stream, KT, s->Wret, m, ldw, L1a, 1.0, 1, nullptr, s->fail);
     NMFB_TRY(check_launch(h, "projfunc(W init)"));
     NMFB_TRY(split_to(h, s->Wret, s->Wrt, s->Wrl, KT, m, ldw));
   }
@@ -420,7 +420,7 @@ int run(nmfb_handle* h, State* s, int K, int T, const nmfb_config* cfg_in, float
           grad_step_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm + off, s->Bt, s->A + off, s->Wnew, K, m, ldw,
                                                                   stepW[t]);  // cnmfsc.m:229
           NMFB_TRY(check_launch(h, "grad_step(W)"));
-          projfunc_kernel<<<K, kProjThreads, 0, h->stream>>>(s->Wnew, m, ldw, L1a, 1.0, 1, nullptr, s->fail);  // 230-232
+          launch_projfunc(h->stream, K, s->Wnew, m, ldw, L1a, 1.0, 1, nullptr, s->fail);  // 230-232
           NMFB_TRY(check_launch(h, "projfunc(W)"));
           NMFB_TRY(split_to(h, s->Wnew, s->Wnt, s->Wnl, K, m, ldw));
           const bool keep = s->fused_resid;

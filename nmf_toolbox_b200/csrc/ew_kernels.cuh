@@ -771,9 +771,13 @@ struct ProjFuse {
   float* lo = nullptr;
   const int* skip = nullptr;  // device flag: non-zero = this launch is a no-op
 };
+// EPT > 0: the vector (len <= kProjThreads * EPT) lives in registers between the fused first and last
+// sweep - a pass then costs two block reductions and no memory traffic; EPT == 0: the vector stays in
+// global memory (L1/L2 resident), any length up to kProjThreads * 32 * kProjMaskWords.
+template <int EPT>
 __global__ void __launch_bounds__(kProjThreads)
-projfunc_kernel(float* __restrict__ X, int len, long long ld, double k1, double k2, int nn,
-                int* iters_out, int* fail_flag, ProjFuse f = ProjFuse()) {
+projfunc_kernel_t(float* __restrict__ X, int len, long long ld, double k1, double k2, int nn,
+                  int* iters_out, int* fail_flag, ProjFuse f) {
   NMFB_STOP_GUARD(f.skip);
   __shared__ double sh[32 * 3];
   __shared__ double bc[4];
@@ -781,26 +785,31 @@ projfunc_kernel(float* __restrict__ X, int len, long long ld, double k1, double 
   float* v = X + voff;
   const int tid = threadIdx.x;
   const float stepf = f.step != nullptr ? static_cast<float>(*f.step) : 0.f;
-  uint32_t zmask[kProjMaskWords];
-  uint32_t negmask[kProjMaskWords];  // signs when nn == 0
+  constexpr int kWords = EPT > 0 ? (EPT + 31) / 32 : kProjMaskWords;
+  uint32_t zmask[kWords];
+  uint32_t negmask[kWords];  // signs when nn == 0
+  float r[EPT > 0 ? EPT : 1];
 #pragma unroll
-  for (int w = 0; w < kProjMaskWords; ++w) zmask[w] = negmask[w] = 0u;
+  for (int w = 0; w < kWords; ++w) zmask[w] = negmask[w] = 0u;
+// q-th element of this thread: e = tid + q * kProjThreads (fully unrolled when the vector is in registers)
+#define NMFB_PROJ_FOR(q, e) \
+  _Pragma("unroll") for (int q = 0, e = tid; (EPT > 0 ? q < EPT : e < len); ++q, e += kProjThreads) if (EPT == 0 || e < len)
+#define NMFB_PROJ_GET(q, e) (EPT > 0 ? r[EPT > 0 ? q : 0] : v[e])
+#define NMFB_PROJ_SET(q, e, x)       \
+  do {                               \
+    if (EPT > 0) r[EPT > 0 ? q : 0] = (x); \
+    else v[e] = (x);                 \
+  } while (0)
 
   // projfunc.m:16-22: v = s + (k1 - sum(s)) / N
   double acc[3] = {0.0, 0.0, 0.0};
-  for (int e = tid, q = 0; e < len; e += kProjThreads, ++q) {
-    float s;
-    if (f.src != nullptr) {
-      s = f.src[voff + e] - stepf * (f.Dp[voff + e] - f.Dn[voff + e]);
-      v[e] = s;
-    } else {
-      s = v[e];
-    }
+  NMFB_PROJ_FOR(q, e) {
+    float s = f.src != nullptr ? f.src[voff + e] - stepf * (f.Dp[voff + e] - f.Dn[voff + e]) : v[e];
     if (!nn && s < 0.f) {
       negmask[q >> 5] |= 1u << (q & 31);
       s = -s;
-      v[e] = s;
     }
+    NMFB_PROJ_SET(q, e, s);
     acc[0] += s;
   }
   block_sum<3>(acc, sh);
@@ -813,12 +822,12 @@ projfunc_kernel(float* __restrict__ X, int len, long long ld, double k1, double 
     // sweep 1: apply pending shift, then a, b, c of projfunc.m:31-36
     const double mid = k1 / (len - nz);
     acc[0] = acc[1] = acc[2] = 0.0;
-    for (int e = tid, q = 0; e < len; e += kProjThreads, ++q) {
+    NMFB_PROJ_FOR(q, e) {
       const bool z = (zmask[q >> 5] >> (q & 31)) & 1u;
       float x = 0.f;
       if (!z) {
-        x = static_cast<float>(static_cast<double>(v[e]) + shift);
-        v[e] = x;
+        x = static_cast<float>(static_cast<double>(NMFB_PROJ_GET(q, e)) + shift);
+        NMFB_PROJ_SET(q, e, x);
       }
       const double w = z ? 0.0 : static_cast<double>(x) - mid;
       acc[0] += w * w;
@@ -835,22 +844,21 @@ projfunc_kernel(float* __restrict__ X, int len, long long ld, double k1, double 
     const double alphap = bc[0];
     // sweep 2: v = alphap*w + v (projfunc.m:38); all(v >= 0)?; zero negatives, tempsum (49-51)
     acc[0] = acc[1] = acc[2] = 0.0;  // [0] any negative, [1] zero count, [2] tempsum
-    for (int e = tid, q = 0; e < len; e += kProjThreads, ++q) {
+    NMFB_PROJ_FOR(q, e) {
       const bool z = (zmask[q >> 5] >> (q & 31)) & 1u;
       if (z) {
         acc[1] += 1.0;
-        continue;
-      }
-      const float x0 = v[e];
-      const float x = static_cast<float>(alphap * (static_cast<double>(x0) - mid) + x0);
-      if (!(x >= 0.f)) acc[0] += 1.0;  // also catches NaN
-      if (x <= 0.f) {
-        zmask[q >> 5] |= 1u << (q & 31);
-        acc[1] += 1.0;
-        v[e] = x;  // finalised below only if the loop continues
       } else {
-        v[e] = x;
-        acc[2] += x;
+        const float x0 = NMFB_PROJ_GET(q, e);
+        const float x = static_cast<float>(alphap * (static_cast<double>(x0) - mid) + x0);
+        if (!(x >= 0.f)) acc[0] += 1.0;  // also catches NaN
+        NMFB_PROJ_SET(q, e, x);          // (entries <= 0 are finalised below only if the loop continues)
+        if (x <= 0.f) {
+          zmask[q >> 5] |= 1u << (q & 31);
+          acc[1] += 1.0;
+        } else {
+          acc[2] += x;
+        }
       }
     }
     block_sum<3>(acc, sh);
@@ -868,24 +876,37 @@ projfunc_kernel(float* __restrict__ X, int len, long long ld, double k1, double 
       break;
     }
     // projfunc.m:50-53: zero the set, spread (k1 - tempsum) over the rest (applied lazily in sweep 1)
-    for (int e = tid, q = 0; e < len; e += kProjThreads, ++q)
-      if ((zmask[q >> 5] >> (q & 31)) & 1u) v[e] = 0.f;
+    NMFB_PROJ_FOR(q, e) {
+      if ((zmask[q >> 5] >> (q & 31)) & 1u) NMFB_PROJ_SET(q, e, 0.f);
+    }
     shift = (k1 - bc[3]) / (len - nz);
     __syncthreads();
   }
-  if (!nn) {  // projfunc.m:58-60
-    for (int e = tid, q = 0; e < len; e += kProjThreads, ++q)
-      if ((negmask[q >> 5] >> (q & 31)) & 1u) v[e] = -v[e];
-  }
-  if (f.hi != nullptr) {  // every thread re-reads only elements it wrote itself
-    for (int e = tid; e < len; e += kProjThreads) {
-      const float x = v[e];
+  // last sweep: signs back (projfunc.m:58-60), result to memory, optional tf32 head / tail
+  NMFB_PROJ_FOR(q, e) {
+    float x = NMFB_PROJ_GET(q, e);
+    if (!nn && ((negmask[q >> 5] >> (q & 31)) & 1u)) x = -x;
+    v[e] = x;
+    if (f.hi != nullptr) {
       const float hi = tf32_rn(x);
       f.hi[voff + e] = hi;
       f.lo[voff + e] = tf32_rn(x - hi);
     }
   }
   if (tid == 0 && iters_out) iters_out[blockIdx.x] = iters;
+#undef NMFB_PROJ_FOR
+#undef NMFB_PROJ_GET
+#undef NMFB_PROJ_SET
+}
+// host-side dispatch on the vector length
+inline void launch_projfunc(cudaStream_t stream, int count, float* X, int len, long long ld, double k1, double k2, int nn,
+                            int* iters_out, int* fail_flag, const ProjFuse& f = ProjFuse()) {
+  if (len <= kProjThreads * 8)
+    projfunc_kernel_t<8><<<count, kProjThreads, 0, stream>>>(X, len, ld, k1, k2, nn, iters_out, fail_flag, f);
+  else if (len <= kProjThreads * 32)
+    projfunc_kernel_t<32><<<count, kProjThreads, 0, stream>>>(X, len, ld, k1, k2, nn, iters_out, fail_flag, f);
+  else
+    projfunc_kernel_t<0><<<count, kProjThreads, 0, stream>>>(X, len, ld, k1, k2, nn, iters_out, fail_flag, f);
 }
 
 // ---------------------------------------------------------------- device-side line search (nmfsc.m:146-179,196-229)

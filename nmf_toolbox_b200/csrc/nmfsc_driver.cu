@@ -77,7 +77,7 @@ int project(nmfb_handle* h, State* s, float* X, int nvec, int len, long long ld,
   if (len > kProjThreads * 32 * kProjMaskWords)
     return h->fail(NMFB_ERR_UNSUPPORTED, "nmfsc: projfunc vectors longer than %d are not supported",
                    kProjThreads * 32 * kProjMaskWords);
-  projfunc_kernel<<<nvec, kProjThreads, 0, h->stream>>>(X, len, ld, k1, 1.0, 1, nullptr, s->fail, f);
+  launch_projfunc(h->stream, nvec, X, len, ld, k1, 1.0, 1, nullptr, s->fail, f);
   return check_launch(h, "projfunc");
 }
 
@@ -368,10 +368,48 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
       return h->fail(NMFB_ERR_CUDA, "cudaEventCreate failed");
   int rc = NMFB_OK, c = 0, queued = 0;
   std::memset(pin, 0, 8 * sizeof(int));
+  // The pattern is ~25 short kernels whose arguments never change (step sizes, objectives and the
+  // iteration counter live in device memory), and launched one by one they are launch-latency bound
+  // (measured: ~200 us of kernel time in a 360 us iteration).  So the first pattern is launched
+  // directly (it also performs every one-off cudaFuncSetAttribute), the second is recorded into a CUDA
+  // graph, and every further iteration is ONE graph launch.  Per-kernel event timing
+  // (nmfb_profile_enable) and NMFB_NO_GRAPH=1 keep the direct launches.
+  cudaGraphExec_t gexec = nullptr;
+  long long per_pattern = 0;
+  {
+    const long long l0 = h->launches;
+    rc = pattern();
+    ++queued;
+    per_pattern = h->launches - l0;
+    const char* ng = std::getenv("NMFB_NO_GRAPH");
+    if (rc == NMFB_OK && !h->profile && !(ng && ng[0] == '1')) {
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+      if (e == cudaSuccess) {
+        const int prc = pattern();
+        h->launches -= per_pattern;  // recorded, not launched
+        cudaError_t e2 = cudaStreamEndCapture(h->stream, &graph);
+        if (prc != NMFB_OK) rc = prc;
+        else if (e2 != cudaSuccess) rc = h->fail(NMFB_ERR_CUDA, "nmfsc: graph capture failed: %s", cudaGetErrorString(e2));
+        else if ((e2 = cudaGraphInstantiate(&gexec, graph, 0)) != cudaSuccess)
+          rc = h->fail(NMFB_ERR_CUDA, "nmfsc: cudaGraphInstantiate failed: %s", cudaGetErrorString(e2));
+        if (graph) cudaGraphDestroy(graph);
+      } else {
+        rc = h->fail(NMFB_ERR_CUDA, "nmfsc: cudaStreamBeginCapture failed: %s", cudaGetErrorString(e));
+      }
+    }
+  }
+  auto queue_pattern = [&]() -> int {
+    if (gexec == nullptr) return pattern();
+    cudaError_t e = cudaGraphLaunch(gexec, h->stream);
+    if (e != cudaSuccess) return h->fail(NMFB_ERR_CUDA, "nmfsc: cudaGraphLaunch failed: %s", cudaGetErrorString(e));
+    h->launches += per_pattern;
+    return NMFB_OK;
+  };
   // a search may halve ~665 times before the step underflows (nmfsc.m:170): generous bound, never reached
   const long long max_patterns = (static_cast<long long>(cfg.maxiter) + 2) * 700;
   while (rc == NMFB_OK) {
-    for (int p = 0; p < kChunkPatterns && rc == NMFB_OK; ++p, ++queued) rc = pattern();
+    for (int p = 0; p < kChunkPatterns && rc == NMFB_OK; ++p, ++queued) rc = queue_pattern();
     if (rc != NMFB_OK) break;
     if (queued > max_patterns) {
       rc = h->fail(NMFB_ERR_CUDA, "internal: nmfsc iteration loop did not finish after %d kernel patterns", queued);
@@ -387,15 +425,16 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
   }
   for (int b = 0; b < 2; ++b) cudaEventDestroy(evs[b]);
   cudaStreamSynchronize(h->stream);
+  if (gexec) cudaGraphExecDestroy(gexec);
   NMFB_TRY(rc);
   LsState fin;
   NMFB_CUDA(h, cudaMemcpy(&fin, s->ls, sizeof(fin), cudaMemcpyDeviceToHost));
   loop_end(h, fin.iter);
   if (fin.failed) return h->fail(NMFB_ERR_PROJFUNC, "projfunc diverged (non-finite values)");
   if (trace)
-    fprintf(stderr, "[nmfb] nmfsc: %d iterations, %d line-search trials, %d patterns queued, loop %.2f ms "
+    fprintf(stderr, "[nmfb] nmfsc: %d iterations, %d line-search trials, %d patterns queued (%s), loop %.2f ms "
                     "(%.1f us per iteration), final steps H %.3g W %.3g\n",
-            fin.iter, fin.trials, queued, h->loop_ms, fin.iter ? 1e3 * h->loop_ms / fin.iter : 0.0, fin.stepH, fin.stepW);
+            fin.iter, fin.trials, queued, gexec ? "CUDA graph" : "direct launches", h->loop_ms, fin.iter ? 1e3 * h->loop_ms / fin.iter : 0.0, fin.stepH, fin.stepW);
   h->halvings.assign(2 * static_cast<size_t>(fin.iter), 0);
   if (fin.iter > 0)
     NMFB_CUDA(h, cudaMemcpy(h->halvings.data(), fin.halvings, h->halvings.size() * sizeof(int), cudaMemcpyDeviceToHost));
