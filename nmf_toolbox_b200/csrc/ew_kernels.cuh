@@ -731,6 +731,21 @@ __global__ void grad_step_kernel(const float* __restrict__ X, const float* __res
     Xnew[o] = X[o] - s * (Dp[o] - Dn[o]);
   }
 }
+// multiplicative step + tf32 head / tail of the result in one pass (nmfsc.m:232 followed by the operand split)
+__global__ void mu_step_split_kernel(float* __restrict__ X, const float* __restrict__ N, const float* __restrict__ D,
+                                     float* __restrict__ hi, float* __restrict__ lo, int len, long long ld,
+                                     const int* skip) {
+  NMFB_STOP_GUARD(skip);
+  const int c = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
+    const long long o = static_cast<long long>(c) * ld + i;
+    const float x = X[o] * (N[o] / fmaxf(D[o], NMFB_EPS));
+    X[o] = x;
+    const float h = tf32_rn(x);
+    hi[o] = h;
+    lo[o] = tf32_rn(x - h);
+  }
+}
 // plain multiplicative step X <- X .* N ./ max(D, eps)   (nmfsc.m:182,232)
 __global__ void mu_step_kernel(float* __restrict__ X, const float* __restrict__ N,
                                const float* __restrict__ D, int len, long long ld, const int* skip = nullptr) {
@@ -936,7 +951,7 @@ struct LsState {
 };
 enum { LS_INIT = 0, LS_TO_HTRIAL, LS_H_TO_WGRAD, LS_TO_WTRIAL, LS_W_TO_COST };
 // single-thread transitions that do not decide anything
-__global__ void ls_advance_kernel(LsState* st, int what, double* scal, double* cost, const int* fail) {
+__device__ inline void ls_advance_body(LsState* st, int what, volatile double* scal, double* cost, const int* fail) {
   if (what == LS_INIT) {  // nmfsc.m:138-139: cost(1) = objective of the initial factors
     cost[0] = 0.5 * scal[0];
     scal[0] = scal[1] = 0.0;
@@ -969,8 +984,11 @@ __global__ void ls_advance_kernel(LsState* st, int what, double* scal, double* c
     st->skip[4] = 0;
   }
 }
+__global__ void ls_advance_kernel(LsState* st, int what, double* scal, double* cost, const int* fail) {
+  ls_advance_body(st, what, scal, cost, fail);
+}
 // end of a trial slot: accept (nmfsc.m:164-166,178 / 215-217,228) or halve (169-174 / 220-225)
-__global__ void ls_decide_kernel(LsState* st, int for_w, double* scal, const int* fail) {
+__device__ inline void ls_decide_body(LsState* st, int for_w, volatile double* scal, const int* fail) {
   const int ph = for_w ? 3 : 1;
   if (st->done || st->skip[ph]) return;
   const double newobj = 0.5 * scal[0];
@@ -993,8 +1011,11 @@ __global__ void ls_decide_kernel(LsState* st, int for_w, double* scal, const int
   }
   for (int g = 0; g < 5; ++g) st->skip[g] = 1;
 }
+__global__ void ls_decide_kernel(LsState* st, int for_w, double* scal, const int* fail) {
+  ls_decide_body(st, for_w, scal, fail);
+}
 // end of an iteration: cost(iter+1) and the stop test (nmfsc.m:237-244)
-__global__ void ls_cost_kernel(LsState* st, double* scal, double* cost) {
+__device__ inline void ls_cost_body(LsState* st, volatile double* scal, double* cost) {
   if (st->done || st->skip[4]) return;
   const int it = st->iter + 1;  // 1-based iteration that just finished
   const double c = 0.5 * scal[0];
@@ -1009,6 +1030,26 @@ __global__ void ls_cost_kernel(LsState* st, double* scal, double* cost) {
     for (int g = 0; g < 5; ++g) st->skip[g] = 1;
   } else {
     st->skip[0] = 0;
+  }
+}
+__global__ void ls_cost_kernel(LsState* st, double* scal, double* cost) { ls_cost_body(st, scal, cost); }
+// What the LAST block of an objective kernel does with the finished sum (saves one launch per objective):
+enum { LSFIN_NONE = 0, LSFIN_DECIDE_H, LSFIN_DECIDE_W, LSFIN_COST, LSFIN_TO_WTRIAL, LSFIN_INIT };
+struct LsFin {
+  int mode = LSFIN_NONE;
+  LsState* st = nullptr;
+  double* cost = nullptr;
+  const int* fail = nullptr;
+  unsigned int* ticket = nullptr;  // zero on entry; reset by the last block
+};
+__device__ inline void ls_finish(const LsFin& f, double* scal) {
+  switch (f.mode) {
+    case LSFIN_DECIDE_H: ls_decide_body(f.st, 0, scal, f.fail); break;
+    case LSFIN_DECIDE_W: ls_decide_body(f.st, 1, scal, f.fail); break;
+    case LSFIN_COST: ls_cost_body(f.st, scal, f.cost); break;
+    case LSFIN_TO_WTRIAL: ls_advance_body(f.st, LS_TO_WTRIAL, scal, f.cost, f.fail); break;
+    case LSFIN_INIT: ls_advance_body(f.st, LS_INIT, scal, f.cost, f.fail); break;
+    default: break;
   }
 }
 // accepted trial -> current factor (master, tf32 head, tf32 tail) in one launch

@@ -100,7 +100,7 @@ int plan_resid(nmfb_handle* h, ResidOp* op, const float* Whi, const float* Wlo, 
   const int per = (total_tiles + splits - 1) / splits;
   splits = (total_tiles + per - 1) / per;
   op->grid = dim3(2 * pairs, splits, 1);
-  op->args = ResidArgs{m, n, Kp, per, scal, nullptr};
+  op->args = ResidArgs{m, n, Kp, per, scal, nullptr, LsFin()};
   op->planned = true;
   return NMFB_OK;
 }

@@ -42,6 +42,7 @@ struct State {
   float *N, *D, *A, *B;
   double *scal, *sq, *cost;
   int* fail;
+  unsigned int* ticket;
   LsState* ls;
   GramOp gramW, gramH;
   GemmOp gemmN, gemmD, gemmA, gemmB, residCur, residH, residW;
@@ -49,17 +50,35 @@ struct State {
   bool fused_resid = false;
 };
 
-// objective 0.5*|V - W*H|^2 into scal[0] (x2), guarded by the phase word `skip`
-int objective(nmfb_handle* h, State* s, GemmOp& op, ResidOp& rs, const int* skip) {
+// Objective 0.5*|V - W*H|^2 (x2 in scal[0]) guarded by the phase word `skip`, followed by what the line
+// search does with it (`fin`: decide a trial, close the iteration, ...).  The streaming kernel lets its last
+// block do that; the panel-GEMM fallback (K > 128) needs the small single-thread kernel.
+int objective(nmfb_handle* h, State* s, GemmOp& op, ResidOp& rs, const int* skip, int fin) {
   NMFB_TRY(prof_mark(h, 1));
   if (s->fused_resid) {
     rs.args.skip = skip;
+    rs.args.fin.mode = fin;
+    rs.args.fin.st = s->ls;
+    rs.args.fin.cost = s->cost;
+    rs.args.fin.fail = s->fail;
+    rs.args.fin.ticket = s->ticket;
     NMFB_TRY(run_resid(h, rs));
   } else {
     op.L.args.stop = skip;
     NMFB_TRY(run_gemm(h, op));
   }
-  return prof_mark(h, 1);
+  NMFB_TRY(prof_mark(h, 1));
+  if (s->fused_resid || fin == LSFIN_NONE) return NMFB_OK;
+  if (fin == LSFIN_DECIDE_H || fin == LSFIN_DECIDE_W) {
+    ls_decide_kernel<<<1, 1, 0, h->stream>>>(s->ls, fin == LSFIN_DECIDE_W ? 1 : 0, s->scal, s->fail);
+    return check_launch(h, "ls_decide");
+  }
+  if (fin == LSFIN_COST) {
+    ls_cost_kernel<<<1, 1, 0, h->stream>>>(s->ls, s->scal, s->cost);
+    return check_launch(h, "ls_cost");
+  }
+  ls_advance_kernel<<<1, 1, 0, h->stream>>>(s->ls, fin == LSFIN_INIT ? LS_INIT : LS_TO_WTRIAL, s->scal, s->cost, s->fail);
+  return check_launch(h, "ls_advance");
 }
 
 int split_to(nmfb_handle* h, const float* src, float* hi, float* lo, int nvec, int len, long long ld,
@@ -70,7 +89,54 @@ int split_to(nmfb_handle* h, const float* src, float* hi, float* lo, int nvec, i
   return check_launch(h, "split_copy");
 }
 
-constexpr int kChunk = 2;  // k-blocks per TMEM accumulation chunk (8 MMA steps)
+// k-blocks per TMEM accumulation chunk of the gradient contractions (x 4 MMA steps each): the tensor core
+// truncates when it adds into the accumulator, so long chunks bias the sums; short ones cost drain time
+static int sc_chunk() {
+  static int v = [] {
+    const char* e = std::getenv("NMFB_SC_CHUNK");
+    const int c = e ? std::atoi(e) : 8;  // parity and the halving sequences are unchanged for 2..16 (measured)
+    return c > 0 ? c : 8;
+  }();
+  return v;
+}
+static int sc_gram_ctas() {  // CTAs (= split-K slabs to sum afterwards) of the small Gram products
+  static int v = [] {
+    const char* e = std::getenv("NMFB_SC_GRAM_CTAS");
+    const int c = e ? std::atoi(e) : 0;
+    return c > 0 ? c : 0;
+  }();
+  return v;
+}
+
+// The iteration alternates tensor-core kernels that need ~200 KB of shared memory with small vector
+// kernels that need almost none.  Left alone, the driver picks a different L1 / shared-memory split for
+// the two kinds and re-partitions the SMs at every switch, which costs an idle gap per kernel boundary;
+// asking for the maximal shared-memory carve-out on the small kernels keeps one configuration.
+void prefer_max_shared_once() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  const char* e = std::getenv("NMFB_NO_CARVEOUT");
+  if (e && e[0] == '1') return;
+  auto set = [](const void* fn) {
+    cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  };
+  set(reinterpret_cast<const void*>(projfunc_kernel_t<8>));
+  set(reinterpret_cast<const void*>(projfunc_kernel_t<32>));
+  set(reinterpret_cast<const void*>(projfunc_kernel_t<0>));
+  set(reinterpret_cast<const void*>(ls_advance_kernel));
+  set(reinterpret_cast<const void*>(ls_decide_kernel));
+  set(reinterpret_cast<const void*>(ls_cost_kernel));
+  set(reinterpret_cast<const void*>(copy3_kernel));
+  set(reinterpret_cast<const void*>(mu_step_split_kernel));
+  set(reinterpret_cast<const void*>(mu_step_kernel));
+  set(reinterpret_cast<const void*>(split_copy_kernel));
+  set(reinterpret_cast<const void*>(gram_reduce_kernel));
+  set(reinterpret_cast<const void*>(split_reduce_kernel));
+  set(reinterpret_cast<const void*>(vec_sums_kernel));
+  set(reinterpret_cast<const void*>(renorm_pair_kernel));
+  cudaGetLastError();
+}
 
 int project(nmfb_handle* h, State* s, float* X, int nvec, int len, long long ld, double k1,
             const ProjFuse& f = ProjFuse()) {
@@ -91,6 +157,7 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
   if (h->Vraw == nullptr) return h->fail(NMFB_ERR_NO_DATA, "nmfsc: call nmfb_set_V first");
   if (K <= 0) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "nmfsc: num_basis_elems must be positive");
   if (comm_size(h->comm) > 1) return h->fail(NMFB_ERR_UNSUPPORTED, "nmfsc: single GPU only");
+  prefer_max_shared_once();
   nmfb_config cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   if (cfg_in) cfg = *cfg_in;
@@ -143,6 +210,7 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
   NMFB_TRY(ar->alloc(h, &s->fail, 1));
   NMFB_TRY(ar->alloc(h, &s->cost, static_cast<size_t>(cfg.maxiter) + 1));  // nmfsc.m:137
   NMFB_TRY(ar->alloc(h, &s->ls, 1));
+  NMFB_TRY(ar->alloc(h, &s->ticket, 1));
   {
     LsState init{};
     init.stepH = init.stepW = 1.0;  // nmfsc.m:133-134
@@ -198,8 +266,8 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
   NMFB_TRY(split_to(h, s->Hm, s->Ht, s->Hl, K, n, ldh));
 
   // ---- contractions
-  NMFB_TRY(plan_gram(h, ar, &s->gramW, s->Wt, Kp, m, ldw, sk0, s->Wl, kChunk));
-  NMFB_TRY(plan_gram(h, ar, &s->gramH, s->Ht, Kp, n, ldh, sk2, s->Hl, kChunk));
+  NMFB_TRY(plan_gram(h, ar, &s->gramW, s->Wt, Kp, m, ldw, sk0, s->Wl, sc_chunk(), sc_gram_ctas()));
+  NMFB_TRY(plan_gram(h, ar, &s->gramH, s->Ht, Kp, n, ldh, sk2, s->Hl, sc_chunk(), sc_gram_ctas()));
   {
     auto three = [](const MatRef& Xhi, const MatRef& Xlo, const MatRef& Yhi, const MatRef& Ylo) {
       ExtraSegs e;  // acc = Xhi*Yhi' (segment 0) + Xlo*Yhi' + Xhi*Ylo'
@@ -236,7 +304,7 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
     ExtraSegs eB = three(Wm_hi, Wm_lo, Gh_hi, Gh_lo);
     NMFB_TRY(plan_store(h, ar, &s->gemmB, Wm_hi, Gh_hi, Kp, nullptr, nullptr, 0, m, Kp, s->B, nullptr, ldw,
                         false, sk2, &eB));
-    for (GemmOp* op : {&s->gemmN, &s->gemmD, &s->gemmA, &s->gemmB}) op->L.args.chunk_kb = kChunk;
+    for (GemmOp* op : {&s->gemmN, &s->gemmD, &s->gemmA, &s->gemmB}) op->L.args.chunk_kb = sc_chunk();
     // objective 0.5*|V - W*H|^2 of (W, H) pairs given as head/tail
     auto plan_resid = [&](GemmOp* op, const float* Whi, const float* Wlo, const float* Hhi, const float* Hlo) {
       MatRef Xh{Whi, m, Kp, ldw, true}, Xl{Wlo, m, Kp, ldw, true};
@@ -246,7 +314,7 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
       op->L.args.Vsrc = h->Vwork;
       op->L.args.ldv = h->ldv;
       op->L.args.scal = s->scal;
-      op->L.args.chunk_kb = kChunk;
+      op->L.args.chunk_kb = sc_chunk();
       std::string pe = set_v_prefetch(&op->L, h->Vwork, m, n, h->ldv);
       if (!pe.empty()) return h->fail(NMFB_ERR_CUDA, "%s", pe.c_str());
       return static_cast<int>(NMFB_OK);
@@ -284,10 +352,8 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
     if (for_w) NMFB_TRY(project(h, s, s->Wnew, K, m, ldw, L1a, f));  // nmfsc.m:205-208
     else NMFB_TRY(project(h, s, s->Hnew, K, n, ldh, L1s, f));        // nmfsc.m:154-157
     NMFB_TRY(prof_mark(h, 2));
-    if (for_w) NMFB_TRY(objective(h, s, s->residW, s->rsW, sk3));    // nmfsc.m:211-212
-    else NMFB_TRY(objective(h, s, s->residH, s->rsH, sk1));          // nmfsc.m:160-161
-    ls_decide_kernel<<<1, 1, 0, h->stream>>>(s->ls, for_w ? 1 : 0, s->scal, s->fail);
-    return check_launch(h, "ls_decide");
+    if (for_w) return objective(h, s, s->residW, s->rsW, sk3, LSFIN_DECIDE_W);  // nmfsc.m:211-212, 215-225
+    return objective(h, s, s->residH, s->rsH, sk1, LSFIN_DECIDE_H);             // nmfsc.m:160-161, 164-174
   };
   // the kernels of one iteration (H first, then W: nmfsc.m:143-244), every one guarded by its phase
   auto pattern = [&]() -> int {
@@ -329,12 +395,10 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
       NMFB_TRY(run_gemm(h, s->gemmA));  // A = V H' (194)
       NMFB_TRY(run_gemm(h, s->gemmB));  // B = V_hat H' = W (H H') (195)
       if (searchW) {
-        NMFB_TRY(objective(h, s, s->residCur, s->rsCur, sk2));  // nmfsc.m:193,197
-        NMFB_TRY(advance(h, s, LS_TO_WTRIAL));
+        NMFB_TRY(objective(h, s, s->residCur, s->rsCur, sk2, LSFIN_TO_WTRIAL));  // nmfsc.m:193,197
       } else {  // nmfsc.m:232
-        mu_step_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, s->A, s->B, m, ldw, sk2);
+        mu_step_split_kernel<<<vec_grid(m, K), 256, 0, h->stream>>>(s->Wm, s->A, s->B, s->Wt, s->Wl, m, ldw, sk2);
         NMFB_TRY(check_launch(h, "mu_step(W)"));
-        NMFB_TRY(split_to(h, s->Wm, s->Wt, s->Wl, K, m, ldw, sk2));
         NMFB_TRY(advance(h, s, LS_W_TO_COST));
       }
       NMFB_TRY(prof_mark(h, 3));
@@ -349,18 +413,15 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
       copy3_kernel<<<copy_blocks, 256, 0, h->stream>>>(s->Wnew, s->Wm, s->Wnt, s->Wt, s->Wnl, s->Wl, cw4, sk4);
       NMFB_TRY(check_launch(h, "copy3(W)"));
     }
-    NMFB_TRY(objective(h, s, s->residCur, s->rsCur, sk4));
-    ls_cost_kernel<<<1, 1, 0, h->stream>>>(s->ls, s->scal, s->cost);
-    return check_launch(h, "ls_cost");
+    return objective(h, s, s->residCur, s->rsCur, sk4, LSFIN_COST);
   };
 
   NMFB_CUDA(h, cudaMemsetAsync(s->scal, 0, 2 * sizeof(double), h->stream));
-  NMFB_TRY(objective(h, s, s->residCur, s->rsCur, nullptr));  // nmfsc.m:138-139
-  NMFB_TRY(advance(h, s, LS_INIT));
+  NMFB_TRY(objective(h, s, s->residCur, s->rsCur, nullptr, LSFIN_INIT));  // nmfsc.m:138-139
   loop_begin(h);
   // Queue patterns in chunks; the host looks at {iter, ncost, done, failed} of the chunk before the one
   // it has just queued, so it never waits for the device while work is outstanding.
-  constexpr int kChunkPatterns = 8;
+  constexpr int kPatternsPerChunk = 8;
   int* pin = h->pinned + 8;  // two slots of four ints
   cudaEvent_t evs[2] = {nullptr, nullptr};
   for (int b = 0; b < 2; ++b)
@@ -409,7 +470,7 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
   // a search may halve ~665 times before the step underflows (nmfsc.m:170): generous bound, never reached
   const long long max_patterns = (static_cast<long long>(cfg.maxiter) + 2) * 700;
   while (rc == NMFB_OK) {
-    for (int p = 0; p < kChunkPatterns && rc == NMFB_OK; ++p, ++queued) rc = queue_pattern();
+    for (int p = 0; p < kPatternsPerChunk && rc == NMFB_OK; ++p, ++queued) rc = queue_pattern();
     if (rc != NMFB_OK) break;
     if (queued > max_patterns) {
       rc = h->fail(NMFB_ERR_CUDA, "internal: nmfsc iteration loop did not finish after %d kernel patterns", queued);

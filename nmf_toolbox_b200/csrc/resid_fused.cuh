@@ -7,6 +7,7 @@
 // (TMA, 1 slot), accumulates S in one of four TMEM buffers and 16 epilogue warps reduce
 // (V - S)^2 straight from TMEM.  Same skeleton as kl_fused.cuh without the second MMA.
 #pragma once
+#include "ew_kernels.cuh"
 #include "kl_fused.cuh"
 
 namespace nmfb {
@@ -24,6 +25,7 @@ struct ResidArgs {
   int tiles_per_split;
   double* scal;  // scal[0] += sum (V - S)^2
   const int* skip;  // device flag: non-zero = do nothing (phase guard of the device-side line search)
+  LsFin fin;        // what the last block does with the finished sum (ew_kernels.cuh: ls_finish)
 };
 
 __global__ void __launch_bounds__(64 + kKlEpiWarps * 32, 1)
@@ -199,6 +201,15 @@ resid_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_const
       double p = 0.0;
       for (int w = 0; w < kKlEpiWarps; ++w) p += red[w];
       atomicAdd(a.scal, p);
+      if (a.fin.mode != LSFIN_NONE) {  // last block: the line-search decision / cost entry on the complete sum
+        __threadfence();
+        const unsigned int total = gridDim.x * gridDim.y;
+        if (atomicAdd(a.fin.ticket, 1u) == total - 1) {
+          *a.fin.ticket = 0u;
+          __threadfence();
+          ls_finish(a.fin, a.scal);
+        }
+      }
     }
   }
 
