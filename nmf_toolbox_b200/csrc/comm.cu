@@ -54,15 +54,6 @@ NcclApi* nccl_api() {
 }  // namespace ncclbind
 using namespace ncclbind;
 
-constexpr int kMaxRanks = 8;
-constexpr int kMaxBlocks = 256;                                   // grid cap of the all-reduce kernel
-constexpr size_t kFlagBytes = kMaxBlocks * kMaxRanks * sizeof(int);  // one flag array (opening / closing)
-constexpr size_t kHeader = 2 * kFlagBytes;                        // region = [flags | data]
-struct PeerTable {
-  char* base[kMaxRanks];  // base[q] = rank q's registered region as seen from this process
-  int rank, nranks;
-};
-
 struct Comm {
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
@@ -75,36 +66,6 @@ struct Comm {
 };
 
 // ---------------------------------------------------------------- peer-memory all-reduce kernels
-__device__ __forceinline__ void st_release_sys(int* p, int v) {
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_acquire_sys(const int* p) {
-  int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// Block b of every rank meets block b of all other ranks (flags[b][rank] in each rank's region
-// header, monotone epochs).  The release store of the signalling thread follows the bar.sync, so it
-// publishes the whole block's earlier writes (and, by stream order, those of earlier kernels).
-__device__ __forceinline__ void p2p_block_barrier(const PeerTable& t, size_t flags_off, int epoch) {
-  __syncthreads();
-  if (threadIdx.x < t.nranks) {
-    const int q = threadIdx.x;
-    const size_t row = flags_off + static_cast<size_t>(blockIdx.x) * kMaxRanks * sizeof(int);
-    st_release_sys(reinterpret_cast<int*>(t.base[q] + row) + t.rank, epoch);
-    const int* mine = reinterpret_cast<const int*>(t.base[t.rank] + row) + q;
-    long long t0 = clock64();
-    while (ld_acquire_sys(mine) - epoch < 0) {
-      if (clock64() - t0 > 30000000000LL) {
-        printf("nmfb: peer barrier timeout (rank %d block %d waiting for rank %d, epoch %d)\n", t.rank, blockIdx.x, q,
-               epoch);
-        __trap();
-      }
-    }
-  }
-  __syncthreads();
-}
-
 template <int N>
 __device__ __forceinline__ void p2p_reduce_slice(const PeerTable& t, size_t f_off, size_t lo, size_t hi) {
   // kU x N independent float4 per thread (64 registers) keep ~10 MB of reads in flight per GPU
@@ -182,6 +143,21 @@ p2p_allreduce_kernel(PeerTable t, int epoch, size_t f_off, size_t nf, size_t d1_
       }
     }
   }
+}
+
+bool comm_peer_table(const nmfb_handle* h, PeerTable* out) {
+  const Comm* c = h->comm;
+  if (!c || !c->p2p || c->nranks <= 1) return false;
+  if (out) *out = c->table;
+  return true;
+}
+int comm_next_epoch(nmfb_handle* h, int count) {
+  const int first = h->comm->epoch + 1;
+  h->comm->epoch += count;
+  return first;
+}
+size_t comm_region_offset(const nmfb_handle* h, const void* p) {
+  return static_cast<size_t>(static_cast<const char*>(p) - h->comm->region);
 }
 
 int comm_size(const Comm* c) { return c ? c->nranks : 1; }

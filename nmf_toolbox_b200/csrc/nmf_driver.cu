@@ -27,6 +27,7 @@
 #include "comm.cuh"
 #include "engine.cuh"
 #include "ew_kernels.cuh"
+#include "w_shard.cuh"
 
 using namespace nmfb;
 
@@ -76,6 +77,10 @@ struct NmfSession {
   double ab_scale = 0.0; // -1/(alpha beta) of the AB cost (nmf.m:214)
   KlOp klW, klH;         // fused KL halves (kl_fused.cuh)
   bool kl_fused = false;
+  // multi-GPU, row-sharded W step (w_shard.cuh): this rank's rows of W, byte offsets inside the peer region
+  bool w_sharded = false;
+  int r0 = 0, mb = 0;
+  size_t a_off = 0, b_off = 0, wt_off = 0, wm_off = 0, x_off = 0;
   float* packed = nullptr;  // multi-GPU: [A | G_H] contiguous fp32 for the single all-reduce
   char* region = nullptr;   // multi-GPU: allocation shared with the peers ([packed | hs | scal | flags])
   int* pinned = nullptr;    // host copy of stop[0..1]
@@ -247,8 +252,6 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     } else {
       s->per_basis = true;
       s->W_fixed = s->H_fixed = false;  // the masks decide per basis; every kernel of the iteration runs
-      if (comm_size(h->comm) > 1 && (cfg.W_fixed_k || cfg.W_fixed))
-        return h->fail(NMFB_ERR_UNSUPPORTED, "fixed W sources with several GPUs");
     }
   }
   const bool kl = s->divergence == NMFB_DIV_KL;
@@ -256,8 +259,6 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   s->two_weight = tw;
   Arena* ar = &s->ar;
 
-  NMFB_TRY(ar->alloc(h, &s->Wm, static_cast<size_t>(Kp) * s->ldw));
-  NMFB_TRY(ar->alloc(h, &s->Wt, static_cast<size_t>(Kp) * s->ldw));
   NMFB_TRY(ar->alloc(h, &s->Hm, static_cast<size_t>(Kp) * s->ldh));
   NMFB_TRY(ar->alloc(h, &s->Ht, static_cast<size_t>(Kp) * s->ldh));
   // packed = [A (Kp x ldw) | G_H (Kp x Kp, KL: unused) | ...]: one buffer so that a
@@ -271,14 +272,39 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   const bool share = comm_size(h->comm) > 1;
   const size_t dbl_off = (packed_floats * sizeof(float) + 255) / 256 * 256;
   if (share) {
+    // region = [packed | hs, scal | W tf32 | W fp32 | exchange slots of the sharded W step]
+    const size_t w_bytes = static_cast<size_t>(Kp) * s->ldw * sizeof(float);
+    const size_t wt_off = (dbl_off + (static_cast<size_t>(Kp) + 8) * sizeof(double) + 255) / 256 * 256;
+    const size_t wm_off = wt_off + (w_bytes + 255) / 256 * 256;
+    const size_t x_off = wm_off + (w_bytes + 255) / 256 * 256;
+    const size_t total = x_off + 2 * static_cast<size_t>(kMaxBlocks) * kMaxRanks * 2 * sizeof(double);
     char* region = nullptr;
-    NMFB_TRY(comm_acquire_region(h, dbl_off + (static_cast<size_t>(Kp) + 8) * sizeof(double), &region));
+    NMFB_TRY(comm_acquire_region(h, total, &region));
     s->packed = reinterpret_cast<float*>(region);
     s->hs = reinterpret_cast<double*>(region + dbl_off);
     s->scal = s->hs + Kp;
     s->region = region;
+    s->Wt = reinterpret_cast<float*>(region + wt_off);
+    s->Wm = reinterpret_cast<float*>(region + wm_off);
+    // Row-sharded W step over peer memory: rank r owns rows [r0, r0 + mb) of W (in units of 4 rows,
+    // padding rows of the leading dimension included).  Needs the peer mapping (else NCCL + the
+    // replicated W step) and a row block that fits the kernel's registers.
+    const int nr = comm_size(h->comm), rk = comm_rank(h->comm);
+    const int rb = round_up((static_cast<int>(s->ldw) + nr - 1) / nr, 4);
+    s->r0 = std::min(static_cast<int>(s->ldw), rk * rb);
+    s->mb = std::min(static_cast<int>(s->ldw), s->r0 + rb) - s->r0;
+    const char* env = std::getenv("NMFB_W_SHARD");
+    s->w_sharded = comm_peer_table(h, nullptr) && !lnmf && !(env && env[0] == '0') && rb <= 4 * kWsCache * kWsThreads;
+    const size_t base = comm_region_offset(h, region);
+    s->a_off = base;
+    s->b_off = tw ? base + w_bytes : 0;
+    s->wt_off = base + wt_off;
+    s->wm_off = base + wm_off;
+    s->x_off = base + x_off;
   } else {
     NMFB_TRY(ar->alloc(h, &s->packed, packed_floats));
+    NMFB_TRY(ar->alloc(h, &s->Wm, static_cast<size_t>(Kp) * s->ldw));
+    NMFB_TRY(ar->alloc(h, &s->Wt, static_cast<size_t>(Kp) * s->ldw));
   }
   s->A = s->packed;
   if (tw) s->B = s->packed + static_cast<size_t>(Kp) * s->ldw;
@@ -415,8 +441,17 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     if (multi || split) {
       NMFB_TRY(plan_store(h, ar, &s->gemmA, Xv, Yh, n, nullptr, nullptr, 0, m, Kp, s->A, nullptr,
                           s->ldw, split, stop));
-      NMFB_TRY(plan_store(h, ar, &s->gemmB, Xw, Yg, Kp, nullptr, nullptr, 0, m, Kp, s->B, nullptr,
-                          s->ldw, false, stop));
+      if (s->w_sharded) {  // B = W G_H only on the rows whose W step this rank takes
+        const int rows = std::max(0, std::min(m, s->r0 + s->mb) - s->r0);
+        if (rows > 0) {
+          MatRef Xwb{s->Wt + s->r0, rows, Kp, s->ldw, true};
+          NMFB_TRY(plan_store(h, ar, &s->gemmB, Xwb, Yg, Kp, nullptr, nullptr, 0, rows, Kp, s->B + s->r0, nullptr,
+                              s->ldw, false, stop));
+        }
+      } else {
+        NMFB_TRY(plan_store(h, ar, &s->gemmB, Xw, Yg, Kp, nullptr, nullptr, 0, m, Kp, s->B, nullptr,
+                            s->ldw, false, stop));
+      }
     } else {
       NMFB_TRY(plan_store(h, ar, &s->gemmA, Xv, Yh, n, &Xw, &Yg, Kp, m, Kp, s->A, s->B, s->ldw, false,
                           stop));
@@ -605,9 +640,14 @@ static int enqueue_cost(nmfb_handle* h, NmfSession* s, int iter, int mode) {
 static int allreduce_w_inputs(nmfb_handle* h, NmfSession* s, bool with_gram) {
   if (comm_size(h->comm) <= 1) return NMFB_OK;
   const size_t nA = static_cast<size_t>(s->Kp) * s->ldw;
-  const size_t count = nA + (with_gram ? static_cast<size_t>(s->Kp) * s->Kp : 0);
+  const size_t nG = with_gram ? static_cast<size_t>(s->Kp) * s->Kp : 0;
   const bool kl = s->divergence == NMFB_DIV_KL;  // hs is only formed (per iteration) by the KL path
-  NMFB_TRY(comm_allreduce(h, s->packed, count, kl ? s->hs : nullptr, kl ? s->Kp : 0, s->scal, 4));
+  // The m x K numerator partials travel only when every rank repeats the whole W step; with the
+  // row-sharded W step (or a fixed W) each rank fetches just its rows itself (w_shard.cuh), and what is
+  // left for the all-reduce are the K x K Gram matrix and the scalar sums.
+  const bool small = s->w_sharded || s->W_fixed;
+  NMFB_TRY(comm_allreduce(h, small ? (nG ? s->packed + nA : nullptr) : s->packed, small ? nG : nA + nG,
+                          kl ? s->hs : nullptr, kl ? s->Kp : 0, s->scal, 4));
   if (with_gram && s->direct_cost) {  // otherwise run_gram_post_allreduce makes the tf32 copy
     const int cnt = s->Kp * s->Kp;
     round_copy_kernel<<<dim3((cnt + 255) / 256, 1), 256, 0, h->stream>>>(s->gramH.g32, s->gramH.gtf, 1, cnt,
@@ -617,7 +657,38 @@ static int allreduce_w_inputs(nmfb_handle* h, NmfSession* s, bool with_gram) {
   return NMFB_OK;
 }
 
+// The whole W step on this rank's rows, partial sums fetched from / results delivered to the peers
+static int enqueue_w_sharded(nmfb_handle* h, NmfSession* s, int mode, bool b_partial) {
+  WShardArgs a{};
+  if (!comm_peer_table(h, &a.t)) return h->fail(NMFB_ERR_CUDA, "internal: sharded W step without a peer mapping");
+  a.mode = mode;
+  a.K = s->K;
+  a.r0 = s->r0;
+  a.mb = s->mb;
+  a.ld = s->ldw;
+  a.a_off = s->a_off;
+  a.b_off = b_partial ? s->b_off : 0;
+  a.Bloc = (mode == WSTEP_EUCLID && !b_partial) ? s->B : nullptr;
+  a.Wm = s->Wm;
+  a.wt_off = s->wt_off;
+  a.x_off = s->x_off;
+  a.wsum = s->wsum;
+  a.hs = s->hs;
+  a.lambda = s->lambda_w;
+  a.lambda_k = s->lamW_k;
+  a.fixed_k = s->fixW_k;
+  a.expo = s->expo;
+  a.stop = s->stop;
+  const int cap = std::min(h->num_sms, kMaxBlocks);  // one co-resident block per SM: blocks spin on their peers
+  a.rounds = (s->K + cap - 1) / cap;
+  const int grid = (s->K + a.rounds - 1) / a.rounds;
+  a.epoch0 = comm_next_epoch(h, a.rounds);
+  w_step_sharded_kernel<<<grid, kWsThreads, 0, h->stream>>>(a);
+  return check_launch(h, "w_step_sharded");
+}
+
 static int enqueue_w_finish(nmfb_handle* h, NmfSession* s, int mode) {
+  if (s->w_sharded) return enqueue_w_sharded(h, s, mode, false);
   WStepArgs w{};
   w.mode = mode;
   w.W = s->Wm;
@@ -742,11 +813,16 @@ static int enqueue_iteration_two_weight(nmfb_handle* h, NmfSession* s, int i) {
     NMFB_TRY(run_gemm(h, s->gemmRb));
   }
   if (multi) {  // column shards: A, B and the cost sums are partial (one all-reduce, as for euclidean / KL)
-    if (s->W_fixed) return h->fail(NMFB_ERR_UNSUPPORTED, "W_fixed with several GPUs");
-    NMFB_TRY(comm_allreduce(h, s->packed, 2 * static_cast<size_t>(s->Kp) * s->ldw, nullptr, 0, s->scal, 4));
+    const bool small = s->w_sharded || s->W_fixed;  // the m x K partials are fetched row block by row block instead
+    NMFB_TRY(comm_allreduce(h, small ? nullptr : s->packed, small ? 0 : 2 * static_cast<size_t>(s->Kp) * s->ldw, nullptr,
+                            0, s->scal, 4));
   }
   if (i > 0) NMFB_TRY(enqueue_cost(h, s, i - 1, cost_mode));
-  if (!s->W_fixed) {
+  if (!s->W_fixed && s->w_sharded) {
+    NMFB_TRY(enqueue_w_sharded(h, s, WSTEP_EUCLID, true));
+    s->gemmS.L.args.want_cost = 0;
+    NMFB_TRY(run_gemm(h, s->gemmS));  // refreshed V_hat (nmf.m:173)
+  } else if (!s->W_fixed) {
     WStepArgs w{};
     w.mode = WSTEP_EUCLID;  // same shape: neg = A + W diag(<W,B>), pos = B + W diag(<W,A>)
     w.W = s->Wm;
@@ -813,11 +889,7 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
     } else if (!s->H_fixed || i == 0 || multi) {
       NMFB_TRY(run_gram(h, s->gramH, stop));
     }
-    if (s->W_fixed) {
-      if (multi) return h->fail(NMFB_ERR_UNSUPPORTED, "W_fixed with several GPUs");
-    } else {
-      NMFB_TRY(run_timed(h, s->gemmA, 0));
-    }
+    if (!s->W_fixed) NMFB_TRY(run_timed(h, s->gemmA, 0));
     if (s->side_gh) NMFB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     NMFB_TRY(allreduce_w_inputs(h, s, true));
     if (multi && !s->direct_cost) {
@@ -1033,6 +1105,23 @@ extern "C" int nmfb_nmf_end(nmfb_handle* h, float* W_out, float* H_out, double* 
     if (cost_out && nc > 0) {
       cudaError_t e = cudaMemcpy(cost_out, s->cost, nc * sizeof(double), cudaMemcpyDeviceToHost);
       if (e != cudaSuccess) rc = h->fail(NMFB_ERR_CUDA, "cost download: %s", cudaGetErrorString(e));
+    }
+  }
+  if (rc == NMFB_OK && s->w_sharded && !s->W_fixed) {
+    // every rank kept only its rows of the fp32 W current: one exchange makes W whole everywhere
+    // (a collective: issued by every rank whether or not it asked for W)
+    WGatherArgs g{};
+    if (comm_peer_table(h, &g.t)) {
+      g.K = s->K;
+      g.r0 = s->r0;
+      g.mb = s->mb;
+      g.ld = s->ldw;
+      g.wm_off = s->wm_off;
+      g.epoch = comm_next_epoch(h, 1);
+      w_gather_rows_kernel<<<std::min(s->K, std::min(h->num_sms, kMaxBlocks)), kWsThreads, 0, h->stream>>>(g);
+      rc = check_launch(h, "w_gather_rows");
+      if (rc == NMFB_OK && cudaStreamSynchronize(h->stream) != cudaSuccess)
+        rc = h->fail(NMFB_ERR_CUDA, "gather of the W rows failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
   }
   const double t1 = now_ms();

@@ -1,0 +1,225 @@
+// Row-sharded W step for column-sharded (multi-GPU) nmf runs.
+//
+// With V and H partitioned by columns every rank holds a PARTIAL numerator A_r = V_r H_r' (m x K) of
+// the W update (nmf.m:149-153).  Instead of all-reducing the m x K partials and then repeating the
+// identical W step on every rank, rank r owns a block of ROWS of W:
+//
+//   1  it reads its row block of every rank's partial A straight from peer memory (NVLink) and sums it
+//      in rank order (the reduce-scatter half of an all-reduce, fused into the consumer),
+//   2  forms the partial column dots <W_k, A_k>, <W_k, B_k> of nmf.m's diag(diag(.)) terms over its
+//      rows and exchanges them with the same block of the other ranks (16 bytes per rank and column),
+//   3  takes the multiplicative step (nmf.m:168) on its rows, exchanges the partial column norms and
+//      sums, normalises (nmf.m:169), and
+//   4  writes the tf32 operand copy of its rows into EVERY rank's W (the all-gather half), keeping the
+//      fp32 master rows local (they are gathered once, at the end of the run).
+//
+// One launch per iteration: block b handles columns b, b + G, ... and only ever synchronises with block
+// b of the other ranks (p2p_block_barrier: flags in the peers' regions, monotone epochs), so blocks of
+// one GPU never wait for each other and a grid of at most one block per SM cannot deadlock.  The
+// element-wise work, the small B = W G_H product and the traffic of the second half of the all-reduce
+// shrink with the number of ranks; what remains replicated is O(K^2).
+#pragma once
+#include "comm.cuh"
+#include "ew_kernels.cuh"
+
+namespace nmfb {
+
+constexpr int kWsThreads = 512;
+constexpr int kWsCache = 4;  // float4 per thread: row blocks of up to 4 * 4 * 512 = 8192 rows
+
+struct WShardArgs {
+  PeerTable t;
+  int mode;           // WSTEP_EUCLID (also IS / AB with expo) or WSTEP_KL
+  int K;              // basis columns
+  int r0, mb;         // this rank's rows [r0, r0 + mb), both multiples of 4 (padding rows included: they stay 0)
+  long long ld;       // leading dimension of W, A, B
+  size_t a_off;       // byte offset of the partial A (K x ld) in every rank's region
+  size_t b_off;       // byte offset of a partial B in the region (IS / AB: both gradients are partial), 0 = none
+  const float* Bloc;  // local B = W G_H on this rank's rows (Euclidean), or null
+  float* Wm;          // fp32 master of W (local; only this rank's rows are kept current)
+  size_t wt_off;      // byte offset of the tf32 operand copy of W in every rank's region
+  size_t x_off;       // byte offset of the exchange slots [2][kMaxBlocks][kMaxRanks] x 2 doubles
+  double* wsum;       // [K] column sums of W (KL: the old sums on entry), replicated
+  const double* hs;   // KL: row sums of H, already summed over the ranks
+  float lambda;
+  const float* lambda_k;
+  const int* fixed_k;
+  float expo;         // AB: outer exponent of both gradients (nmf.m:159-163); 0 or 1 = none
+  const int* stop;
+  int epoch0, rounds;
+};
+
+__device__ __forceinline__ float4 ld_peer4(const char* base, size_t off_bytes, long long idx4) {
+  return __ldcv(reinterpret_cast<const float4*>(base + off_bytes) + idx4);
+}
+
+__global__ void __launch_bounds__(kWsThreads) w_step_sharded_kernel(WShardArgs a) {
+  NMFB_STOP_GUARD(a.stop);
+  __shared__ double sh[32 * 2];
+  __shared__ double bc[4];
+  const int tid = threadIdx.x;
+  const int N = a.t.nranks;
+  const bool kl = a.mode == WSTEP_KL;
+  const bool powered = a.expo != 0.f && a.expo != 1.f;
+  for (int round = 0; round < a.rounds; ++round) {
+    const int k = blockIdx.x + round * gridDim.x;
+    const bool active = k < a.K && !(a.fixed_k != nullptr && a.fixed_k[k] != 0);
+    const long long col4 = (static_cast<long long>(k) * a.ld + a.r0) >> 2;  // float4 index of (r0, k)
+    float4 w[kWsCache], av[kWsCache], bv[kWsCache];
+    float s0 = 0.f, s1 = 0.f;
+    if (active) {
+      // ---- 1: this rank's rows of column k: W, the summed numerator (and denominator) partials
+#pragma unroll
+      for (int q = 0; q < kWsCache; ++q) {
+        const int i4 = tid + q * kWsThreads;
+        const bool ok = 4 * i4 < a.mb;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        w[q] = ok ? reinterpret_cast<const float4*>(a.Wm)[col4 + i4] : z;
+        float4 sa = z, sb = z;
+        if (ok) {
+          for (int r = 0; r < N; ++r) {  // fixed rank order: every rank forms the same sums
+            const float4 x = ld_peer4(a.t.base[r], a.a_off, col4 + i4);
+            sa.x += x.x; sa.y += x.y; sa.z += x.z; sa.w += x.w;
+          }
+          if (a.Bloc != nullptr) {
+            sb = reinterpret_cast<const float4*>(a.Bloc)[col4 + i4];
+          } else if (a.b_off != 0) {
+            for (int r = 0; r < N; ++r) {
+              const float4 x = ld_peer4(a.t.base[r], a.b_off, col4 + i4);
+              sb.x += x.x; sb.y += x.y; sb.z += x.z; sb.w += x.w;
+            }
+          }
+        }
+        av[q] = sa;
+        bv[q] = sb;
+        s0 = fmaf(w[q].x, sa.x, fmaf(w[q].y, sa.y, fmaf(w[q].z, sa.z, fmaf(w[q].w, sa.w, s0))));
+        s1 = fmaf(w[q].x, sb.x, fmaf(w[q].y, sb.y, fmaf(w[q].z, sb.z, fmaf(w[q].w, sb.w, s1))));
+      }
+    }
+    // ---- 2: partial column dots -> every rank
+    double acc[2] = {s0, s1};
+    block_sum<2>(acc, sh);
+    if (tid == 0) {
+      bc[0] = acc[0];
+      bc[1] = acc[1];
+    }
+    __syncthreads();
+    if (tid < N) {
+      double* slot = reinterpret_cast<double*>(a.t.base[tid] + a.x_off) +
+                     (static_cast<size_t>(blockIdx.x) * kMaxRanks + a.t.rank) * 2;
+      slot[0] = bc[0];
+      slot[1] = bc[1];
+    }
+    p2p_block_barrier(a.t, 2 * kFlagBytes, a.epoch0 + round);
+    double d0 = 0.0, d1 = 0.0;
+    {
+      const double* mine = reinterpret_cast<const double*>(a.t.base[a.t.rank] + a.x_off) +
+                           static_cast<size_t>(blockIdx.x) * kMaxRanks * 2;
+      for (int r = 0; r < N; ++r) {
+        d0 += __ldcv(mine + 2 * r);
+        d1 += __ldcv(mine + 2 * r + 1);
+      }
+    }
+    float pc = 0.f, qc = 0.f, bterm = 0.f, lambda = a.lambda;
+    if (active) {
+      if (a.lambda_k != nullptr) lambda = a.lambda_k[k];
+      if (kl) {  // nmf.m:152-153
+        pc = static_cast<float>(a.hs[k] * a.wsum[k]);
+        qc = static_cast<float>(d0);
+        bterm = static_cast<float>(a.hs[k]);
+      } else {  // nmf.m:149-150
+        pc = static_cast<float>(d1);
+        qc = static_cast<float>(d0);
+      }
+    }
+    // ---- 3: multiplicative step on the own rows, partial norm and sum
+    float s2 = 0.f, s3 = 0.f;
+    if (active) {
+#pragma unroll
+      for (int q = 0; q < kWsCache; ++q) {
+        const bool ok = 4 * (tid + q * kWsThreads) < a.mb;
+        float wi[4] = {w[q].x, w[q].y, w[q].z, w[q].w};
+        const float ai[4] = {av[q].x, av[q].y, av[q].z, av[q].w};
+        const float bi[4] = {bv[q].x, bv[q].y, bv[q].z, bv[q].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float neg = ai[e] + wi[e] * pc;
+          float pos = (kl ? bterm : bi[e]) + wi[e] * qc;
+          if (powered) {
+            neg = powf(neg, a.expo);
+            pos = powf(pos, a.expo);
+          }
+          const float wn = ok ? wi[e] * (neg / fmaxf(pos + lambda, NMFB_EPS)) : 0.f;  // nmf.m:168
+          wi[e] = wn;
+          s2 = fmaf(wn, wn, s2);
+          s3 += wn;
+        }
+        w[q] = make_float4(wi[0], wi[1], wi[2], wi[3]);
+      }
+    }
+    acc[0] = s2;
+    acc[1] = s3;
+    block_sum<2>(acc, sh);
+    if (tid == 0) {
+      bc[2] = acc[0];
+      bc[3] = acc[1];
+    }
+    __syncthreads();
+    if (tid < N) {
+      double* slot = reinterpret_cast<double*>(a.t.base[tid] + a.x_off) +
+                     ((static_cast<size_t>(kMaxBlocks) + blockIdx.x) * kMaxRanks + a.t.rank) * 2;
+      slot[0] = bc[2];
+      slot[1] = bc[3];
+    }
+    p2p_block_barrier(a.t, 3 * kFlagBytes, a.epoch0 + round);
+    d0 = d1 = 0.0;
+    {
+      const double* mine = reinterpret_cast<const double*>(a.t.base[a.t.rank] + a.x_off) +
+                           (static_cast<size_t>(kMaxBlocks) + blockIdx.x) * kMaxRanks * 2;
+      for (int r = 0; r < N; ++r) {
+        d0 += __ldcv(mine + 2 * r);
+        d1 += __ldcv(mine + 2 * r + 1);
+      }
+    }
+    // ---- 4: unit L2 columns (nmf.m:169); master rows stay here, the tf32 rows go to every rank
+    if (active) {
+      const float mul = static_cast<float>(1.0 / sqrt(d0));
+      if (tid == 0) a.wsum[k] = static_cast<double>(mul) * d1;
+#pragma unroll
+      for (int q = 0; q < kWsCache; ++q) {
+        const int i4 = tid + q * kWsThreads;
+        if (4 * i4 < a.mb) {
+          const float4 x = make_float4(w[q].x * mul, w[q].y * mul, w[q].z * mul, w[q].w * mul);
+          reinterpret_cast<float4*>(a.Wm)[col4 + i4] = x;
+          const float4 xt = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
+          for (int r = 0; r < N; ++r) reinterpret_cast<float4*>(a.t.base[r] + a.wt_off)[col4 + i4] = xt;
+        }
+      }
+    }
+  }
+  // closing: the rows every other rank owes us have landed (and ours have been delivered)
+  p2p_block_barrier(a.t, 4 * kFlagBytes, a.epoch0);
+}
+
+// End of a run: every rank sends its rows of the fp32 master to all ranks (W is returned replicated).
+struct WGatherArgs {
+  PeerTable t;
+  int K, r0, mb;
+  long long ld;
+  size_t wm_off;  // byte offset of the fp32 master in every rank's region
+  int epoch;
+};
+__global__ void __launch_bounds__(kWsThreads) w_gather_rows_kernel(WGatherArgs a) {
+  const float4* src = reinterpret_cast<const float4*>(a.t.base[a.t.rank] + a.wm_off);
+  for (int k = blockIdx.x; k < a.K; k += gridDim.x) {
+    const long long col4 = (static_cast<long long>(k) * a.ld + a.r0) >> 2;
+    for (int i4 = threadIdx.x; 4 * i4 < a.mb; i4 += blockDim.x) {
+      const float4 x = src[col4 + i4];
+      for (int r = 0; r < a.t.nranks; ++r)
+        if (r != a.t.rank) reinterpret_cast<float4*>(a.t.base[r] + a.wm_off)[col4 + i4] = x;
+    }
+  }
+  p2p_block_barrier(a.t, 5 * kFlagBytes, a.epoch);
+}
+
+}  // namespace nmfb

@@ -10,6 +10,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def variant_config(variant, K):
+    """Extra config fields of a test variant (shared with tests/test_gpu_multi.py)."""
+    if variant == "w_fixed":  # nmf.m:146
+        return dict(W_fixed=True)
+    if variant == "per_source":  # first third of the bases fixed in W, different sparsity levels (nmf.m:51-60)
+        k1 = K // 3
+        return dict(W_sparsity=None, H_sparsity=None,
+                    W_fixed_k=[1] * k1 + [0] * (K - k1), W_sparsity_k=[0.0] * k1 + [0.1] * (K - k1),
+                    H_sparsity_k=[0.2] * k1 + [0.0] * (K - k1))
+    return {}
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -17,6 +29,7 @@ def main():
     from nmf_toolbox_b200.distributed import nmf_sharded, shard_bounds
 
     out, div, m, n, K, iters = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
+    variant = sys.argv[7] if len(sys.argv) > 7 else "plain"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -28,6 +41,7 @@ def main():
     h = api.Handle(local)
     cfg = dict(divergence=div, W_init=W0, H_init=H0[:, lo:hi], maxiter=iters, tolerance=1e-300,
                W_sparsity=0.05, H_sparsity=0.1)
+    cfg.update(variant_config(variant, K))
     W, H, cost = nmf_sharded(h, dist, V[:, lo:hi], K, cfg, rank, world)
     parts = [None] * world
     dist.all_gather_object(parts, (lo, hi, H))

@@ -11,21 +11,31 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("div", ["euclidean", "kl", "is"])
-def test_two_gpu_matches_single_and_oracle(div, tmp_path):
+@pytest.mark.parametrize("div,variant,w_shard,m,nproc", [
+    ("euclidean", "plain", "1", 384, 2), ("kl", "plain", "1", 384, 2), ("is", "plain", "1", 384, 2),
+    ("euclidean", "plain", "0", 384, 2),       # replicated W step after an all-reduce of the m x K partials
+    ("euclidean", "plain", "1", 1030, 2),      # row blocks that do not divide evenly, m % 4 != 0
+    ("euclidean", "w_fixed", "1", 384, 2), ("kl", "w_fixed", "1", 384, 2),
+    ("euclidean", "per_source", "1", 384, 2), ("kl", "per_source", "1", 384, 2),
+    ("euclidean", "plain", "1", 1030, 4), ("kl", "plain", "1", 384, 4), ("euclidean", "plain", "1", 2050, 8),
+])
+def test_multi_gpu_matches_single_and_oracle(div, variant, w_shard, m, nproc, tmp_path):
     import torch
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < nproc:
+        pytest.skip("needs %d GPUs" % nproc)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from multi_gpu_worker import variant_config
     from nmf_toolbox_b200 import api
     from oracle import nmf_oracle as O
 
-    m, n, K, iters = 384, 1000, 24, 30
+    n, K, iters = 1000, 24, 30
     out = str(tmp_path / "multi.npz")
     port = 29600 + os.getpid() % 300
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_worker.py"), out, div, str(m), str(n), str(K), str(iters)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc, "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_worker.py"), out, div, str(m),
+           str(n), str(K), str(iters), variant]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, NMFB_W_SHARD=w_shard))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     got = np.load(out)
     rng = np.random.default_rng(21)
@@ -33,10 +43,19 @@ def test_two_gpu_matches_single_and_oracle(div, tmp_path):
     W0 = rng.random((m, K)) + 1e-3
     H0 = rng.random((K, n)) + 1e-3
     cfg = dict(divergence=div, W_init=W0, H_init=H0, maxiter=iters, tolerance=1e-300, W_sparsity=0.05, H_sparsity=0.1)
+    cfg.update(variant_config(variant, K))
     h = api.Handle(0)
-    W1, H1, c1 = api.nmf(V, K, cfg, handle=h)
+    h.set_V(V)
+    W1, H1, c1 = h.nmf(K, cfg)
     h.close()
-    Wo, Ho, co = O.nmf(V, K, cfg)
+    if variant == "per_source":  # the oracle takes the per-source settings in the reference's cell-array form
+        k1 = K // 3
+        ocfg = dict(divergence=div, W_init=[W0[:, :k1], W0[:, k1:]], H_init=[H0[:k1], H0[k1:]], maxiter=iters,
+                    tolerance=1e-300, W_fixed=[True, False], W_sparsity=[0.0, 0.1], H_sparsity=[0.2, 0.0])
+        Wl, Hl, co = O.nmf(V, [k1, K - k1], ocfg)
+        Wo, Ho = np.concatenate(Wl, 1), np.concatenate(Hl, 0)
+    else:
+        Wo, Ho, co = O.nmf(V, K, cfg)
     assert len(got["cost"]) == iters
     np.testing.assert_allclose(got["cost"], c1, rtol=1e-6)   # only the summation order differs
     np.testing.assert_allclose(got["cost"], co, rtol=1e-4)
