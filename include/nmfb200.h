@@ -135,6 +135,23 @@ int nmfb_nmf(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, float*
 int nmfb_lnmf(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, float* H_out, double* cost_out,
               int* n_cost);
 
+/* [W, H, Z, A, cost] = constrainednmf(V, labels, num_basis_elems, config)  (constrainednmf.m:1; SURVEY 8f
+ * item 4).  Label-constrained NMF V ~ W*Z*A: the W step is nmf.m's (constrainednmf.m:185-209), the encoding is
+ * H = Z*A with A the 0/1 label-indicator matrix, and Z takes the multiplicative step on the gradients summed
+ * over the samples of a class (213-237).  The label handling of constrainednmf.m:147-170 is host work and
+ * stays with the caller (nmf_toolbox_b200/api.py, matlab/constrainednmf.m): V must be set with its columns in
+ * the reference's ORDERED arrangement (unlabeled samples first, then the classes, each contiguous), and
+ * col2z[j] in [0, nz) (non-decreasing, every value used) names the column of Z that sample j reads, i.e. the
+ * row of A holding its 1.  config: divergence / alpha / beta, W_init, W_sparsity, W_fixed, maxiter, tolerance
+ * as for nmfb_nmf; H_sparsity and H_fixed carry the reference's Z_sparsity and Z_fixed; H_init is ignored.
+ * Z_init (K x nz column-major, may be NULL = uniform random) is an EXTENSION: the reference draws Z = rand(...)
+ * unconditionally (line 174), which no test could reproduce.  H_out (K x n) is in the ordered arrangement.
+ * The non-dual alpha-beta branch of the reference's Z update multiplies mismatched matrices (line 229) and
+ * fails unless m == num_basis_elems: NMFB_ERR_UNSUPPORTED.  KL needs num_basis_elems <= 128.  One GPU. */
+int nmfb_constrainednmf(nmfb_handle* h, int K, const nmfb_config* cfg, const int* col2z, int nz,
+                        const float* Z_init, float* W_out, float* H_out, float* Z_out, double* cost_out,
+                        int* n_cost);
+
 /* W_out: m*K*T floats (m x K x T column-major). */
 int nmfb_cnmf(nmfb_handle* h, int K, int T, const nmfb_config* cfg, float* W_out, float* H_out,
               double* cost_out, int* n_cost);

@@ -24,7 +24,8 @@ import numpy as np
 from . import _lib
 
 __all__ = [
-    "NmfbError", "Handle", "nmf", "cnmf", "nmfsc", "ReconstructFromDecomposition", "projfunc",
+    "NmfbError", "Handle", "nmf", "cnmf", "nmfsc", "cnmfsc", "lnmf", "constrainednmf", "ReconstructFromDecomposition",
+    "projfunc",
     "default_handle",
 ]
 
@@ -90,6 +91,7 @@ def _bind(lib):
         "nmfb_nmf": ([P, I, ctypes.POINTER(_Config), P, P, P, PI], I),
         "nmfb_lnmf": ([P, I, ctypes.POINTER(_Config), P, P, P, PI], I),
         "nmfb_cnmfsc": ([P, I, I, ctypes.POINTER(_Config), P, P, P, PI], I),
+        "nmfb_constrainednmf": ([P, I, ctypes.POINTER(_Config), P, I, P, P, P, P, P, PI], I),
         "nmfb_cnmf": ([P, I, I, ctypes.POINTER(_Config), P, P, P, PI], I),
         "nmfb_nmfsc": ([P, I, ctypes.POINTER(_Config), P, P, P, PI], I),
         "nmfb_reconstruct": ([P, P, P, I, I, I, I, P], I),
@@ -289,6 +291,33 @@ class Handle:
         del keep
         return W, H, cost[: nc.value].copy()
 
+    def constrainednmf(self, K: int, col2z, nz: int, config=None):
+        """nmfb_constrainednmf on the V currently held (columns already in the ordered arrangement).
+        Returns W, H (ordered), Z, cost."""
+        m, n = self.shape
+        cfg = dict(config or {})
+        cfg["H_sparsity"] = cfg.pop("Z_sparsity", None)  # the C struct carries them in the H fields
+        cfg["H_fixed"] = cfg.pop("Z_fixed", None)
+        Z0 = cfg.pop("Z_init", None)
+        cfg.pop("H_init", None)
+        c, keep, maxiter = self._config(cfg, m, n, K)
+        col2z = np.ascontiguousarray(np.asarray(col2z, dtype=np.int32))
+        if col2z.size != n:
+            raise NmfbError(1, "the column map needs one entry per sample")
+        if Z0 is not None and np.size(Z0) > 0:
+            Z0 = _f32_colmajor(Z0, (K, nz))
+        else:
+            Z0 = None
+        W = np.empty((m, K), dtype=np.float32, order="F")
+        H = np.empty((K, n), dtype=np.float32, order="F")
+        Z = np.empty((K, nz), dtype=np.float32, order="F")
+        cost = np.zeros(maxiter, dtype=np.float64)
+        nc = ctypes.c_int(0)
+        self._check(self.lib.nmfb_constrainednmf(self._h, K, ctypes.byref(c), _ptr(col2z), int(nz), _ptr(Z0), _ptr(W),
+                                                 _ptr(H), _ptr(Z), _ptr(cost), ctypes.byref(nc)))
+        del keep
+        return W, H, Z, cost[: nc.value].copy()
+
     def cnmf(self, K: int, T: int, config=None):
         m, n = self.shape
         c, keep, maxiter = self._config(config, m, n, K, T)
@@ -463,6 +492,51 @@ def cnmf(V, num_basis_elems, context_len, config=None, handle: Optional[Handle] 
         W, H, cost = h.cnmf(sum(sizes), int(context_len), cfg)
         return _split(W, sizes, 1), _split(H, sizes, 0), cost
     return h.cnmf(int(num_basis_elems), int(context_len), config)
+
+
+def _label_arrangement(labels):
+    """constrainednmf.m:147-170 (host work): labels -> (sorted_idx, col2z of the ordered samples, nz, A ordered).
+    Unlabeled samples (label -1) come first and keep a column of Z each; every class shares one."""
+    labels = np.asarray(labels).ravel()
+    n = labels.size
+    num_labeled = int(np.sum(labels > -1))                 # line 149
+    uniq, inv = np.unique(labels, return_inverse=True)     # lines 151 / 156
+    proc = inv + 1
+    if num_labeled < n:
+        proc = proc - 1                                    # lines 152-153
+        proc[proc == 0] = -1
+        num_classes = len(uniq) - 1
+    else:
+        num_classes = len(uniq)
+    sorted_idx = np.argsort(proc, kind="stable")           # line 163
+    sorted_labels = proc[sorted_idx]
+    n_unl = n - num_labeled
+    col2z = np.where(sorted_labels < 0, np.arange(n), n_unl + sorted_labels - 1).astype(np.int32)
+    nz = n_unl + num_classes
+    A = np.zeros((nz, n), dtype=np.float32)                # lines 166-170
+    A[col2z, np.arange(n)] = 1
+    return sorted_idx, col2z, nz, A
+
+
+def constrainednmf(V, labels, num_basis_elems, config=None, handle: Optional[Handle] = None):
+    """``[W, H, Z, A, cost] = constrainednmf(V, labels, num_basis_elems, config)`` (constrainednmf.m:1).
+    ``config`` fields as in the reference (``W_init``, ``W_sparsity``, ``Z_sparsity``, ``W_fixed``, ``Z_fixed``,
+    ``divergence``, ``alpha``, ``beta``, ``maxiter``, ``tolerance``) plus the extension ``Z_init``
+    (num_basis_elems x (n_unlabeled + num_classes), ordered arrangement; the reference always draws rand).
+    H and A are returned in the original sample order (constrainednmf.m:260-267)."""
+    h = handle or default_handle()
+    V = np.asarray(V)
+    labels = np.asarray(labels).ravel()
+    if V.ndim != 2 or labels.size != V.shape[1]:  # constrainednmf.m:98
+        raise NmfbError(1, "Length of the label vector not equal to number of samples.")
+    sorted_idx, col2z, nz, A_sorted = _label_arrangement(labels)
+    h.set_V(V[:, sorted_idx])                     # constrainednmf.m:164
+    W, H_sorted, Z, cost = h.constrainednmf(int(num_basis_elems), col2z, nz, config)
+    H = np.empty_like(H_sorted)
+    H[:, sorted_idx] = H_sorted
+    A = np.zeros_like(A_sorted)
+    A[:, sorted_idx] = A_sorted
+    return W, H, Z, A, cost
 
 
 def nmfsc(V, num_basis_elems, config=None, handle: Optional[Handle] = None):

@@ -92,6 +92,10 @@ struct nmfb_handle {
 
   nmfb::Comm* comm = nullptr;
   NmfSession* sess = nullptr;
+  // label constraint of the next nmf session (nmfb_constrainednmf): host pointers, consumed by the setup
+  const int* tie_col2z = nullptr;
+  int tie_nz = 0;
+  const float* tie_Zinit = nullptr;
 
   // device time of the iteration loop of the last one-call entry point (nmfb_last_loop)
   double loop_ms = 0.0;

@@ -664,6 +664,82 @@ __global__ void h_finish_kernel(const float* __restrict__ N, const float* __rest
   }
 }
 
+// ---------------------------------------------------------------- label-constrained factor (constrainednmf.m)
+// H = Z*A with A the 0/1 label-indicator matrix of constrainednmf.m:166-170 (samples ordered so that one
+// class is contiguous): column j of H is column col2z[j] of Z.
+__global__ void tied_gather_kernel(const float* __restrict__ Z, long long ldz, const int* __restrict__ col2z,
+                                   float* __restrict__ Hm, float* __restrict__ Ht, long long ldh, int n,
+                                   const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  const int k = blockIdx.y;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const float z = Z[k * ldz + col2z[j]];
+    Hm[k * ldh + j] = z;
+    Ht[k * ldh + j] = tf32_rn(z);
+  }
+}
+// Z step (constrainednmf.m:213-237): with N = W'Qn and D = W'Qp (K x n) the gradients are N*A' and D*A',
+// i.e. sums over the samples [seg[z], seg[z+1]) that share column z of Z:
+//   Z <- Z .* (N A')^e ./ max((D A')^e + lambda, eps);   H = Z A
+// One warp per (k, z).  N may be given as split slabs (fused KL kernel); D as a matrix or, for KL, as the
+// per-basis value dvec[k] = sum_i W_ik (constrainednmf.m:219: W' * ones(m, n) * A').
+// scal[0] += <N, tf32(H_new)>, scal[1] += sum(Z_new)  (the sparsity term is on Z, constrainednmf.m:251)
+__global__ void tied_update_kernel(const float* __restrict__ Nparts, int splits, long long slab, long long ldn,
+                                   const float* __restrict__ D, const float* __restrict__ dvec,
+                                   float* __restrict__ Z, long long ldz, float* __restrict__ Hm,
+                                   float* __restrict__ Ht, long long ldh, const int* __restrict__ seg, int nz, int K,
+                                   float lambda, int freeze, float expo, double* scal, const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  __shared__ double sh[64];
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const long long total = static_cast<long long>(K) * nz;
+  const bool powered = expo != 0.f && expo != 1.f;
+  double acc[2] = {0.0, 0.0};
+  for (long long p = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); p < total;
+       p += static_cast<long long>(gridDim.x) * warps_per_block) {
+    const int k = static_cast<int>(p / nz), z = static_cast<int>(p % nz);
+    const int j0 = seg[z], j1 = seg[z + 1];
+    float neg = 0.f, pos = 0.f;
+    for (int j = j0 + lane; j < j1; j += 32) {
+      float nv = 0.f;
+      for (int sp = 0; sp < splits; ++sp) nv += Nparts[sp * slab + k * ldn + j];
+      neg += nv;
+      if (D != nullptr) pos += D[k * ldh + j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      neg += __shfl_xor_sync(0xffffffffu, neg, o);
+      pos += __shfl_xor_sync(0xffffffffu, pos, o);
+    }
+    if (D == nullptr) pos = dvec[k] * static_cast<float>(j1 - j0);
+    const float neg_raw = neg;
+    if (powered) {
+      neg = powf(neg, expo);
+      pos = powf(pos, expo);
+    }
+    float zv = Z[k * ldz + z];
+    if (!freeze) zv = zv * (neg / fmaxf(pos + lambda, NMFB_EPS));  // constrainednmf.m:235
+    const float zt = tf32_rn(zv);
+    if (!freeze) {
+      if (lane == 0) Z[k * ldz + z] = zv;
+      for (int j = j0 + lane; j < j1; j += 32) {  // H = Z*A (constrainednmf.m:237)
+        Hm[k * ldh + j] = zv;
+        Ht[k * ldh + j] = zt;
+      }
+    }
+    if (lane == 0) {
+      acc[0] += static_cast<double>(neg_raw) * zt;
+      acc[1] += zv;
+    }
+  }
+  block_sum<2>(acc, sh);
+  if (threadIdx.x == 0) {
+    atomicAdd(scal + 0, acc[0]);
+    atomicAdd(scal + 1, acc[1]);
+  }
+}
+
 // ---------------------------------------------------------------- convolutive helpers
 // Hs[k + K*t][j] = tf32(H[k][j - t]) for j >= t, else 0   (cnmf.m:188, RFD.m:37)
 __global__ void hstack_kernel(const float* __restrict__ H, float* __restrict__ Hs, int K, int T, int n,

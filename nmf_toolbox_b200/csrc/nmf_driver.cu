@@ -77,6 +77,12 @@ struct NmfSession {
   double ab_scale = 0.0; // -1/(alpha beta) of the AB cost (nmf.m:214)
   KlOp klW, klH;         // fused KL halves (kl_fused.cuh)
   bool kl_fused = false;
+  // constrainednmf.m: H = Z*A, A the 0/1 label matrix (columns of H tied to columns of Z)
+  bool tied = false;
+  int nz = 0;
+  long long ldz = 0;
+  float* Zm = nullptr;
+  int *col2z = nullptr, *seg = nullptr;
   // multi-GPU, row-sharded W step (w_shard.cuh): this rank's rows of W, byte offsets inside the peer region
   bool w_sharded = false;
   int r0 = 0, mb = 0;
@@ -258,6 +264,25 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
   const bool tw = s->divergence == NMFB_DIV_IS || s->divergence == NMFB_DIV_AB;
   s->two_weight = tw;
   Arena* ar = &s->ar;
+  std::vector<int> seg_host;
+  if (h->tie_col2z != nullptr) {  // nmfb_constrainednmf: columns of H are tied through the label matrix
+    s->tied = true;
+    s->nz = h->tie_nz;
+    s->ldz = round_up(s->nz, 4);
+    if (comm_size(h->comm) > 1) return h->fail(NMFB_ERR_UNSUPPORTED, "constrainednmf: one GPU only");
+    if (s->per_basis) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "constrainednmf has no per-source settings");
+    if (s->nz <= 0 || s->nz > n) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "constrainednmf: bad number of Z columns");
+    seg_host.assign(static_cast<size_t>(s->nz) + 1, 0);
+    for (int j = 0; j < n; ++j) {
+      const int z = h->tie_col2z[j];
+      if (z < 0 || z >= s->nz || (j > 0 && z < h->tie_col2z[j - 1]))
+        return h->fail(NMFB_ERR_INVALID_ARGUMENT, "constrainednmf: the column map must be non-decreasing in [0, nz)");
+      seg_host[z + 1] = j + 1;
+    }
+    for (int z = 0; z < s->nz; ++z) {
+      if (seg_host[z + 1] == 0) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "constrainednmf: column %d of Z has no sample", z);
+    }
+  }
 
   NMFB_TRY(ar->alloc(h, &s->Hm, static_cast<size_t>(Kp) * s->ldh));
   NMFB_TRY(ar->alloc(h, &s->Ht, static_cast<size_t>(Kp) * s->ldh));
@@ -355,7 +380,25 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
       fill_uniform(tmp, cfg.seed * 2 + 2, true);
       Hsrc = tmp.data();
     }
-    NMFB_TRY(upload_H(h, ar, Hsrc, K, n, s->Hm, s->ldh));
+    if (s->tied) {
+      // constrainednmf.m:174-177: Z (given, or rand) and H = Z*A
+      NMFB_TRY(ar->alloc(h, &s->Zm, static_cast<size_t>(Kp) * s->ldz));
+      NMFB_TRY(ar->alloc(h, &s->col2z, n));
+      NMFB_TRY(ar->alloc(h, &s->seg, static_cast<size_t>(s->nz) + 1));
+      NMFB_CUDA(h, cudaMemcpyAsync(s->col2z, h->tie_col2z, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      NMFB_CUDA(h, cudaMemcpyAsync(s->seg, seg_host.data(), seg_host.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      const float* Zsrc = h->tie_Zinit;
+      if (!Zsrc) {
+        tmp.resize(static_cast<size_t>(K) * s->nz);
+        fill_uniform(tmp, cfg.seed * 2 + 2, false);
+        Zsrc = tmp.data();
+      }
+      NMFB_TRY(upload_H(h, ar, Zsrc, K, s->nz, s->Zm, s->ldz));
+      tied_gather_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Zm, s->ldz, s->col2z, s->Hm, s->Ht, s->ldh, n, nullptr);
+      NMFB_TRY(check_launch(h, "tied_gather(H init)"));
+    } else {
+      NMFB_TRY(upload_H(h, ar, Hsrc, K, n, s->Hm, s->ldh));
+    }
     NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   // W columns -> unit L2 (also for a user-supplied W_init, nmf.m:133); H is not rescaled
@@ -404,6 +447,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     s->h_split = ctasH * 2 <= h->num_sms && n > kTileM;
     if (const char* e2 = std::getenv("NMFB_H_SPLIT")) s->h_split = e2[0] == '1';  // tests force either path
     if (s->per_basis) s->h_split = true;  // per-basis lambda / fixed rows live in h_finish, not in the fused epilogue
+    if (s->tied) s->h_split = true;       // the Z step sums N and D over the samples of a class (tied_update_kernel)
     s->overlap = !multi && !s->direct_cost && !s->W_fixed && !s->H_fixed && !(tilesA * 2 <= h->num_sms) &&
                  !(env && env[0] == '0') && m > kTileM && ctasA + 8 <= h->num_sms;
     const bool can_side = !s->direct_cost && !s->W_fixed && !s->H_fixed && !(env && env[0] == '0') && m > kTileM &&
@@ -553,6 +597,8 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     }
     if (!s->kl_fused && s->lnmf)
       return h->fail(NMFB_ERR_UNSUPPORTED, "lnmf needs the fused KL kernel (num_basis_elems <= 128)");
+    if (!s->kl_fused && s->tied)
+      return h->fail(NMFB_ERR_UNSUPPORTED, "constrainednmf with the KL divergence needs the fused KL kernel (num_basis_elems <= 128)");
     if (!s->kl_fused && s->per_basis)
       return h->fail(NMFB_ERR_UNSUPPORTED, "per-source settings with the unfused KL path (K > 128)");
     if (!s->kl_fused) {
@@ -679,11 +725,11 @@ static int enqueue_w_sharded(nmfb_handle* h, NmfSession* s, int mode, bool b_par
   a.fixed_k = s->fixW_k;
   a.expo = s->expo;
   a.stop = s->stop;
-  const int cap = std::min(h->num_sms, kMaxBlocks);  // one co-resident block per SM: blocks spin on their peers
+  const int cap = w_shard_capacity(a.t.nranks, h->num_sms);  // blocks spin on their peers: all must be resident
   a.rounds = (s->K + cap - 1) / cap;
   const int grid = (s->K + a.rounds - 1) / a.rounds;
   a.epoch0 = comm_next_epoch(h, a.rounds);
-  w_step_sharded_kernel<<<grid, kWsThreads, 0, h->stream>>>(a);
+  launch_w_step_sharded(a, grid, h->stream);
   return check_launch(h, "w_step_sharded");
 }
 
@@ -802,6 +848,17 @@ extern "C" int nmfb_profile_get(nmfb_handle* h, double* ms_w, double* ms_h, int*
   return NMFB_OK;
 }
 
+// Z step + H = Z*A of constrainednmf.m:213-237 from N (possibly as split slabs) and D (matrix or per-basis value)
+static int enqueue_tied_update(nmfb_handle* h, NmfSession* s, const float* Nparts, int splits, long long slab,
+                               long long ldn, const float* D, const float* dvec, float expo) {
+  const long long pairs = static_cast<long long>(s->K) * s->nz;
+  const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(h->num_sms * 8, (pairs + 7) / 8)));
+  tied_update_kernel<<<blocks, 256, 0, h->stream>>>(Nparts, splits, slab, ldn, D, dvec, s->Zm, s->ldz, s->Hm, s->Ht,
+                                                    s->ldh, s->seg, s->nz, s->K, s->lambda_h, s->H_fixed ? 1 : 0, expo,
+                                                    s->scal, s->stop);
+  return check_launch(h, "tied_update");
+}
+
 static int enqueue_iteration_two_weight(nmfb_handle* h, NmfSession* s, int i) {
   const int K = s->K, n = s->n;
   const int cost_mode = s->divergence == NMFB_DIV_IS ? 4 : 5;
@@ -846,6 +903,7 @@ static int enqueue_iteration_two_weight(nmfb_handle* h, NmfSession* s, int i) {
   }
   NMFB_TRY(run_gemm(h, s->gemmHn));
   NMFB_TRY(run_gemm(h, s->gemmHd));
+  if (s->tied) return enqueue_tied_update(h, s, s->Nbuf, 1, 0, s->ldh, s->Dbuf, nullptr, s->expo);
   h_finish_kernel<<<dim3(std::max(1, std::min(64, (n + 1023) / 1024)), K), 256, 0, h->stream>>>(
       s->Nbuf, s->Dbuf, s->Hm, s->Ht, s->ldh, n, s->lambda_h, s->H_fixed ? 1 : 0, s->scal, s->stop, s->expo, s->lamH_k,
       s->fixH_k);
@@ -923,10 +981,14 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
     if (s->h_split) {
       NMFB_TRY(prof_mark(h, 1));
       NMFB_TRY(run_gemm(h, s->gemmH));  // N (split-K, summed) and D = G_W H
-      h_finish_kernel<<<dim3(std::max(1, std::min(64, (n + 1023) / 1024)), K), 256, 0, h->stream>>>(
-          s->Nbuf, s->Dbuf, s->Hm, s->Ht, s->ldh, n, s->lambda_h, s->H_fixed ? 1 : 0, s->scal, stop, 0.f, s->lamH_k,
-          s->fixH_k);
-      NMFB_TRY(check_launch(h, "h_finish"));
+      if (s->tied) {
+        NMFB_TRY(enqueue_tied_update(h, s, s->Nbuf, 1, 0, s->ldh, s->Dbuf, nullptr, 0.f));
+      } else {
+        h_finish_kernel<<<dim3(std::max(1, std::min(64, (n + 1023) / 1024)), K), 256, 0, h->stream>>>(
+            s->Nbuf, s->Dbuf, s->Hm, s->Ht, s->ldh, n, s->lambda_h, s->H_fixed ? 1 : 0, s->scal, stop, 0.f, s->lamH_k,
+            s->fixH_k);
+        NMFB_TRY(check_launch(h, "h_finish"));
+      }
       NMFB_TRY(prof_mark(h, 1));
     } else {
       NMFB_TRY(run_timed(h, s->gemmH, 1));
@@ -978,11 +1040,15 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
       NMFB_TRY(prof_mark(h, 1));
       NMFB_TRY(run_kl(h, s->klH));
       NMFB_TRY(prof_mark(h, 1));
-      kl_h_finish_kernel<<<dim3(std::max(1, std::min(64, (n + 1023) / 1024)), K), 256, 0, h->stream>>>(s->klH.parts, s->klH.splits, s->klH.args.slab,
-                                                                s->klH.args.ldo, s->Hm, s->Ht, s->ldh, s->wsf,
-                                                                s->lambda_h, n, s->H_fixed ? 1 : 0, s->scal, stop,
-                                                                s->lamH_k, s->fixH_k, s->lnmf ? 1 : 0);
-      NMFB_TRY(check_launch(h, "kl_h_finish"));
+      if (s->tied) {
+        NMFB_TRY(enqueue_tied_update(h, s, s->klH.parts, s->klH.splits, s->klH.args.slab, s->klH.args.ldo, nullptr,
+                                     s->wsf, 0.f));
+      } else {
+        kl_h_finish_kernel<<<dim3(std::max(1, std::min(64, (n + 1023) / 1024)), K), 256, 0, h->stream>>>(
+            s->klH.parts, s->klH.splits, s->klH.args.slab, s->klH.args.ldo, s->Hm, s->Ht, s->ldh, s->wsf, s->lambda_h, n,
+            s->H_fixed ? 1 : 0, s->scal, stop, s->lamH_k, s->fixH_k, s->lnmf ? 1 : 0);
+        NMFB_TRY(check_launch(h, "kl_h_finish"));
+      }
     } else {
       NMFB_TRY(run_gemm(h, s->gemmH));
     }
@@ -1179,4 +1245,53 @@ extern "C" int nmfb_nmf(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_
 extern "C" int nmfb_lnmf(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, float* H_out,
                          double* cost_out, int* n_cost) {
   return nmf_call(h, K, cfg, W_out, H_out, cost_out, n_cost, true);
+}
+
+// constrainednmf.m:1 - label-constrained NMF V ~ W*Z*A (Liu & Wu): the W step is nmf.m's, the encoding is
+// H = Z*A with A the label-indicator matrix, and Z takes the multiplicative step on the class-summed
+// gradients (constrainednmf.m:213-237).  The caller orders the samples as the reference does (unlabeled
+// first, classes contiguous; constrainednmf.m:147-164) and passes the column map of that arrangement.
+extern "C" int nmfb_constrainednmf(nmfb_handle* h, int K, const nmfb_config* cfg, const int* col2z, int nz,
+                                   const float* Z_init, float* W_out, float* H_out, float* Z_out, double* cost_out,
+                                   int* n_cost) {
+  if (!h) return NMFB_ERR_INVALID_ARGUMENT;
+  if (!col2z || nz <= 0) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "constrainednmf: column map missing");
+  if (cfg && cfg->divergence == NMFB_DIV_AB && cfg->alpha != 0 && h->m != K)
+    // constrainednmf.m:229 multiplies a K x n by an m x n matrix element-wise in the non-dual AB branch
+    return h->fail(NMFB_ERR_UNSUPPORTED, "Matrix dimensions must agree. (constrainednmf.m:229: the non-dual "
+                                         "alpha-beta Z update of the reference is only defined for m == num_basis_elems)");
+  h->tie_col2z = col2z;
+  h->tie_nz = nz;
+  h->tie_Zinit = Z_init;
+  const double t0 = now_ms();
+  int rc = nmf_begin_impl(h, K, cfg, false);
+  h->tie_col2z = nullptr;
+  h->tie_Zinit = nullptr;
+  if (rc != NMFB_OK) return rc;
+  (void)t0;
+  NmfSession* s = h->sess;
+  loop_begin(h);
+  rc = run_chunked(h, s->maxiter, s->stop, [&](int i) {
+    int r = enqueue_iteration(h, s, i);
+    if (r == NMFB_OK) ++s->iters_enqueued;
+    return r;
+  });
+  if (rc != NMFB_OK) {
+    nmf_session_release(h);
+    return rc;
+  }
+  cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->stream2);
+  loop_end(h, s->iters_enqueued);
+  if (Z_out) {
+    rc = download_H(h, s->Zm, s->ldz, s->K, s->nz, Z_out);
+    if (rc != NMFB_OK) {
+      nmf_session_release(h);
+      return rc;
+    }
+  }
+  int nc_local = 0;
+  rc = nmfb_nmf_end(h, W_out, H_out, cost_out, n_cost ? n_cost : &nc_local);
+  h->loop_iters = n_cost ? *n_cost : nc_local;
+  return rc;
 }

@@ -19,6 +19,8 @@
 // element-wise work, the small B = W G_H product and the traffic of the second half of the all-reduce
 // shrink with the number of ranks; what remains replicated is O(K^2).
 #pragma once
+#include <algorithm>
+
 #include "comm.cuh"
 #include "ew_kernels.cuh"
 
@@ -52,48 +54,64 @@ struct WShardArgs {
 __device__ __forceinline__ float4 ld_peer4(const char* base, size_t off_bytes, long long idx4) {
   return __ldcv(reinterpret_cast<const float4*>(base + off_bytes) + idx4);
 }
+__device__ __forceinline__ void add4(float4& s, const float4& x) {
+  s.x += x.x;
+  s.y += x.y;
+  s.z += x.z;
+  s.w += x.w;
+}
+// Sum over the ranks (fixed order: every rank forms the same sums) of float4 element idx4 of the buffer at
+// byte offset `off` of every region.  All N loads are issued before the first add: a remote load takes
+// a microsecond or two over NVLink, so the number in flight is what counts.
+template <int N>
+__device__ __forceinline__ float4 sum_peers4(const PeerTable& t, size_t off, long long idx4) {
+  float4 x[N];
+#pragma unroll
+  for (int r = 0; r < N; ++r) x[r] = ld_peer4(t.base[r], off, idx4);
+  float4 s = x[0];
+#pragma unroll
+  for (int r = 1; r < N; ++r) add4(s, x[r]);
+  return s;
+}
 
-__global__ void __launch_bounds__(kWsThreads) w_step_sharded_kernel(WShardArgs a) {
+// N = number of ranks (compile time: the peer loads are unrolled).  Only the summed numerator rows stay in
+// registers between the phases (they came over NVLink); W and the local B are re-read from L2, which keeps
+// the kernel at two resident blocks per SM - a grid of K <= 256 columns then needs a single round.
+template <int N>
+__global__ void __launch_bounds__(kWsThreads, 2) w_step_sharded_kernel(WShardArgs a) {
   NMFB_STOP_GUARD(a.stop);
   __shared__ double sh[32 * 2];
   __shared__ double bc[4];
   const int tid = threadIdx.x;
-  const int N = a.t.nranks;
   const bool kl = a.mode == WSTEP_KL;
   const bool powered = a.expo != 0.f && a.expo != 1.f;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int round = 0; round < a.rounds; ++round) {
     const int k = blockIdx.x + round * gridDim.x;
     const bool active = k < a.K && !(a.fixed_k != nullptr && a.fixed_k[k] != 0);
     const long long col4 = (static_cast<long long>(k) * a.ld + a.r0) >> 2;  // float4 index of (r0, k)
-    float4 w[kWsCache], av[kWsCache], bv[kWsCache];
+    const float4* Wcol = reinterpret_cast<const float4*>(a.Wm) + col4;
+    const float4* Bcol = a.Bloc != nullptr ? reinterpret_cast<const float4*>(a.Bloc) + col4 : nullptr;
+    float4 av[kWsCache], bv[kWsCache];  // bv only carries data when B is partial as well (IS / AB)
     float s0 = 0.f, s1 = 0.f;
     if (active) {
-      // ---- 1: this rank's rows of column k: W, the summed numerator (and denominator) partials
+      // ---- 1: the summed numerator (and, for IS / AB, denominator) partials of this rank's rows
 #pragma unroll
       for (int q = 0; q < kWsCache; ++q) {
         const int i4 = tid + q * kWsThreads;
         const bool ok = 4 * i4 < a.mb;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        w[q] = ok ? reinterpret_cast<const float4*>(a.Wm)[col4 + i4] : z;
-        float4 sa = z, sb = z;
-        if (ok) {
-          for (int r = 0; r < N; ++r) {  // fixed rank order: every rank forms the same sums
-            const float4 x = ld_peer4(a.t.base[r], a.a_off, col4 + i4);
-            sa.x += x.x; sa.y += x.y; sa.z += x.z; sa.w += x.w;
-          }
-          if (a.Bloc != nullptr) {
-            sb = reinterpret_cast<const float4*>(a.Bloc)[col4 + i4];
-          } else if (a.b_off != 0) {
-            for (int r = 0; r < N; ++r) {
-              const float4 x = ld_peer4(a.t.base[r], a.b_off, col4 + i4);
-              sb.x += x.x; sb.y += x.y; sb.z += x.z; sb.w += x.w;
-            }
-          }
+        av[q] = ok ? sum_peers4<N>(a.t, a.a_off, col4 + i4) : zero4;
+        bv[q] = (ok && a.b_off != 0) ? sum_peers4<N>(a.t, a.b_off, col4 + i4) : zero4;
+      }
+#pragma unroll
+      for (int q = 0; q < kWsCache; ++q) {
+        const int i4 = tid + q * kWsThreads;
+        if (4 * i4 < a.mb) {
+          const float4 w = Wcol[i4];
+          const float4 b = Bcol != nullptr ? Bcol[i4] : bv[q];
+          s0 = fmaf(w.x, av[q].x, fmaf(w.y, av[q].y, fmaf(w.z, av[q].z, fmaf(w.w, av[q].w, s0))));
+          s1 = fmaf(w.x, b.x, fmaf(w.y, b.y, fmaf(w.z, b.z, fmaf(w.w, b.w, s1))));
         }
-        av[q] = sa;
-        bv[q] = sb;
-        s0 = fmaf(w[q].x, sa.x, fmaf(w[q].y, sa.y, fmaf(w[q].z, sa.z, fmaf(w[q].w, sa.w, s0))));
-        s1 = fmaf(w[q].x, sb.x, fmaf(w[q].y, sb.y, fmaf(w[q].z, sb.z, fmaf(w[q].w, sb.w, s1))));
       }
     }
     // ---- 2: partial column dots -> every rank
@@ -115,6 +133,7 @@ __global__ void __launch_bounds__(kWsThreads) w_step_sharded_kernel(WShardArgs a
     {
       const double* mine = reinterpret_cast<const double*>(a.t.base[a.t.rank] + a.x_off) +
                            static_cast<size_t>(blockIdx.x) * kMaxRanks * 2;
+#pragma unroll
       for (int r = 0; r < N; ++r) {
         d0 += __ldcv(mine + 2 * r);
         d1 += __ldcv(mine + 2 * r + 1);
@@ -132,29 +151,33 @@ __global__ void __launch_bounds__(kWsThreads) w_step_sharded_kernel(WShardArgs a
         qc = static_cast<float>(d0);
       }
     }
-    // ---- 3: multiplicative step on the own rows, partial norm and sum
+    // ---- 3: multiplicative step on the own rows (kept in av), partial norm and sum
     float s2 = 0.f, s3 = 0.f;
     if (active) {
 #pragma unroll
       for (int q = 0; q < kWsCache; ++q) {
-        const bool ok = 4 * (tid + q * kWsThreads) < a.mb;
-        float wi[4] = {w[q].x, w[q].y, w[q].z, w[q].w};
-        const float ai[4] = {av[q].x, av[q].y, av[q].z, av[q].w};
-        const float bi[4] = {bv[q].x, bv[q].y, bv[q].z, bv[q].w};
+        const int i4 = tid + q * kWsThreads;
+        if (4 * i4 < a.mb) {
+          const float4 w = Wcol[i4];
+          const float4 b = Bcol != nullptr ? Bcol[i4] : bv[q];
+          const float wi[4] = {w.x, w.y, w.z, w.w};
+          const float ai[4] = {av[q].x, av[q].y, av[q].z, av[q].w};
+          const float bi[4] = {b.x, b.y, b.z, b.w};
+          float wn[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float neg = ai[e] + wi[e] * pc;
-          float pos = (kl ? bterm : bi[e]) + wi[e] * qc;
-          if (powered) {
-            neg = powf(neg, a.expo);
-            pos = powf(pos, a.expo);
+          for (int e = 0; e < 4; ++e) {
+            float neg = ai[e] + wi[e] * pc;
+            float pos = (kl ? bterm : bi[e]) + wi[e] * qc;
+            if (powered) {
+              neg = powf(neg, a.expo);
+              pos = powf(pos, a.expo);
+            }
+            wn[e] = wi[e] * (neg / fmaxf(pos + lambda, NMFB_EPS));  // nmf.m:168
+            s2 = fmaf(wn[e], wn[e], s2);
+            s3 += wn[e];
           }
-          const float wn = ok ? wi[e] * (neg / fmaxf(pos + lambda, NMFB_EPS)) : 0.f;  // nmf.m:168
-          wi[e] = wn;
-          s2 = fmaf(wn, wn, s2);
-          s3 += wn;
+          av[q] = make_float4(wn[0], wn[1], wn[2], wn[3]);
         }
-        w[q] = make_float4(wi[0], wi[1], wi[2], wi[3]);
       }
     }
     acc[0] = s2;
@@ -176,6 +199,7 @@ __global__ void __launch_bounds__(kWsThreads) w_step_sharded_kernel(WShardArgs a
     {
       const double* mine = reinterpret_cast<const double*>(a.t.base[a.t.rank] + a.x_off) +
                            (static_cast<size_t>(kMaxBlocks) + blockIdx.x) * kMaxRanks * 2;
+#pragma unroll
       for (int r = 0; r < N; ++r) {
         d0 += __ldcv(mine + 2 * r);
         d1 += __ldcv(mine + 2 * r + 1);
@@ -185,13 +209,15 @@ __global__ void __launch_bounds__(kWsThreads) w_step_sharded_kernel(WShardArgs a
     if (active) {
       const float mul = static_cast<float>(1.0 / sqrt(d0));
       if (tid == 0) a.wsum[k] = static_cast<double>(mul) * d1;
+      float4* Wout = reinterpret_cast<float4*>(a.Wm) + col4;
 #pragma unroll
       for (int q = 0; q < kWsCache; ++q) {
         const int i4 = tid + q * kWsThreads;
         if (4 * i4 < a.mb) {
-          const float4 x = make_float4(w[q].x * mul, w[q].y * mul, w[q].z * mul, w[q].w * mul);
-          reinterpret_cast<float4*>(a.Wm)[col4 + i4] = x;
+          const float4 x = make_float4(av[q].x * mul, av[q].y * mul, av[q].z * mul, av[q].w * mul);
+          Wout[i4] = x;
           const float4 xt = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
+#pragma unroll
           for (int r = 0; r < N; ++r) reinterpret_cast<float4*>(a.t.base[r] + a.wt_off)[col4 + i4] = xt;
         }
       }
@@ -199,6 +225,40 @@ __global__ void __launch_bounds__(kWsThreads) w_step_sharded_kernel(WShardArgs a
   }
   // closing: the rows every other rank owes us have landed (and ours have been delivered)
   p2p_block_barrier(a.t, 4 * kFlagBytes, a.epoch0);
+}
+
+// resident blocks of the kernel on one GPU (blocks spin on their peers, so the grid must fit)
+template <int N>
+inline int w_shard_capacity(int num_sms) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, w_step_sharded_kernel<N>, kWsThreads, 0) != cudaSuccess ||
+      per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  return std::min(kMaxBlocks, per_sm * num_sms);
+}
+inline int w_shard_capacity(int nranks, int num_sms) {
+  switch (nranks) {
+    case 2: return w_shard_capacity<2>(num_sms);
+    case 3: return w_shard_capacity<3>(num_sms);
+    case 4: return w_shard_capacity<4>(num_sms);
+    case 5: return w_shard_capacity<5>(num_sms);
+    case 6: return w_shard_capacity<6>(num_sms);
+    case 7: return w_shard_capacity<7>(num_sms);
+    default: return w_shard_capacity<8>(num_sms);
+  }
+}
+inline void launch_w_step_sharded(const WShardArgs& a, int grid, cudaStream_t stream) {
+  switch (a.t.nranks) {
+    case 2: w_step_sharded_kernel<2><<<grid, kWsThreads, 0, stream>>>(a); break;
+    case 3: w_step_sharded_kernel<3><<<grid, kWsThreads, 0, stream>>>(a); break;
+    case 4: w_step_sharded_kernel<4><<<grid, kWsThreads, 0, stream>>>(a); break;
+    case 5: w_step_sharded_kernel<5><<<grid, kWsThreads, 0, stream>>>(a); break;
+    case 6: w_step_sharded_kernel<6><<<grid, kWsThreads, 0, stream>>>(a); break;
+    case 7: w_step_sharded_kernel<7><<<grid, kWsThreads, 0, stream>>>(a); break;
+    default: w_step_sharded_kernel<8><<<grid, kWsThreads, 0, stream>>>(a); break;
+  }
 }
 
 // End of a run: every rank sends its rows of the fp32 master to all ranks (W is returned replicated).

@@ -2,7 +2,7 @@
 
 Literal, line-by-line NumPy float64 restatement of the reference's MATLAB hot
 path (colinvaz/nmf-toolbox): ``nmf.m``, ``cnmf.m``, ``nmfsc.m``, ``projfunc.m``
-and ``ReconstructFromDecomposition.m``, plus ``cnmfsc.m`` and ``lnmf.m``.  It deliberately keeps the reference's
+and ``ReconstructFromDecomposition.m``, plus ``cnmfsc.m``, ``lnmf.m`` and ``constrainednmf.m``.  It deliberately keeps the reference's
 exact operation sequence - the dense ``ones(n, m)`` products, the
 ``diag(diag(...))`` terms, the per-frame loops, the redundant GEMMs - so that it
 is a readable statement of WHAT the reference computes, not a fast one.
@@ -40,6 +40,8 @@ __all__ = [
     "nmfsc",
     "cnmfsc",
     "lnmf",
+    "constrainednmf",
+    "constrained_label_matrix",
 ]
 
 
@@ -757,3 +759,150 @@ def cnmfsc(V, num_basis_elems, context_len, config=None, rng=None, info=None):
         info["trials_H"] = trials_H
         info["trials_W"] = trials_W
     return W, H, cost
+
+
+# --------------------------------------------------------------------------
+# constrainednmf.m:90-267
+# --------------------------------------------------------------------------
+def constrained_label_matrix(labels):
+    """constrainednmf.m:147-170: class labels -> (sorted_idx, A).
+
+    Samples are reordered so that unlabeled ones (label -1) come first and samples of one class are
+    contiguous; ``A`` is the (n_unlabeled + num_classes) x n indicator matrix of that ORDERED
+    arrangement: identity on the unlabeled samples, one row per class below it."""
+    labels = np.asarray(labels).ravel()
+    n = labels.size
+    num_labeled = int(np.sum(labels > -1))  # constrainednmf.m:149
+    uniq, inv = np.unique(labels, return_inverse=True)  # constrainednmf.m:151 / 156 (1-based in MATLAB)
+    proc = inv + 1
+    if num_labeled < n:  # some unlabeled samples (they got processed label 1)
+        proc = proc - 1  # constrainednmf.m:152
+        proc[proc == 0] = -1  # constrainednmf.m:153
+        num_classes = len(uniq) - 1  # constrainednmf.m:154
+    else:
+        num_classes = len(uniq)  # constrainednmf.m:170
+    sorted_idx = np.argsort(proc, kind="stable")  # constrainednmf.m:163 (MATLAB's sort is stable)
+    sorted_labels = proc[sorted_idx]
+    n_unl = n - num_labeled
+    C = np.zeros((num_classes, num_labeled))  # constrainednmf.m:166-169
+    for samp in range(n_unl, n):
+        C[sorted_labels[samp] - 1, samp - n_unl] = 1
+    A = np.block([[np.eye(n_unl), np.zeros((n_unl, num_labeled))],  # constrainednmf.m:170
+                  [np.zeros((num_classes, n_unl)), C]])
+    return sorted_idx, A
+
+
+def constrainednmf(V, labels, num_basis_elems, config=None, rng=None):
+    """``[W, H, Z, A, cost] = constrainednmf(V, labels, num_basis_elems, config)`` - constrainednmf.m:1.
+
+    Extension for reproducibility (the reference draws ``Z = rand(...)`` unconditionally at line 174):
+    ``config['Z_init']``, a num_basis_elems x (n_unlabeled + num_classes) matrix in the ORDERED
+    arrangement (unlabeled samples first, then one column per class)."""
+    V = np.asarray(V, dtype=np.float64)
+    m, n = V.shape  # constrainednmf.m:96
+    labels = np.asarray(labels).ravel()
+    if labels.size != n:  # constrainednmf.m:98
+        raise ReferenceError_("Length of the label vector not equal to number of samples.")
+    cfg = dict(config or {})
+    rng = rng or np.random.default_rng(0)
+    K = int(num_basis_elems)
+    W = np.array(cfg["W_init"], dtype=np.float64) if cfg.get("W_init") is not None else rng.random((m, K))  # 100-102
+    lam_w = cfg.get("W_sparsity") or 0  # 103-105
+    lam_z = cfg.get("Z_sparsity") or 0  # 106-108
+    W_fixed = bool(cfg.get("W_fixed") or False)  # 109-111
+    Z_fixed = bool(cfg.get("Z_fixed") or False)  # 112-114
+    div = cfg.get("divergence", "euclidean")  # 115-117
+    is_ab = div in ("ab_divergence", "ab")
+    alpha = cfg.get("alpha", 1) if is_ab else 1  # 118-122
+    beta = cfg.get("beta", 1) if is_ab else 1  # 123-127
+    use_dual = alpha == 0  # 128-132
+    maxiter = cfg.get("maxiter")
+    if maxiter is None or maxiter <= 0:  # 133-135
+        maxiter = 100
+    tol = cfg.get("tolerance")
+    if tol is None or tol <= 0:  # 136-138
+        tol = 1e-3
+    if is_ab and alpha == 0 and beta == 0:  # 140-142
+        raise ReferenceError_("alpha = 0 and beta = 0 is not supported at this time.")
+    W = W @ np.diag(1.0 / np.sqrt(np.sum(W ** 2, axis=0)))  # 144-145
+
+    sorted_idx, A = constrained_label_matrix(labels)  # 147-170
+    V = V[:, sorted_idx]  # 164
+    nz = A.shape[0]
+    Z = np.array(cfg["Z_init"], dtype=np.float64) if cfg.get("Z_init") is not None else rng.random((K, nz))  # 174
+    H = Z @ A  # 177
+    V_hat = reconstruct_from_decomposition(W, H)  # 179
+    cost = np.zeros(int(maxiter))  # 181
+    ones_nm, ones_mn = np.ones((n, m)), np.ones((m, n))
+
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for it in range(1, int(maxiter) + 1):  # 183
+            if not W_fixed:  # 185
+                if div == "euclidean":  # 187-189
+                    neg = V @ H.T + W @ _diagdiag(H @ V_hat.T @ W)
+                    pos = V_hat @ H.T + W @ _diagdiag(H @ V.T @ W)
+                elif div in ("kl_divergence", "kl"):  # 190-192
+                    neg = (V / V_hat) @ H.T + W @ _diagdiag(H @ ones_nm @ W)
+                    pos = ones_mn @ H.T + W @ _diagdiag(H @ (V.T / V_hat.T) @ W)
+                elif div in ("is_divergence", "is"):  # 193-195
+                    neg = (V / V_hat ** 2) @ H.T + W @ _diagdiag(H @ (ones_nm / V_hat.T) @ W)
+                    pos = (ones_mn / V_hat) @ H.T + W @ _diagdiag(H @ (V.T / V_hat.T ** 2) @ W)
+                elif is_ab:  # 196-203
+                    if use_dual:
+                        neg = ((V ** (alpha - 1) * V_hat ** beta) @ H.T
+                               + W @ _diagdiag(H @ V.T ** (alpha + beta - 1) @ W)) ** (1.0 / beta)
+                        pos = (V ** (alpha + beta - 1) @ H.T
+                               + W @ _diagdiag(H @ (V ** (alpha - 1) * V_hat ** beta).T @ W)) ** (1.0 / beta)
+                    else:
+                        neg = ((V ** alpha * V_hat ** (beta - 1)) @ H.T
+                               + W @ _diagdiag(H @ V_hat.T ** (alpha + beta - 1) @ W)) ** (1.0 / alpha)
+                        pos = (V_hat ** (alpha + beta - 1) @ H.T
+                               + W @ _diagdiag(H @ (V ** alpha * V_hat ** (beta - 1)).T @ W)) ** (1.0 / alpha)
+                else:  # 204-205
+                    raise ReferenceError_(
+                        "No update equations defined for cost function with divergence type " + str(div))
+                W = W * (neg / np.fmax(pos + lam_w, EPS))  # 207
+                W = W @ np.diag(1.0 / np.sqrt(np.sum(W ** 2, axis=0)))  # 208
+            V_hat = reconstruct_from_decomposition(W, H)  # 210
+
+            if not Z_fixed:  # 213
+                if div == "euclidean":  # 215-217
+                    neg = W.T @ V @ A.T
+                    pos = W.T @ V_hat @ A.T
+                elif div in ("kl_divergence", "kl"):  # 218-220
+                    neg = W.T @ (V / V_hat) @ A.T
+                    pos = W.T @ ones_mn @ A.T
+                elif div in ("is_divergence", "is"):  # 221-223
+                    neg = W.T @ (V / V_hat ** 2) @ A.T
+                    pos = W.T @ (ones_mn / (W @ H)) @ A.T
+                elif is_ab:  # 224-231
+                    if use_dual:
+                        neg = (W.T @ (V ** (alpha - 1) * V_hat ** beta) @ A.T) ** (1.0 / beta)
+                        pos = (W.T @ V ** (alpha + beta - 1) @ A.T) ** (1.0 / beta)
+                    else:
+                        # constrainednmf.m:229 reads  W' * V.^alpha .* V_hat.^(beta-1) * A'  - MATLAB
+                        # evaluates * and .* left to right, so a K x n matrix meets an m x n one:
+                        # "Matrix dimensions must agree" unless m == K (a defect of the reference)
+                        if m != K:
+                            raise ReferenceError_("Matrix dimensions must agree.")
+                        neg = ((W.T @ V ** alpha) * V_hat ** (beta - 1) @ A.T) ** (1.0 / alpha)
+                        pos = (W.T @ V_hat ** (alpha + beta - 1) @ A.T) ** (1.0 / alpha)
+                else:  # 232-233
+                    raise ReferenceError_(
+                        "No update equations defined for cost function with divergence type " + str(div))
+                Z = Z * (neg / np.fmax(pos + lam_z, EPS))  # 235
+            H = Z @ A  # 237
+            V_hat = reconstruct_from_decomposition(W, H)  # 238
+
+            c = _cost(div, V, V_hat, alpha, beta)  # 241-250
+            c = c + lam_w * np.sum(np.abs(W)) + lam_z * np.sum(np.abs(Z))  # 251
+            cost[it - 1] = c
+            if it > 1 and cost[it - 1] < cost[it - 2] and cost[it - 2] - cost[it - 1] < tol:  # 254-257
+                cost = cost[:it]
+                break
+
+    # constrainednmf.m:260-267: A (and with it H) back in the original sample order
+    A_out = np.zeros_like(A)
+    A_out[:, sorted_idx] = A
+    H = Z @ A_out
+    return W, H, Z, A_out, cost

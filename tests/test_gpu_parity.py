@@ -421,6 +421,54 @@ def test_lnmf_stop_leaves_cost_untrimmed(api, handle):
     assert e.value.code == 3
 
 
+# ---------------------------------------------------------------- constrainednmf
+@pytest.mark.parametrize("div,extra", [("euclidean", {}), ("kl", {}), ("is", {}),
+                                       ("euclidean", dict(W_sparsity=0.05, Z_sparsity=0.1)),
+                                       ("kl", dict(W_sparsity=0.02, Z_sparsity=0.05)),
+                                       ("euclidean", dict(Z_fixed=True)), ("kl", dict(W_fixed=True))])
+@pytest.mark.parametrize("m,n,K,classes,unl", [(200, 330, 8, 5, 0.3), (129, 1000, 24, 12, 0.0), (300, 257, 6, 3, 0.9)])
+def test_constrainednmf_vs_oracle(api, handle, div, extra, m, n, K, classes, unl):
+    """constrainednmf.m:183-257 on the nmf kernels: W step as nmf.m, Z step on the class-summed gradients,
+    H = Z*A; labels with gaps and unlabeled samples (-1), outputs in the original sample order."""
+    rng = np.random.default_rng(m + K)
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    labels = rng.integers(0, classes, size=n) * 3 + 1
+    labels[rng.random(n) < unl] = -1
+    nz = int((labels < 0).sum()) + len(np.unique(labels[labels >= 0]))
+    cfg = dict(divergence=div, W_init=rng.random((m, K)) + 1e-3, Z_init=rng.random((K, nz)) + 1e-3, maxiter=40,
+               tolerance=1e-300, **extra)
+    W, H, Z, A, c = api.constrainednmf(V, labels, K, cfg, handle=handle)
+    Wo, Ho, Zo, Ao, co = O.constrainednmf(V, labels, K, cfg)
+    assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
+    assert np.array_equal(A, Ao)
+    np.testing.assert_allclose(H, Z.astype(np.float64) @ A, rtol=1e-6)
+    np.testing.assert_allclose(np.linalg.norm(Z - Zo) / np.linalg.norm(Zo), 0, atol=5e-3)
+    if extra.get("Z_fixed"):
+        np.testing.assert_allclose(Z, cfg["Z_init"], rtol=2e-6)
+
+
+def test_constrainednmf_ab_dual_and_errors(api, handle):
+    rng = np.random.default_rng(9)
+    m, n, K = 120, 150, 5
+    V = np.maximum(rng.random((m, n)), 2.0 ** -10)
+    labels = rng.integers(-1, 3, size=n)
+    nz = int((labels < 0).sum()) + 3
+    cfg = dict(divergence="ab", alpha=0, beta=1.0, W_init=rng.random((m, K)) + 1e-3, Z_init=rng.random((K, nz)) + 1e-3,
+               maxiter=15, tolerance=1e-300)
+    W, H, Z, A, c = api.constrainednmf(V, labels, K, cfg, handle=handle)  # dual updates (constrainednmf.m:128-132)
+    Wo, Ho, Zo, Ao, co = O.constrainednmf(V, labels, K, cfg)
+    assert recon_err(W, H, Wo, Ho) < RECON_TOL
+    assert np.all(~np.isfinite(c)) and np.all(~np.isfinite(co))  # -1/(alpha*beta) with alpha = 0 (constrainednmf.m:249)
+    with pytest.raises(api.NmfbError) as e:  # constrainednmf.m:229 cannot be evaluated unless m == K
+        api.constrainednmf(V, labels, K, dict(cfg, alpha=0.5), handle=handle)
+    assert e.value.code == 3
+    with pytest.raises(api.NmfbError) as e:  # constrainednmf.m:140-142
+        api.constrainednmf(V, labels, K, dict(cfg, alpha=0, beta=0), handle=handle)
+    assert e.value.code == 5
+    with pytest.raises(api.NmfbError):  # constrainednmf.m:98
+        api.constrainednmf(V, labels[:-1], K, cfg, handle=handle)
+
+
 # ---------------------------------------------------------------- nmf, multi-source cell arrays
 @pytest.mark.parametrize("div", ["euclidean", "kl", "is"])
 @pytest.mark.parametrize("case", ["sparsity", "w_fixed", "h_fixed", "mixed"])

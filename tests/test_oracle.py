@@ -278,3 +278,53 @@ def test_cnmfsc_gram_forms_of_the_w_gradients():
         np.testing.assert_allclose(neg, V @ Hsh.T, rtol=1e-12)
         np.testing.assert_allclose(pos_mu, V_hat @ Hsh.T, rtol=1e-11)
         np.testing.assert_allclose(pos_sparse, (Wprev @ H) @ Hsh.T, rtol=1e-11)  # V_hat = RFD(Wnew, H), line 235
+
+
+# ---------------------------------------------------------------- constrainednmf.m
+def test_constrainednmf_all_unlabeled_is_nmf():
+    """With every sample unlabeled A = I (constrainednmf.m:170), so V ~ W*Z*A is plain nmf with H = Z: the two
+    restatements (written from different files of the reference) must agree to rounding."""
+    rng = np.random.default_rng(3)
+    m, n, K = 30, 44, 4
+    V = rng.random((m, n)) + 0.01
+    W0, Z0 = rng.random((m, K)) + 0.1, rng.random((K, n)) + 0.1
+    for div in ("euclidean", "kl", "is"):
+        cfg = dict(divergence=div, W_init=W0, maxiter=25, tolerance=1e-300, W_sparsity=0.05)
+        W, H, Z, A, c = O.constrainednmf(V, -np.ones(n, int), K, dict(cfg, Z_init=Z0, Z_sparsity=0.1))
+        Wn, Hn, cn = O.nmf(V, K, dict(cfg, H_init=Z0, H_sparsity=0.1))
+        assert np.array_equal(A, np.eye(n))
+        np.testing.assert_allclose(c, cn, rtol=1e-12)
+        np.testing.assert_allclose(W, Wn, rtol=1e-10)
+        np.testing.assert_allclose(H, Hn, rtol=1e-10)
+        np.testing.assert_allclose(Z, Hn, rtol=1e-10)
+
+
+def test_constrainednmf_labels_tie_columns_and_cost_decreases():
+    rng = np.random.default_rng(4)
+    m, n, K = 25, 60, 3
+    V = rng.random((m, n)) + 0.01
+    labels = rng.integers(-1, 4, size=n) * 5  # classes 0, 5, 10, 15 and unlabeled (-5 -> treated as a class!)
+    labels[labels < 0] = -1
+    W, H, Z, A, c = O.constrainednmf(V, labels, K, dict(maxiter=40, tolerance=1e-300, W_init=rng.random((m, K)),
+                                                        Z_init=rng.random((K, int((labels < 0).sum()) + 4))))
+    assert A.shape == ((labels < 0).sum() + 4, n) and np.all(A.sum(0) == 1)
+    np.testing.assert_allclose(H, Z @ A)
+    for cls in (0, 5, 10, 15):  # samples of one class share their encoding (constrainednmf.m:237)
+        cols = np.flatnonzero(labels == cls)
+        assert np.all(H[:, cols] == H[:, cols[:1]])
+    assert np.all(np.diff(c) <= 1e-9 * c[:-1])
+    np.testing.assert_allclose((W ** 2).sum(0), 1.0, rtol=1e-12)  # constrainednmf.m:208
+
+
+def test_constrainednmf_reference_defects_reproduced():
+    rng = np.random.default_rng(5)
+    V = rng.random((12, 20)) + 0.01
+    lab = rng.integers(0, 3, size=20)
+    with pytest.raises(O.ReferenceError_):  # constrainednmf.m:229: K x n .* m x n
+        O.constrainednmf(V, lab, 4, dict(divergence="ab", alpha=0.5, beta=1.0, maxiter=2))
+    with pytest.raises(O.ReferenceError_):  # constrainednmf.m:140-142
+        O.constrainednmf(V, lab, 4, dict(divergence="ab", alpha=0, beta=0, maxiter=2))
+    with pytest.raises(O.ReferenceError_):  # constrainednmf.m:98
+        O.constrainednmf(V, lab[:-1], 4, dict(maxiter=2))
+    W, H, Z, A, c = O.constrainednmf(V, lab, 4, dict(divergence="ab", alpha=0, beta=1.0, maxiter=5, tolerance=1e-300))
+    assert len(c) == 5  # the dual branch (alpha = 0) is well defined; its cost is Inf/NaN (-1/(alpha*beta))
