@@ -32,7 +32,7 @@ constexpr int kMaxRanks = 8;
 constexpr int kMaxBlocks = 256;                                      // grid cap of kernels with per-block barriers
 constexpr size_t kFlagBytes = kMaxBlocks * kMaxRanks * sizeof(int);  // one barrier site: flags[block][rank]
 // Barrier sites (each with its own monotone epoch sequence): 0/1 all-reduce open/close, 2..4 sharded W step
-// (dots, norms, closing), 5 row gather of the fp32 W at the end of a run
+// (4 closing, 6 opening), 5 row gather of the fp32 W at the end of a run
 constexpr int kBarrierSites = 8;
 constexpr size_t kHeader = kBarrierSites * kFlagBytes;  // region = [flags | data]
 struct PeerTable {

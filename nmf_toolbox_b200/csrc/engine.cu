@@ -28,7 +28,7 @@ dim3 vec_grid(int len, int nvec, int threads) {
 
 static int plan_common(nmfb_handle* h, GemmOp* op, const MatRef& X0, const MatRef& Y0,
                        long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1,
-                       int rows, int ncols, int splits_hint, const ExtraSegs* segs = nullptr) {
+                       int rows, int ncols, int splits_hint, const ExtraSegs* segs = nullptr, int tile_n = 0) {
   GemmOperand x0 = operand(X0), y0 = operand(Y0), x1{}, y1{};
   if (X1) {
     x1 = operand(*X1);
@@ -36,7 +36,7 @@ static int plan_common(nmfb_handle* h, GemmOp* op, const MatRef& X0, const MatRe
   }
   const int cg = pair_eligible(rows, ncols, Y0.mn, Y1 ? Y1->mn : false) ? 2 : 1;
   std::string e = plan_gemm(&op->L, x0, y0, kdim0, X1 ? &x1 : nullptr, X1 ? &y1 : nullptr, kdim1,
-                            rows, ncols, splits_hint, h->num_sms, cg);
+                            rows, ncols, splits_hint, h->num_sms, cg, tile_n);
   if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "plan_gemm: %s", e.c_str());
   for (int sgi = 0; segs && sgi < segs->n; ++sgi) {
     e = add_segment(&op->L, sgi + 1, operand(segs->X[sgi]), operand(segs->Y[sgi]), h->num_sms, splits_hint);
@@ -72,9 +72,9 @@ int plan_store(nmfb_handle* h, Arena* ar, GemmOp* op, const MatRef& X0, const Ma
 
 int plan_fused(nmfb_handle* h, GemmOp* op, int epi, const MatRef& X0, const MatRef& Y0,
                long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1, int rows,
-               int ncols, int ncols_valid, const int* stop, const ExtraSegs* segs) {
+               int ncols, int ncols_valid, const int* stop, const ExtraSegs* segs, int tile_n) {
   op->epi = epi;
-  NMFB_TRY(plan_common(h, op, X0, Y0, kdim0, X1, Y1, kdim1, rows, ncols, 1, segs));
+  NMFB_TRY(plan_common(h, op, X0, Y0, kdim0, X1, Y1, kdim1, rows, ncols, 1, segs, tile_n));
   op->L.args.stop = stop;
   op->L.args.ncols_valid = ncols_valid;
   return NMFB_OK;

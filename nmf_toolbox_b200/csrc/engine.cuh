@@ -219,7 +219,7 @@ int plan_store(nmfb_handle* h, Arena* ar, GemmOp* op, const MatRef& X0, const Ma
                const int* stop, const ExtraSegs* segs = nullptr);
 int plan_fused(nmfb_handle* h, GemmOp* op, int epi, const MatRef& X0, const MatRef& Y0,
                long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1, int rows,
-               int ncols, int ncols_valid, const int* stop, const ExtraSegs* segs = nullptr);
+               int ncols, int ncols_valid, const int* stop, const ExtraSegs* segs = nullptr, int tile_n = 0);
 int run_gemm(nmfb_handle* h, const GemmOp& op);
 
 // Gram matrix G = M M' of a factor stored as nvec contiguous vectors of length len

@@ -76,7 +76,7 @@ bool pair_eligible(int rows, int ncols, bool y_mn_major0, bool y_mn_major1) {
 
 std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const GemmOperand& Y0, long long kdim0,
                       const GemmOperand* X1, const GemmOperand* Y1, long long kdim1, int rows,
-                      int ncols, int splits_hint, int num_sms, int cg) {
+                      int ncols, int splits_hint, int num_sms, int cg, int tile_n) {
   if (ncols <= 0 || ncols % 32 != 0) return "plan_gemm: ncols must be a positive multiple of 32";
   if (cg != 1 && cg != 2) return "plan_gemm: cta group must be 1 or 2";
   std::memset(L, 0, sizeof(*L));
@@ -84,7 +84,10 @@ std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const GemmOperand& Y
   GemmArgs& a = L->args;
   a.rows = rows;
   a.ncols = ncols;
-  a.box_n = std::min(ncols, kMaxN);
+  if (tile_n < 0 || tile_n > kMaxN || tile_n % 32 != 0) return "plan_gemm: tile_n must be a multiple of 32 up to 256";
+  a.tile_n = tile_n;
+  const int tn = tile_n > 0 ? tile_n : kMaxN;
+  a.box_n = std::min(ncols, tn);
   a.nkb0 = static_cast<int>((kdim0 + kBlockK - 1) / kBlockK);
   a.nkb_seg = a.nkb0;
   a.chunk_kb = 0;
@@ -97,7 +100,7 @@ std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const GemmOperand& Y
   a.ncols_valid = ncols;
   const int tile_rows = kTileM * cg;
   const int tiles = (rows + tile_rows - 1) / tile_rows;
-  const int chunks = (ncols + kMaxN - 1) / kMaxN;
+  const int chunks = (ncols + tn - 1) / tn;
   int splits = 1;
   a.kb_per_split = std::max(a.nkb0, 1);
   if (splits_hint != 1) {

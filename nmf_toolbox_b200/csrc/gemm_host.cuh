@@ -50,7 +50,7 @@ bool pair_eligible(int rows, int ncols, bool y_mn_major0, bool y_mn_major1);
 //   kdim0 : contraction length of phase 0;  kdim1: of phase 1 (0 = none)
 std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const GemmOperand& Y0, long long kdim0,
                       const GemmOperand* X1, const GemmOperand* Y1, long long kdim1, int rows,
-                      int ncols, int splits_hint, int num_sms, int cg = 1);
+                      int ncols, int splits_hint, int num_sms, int cg = 1, int tile_n = 0);
 
 // Adds operand pair number `seg` (1 or 2) to phase 0: acc0 += Xs * Ys' over the same contraction.
 // Must be called after plan_gemm and before any split bookkeeping is read.

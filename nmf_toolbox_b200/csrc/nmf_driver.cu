@@ -43,6 +43,7 @@ struct NmfSession {
   bool side_gh = false;  // several GPUs: gram(H) runs beside the A GEMM, joined before the all-reduce
   unsigned int* gates = nullptr;  // [0] G_H ready for iteration i (value i+1), [1] G_W ready
   bool h_split = false;  // too few sample tiles for the fused H update: split-K GEMM + h_finish
+  int h_tile_n = 0;      // fused H update with narrower tiles (more CTAs) instead of split-K
   float *Nbuf = nullptr, *Dbuf = nullptr;
   float lambda_w = 0.f, lambda_h = 0.f;
   // per-basis settings of a multi-source run (nmfb_config::*_k); null = the scalars apply
@@ -85,6 +86,9 @@ struct NmfSession {
   int *col2z = nullptr, *seg = nullptr;
   // multi-GPU, row-sharded W step (w_shard.cuh): this rank's rows of W, byte offsets inside the peer region
   bool w_sharded = false;
+  bool ws_open_barrier = false;  // the small all-reduce runs on the side stream: the sharded kernel meets the peers itself
+  unsigned long long* ws_timing = nullptr;  // NMFB_WS_TIMING=1: per-block phase stamps of the last sharded W step
+  int ws_grid = 0;
   int r0 = 0, mb = 0;
   size_t a_off = 0, b_off = 0, wt_off = 0, wm_off = 0, x_off = 0;
   float* packed = nullptr;  // multi-GPU: [A | G_H] contiguous fp32 for the single all-reduce
@@ -302,7 +306,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     const size_t wt_off = (dbl_off + (static_cast<size_t>(Kp) + 8) * sizeof(double) + 255) / 256 * 256;
     const size_t wm_off = wt_off + (w_bytes + 255) / 256 * 256;
     const size_t x_off = wm_off + (w_bytes + 255) / 256 * 256;
-    const size_t total = x_off + 2 * static_cast<size_t>(kMaxBlocks) * kMaxRanks * 2 * sizeof(double);
+    const size_t total = x_off + 2 * static_cast<size_t>(kMaxBlocks) * kMaxRanks * 32;
     char* region = nullptr;
     NMFB_TRY(comm_acquire_region(h, total, &region));
     s->packed = reinterpret_cast<float*>(region);
@@ -320,6 +324,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     s->mb = std::min(static_cast<int>(s->ldw), s->r0 + rb) - s->r0;
     const char* env = std::getenv("NMFB_W_SHARD");
     s->w_sharded = comm_peer_table(h, nullptr) && !lnmf && !(env && env[0] == '0') && rb <= 4 * kWsCache * kWsThreads;
+    if (s->w_sharded && std::getenv("NMFB_WS_TIMING")) NMFB_TRY(ar->alloc(h, &s->ws_timing, 8 * kMaxBlocks));
     const size_t base = comm_region_offset(h, region);
     s->a_off = base;
     s->b_off = tw ? base + w_bytes : 0;
@@ -445,6 +450,14 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     const int ctasH = ((n + 2 * kTileM - 1) / (2 * kTileM)) * 2 * ((Kp + kMaxN - 1) / kMaxN);
     const char* env = std::getenv("NMFB_OVERLAP");
     s->h_split = ctasH * 2 <= h->num_sms && n > kTileM;
+    // Experiment (NMFB_H_TILEN=<width>): with few sample tiles, narrower tiles instead of split-K - twice the
+    // CTAs, each still runs the whole contraction and keeps the fused H update.  Measured at 2 GPUs
+    // (16384 x 8192 shard, K = 256): 222 us against 144 us for split-K + h_finish - every CTA streams the V
+    // tile for half the tensor work, so the kernel becomes load-bound.  Off by default.
+    int& h_tile_n = s->h_tile_n;
+    h_tile_n = 0;
+    if (const char* e3 = std::getenv("NMFB_H_TILEN")) h_tile_n = std::atoi(e3);
+    if (h_tile_n > 0) s->h_split = false;
     if (const char* e2 = std::getenv("NMFB_H_SPLIT")) s->h_split = e2[0] == '1';  // tests force either path
     if (s->per_basis) s->h_split = true;  // per-basis lambda / fixed rows live in h_finish, not in the fused epilogue
     if (s->tied) s->h_split = true;       // the Z step sums N and D over the samples of a class (tied_update_kernel)
@@ -457,9 +470,14 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     // a grid of more CTAs than SMs spinning at the gate would never let it start (deadlock).  The fused
     // kernel launches ctasH CTAs; the split-K variant is planned below with num_sms - 20 as its budget,
     // which it can only honour when the unsplit grid already fits (choose_splits never goes below 1).
-    const bool h_grid_fits = s->h_split ? ctasH + 20 <= h->num_sms : ctasH + 8 <= h->num_sms;
+    const int ctasHf = h_tile_n > 0 ? ctasH * ((Kp + h_tile_n - 1) / h_tile_n) : ctasH;  // fused kernel's grid
+    const bool h_grid_fits = s->h_split ? ctasH + 20 <= h->num_sms : ctasHf + 8 <= h->num_sms;
     s->gate_h = ((s->overlap && !s->h_split) || (can_side && s->h_split)) && h_grid_fits;
     s->side_gh = multi && can_side;
+    {
+      const char* e4 = std::getenv("NMFB_WS_SIDE");
+      s->ws_open_barrier = s->w_sharded && s->side_gh && !s->direct_cost && !(e4 && e4[0] == '0');
+    }
   }
   NMFB_TRY(plan_gram(h, ar, &s->gramW, s->Wt, Kp, m, s->ldw, stop, nullptr, 0, s->gate_h ? 20 : 0));
   if (!kl) {
@@ -540,7 +558,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
       h->num_sms = sms;
       NMFB_TRY(rc);
     } else {
-    NMFB_TRY(plan_fused(h, &s->gemmH, EPI_HUPDATE, Xvt, Yw, m, &Xh, &Ygw, Kp, n, Kp, Kp, stop));
+    NMFB_TRY(plan_fused(h, &s->gemmH, EPI_HUPDATE, Xvt, Yw, m, &Xh, &Ygw, Kp, n, Kp, Kp, stop, nullptr, s->h_tile_n));
     }
     if (s->gate_h) {
       const dim3 g = s->gemmH.L.grid;
@@ -706,6 +724,7 @@ static int allreduce_w_inputs(nmfb_handle* h, NmfSession* s, bool with_gram) {
 // The whole W step on this rank's rows, partial sums fetched from / results delivered to the peers
 static int enqueue_w_sharded(nmfb_handle* h, NmfSession* s, int mode, bool b_partial) {
   WShardArgs a{};
+  a.open_barrier = s->ws_open_barrier ? 1 : 0;
   if (!comm_peer_table(h, &a.t)) return h->fail(NMFB_ERR_CUDA, "internal: sharded W step without a peer mapping");
   a.mode = mode;
   a.K = s->K;
@@ -725,11 +744,18 @@ static int enqueue_w_sharded(nmfb_handle* h, NmfSession* s, int mode, bool b_par
   a.fixed_k = s->fixW_k;
   a.expo = s->expo;
   a.stop = s->stop;
-  const int cap = w_shard_capacity(a.t.nranks, h->num_sms);  // blocks spin on their peers: all must be resident
+  // TMA bulk copies for the peer traffic when one column of W fits the staging buffer (and only the numerator
+  // is partial); NMFB_W_BULK=0 keeps the load / store path
+  const size_t smem = static_cast<size_t>(a.t.nranks) * a.mb * sizeof(float);
+  const char* env = std::getenv("NMFB_W_BULK");
+  const bool bulk = !b_partial && smem <= 96 * 1024 && !(env && env[0] == '0');
+  const int cap = w_shard_capacity(a.t.nranks, h->num_sms, bulk, smem);  // blocks spin on their peers: all resident
   a.rounds = (s->K + cap - 1) / cap;
   const int grid = (s->K + a.rounds - 1) / a.rounds;
   a.epoch0 = comm_next_epoch(h, a.rounds);
-  launch_w_step_sharded(a, grid, h->stream);
+  a.timing = s->ws_timing;
+  launch_w_step_sharded(a, grid, bulk, smem, h->stream);
+  s->ws_grid = grid;
   return check_launch(h, "w_step_sharded");
 }
 
@@ -941,6 +967,16 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
       cudaStream_t main_stream = h->stream;
       h->stream = h->stream2;
       int rc = run_gram(h, s->gramH, stop);
+      if (rc == NMFB_OK && s->ws_open_barrier) {
+        // row-sharded W step: what is left to all-reduce (G_H, the scalar sums) and the cost / stop test of the
+        // previous iteration also run beside the A GEMM
+        rc = allreduce_w_inputs(h, s, true);
+        if (rc == NMFB_OK) {
+          CostArgs c{};
+          fill_cost_args(s, &c, i - 1, 0);
+          rc = run_gram_post_allreduce(h, s->gramH, s->ticket, c, i > 0);
+        }
+      }
       h->stream = main_stream;
       NMFB_TRY(rc);
       NMFB_CUDA(h, cudaEventRecord(h->ev_join, h->stream2));
@@ -949,6 +985,9 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
     }
     if (!s->W_fixed) NMFB_TRY(run_timed(h, s->gemmA, 0));
     if (s->side_gh) NMFB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    if (s->side_gh && s->ws_open_barrier) {
+      // (all-reduce and cost already queued on the side stream)
+    } else {
     NMFB_TRY(allreduce_w_inputs(h, s, true));
     if (multi && !s->direct_cost) {
       CostArgs c{};
@@ -956,6 +995,7 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
       NMFB_TRY(run_gram_post_allreduce(h, s->gramH, s->ticket, c, i > 0));
     } else if (i > 0 && !s->direct_cost && !fused_cost) {
       NMFB_TRY(enqueue_cost(h, s, i - 1, 0));
+    }
     }
     if (!s->W_fixed) {
       if (s->gemmB.planned) NMFB_TRY(run_gemm(h, s->gemmB));
@@ -1172,6 +1212,21 @@ extern "C" int nmfb_nmf_end(nmfb_handle* h, float* W_out, float* H_out, double* 
       cudaError_t e = cudaMemcpy(cost_out, s->cost, nc * sizeof(double), cudaMemcpyDeviceToHost);
       if (e != cudaSuccess) rc = h->fail(NMFB_ERR_CUDA, "cost download: %s", cudaGetErrorString(e));
     }
+  }
+  if (rc == NMFB_OK && s->ws_timing != nullptr && s->ws_grid > 0) {
+    std::vector<unsigned long long> t(8 * static_cast<size_t>(s->ws_grid));
+    cudaStreamSynchronize(h->stream);
+    cudaMemcpy(t.data(), s->ws_timing, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull, t6 = 0;
+    double ph[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < s->ws_grid; ++b) {
+      t0 = std::min(t0, t[b * 8]);
+      t6 = std::max(t6, t[b * 8 + 6]);
+      for (int i = 0; i < 6; ++i) ph[i] += static_cast<double>(t[b * 8 + i + 1] - t[b * 8 + i]) / s->ws_grid;
+    }
+    fprintf(stderr, "[nmfb] sharded W step, rank %d, last launch: %d blocks, kernel span %.1f us; mean per block (us): peer rows + dots %.1f, "
+                    "barrier %.1f, step + norms %.1f, barrier %.1f, normalise + deliver rows %.1f, closing barrier %.1f\n",
+            comm_rank(h->comm), s->ws_grid, (t6 - t0) * 1e-3, ph[0] * 1e-3, ph[1] * 1e-3, ph[2] * 1e-3, ph[3] * 1e-3, ph[4] * 1e-3, ph[5] * 1e-3);
   }
   if (rc == NMFB_OK && s->w_sharded && !s->W_fixed) {
     // every rank kept only its rows of the fp32 W current: one exchange makes W whole everywhere

@@ -82,7 +82,9 @@ struct GemmArgs {
   int rows;          // valid output rows (rows of X)
   int ncols;         // output columns (multiple of 32; rows of Y beyond its extent read as zero)
   int ncols_valid;   // EPI_RECON / EPI_RESID / EPI_KLQ: columns that exist in V (<= ncols)
-  int box_n;         // rows of the Y TMA box = min(ncols, 256)
+  int box_n;         // rows of the Y TMA box = min(ncols, tile width)
+  int tile_n;        // output columns per CTA (0 = 256): narrower tiles put more CTAs on a problem with few
+                     // row tiles while keeping fused epilogues (every CTA still runs the whole contraction)
   int nkb0;          // phase-0 k-blocks in total (over all splits and segments)
   int nkb_seg;       // phase 0 may be a sum over up to 3 operand pairs ("segments", e.g. the
                      // hi/lo terms of a split-tf32 product); k-blocks per segment
@@ -242,8 +244,9 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
   const int r0 = CG == 2 ? static_cast<int>(blockIdx.x >> 1) * (2 * kTileM) + static_cast<int>(rank) * kTileM
                          : static_cast<int>(blockIdx.x) * kTileM;
-  const int n0 = blockIdx.y * kMaxN;
-  const int bn = min(a.ncols - n0, kMaxN);  // multiple of 32
+  const int tile_n = a.tile_n > 0 ? a.tile_n : kMaxN;
+  const int n0 = blockIdx.y * tile_n;
+  const int bn = min(a.ncols - n0, tile_n);  // multiple of 32
   const int split = blockIdx.z;
   const int kb_begin = split * a.kb_per_split;
   const int n0kb = max(0, min(a.nkb0, kb_begin + a.kb_per_split) - kb_begin);
