@@ -6,6 +6,7 @@
 //   [W, H, cost] = nmfb_mex('nmf',   V, K, cfg)        % cfg: struct, fields as nmf.m:17-65
 //   [W, H, cost] = nmfb_mex('cnmf',  V, K, T, cfg)
 //   [W, H, cost] = nmfb_mex('nmfsc', V, K, cfg)
+//   [W, H, Z, cost] = nmfb_mex('constrainednmf', V_ordered, K, col2z, nz, cfg)   % see matlab/constrainednmf.m
 //   V_hat        = nmfb_mex('reconstruct', W, H)
 //   [v, iters]   = nmfb_mex('projfunc', s, k1, k2, nn)
 //
@@ -193,6 +194,47 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     if (nlhs > 2) {
       plhs[2] = mxCreateDoubleMatrix(ncost, 1, mxREAL);  // trimmed like nmf.m:222
       std::memcpy(mxGetPr(plhs[2]), cost.data(), ncost * sizeof(double));
+    }
+  } else if (cmd == "constrainednmf") {
+    // [W, H, Z, cost] = nmfb_mex('constrainednmf', V_ordered, K, col2z (int32, n x 1), nz, cfg)
+    if (nrhs < 5) mexErrMsgIdAndTxt("nmfb:usage", "constrainednmf: V, K, col2z, nz[, cfg]");
+    const mxArray* V = prhs[1];
+    const int m = static_cast<int>(mxGetM(V)), n = static_cast<int>(mxGetN(V));
+    const int K = static_cast<int>(mxGetScalar(prhs[2]));
+    const int nz = static_cast<int>(mxGetScalar(prhs[4]));
+    if (!mxIsInt32(prhs[3]) || static_cast<int>(mxGetNumberOfElements(prhs[3])) != n)
+      mexErrMsgIdAndTxt("nmfb:invalidArgument", "col2z must be an int32 vector with one entry per sample");
+    if (K <= 0 || nz <= 0 || m <= 0 || n <= 0) mexErrMsgIdAndTxt("nmfb:invalidArgument", "sizes must be positive");
+    const mxArray* cfg = nrhs > 5 ? prhs[5] : nullptr;
+    std::vector<float> Vf = to_single(V), W0, Z0;
+    check(nmfb_set_V(h, Vf.data(), m, n));
+    nmfb_config c;
+    std::memset(&c, 0, sizeof(c));
+    c.divergence = divergence_code(cfg);
+    c.alpha = field(cfg, "alpha", 1);
+    c.beta = field(cfg, "beta", 1);
+    c.W_sparsity = field(cfg, "W_sparsity", 0);
+    c.H_sparsity = field(cfg, "H_sparsity", 0);  // Z_sparsity (renamed by constrainednmf.m)
+    c.W_fixed = field(cfg, "W_fixed", 0) != 0;
+    c.H_fixed = field(cfg, "H_fixed", 0) != 0;   // Z_fixed
+    c.maxiter = static_cast<int>(field(cfg, "maxiter", 0));
+    c.tolerance = field(cfg, "tolerance", 0);
+    const mxArray* w = init_field(cfg, "W_init", static_cast<size_t>(m) * K);
+    const mxArray* z = init_field(cfg, "Z_init", static_cast<size_t>(K) * nz);
+    if (w) { W0 = to_single(w); c.W_init = W0.data(); }
+    if (z) Z0 = to_single(z);
+    const int maxiter = c.maxiter > 0 ? c.maxiter : 100;
+    std::vector<float> W(static_cast<size_t>(m) * K), H(static_cast<size_t>(K) * n), Z(static_cast<size_t>(K) * nz);
+    std::vector<double> cost(maxiter + 1);
+    int ncost = 0;
+    check(nmfb_constrainednmf(h, K, &c, static_cast<const int*>(mxGetData(prhs[3])), nz, z ? Z0.data() : nullptr, W.data(),
+                              H.data(), Z.data(), cost.data(), &ncost));
+    plhs[0] = from_single(W, m, K);
+    if (nlhs > 1) plhs[1] = from_single(H, K, n);
+    if (nlhs > 2) plhs[2] = from_single(Z, K, nz);
+    if (nlhs > 3) {
+      plhs[3] = mxCreateDoubleMatrix(ncost, 1, mxREAL);
+      std::memcpy(mxGetPr(plhs[3]), cost.data(), ncost * sizeof(double));
     }
   } else if (cmd == "reconstruct") {
     const mxArray* W = prhs[1];

@@ -1,12 +1,12 @@
-// Kernel-level test hooks (C ABI, device pointers in/out).  Used only by
-// tests/ to check panel_gemm against a plain fp32 matmul on the same GPU.
+// Kernel-level test hooks (C ABI, device pointers in/out).  Used only by tests/ to check panel_gemm against a
+// plain matmul on the same GPU.  NOT part of libnmfb200.so: built into tests/libnmfb200_test.so together with
+// gemm_host.cu (csrc/testlib.cu), so the product library exports nothing but include/nmfb200.h.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
 #include <vector>
 
-#include "comm.cuh"
 #include "gemm_host.cuh"
 
 using namespace nmfb;
@@ -92,30 +92,6 @@ int nmfb_debug_gemm_hupdate(const nmfb_debug_mat* X0, const nmfb_debug_mat* Y0, 
   cudaError_t ce = cudaDeviceSynchronize();
   if (ce != cudaSuccess) return fail(err, errlen, std::string("sync: ") + cudaGetErrorString(ce));
   return 0;
-}
-
-// Time `iters` all-reduces of nf floats (+ 8 doubles) in the communicator's shared region; returns the
-// mean milliseconds per all-reduce and the first float after the last one (for a value check:
-// every rank starts from rank+1 and re-seeds between repetitions).
-int nmfb_debug_allreduce(nmfb_handle* h, long long nf, int iters, double* ms_out, float* first_out) {
-  char* region = nullptr;
-  const size_t dbl_off = (static_cast<size_t>(nf) * 4 + 255) / 256 * 256;
-  NMFB_TRY(comm_acquire_region(h, dbl_off + 64, &region));
-  float* f = reinterpret_cast<float*>(region);
-  double* d = reinterpret_cast<double*>(region + dbl_off);
-  std::vector<float> seed(static_cast<size_t>(nf), static_cast<float>(comm_rank(h->comm) + 1));
-  NMFB_CUDA(h, cudaMemcpyAsync(f, seed.data(), nf * 4, cudaMemcpyHostToDevice, h->stream));
-  NMFB_TRY(comm_allreduce(h, f, nf, d, 8, nullptr, 0));
-  NMFB_CUDA(h, cudaMemcpyAsync(first_out, f + nf - 1, 4, cudaMemcpyDeviceToHost, h->stream));
-  NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
-  NMFB_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-  for (int i = 0; i < iters; ++i) NMFB_TRY(comm_allreduce(h, f, nf, d, 8, nullptr, 0));
-  NMFB_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-  NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
-  float ms = 0.f;
-  NMFB_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-  *ms_out = ms / iters;
-  return NMFB_OK;
 }
 
 }  // extern "C"

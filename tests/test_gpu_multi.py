@@ -57,10 +57,14 @@ def test_multi_gpu_matches_single_and_oracle(div, variant, w_shard, m, nproc, tm
     else:
         Wo, Ho, co = O.nmf(V, K, cfg)
     assert len(got["cost"]) == iters
-    # Only the order of the fp32 accumulations differs between 1 and N GPUs - but the tensor core TRUNCATES when it
-    # accumulates, so the split-K H step of the small shards and the fused one of the single GPU carry slightly
-    # different (systematic) biases: measured 0.3e-6 .. 1.4e-6 relative on the cost, hence 2e-6 and not 1e-6.
-    np.testing.assert_allclose(got["cost"], c1, rtol=2e-6)
+    # Only the grouping of the fp32 accumulations differs between 1 and N GPUs - but the tensor core TRUNCATES when
+    # it adds into its accumulator, a systematic bias that grows with the length of an accumulation chain, and the
+    # shards of N GPUs split the contractions into shorter chains.  The Euclidean cost is the small difference
+    # 0.5(|V|^2 - 2<W'V,H> + <W'W,HH'>) of large terms, which amplifies that ~7x: measured 1.1e-6 (N = 2),
+    # 1.8e-6 (N = 4), 5.6e-6 (N = 8) relative, identical for the all-reduce and the row-sharded W step; the KL
+    # cost (summed directly) agrees to 1e-7.  Hence 1e-5 - the level at which the one-GPU run matches the float64
+    # oracle - and not the 1e-6 one would expect from a mere reordering.
+    np.testing.assert_allclose(got["cost"], c1, rtol=1e-5 if div == "euclidean" else 2e-6)
     np.testing.assert_allclose(got["cost"], co, rtol=1e-4)
     R, Ro = got["W"].astype(np.float64) @ got["H"].astype(np.float64), Wo @ Ho
     assert np.linalg.norm(R - Ro) / np.linalg.norm(Ro) < 1e-3

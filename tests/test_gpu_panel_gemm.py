@@ -35,10 +35,18 @@ class DebugMat(ctypes.Structure):
     ]
 
 
-def _lib():
-    from nmf_toolbox_b200 import _lib as L
+_TEST_LIB = None
 
-    return L.load()
+
+def _lib():
+    """tests/libnmfb200_test.so: panel_gemm + the kernel-level hooks (built by __graft_entry__.build())."""
+    global _TEST_LIB
+    if _TEST_LIB is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnmfb200_test.so")
+        if not os.path.exists(path):
+            raise RuntimeError(path + " not found: run `python __graft_entry__.py` (build())")
+        _TEST_LIB = ctypes.CDLL(path, mode=ctypes.RTLD_LOCAL)
+    return _TEST_LIB
 
 
 def tf32_round(x):
