@@ -128,7 +128,7 @@ int nmfb_nmf(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, float*
              double* cost_out, int* n_cost);
 /* [W, H, cost] = lnmf(V, num_basis_elems, config)  (lnmf.m:1).
  * KL-type updates with unit-sum bases and H <- sqrt(H .* W'(V./V_hat)) (lnmf.m:63-83) on the fused
- * KL kernels (num_basis_elems <= 128, one GPU).  config: W_init, H_init, W_fixed, H_fixed, maxiter,
+ * KL kernels (num_basis_elems <= 128; the unfused contractions beyond that; one GPU).  config: W_init, H_init, W_fixed, H_fixed, maxiter,
  * tolerance (divergence and sparsity fields are ignored: lnmf.m has none).  As in the reference the
  * cost vector is NOT trimmed when the loop stops early (lnmf.m:88-90): *n_cost == maxiter, entries
  * after the stopping iteration are 0. */
@@ -147,7 +147,7 @@ int nmfb_lnmf(nmfb_handle* h, int K, const nmfb_config* cfg, float* W_out, float
  * Z_init (K x nz column-major, may be NULL = uniform random) is an EXTENSION: the reference draws Z = rand(...)
  * unconditionally (line 174), which no test could reproduce.  H_out (K x n) is in the ordered arrangement.
  * The non-dual alpha-beta branch of the reference's Z update multiplies mismatched matrices (line 229) and
- * fails unless m == num_basis_elems: NMFB_ERR_UNSUPPORTED.  KL needs num_basis_elems <= 128.  One GPU. */
+ * fails unless m == num_basis_elems: NMFB_ERR_UNSUPPORTED.  One GPU. */
 int nmfb_constrainednmf(nmfb_handle* h, int K, const nmfb_config* cfg, const int* col2z, int nz,
                         const float* Z_init, float* W_out, float* H_out, float* Z_out, double* cost_out,
                         int* n_cost);

@@ -14,6 +14,14 @@
 //   - the Euclidean cost is 0.5*(|V|^2 - 2<Wc'V, Hs> + <Wc'Wc, Hs*Hs'>).
 // Basis k is normalised over all frames by |W(:,k,:)|_F / T (cnmf.m:196-199);
 // H is compensated for that only at initialisation (cnmf.m:163).
+//
+// Several GPUs (Euclidean / 'frobenius'): V and H are sharded by columns (time), W is replicated.  The shifts of
+// cnmf.m:188 (H moved right by t-1) and cnmf.m:219 (V, V_hat moved left by t-1) reach T-1 columns across a shard
+// boundary, so every rank keeps a HALO: the T-1 columns of H before and after its own ones (exchanged once per
+// iteration through the peer region, a few KB) and the T-1 columns of V after them (exchanged once, at setup).
+// With those, Hs, P = Wc'V and D = (Wc'Wc)Hs are formed locally on own + halo columns and folded for the own
+// columns; what crosses the GPUs per iteration besides the H halo is one all-reduce of [A | Hs Hs'] and the
+// scalar sums, as for nmf.
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -30,6 +38,16 @@ struct CnmfState {
   Arena ar;
   int K = 0, T = 0, KT = 0, KTp = 0, m = 0, n = 0;
   long long ldw = 0, ldh = 0;
+  // column shards: own columns n, halo columns hL (left, H only) and hR (right, H and V); nx = n + hR columns
+  // of Hs / P / D; the H master lives in a buffer of hL + n + hR columns (leading dimension ldhm), Hm points
+  // at the first own column
+  bool multi = false;
+  int hL = 0, hR = 0, nx = 0, halo = 0, rank = 0, nranks = 1;
+  long long ldhm = 0;
+  float *Hx = nullptr, *Vx = nullptr, *packed = nullptr;
+  const float* Vmma = nullptr;
+  size_t send_off = 0;  // byte offset of this rank's [2][K][halo] H columns (first / last own ones) in the region
+  GemmOp gemmB;
   bool W_fixed = false, H_fixed = false, frobenius = false;
   float lambda_w = 0.f, lambda_h = 0.f;
   int maxiter = 100;
@@ -91,8 +109,65 @@ int enqueue_w_scale(nmfb_handle* h, CnmfState* s) {
   return check_launch(h, "w_normalize");
 }
 
+// H halo exchange: every rank publishes its first and its last `halo` own columns of H, meets its peers, and reads
+// the left neighbour's last / the right neighbour's first columns into its halo columns.  One block.  (The slots are
+// rewritten one iteration later, behind the all-reduce of this iteration, which no rank passes before every rank has
+// left this kernel.)
+struct HaloArgs {
+  PeerTable t;
+  float* Hm;         // first own column
+  long long ld;
+  int K, n, halo, hL, hR;
+  size_t send_off;   // region byte offset of [first | last] columns, K * halo floats each
+  int epoch;
+  const int* stop;
+};
+__global__ void cnmf_halo_kernel(HaloArgs a) {
+  NMFB_STOP_GUARD(a.stop);
+  float* mine = reinterpret_cast<float*>(a.t.base[a.t.rank] + a.send_off);
+  const int cnt = a.K * a.halo;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int k = i / a.halo, c = i % a.halo;
+    mine[i] = a.Hm[k * a.ld + c];                          // first own columns -> left neighbour's right halo
+    mine[cnt + i] = a.Hm[k * a.ld + (a.n - a.halo + c)];   // last own columns  -> right neighbour's left halo
+  }
+  p2p_block_barrier(a.t, 7 * kFlagBytes, a.epoch);
+  if (a.hL > 0) {
+    const float* left = reinterpret_cast<const float*>(a.t.base[a.t.rank - 1] + a.send_off) + cnt;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const int k = i / a.halo, c = i % a.halo;
+      a.Hm[k * a.ld - a.halo + c] = __ldcv(left + i);
+    }
+  }
+  if (a.hR > 0) {
+    const float* right = reinterpret_cast<const float*>(a.t.base[a.t.rank + 1] + a.send_off);
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const int k = i / a.halo, c = i % a.halo;
+      if (c < a.hR) a.Hm[k * a.ld + a.n + c] = __ldcv(right + i);
+    }
+  }
+}
+int enqueue_halo(nmfb_handle* h, CnmfState* s, const int* stop) {
+  if (!s->multi || s->halo == 0) return NMFB_OK;
+  HaloArgs a{};
+  if (!comm_peer_table(h, &a.t)) return h->fail(NMFB_ERR_CUDA, "internal: cnmf halo exchange without a peer mapping");
+  a.Hm = s->Hm;
+  a.ld = s->ldhm;
+  a.K = s->K;
+  a.n = s->n;
+  a.halo = s->halo;
+  a.hL = s->hL;
+  a.hR = s->hR;
+  a.send_off = s->send_off;
+  a.epoch = comm_next_epoch(h, 1);
+  a.stop = stop;
+  cnmf_halo_kernel<<<1, 256, 0, h->stream>>>(a);
+  return check_launch(h, "cnmf_halo");
+}
+
 int enqueue_hstack(nmfb_handle* h, CnmfState* s, const int* stop) {
-  hstack_kernel<<<vec_grid(s->n, s->KT), 256, 0, h->stream>>>(s->Hm, s->Hs, s->K, s->T, s->n, s->ldh, stop);
+  NMFB_TRY(enqueue_halo(h, s, stop));
+  hstack_kernel<<<vec_grid(s->nx, s->KT), 256, 0, h->stream>>>(s->Hm, s->Hs, s->K, s->T, s->nx, s->ldhm, s->ldh, s->hL, stop);
   return check_launch(h, "hstack");
 }
 
@@ -133,7 +208,7 @@ int enqueue_iteration_two_weight(nmfb_handle* h, CnmfState* s, int i) {
   }
   NMFB_TRY(run_gemm(h, s->gemmPn));
   NMFB_TRY(run_gemm(h, s->gemmPd));
-  fold_update_kernel<<<vec_grid(s->n, s->K), 256, 0, h->stream>>>(s->P, s->D, s->Hm, s->K, s->T, s->n, s->ldh,
+  fold_update_kernel<<<vec_grid(s->n, s->K), 256, 0, h->stream>>>(s->P, s->D, s->Hm, s->K, s->T, s->n, s->nx, s->ldh, s->ldhm,
                                                                   s->lambda_h, s->H_fixed ? 1 : 0, s->scal, stop,
                                                                   s->expo, s->kl_quirk ? 1 : 0);
   return check_launch(h, "fold_update");
@@ -147,10 +222,23 @@ int enqueue_iteration(nmfb_handle* h, CnmfState* s, int i) {
     NMFB_TRY(enqueue_hstack(h, s, stop));
     NMFB_TRY(run_gram(h, s->gramH, stop));
   }
+  if (s->multi) {  // partial sums over the column shards: [A | Hs Hs'] and the scalars in one all-reduce
+    if (!s->W_fixed) NMFB_TRY(run_gemm(h, s->gemmA));
+    const size_t nA = static_cast<size_t>(s->KTp) * s->ldw, nG = static_cast<size_t>(s->KTp) * s->KTp;
+    const bool sendA = !s->W_fixed, sendG = !s->H_fixed || i == 0;  // (a fixed H keeps its summed Gram matrix)
+    float* first = sendA ? s->packed : (sendG ? s->packed + nA : nullptr);
+    NMFB_TRY(comm_allreduce(h, first, (sendA ? nA : 0) + (sendG ? nG : 0), nullptr, 0, s->scal, 4));
+    if (sendG) {
+      const int cnt = s->KTp * s->KTp;
+      round_copy_kernel<<<dim3((cnt + 255) / 256, 1), 256, 0, h->stream>>>(s->gramH.g32, s->gramH.gtf, 1, cnt, cnt, stop);
+      NMFB_TRY(check_launch(h, "round_copy(G_H)"));
+    }
+  }
   if (i > 0) NMFB_TRY(enqueue_cost(h, s, i - 1));
   if (!s->W_fixed) {
     NMFB_TRY(prof_mark(h, 0));
-    NMFB_TRY(run_gemm(h, s->gemmA));  // A = V Hs', B = Wc (Hs Hs')
+    if (s->multi) NMFB_TRY(run_gemm(h, s->gemmB));  // B = Wc (Hs Hs') with the summed Gram matrix
+    else NMFB_TRY(run_gemm(h, s->gemmA));           // A = V Hs', B = Wc (Hs Hs')
     NMFB_TRY(prof_mark(h, 0));
     WStepArgs w{};  // dots, multiplicative step and per-basis normalisation in one launch (CTA per basis)
     w.mode = WSTEP_EUCLID;
@@ -177,7 +265,7 @@ int enqueue_iteration(nmfb_handle* h, CnmfState* s, int i) {
   NMFB_TRY(run_gemm(h, s->gemmP));
   NMFB_TRY(prof_mark(h, 1));
   NMFB_TRY(prof_mark(h, 2));
-  fold_update_kernel<<<vec_grid(s->n, s->K), 256, 0, h->stream>>>(s->P, s->D, s->Hm, s->K, s->T, s->n, s->ldh,
+  fold_update_kernel<<<vec_grid(s->n, s->K), 256, 0, h->stream>>>(s->P, s->D, s->Hm, s->K, s->T, s->n, s->nx, s->ldh, s->ldhm,
                                                                   s->lambda_h, s->H_fixed ? 1 : 0, s->scal,
                                                                   stop);
   NMFB_TRY(check_launch(h, "fold_update"));
@@ -194,7 +282,7 @@ int cnmf_finish(nmfb_handle* h, CnmfState* s, float* W_out, float* H_out, double
   if (cost_out && nc > 0)
     NMFB_CUDA(h, cudaMemcpy(cost_out, s->cost, nc * sizeof(double), cudaMemcpyDeviceToHost));
   if (W_out) NMFB_TRY(download_colmajor(h, s->Wm, s->ldw, s->m, s->KT, W_out));
-  if (H_out) NMFB_TRY(download_H(h, s->Hm, s->ldh, s->K, s->n, H_out));
+  if (H_out) NMFB_TRY(download_H(h, s->Hm, s->ldhm, s->K, s->n, H_out));
   return NMFB_OK;
 }
 
@@ -202,8 +290,9 @@ int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_
              float* H_out, double* cost_out, int* n_cost) {
   if (h->Vraw == nullptr) return h->fail(NMFB_ERR_NO_DATA, "cnmf: call nmfb_set_V first");
   if (K <= 0 || T <= 0) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "cnmf: K and context_len must be positive");
-  if (comm_size(h->comm) > 1)
-    return h->fail(NMFB_ERR_UNSUPPORTED, "cnmf: column sharding needs a (T-1)-column halo exchange; single GPU only");
+  s->multi = comm_size(h->comm) > 1;
+  s->nranks = comm_size(h->comm);
+  s->rank = comm_rank(h->comm);
   nmfb_config cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   if (cfg_in) cfg = *cfg_in;
@@ -246,7 +335,44 @@ int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_
   s->m = m;
   s->n = n;
   s->ldw = round_up(m, 4);
-  s->ldh = round_up(n, 4);
+  s->nx = n;
+  s->ldh = s->ldhm = round_up(n, 4);
+  char* region = nullptr;
+  size_t vhalo_off = 0;
+  if (s->multi) {
+    if (s->two_weight)
+      return h->fail(NMFB_ERR_UNSUPPORTED, "cnmf on several GPUs: 'euclidean' / 'frobenius' only");
+    s->halo = T - 1;
+    // region = [A (KTp x ldw) | Hs Hs' (KTp x KTp)] [scal 8 | shard sizes 8 doubles] [V halo: halo x ldv] [H columns 2 x K x halo]
+    const size_t nA = static_cast<size_t>(s->KTp) * s->ldw, nG = static_cast<size_t>(s->KTp) * s->KTp;
+    const size_t dbl_off = ((nA + nG) * sizeof(float) + 255) / 256 * 256;
+    vhalo_off = dbl_off + 256;
+    const size_t send_off = vhalo_off + (static_cast<size_t>(std::max(1, s->halo)) * h->ldv * sizeof(float) + 255) / 256 * 256;
+    const size_t total = send_off + 2 * static_cast<size_t>(K) * std::max(1, s->halo) * sizeof(float);
+    NMFB_TRY(comm_acquire_region(h, total, &region));
+    if (!comm_peer_table(h, nullptr))
+      return h->fail(NMFB_ERR_UNSUPPORTED, "cnmf on several GPUs needs peer access between them (CUDA IPC over NVLink)");
+    s->packed = reinterpret_cast<float*>(region);
+    s->scal = reinterpret_cast<double*>(region + dbl_off);
+    s->send_off = comm_region_offset(h, region) + send_off;
+    // every rank learns all shard widths: halos only reach the direct neighbours
+    double* table = s->scal + 8;
+    double mine = n;
+    NMFB_CUDA(h, cudaMemcpyAsync(table + s->rank, &mine, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    NMFB_TRY(comm_allreduce(h, nullptr, 0, table, s->nranks, nullptr, 0));
+    double widths[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    NMFB_CUDA(h, cudaMemcpyAsync(widths, table, s->nranks * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int q = 0; q < s->nranks; ++q)
+      if (widths[q] < s->halo)
+        return h->fail(NMFB_ERR_INVALID_ARGUMENT, "cnmf on several GPUs: every shard needs at least context_len - 1 = %d "
+                                                  "columns (rank %d has %d)", s->halo, q, static_cast<int>(widths[q]));
+    s->hL = s->rank > 0 ? s->halo : 0;
+    s->hR = s->rank + 1 < s->nranks ? s->halo : 0;
+    s->nx = n + s->hR;
+    s->ldh = round_up(s->nx, 4);
+    s->ldhm = round_up(s->hL + n + s->hR, 4);
+  }
   s->W_fixed = cfg.W_fixed != 0;
   s->H_fixed = cfg.H_fixed != 0;
   s->lambda_w = static_cast<float>(cfg.W_sparsity);
@@ -257,9 +383,11 @@ int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_
   Arena* ar = &s->ar;
   NMFB_TRY(ar->alloc(h, &s->Wm, static_cast<size_t>(KTp) * s->ldw));
   NMFB_TRY(ar->alloc(h, &s->Wt, static_cast<size_t>(KTp) * s->ldw));
-  NMFB_TRY(ar->alloc(h, &s->Hm, static_cast<size_t>(K) * s->ldh));
+  NMFB_TRY(ar->alloc(h, &s->Hx, static_cast<size_t>(K) * s->ldhm));
+  s->Hm = s->Hx + s->hL;
   NMFB_TRY(ar->alloc(h, &s->Hs, static_cast<size_t>(KTp) * s->ldh));
-  NMFB_TRY(ar->alloc(h, &s->A, static_cast<size_t>(KTp) * s->ldw));
+  if (s->multi) s->A = s->packed;
+  else NMFB_TRY(ar->alloc(h, &s->A, static_cast<size_t>(KTp) * s->ldw));
   NMFB_TRY(ar->alloc(h, &s->B, static_cast<size_t>(KTp) * s->ldw));
   NMFB_TRY(ar->alloc(h, &s->P, static_cast<size_t>(KTp) * s->ldh));
   NMFB_TRY(ar->alloc(h, &s->D, static_cast<size_t>(KTp) * s->ldh));
@@ -270,7 +398,7 @@ int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_
   NMFB_TRY(ar->alloc(h, &s->ab, 4 * KTp));  // [ab | norm2 | wsum]: WStepArgs::acc
   s->norm2 = s->ab + 2 * KTp;
   s->wsum = s->ab + 3 * KTp;
-  NMFB_TRY(ar->alloc(h, &s->scal, 8));
+  if (!s->multi) NMFB_TRY(ar->alloc(h, &s->scal, 8));
   NMFB_TRY(ar->alloc(h, &s->cost, static_cast<size_t>(s->maxiter) + 1));
   NMFB_TRY(ar->alloc(h, &s->stop, 2));
 
@@ -290,7 +418,7 @@ int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_
       fill_uniform(tmp, cfg.seed * 2 + 2, true);
       Hsrc = tmp.data();
     }
-    NMFB_TRY(upload_H(h, ar, Hsrc, K, n, s->Hm, s->ldh));
+    NMFB_TRY(upload_H(h, ar, Hsrc, K, n, s->Hm, s->ldhm));
     NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   // cnmf.m:157-166: W(:,k,:) /= w_norm, H(k,:) *= w_norm with w_norm = |W(:,k,:)|_F / T
@@ -299,12 +427,33 @@ int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_
   w_normalize_kernel<<<vec_grid(m, KT), 256, 0, h->stream>>>(s->Wm, s->Wt, m, s->ldw, K, T, 1, s->norm2,
                                                              s->wsum, s->hscale, nullptr);
   NMFB_TRY(check_launch(h, "w_normalize(init)"));
-  row_scale_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, nullptr, n, s->ldh, s->hscale, 0);
+  row_scale_kernel<<<vec_grid(n, K), 256, 0, h->stream>>>(s->Hm, nullptr, n, s->ldhm, s->hscale, 0);
   NMFB_TRY(check_launch(h, "row_scale(H init)"));
 
   double* sq = nullptr;
   NMFB_TRY(ar->alloc(h, &sq, 1));
   NMFB_TRY(prepare_v_work(h, false, true, sq, nullptr));
+  s->Vmma = h->Vwork;
+  if (s->multi) {
+    NMFB_TRY(comm_allreduce(h, nullptr, 0, sq, 1, nullptr, 0));  // |V|^2 over all column shards
+    // V with the T-1 columns that follow the shard (cnmf.m:219 shifts V left): own columns + the right
+    // neighbour's first ones, fetched once through the peer region
+    NMFB_TRY(ar->alloc(h, &s->Vx, static_cast<size_t>(s->nx) * h->ldv));
+    NMFB_CUDA(h, cudaMemcpyAsync(s->Vx, h->Vwork, static_cast<size_t>(n) * h->ldv * sizeof(float), cudaMemcpyDeviceToDevice,
+                                 h->stream));
+    if (s->halo > 0) {
+      NMFB_CUDA(h, cudaMemcpyAsync(region + vhalo_off, h->Vwork, static_cast<size_t>(s->halo) * h->ldv * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, h->stream));
+      NMFB_TRY(comm_allreduce(h, nullptr, 0, nullptr, 0, s->scal, 4));  // (zeros) - used as a barrier: halos are published
+      PeerTable t;
+      comm_peer_table(h, &t);
+      if (s->hR > 0)
+        NMFB_CUDA(h, cudaMemcpyAsync(s->Vx + static_cast<size_t>(n) * h->ldv,
+                                     t.base[s->rank + 1] + comm_region_offset(h, region) + vhalo_off,
+                                     static_cast<size_t>(s->hR) * h->ldv * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    s->Vmma = s->Vx;
+  }
   NMFB_CUDA(h, cudaMemcpyAsync(&s->vsq, sq, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
 
@@ -352,21 +501,29 @@ int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_
     return cnmf_finish(h, s, W_out, H_out, cost_out, n_cost);
   }
   NMFB_TRY(plan_gram(h, ar, &s->gramW, s->Wt, KTp, m, s->ldw, stop));
-  NMFB_TRY(plan_gram(h, ar, &s->gramH, s->Hs, KTp, n, s->ldh, stop));
+  NMFB_TRY(plan_gram(h, ar, &s->gramH, s->Hs, KTp, n, s->ldh, stop));  // own columns only
+  if (s->multi) s->gramH.g32 = s->packed + static_cast<size_t>(KTp) * s->ldw;  // behind A: one all-reduce
   {
-    MatRef Xv{h->Vwork, m, n, h->ldv, true};
+    const int nx = s->nx;  // own + right-halo columns
+    MatRef Xv{s->Vmma, m, n, h->ldv, true};
     MatRef Yh{s->Hs, n, KTp, s->ldh, false};
     MatRef Xw{s->Wt, m, KTp, s->ldw, true};
     MatRef Yg{s->gramH.gtf, KTp, KTp, KTp, false};
     const int tiles = (m + kTileM - 1) / kTileM * ((KTp + kMaxN - 1) / kMaxN);
-    NMFB_TRY(plan_store(h, ar, &s->gemmA, Xv, Yh, n, &Xw, &Yg, KTp, m, KTp, s->A, s->B, s->ldw,
-                        tiles * 2 <= h->num_sms, stop));
-    MatRef Xvt{h->Vwork, m, n, h->ldv, false};
+    if (s->multi) {  // A is a partial sum: B = Wc (Hs Hs') waits for the all-reduce
+      NMFB_TRY(plan_store(h, ar, &s->gemmA, Xv, Yh, n, nullptr, nullptr, 0, m, KTp, s->A, nullptr, s->ldw,
+                          tiles * 2 <= h->num_sms, stop));
+      NMFB_TRY(plan_store(h, ar, &s->gemmB, Xw, Yg, KTp, nullptr, nullptr, 0, m, KTp, s->B, nullptr, s->ldw, false, stop));
+    } else {
+      NMFB_TRY(plan_store(h, ar, &s->gemmA, Xv, Yh, n, &Xw, &Yg, KTp, m, KTp, s->A, s->B, s->ldw,
+                          tiles * 2 <= h->num_sms, stop));
+    }
+    MatRef Xvt{s->Vmma, m, nx, h->ldv, false};
     MatRef Yw{s->Wt, m, KTp, s->ldw, false};
-    MatRef Xh{s->Hs, n, KTp, s->ldh, true};
+    MatRef Xh{s->Hs, nx, KTp, s->ldh, true};
     MatRef Ygw{s->gramW.gtf, KTp, KTp, KTp, false};
-    const int tiles_h = (n + kTileM - 1) / kTileM * ((KTp + kMaxN - 1) / kMaxN);
-    NMFB_TRY(plan_store(h, ar, &s->gemmP, Xvt, Yw, m, &Xh, &Ygw, KTp, n, KTp, s->P, s->D, s->ldh,
+    const int tiles_h = (nx + kTileM - 1) / kTileM * ((KTp + kMaxN - 1) / kMaxN);
+    NMFB_TRY(plan_store(h, ar, &s->gemmP, Xvt, Yw, m, &Xh, &Ygw, KTp, nx, KTp, s->P, s->D, s->ldh,
                         tiles_h * 2 <= h->num_sms, stop));
   }
   if (s->W_fixed) NMFB_TRY(run_gram(h, s->gramW, nullptr));
@@ -378,6 +535,8 @@ int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_
   // cost of the last executed iteration needs Hs Hs' of the final H
   NMFB_TRY(enqueue_hstack(h, s, stop));
   NMFB_TRY(run_gram(h, s->gramH, stop));
+  if (s->multi)
+    NMFB_TRY(comm_allreduce(h, s->gramH.g32, static_cast<size_t>(KTp) * KTp, nullptr, 0, s->scal, 4));
   NMFB_TRY(enqueue_cost(h, s, s->maxiter - 1));
   return cnmf_finish(h, s, W_out, H_out, cost_out, n_cost);
 }

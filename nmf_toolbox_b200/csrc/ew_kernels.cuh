@@ -742,19 +742,24 @@ __global__ void tied_update_kernel(const float* __restrict__ Nparts, int splits,
 
 // ---------------------------------------------------------------- convolutive helpers
 // Hs[k + K*t][j] = tf32(H[k][j - t]) for j >= t, else 0   (cnmf.m:188, RFD.m:37)
+// Column shards (several GPUs): H points at the shard's first own column inside a buffer that holds `left`
+// columns of the left neighbour before it (the halo), so the shift reaches back to j - t >= -left; n then
+// also covers the right halo columns.  ldh / lds: leading dimensions of H and Hs.
 __global__ void hstack_kernel(const float* __restrict__ H, float* __restrict__ Hs, int K, int T, int n,
-                              long long ld, const int* stop) {
+                              long long ldh, long long lds, int left, const int* stop) {
   NMFB_STOP_GUARD(stop);
   const int c = blockIdx.y;  // 0 .. K*T-1
   const int k = c % K, t = c / K;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
-    Hs[c * ld + j] = (j >= t) ? tf32_rn(H[k * ld + (j - t)]) : 0.f;
+    Hs[c * lds + j] = (j + left >= t) ? tf32_rn(H[k * ldh + (j - t)]) : 0.f;
 }
 
 // neg[k][j] = sum_t P[k+K*t][j+t], pos likewise from D (cnmf.m:218-227, euclidean);
 // H <- H .* neg ./ max(pos + lambda, eps) (cnmf.m:231); scal[0] += <neg, tf32(Hnew)>, scal[1] += sum Hnew
+// n_src >= n: columns available in P and D (a column shard also holds the T-1 columns that follow it);
+// ldp / ld: leading dimensions of P, D and of H.
 __global__ void fold_update_kernel(const float* __restrict__ P, const float* __restrict__ D,
-                                   float* __restrict__ H, int K, int T, int n, long long ld,
+                                   float* __restrict__ H, int K, int T, int n, int n_src, long long ldp, long long ld,
                                    float lambda, int freeze, double* scal, const int* stop,
                                    float expo = 0.f, int pos_unshifted = 0) {
   // expo: outer exponent of both gradients (AB divergence, cnmf.m:229-232); pos_unshifted: the KL
@@ -769,8 +774,8 @@ __global__ void fold_update_kernel(const float* __restrict__ P, const float* __r
     // branch-free body (clamped index + select) so that the 2T loads of a thread are issued together
 #pragma unroll 4
     for (int t = 0; t < T; ++t) {
-      const bool ok = j + t < n;
-      const long long row = static_cast<long long>(k + K * t) * ld;
+      const bool ok = j + t < n_src;
+      const long long row = static_cast<long long>(k + K * t) * ldp;
       const float p = P[row + (ok ? j + t : j)];
       const float d = D[row + ((ok && !pos_unshifted) ? j + t : j)];
       neg += ok ? p : 0.f;

@@ -78,6 +78,7 @@ struct NmfSession {
   double ab_scale = 0.0; // -1/(alpha beta) of the AB cost (nmf.m:214)
   KlOp klW, klH;         // fused KL halves (kl_fused.cuh)
   bool kl_fused = false;
+  bool kl_store_n = false;  // unfused KL whose H step needs N = W'Q as a matrix (lnmf, per-source settings, tied Z)
   // constrainednmf.m: H = Z*A, A the 0/1 label matrix (columns of H tied to columns of Z)
   bool tied = false;
   int nz = 0;
@@ -613,12 +614,10 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
         s->kl_fused = true;
       }
     }
-    if (!s->kl_fused && s->lnmf)
-      return h->fail(NMFB_ERR_UNSUPPORTED, "lnmf needs the fused KL kernel (num_basis_elems <= 128)");
-    if (!s->kl_fused && s->tied)
-      return h->fail(NMFB_ERR_UNSUPPORTED, "constrainednmf with the KL divergence needs the fused KL kernel (num_basis_elems <= 128)");
-    if (!s->kl_fused && s->per_basis)
-      return h->fail(NMFB_ERR_UNSUPPORTED, "per-source settings with the unfused KL path (K > 128)");
+    // lnmf's square-root step, per-source settings and the label-tied Z step are not forms of the fused
+    // H-update epilogue: without the fused KL kernel (K > 128) they take N = W'Q as a stored matrix and
+    // finish in kl_h_finish / tied_update
+    s->kl_store_n = !s->kl_fused && (s->lnmf || s->tied || s->per_basis);
     if (!s->kl_fused) {
     // Unfused fallback (K > 128 or not enough memory for the row-major copy of V):
     // S = W H (both operands MN-major), Q = V ./ S materialised in HBM
@@ -645,6 +644,12 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     // H update: N = W'Q, D = ws
     MatRef Xqt{s->Q, m, n, h->ldv, false};
     MatRef Yw{s->Wt, m, Kp, s->ldw, false};
+    if (s->kl_store_n) {
+      NMFB_TRY(ar->alloc(h, &s->Nbuf, static_cast<size_t>(Kp) * s->ldh));
+      const int tiles_h = (n + kTileM - 1) / kTileM * ((Kp + kMaxN - 1) / kMaxN);
+      NMFB_TRY(plan_store(h, ar, &s->gemmH, Xqt, Yw, m, nullptr, nullptr, 0, n, Kp, s->Nbuf, nullptr, s->ldh,
+                          tiles_h * 2 <= h->num_sms, stop));
+    } else {
     NMFB_TRY(plan_fused(h, &s->gemmH, EPI_HUPDATE, Xqt, Yw, m, nullptr, nullptr, 0, n, Kp, Kp, stop));
     GemmArgs& a = s->gemmH.L.args;
     a.Hm = s->Hm;
@@ -658,6 +663,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     if (!std::getenv("NMFB_NO_HPREFETCH")) {
       std::string e = set_h_prefetch(&s->gemmH.L, s->Hm, n, Kp, s->ldh);
       if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "%s", e.c_str());
+    }
     }
     }
   }
@@ -1091,6 +1097,14 @@ static int enqueue_iteration(nmfb_handle* h, NmfSession* s, int i) {
       }
     } else {
       NMFB_TRY(run_gemm(h, s->gemmH));
+      if (s->kl_store_n && s->tied) {
+        NMFB_TRY(enqueue_tied_update(h, s, s->Nbuf, 1, 0, s->ldh, nullptr, s->wsf, 0.f));
+      } else if (s->kl_store_n) {
+        kl_h_finish_kernel<<<dim3(std::max(1, std::min(64, (n + 1023) / 1024)), K), 256, 0, h->stream>>>(
+            s->Nbuf, 1, 0, s->ldh, s->Hm, s->Ht, s->ldh, s->wsf, s->lambda_h, n, s->H_fixed ? 1 : 0, s->scal, stop,
+            s->lamH_k, s->fixH_k, s->lnmf ? 1 : 0);
+        NMFB_TRY(check_launch(h, "kl_h_finish"));
+      }
     }
   }
   return NMFB_OK;

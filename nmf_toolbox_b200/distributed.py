@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["shard_bounds", "shard_columns", "init_comm", "nmf_sharded", "pack_layout"]
+__all__ = ["shard_bounds", "shard_columns", "init_comm", "nmf_sharded", "cnmf_sharded", "pack_layout"]
 
 
 def shard_bounds(n: int, world: int, rank: int):
@@ -58,3 +58,16 @@ def nmf_sharded(handle, dist, V_shard, num_basis_elems, config, rank: int, world
     init_comm(handle, dist, rank, world)
     handle.set_V(V_shard)
     return handle.nmf(int(num_basis_elems), config)
+
+
+def cnmf_sharded(handle, dist, V_shard, num_basis_elems, context_len, config, rank: int, world: int):
+    """``cnmf`` ('euclidean' / 'frobenius') on this rank's block of CONSECUTIVE columns (time frames) of V.
+    ``config['H_init']`` is the rank's shard of H_init, ``config['W_init']`` the full m x K x T tensor.  The
+    engine exchanges the (context_len - 1)-column halos of H (every iteration) and of V (once) with the
+    neighbouring ranks itself; every shard must hold at least context_len - 1 columns.
+    Returns (W replicated, H shard, global cost trace)."""
+    if config is None or config.get("W_init") is None or config.get("H_init") is None:
+        raise ValueError("sharded runs need explicit W_init / H_init (every rank must start from the same W)")
+    init_comm(handle, dist, rank, world)
+    handle.set_V(V_shard)
+    return handle.cnmf(int(num_basis_elems), int(context_len), config)

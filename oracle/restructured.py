@@ -169,6 +169,88 @@ def cnmf_stacked(V, K, T, config):
     return W3, H, cost
 
 
+def cnmf_stacked_sharded(V, K, T, config, shards):
+    """cnmf.m, Euclidean, as cnmf_driver.cu runs it on `shards` column-sharded ranks (simulated in one
+    process): every rank owns consecutive columns [lo, hi) of V and H, keeps the T-1 columns of H before and
+    after them and the T-1 columns of V after them (halos), forms Hs, P = Wc'V and D = (Wc'Wc)Hs on own + halo
+    columns and folds for its own columns; A = V Hs', Hs Hs' and the scalar sums are summed over the ranks,
+    the W step is replicated.  Must agree with the literal cnmf to rounding for any `shards`."""
+    V = np.asarray(V, dtype=np.float64)
+    m, n = V.shape
+    lamW = max(float(config.get("W_sparsity", 0) or 0), 0.0)
+    lamH = max(float(config.get("H_sparsity", 0) or 0), 0.0)
+    maxiter = int(config.get("maxiter", 100) or 100)
+    h = T - 1
+    W3 = np.array(config["W_init"], dtype=np.float64)
+    H = np.array(config["H_init"], dtype=np.float64)
+    wn = np.sqrt(np.sum(W3 ** 2, axis=(0, 2))) / T
+    W3 = W3 / wn[None, :, None]
+    H = H * wn[:, None]
+    Wc = np.concatenate([W3[:, :, t] for t in range(T)], axis=1)
+    bounds = _col_blocks(n, shards)
+    assert all(hi - lo >= h for lo, hi in bounds), "every shard needs at least T-1 columns"
+    Hown = [H[:, lo:hi].copy() for lo, hi in bounds]  # each rank's own columns
+    vsq = np.sum(V ** 2)
+    cost = np.zeros(maxiter)
+
+    def local_views(r):
+        """(hL, hR, H with halos, Hs over own + right-halo columns) of rank r after a halo exchange."""
+        lo, hi = bounds[r]
+        hL = h if r > 0 else 0
+        hR = h if r + 1 < shards else 0
+        left = Hown[r - 1][:, Hown[r - 1].shape[1] - hL:] if hL else np.zeros((K, 0))
+        right = Hown[r + 1][:, :hR] if hR else np.zeros((K, 0))
+        Hx = np.concatenate([left, Hown[r], right], axis=1)
+        nx = (hi - lo) + hR
+        Hs = np.zeros((K * T, nx))
+        for t in range(T):  # hstack_kernel: Hs_t[:, j] = Hx[:, hL + j - t] when j + hL >= t
+            for j in range(nx):
+                if j + hL >= t:
+                    Hs[t * K:(t + 1) * K, j] = Hx[:, hL + j - t]
+        return hL, hR, Hs
+
+    for it in range(maxiter):
+        A = np.zeros((m, K * T))
+        G = np.zeros((K * T, K * T))
+        loc = []
+        for r, (lo, hi) in enumerate(bounds):
+            hL, hR, Hs = local_views(r)
+            nown = hi - lo
+            A += V[:, lo:hi] @ Hs[:, :nown].T       # own columns only
+            G += Hs[:, :nown] @ Hs[:, :nown].T
+            loc.append((hR, Hs))
+        B = Wc @ G
+        av = np.sum(Wc * A, axis=0)
+        bv = np.sum(Wc * B, axis=0)
+        Wc = Wc * ((A + Wc * bv) / np.fmax(B + Wc * av + lamW, EPS))
+        ss = np.sum(Wc ** 2, axis=0).reshape(T, K).sum(axis=0)
+        Wc = Wc / np.tile(np.sqrt(ss) / T, T)[None, :]
+        GW = Wc.T @ Wc
+        dot_nh = 0.0
+        for r, (lo, hi) in enumerate(bounds):
+            hR, Hs = loc[r]
+            nown = hi - lo
+            P = Wc.T @ V[:, lo:hi + hR]              # own + right-halo columns of V
+            D = GW @ Hs
+            neg = np.zeros((K, nown))
+            pos = np.zeros((K, nown))
+            for t in range(T):                       # fold_update_kernel: j + t < n_src
+                w = min(nown, nown + hR - t)
+                neg[:, :w] += P[t * K:(t + 1) * K, t:t + w]
+                pos[:, :w] += D[t * K:(t + 1) * K, t:t + w]
+            Hown[r] = Hown[r] * (neg / np.fmax(pos + lamH, EPS))
+            dot_nh += np.sum(neg * Hown[r])          # <fold(P), H_new> = <P, Hs_new> summed over the ranks
+        G2 = np.zeros((K * T, K * T))
+        for r, (lo, hi) in enumerate(bounds):
+            _, _, Hs = local_views(r)
+            G2 += Hs[:, :hi - lo] @ Hs[:, :hi - lo].T
+        c = 0.5 * (vsq - 2.0 * dot_nh + np.sum(GW * G2))
+        c += lamW * np.sum(np.abs(Wc)) + lamH * sum(np.sum(np.abs(x)) for x in Hown)
+        cost[it] = c
+    W3 = np.stack([Wc[:, t * K:(t + 1) * K] for t in range(T)], axis=2)
+    return W3, np.concatenate(Hown, axis=1), cost
+
+
 # --------------------------------------------------------------------------
 # IS / AB divergences ("two-weight" form of nmf_driver.cu::plan_two_weight and
 # cnmf_driver.cu): both gradients are contractions with element-wise weights.

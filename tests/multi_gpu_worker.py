@@ -42,7 +42,15 @@ def main():
     cfg = dict(divergence=div, W_init=W0, H_init=H0[:, lo:hi], maxiter=iters, tolerance=1e-300,
                W_sparsity=0.05, H_sparsity=0.1)
     cfg.update(variant_config(variant, K))
-    W, H, cost = nmf_sharded(h, dist, V[:, lo:hi], K, cfg, rank, world)
+    if variant.startswith("cnmf"):  # convolutive: column shards with (T-1)-column halos
+        from nmf_toolbox_b200.distributed import cnmf_sharded
+        T = int(variant[4:])
+        W0 = rng.random((m, K, T)) + 1e-3
+        cfg = dict(divergence=div, W_init=W0, H_init=H0[:, lo:hi], maxiter=iters, tolerance=1e-300,
+                   W_sparsity=0.05, H_sparsity=0.1)
+        W, H, cost = cnmf_sharded(h, dist, V[:, lo:hi], K, T, cfg, rank, world)
+    else:
+        W, H, cost = nmf_sharded(h, dist, V[:, lo:hi], K, cfg, rank, world)
     parts = [None] * world
     dist.all_gather_object(parts, (lo, hi, H))
     if rank == 0:

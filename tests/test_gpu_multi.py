@@ -68,3 +68,43 @@ def test_multi_gpu_matches_single_and_oracle(div, variant, w_shard, m, nproc, tm
     np.testing.assert_allclose(got["cost"], co, rtol=1e-4)
     R, Ro = got["W"].astype(np.float64) @ got["H"].astype(np.float64), Wo @ Ho
     assert np.linalg.norm(R - Ro) / np.linalg.norm(Ro) < 1e-3
+
+
+@pytest.mark.parametrize("div,T,n,nproc", [("euclidean", 4, 1000, 2), ("frobenius", 8, 517, 2), ("euclidean", 5, 1203, 4),
+                                           ("euclidean", 8, 2000, 8)])
+def test_multi_gpu_cnmf_halo(div, T, n, nproc, tmp_path):
+    """cnmf.m on column shards: the shifts of cnmf.m:188,219 reach T-1 columns into the neighbouring shards (halo
+    exchange of H per iteration, of V once); same cost curve as one GPU and as the oracle, W identical on all ranks."""
+    import torch
+
+    if torch.cuda.device_count() < nproc:
+        pytest.skip("needs %d GPUs" % nproc)
+    from nmf_toolbox_b200 import api
+    from oracle import nmf_oracle as O
+
+    m, K, iters = 200, 8, 25
+    out = str(tmp_path / "multi.npz")
+    port = 29600 + os.getpid() % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc, "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_worker.py"), out, div, str(m),
+           str(n), str(K), str(iters), "cnmf%d" % T]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    got = np.load(out)
+    rng = np.random.default_rng(21)  # the worker's stream: V, (W0 of nmf), H0, then the cnmf tensor
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    rng.random((m, K))
+    H0 = rng.random((K, n)) + 1e-3
+    W0 = rng.random((m, K, T)) + 1e-3
+    cfg = dict(divergence=div, W_init=W0, H_init=H0, maxiter=iters, tolerance=1e-300, W_sparsity=0.05, H_sparsity=0.1)
+    h = api.Handle(0)
+    h.set_V(V)
+    W1, H1, c1 = h.cnmf(K, T, cfg)
+    h.close()
+    Wo, Ho, co = O.cnmf(V, K, T, cfg)
+    assert len(got["cost"]) == iters
+    np.testing.assert_allclose(got["cost"], c1, rtol=1e-5)
+    np.testing.assert_allclose(got["cost"], co, rtol=1e-4)
+    R = O.reconstruct_from_decomposition(got["W"].astype(np.float64), got["H"].astype(np.float64))
+    Ro = O.reconstruct_from_decomposition(Wo, Ho)
+    assert np.linalg.norm(R - Ro) / np.linalg.norm(Ro) < 1e-3

@@ -416,9 +416,32 @@ def test_lnmf_stop_leaves_cost_untrimmed(api, handle):
         W, H, c = api.lnmf(V, 4, cfg2, handle=handle)
         Wo, Ho, co = O.lnmf(V, 4, cfg2)
         assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
-    with pytest.raises(api.NmfbError) as e:  # the fused KL kernels hold at most 128 bases
-        api.lnmf(V, 130, dict(maxiter=2), handle=handle)
-    assert e.value.code == 3
+
+
+def test_kl_variants_beyond_the_fused_kernel(api, handle):
+    """K > 128 does not fit the fused KL kernel's tensor-memory plan: lnmf (lnmf.m:71-92), per-source settings
+    (nmf.m:51-60) and constrainednmf's Z step then run on the unfused contractions with N = W'(V./V_hat) stored."""
+    rng = np.random.default_rng(44)
+    m, n, K = 300, 420, 136
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    cfg = dict(W_init=rng.random((m, K)) + 1e-3, H_init=rng.random((K, n)) + 1e-3, maxiter=12, tolerance=1e-300)
+    W, H, c = api.lnmf(V, K, cfg, handle=handle)
+    Wo, Ho, co = O.lnmf(V, K, cfg)
+    assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
+    sizes = [100, 36]
+    cfg2 = dict(divergence="kl", W_init=[cfg["W_init"][:, :100], cfg["W_init"][:, 100:]],
+                H_init=[cfg["H_init"][:100], cfg["H_init"][100:]], W_sparsity=[0.0, 0.05], H_sparsity=[0.1, 0.0],
+                H_fixed=[False, True], maxiter=12, tolerance=1e-300)
+    W, H, c = api.nmf(V, sizes, cfg2, handle=handle)
+    Wo, Ho, co = O.nmf(V, sizes, cfg2)
+    assert cost_err(c, co) < COST_TOL
+    assert recon_err(np.concatenate(W, 1), np.concatenate(H, 0), np.concatenate(Wo, 1), np.concatenate(Ho, 0)) < RECON_TOL
+    labels = rng.integers(-1, 6, size=n)
+    nz = int((labels < 0).sum()) + 6
+    cfg3 = dict(divergence="kl", W_init=cfg["W_init"], Z_init=rng.random((K, nz)) + 1e-3, maxiter=12, tolerance=1e-300)
+    W, H, Z, A, c = api.constrainednmf(V, labels, K, cfg3, handle=handle)
+    Wo, Ho, Zo, Ao, co = O.constrainednmf(V, labels, K, cfg3)
+    assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
 
 
 # ---------------------------------------------------------------- constrainednmf (SURVEY 8f item 4)
@@ -450,15 +473,20 @@ def test_constrainednmf_vs_oracle(api, handle, div, extra, m, n, K, classes, unl
 def test_constrainednmf_ab_dual_and_errors(api, handle):
     rng = np.random.default_rng(9)
     m, n, K = 120, 150, 5
-    V = np.maximum(rng.random((m, n)), 2.0 ** -10)
+    V = 0.5 + rng.random((m, n))
     labels = rng.integers(-1, 3, size=n)
     nz = int((labels < 0).sum()) + 3
+    # dual updates (constrainednmf.m:128-132); as in nmf.m they collapse the encoding within a few iterations on
+    # the reference, so the factors are compared after two
     cfg = dict(divergence="ab", alpha=0, beta=1.0, W_init=rng.random((m, K)) + 1e-3, Z_init=rng.random((K, nz)) + 1e-3,
-               maxiter=15, tolerance=1e-300)
-    W, H, Z, A, c = api.constrainednmf(V, labels, K, cfg, handle=handle)  # dual updates (constrainednmf.m:128-132)
-    Wo, Ho, Zo, Ao, co = O.constrainednmf(V, labels, K, cfg)
-    assert recon_err(W, H, Wo, Ho) < RECON_TOL
-    assert np.all(~np.isfinite(c)) and np.all(~np.isfinite(co))  # -1/(alpha*beta) with alpha = 0 (constrainednmf.m:249)
+               maxiter=2, tolerance=1e-300)
+    W, H, Z, A, c = api.constrainednmf(V, labels, K, cfg, handle=handle)
+    with np.errstate(all="ignore"):
+        Wo, Ho, Zo, Ao, co = O.constrainednmf(V, labels, K, cfg)
+    assert np.isfinite(Wo).all() and np.isfinite(Zo).all()
+    np.testing.assert_allclose(W, Wo, rtol=5e-3, atol=1e-6)
+    np.testing.assert_allclose(Z, Zo, rtol=5e-3, atol=1e-12)
+    assert np.array_equal(np.isfinite(c), np.isfinite(co))  # -1/(alpha*beta) with alpha = 0 (constrainednmf.m:249)
     with pytest.raises(api.NmfbError) as e:  # constrainednmf.m:229 cannot be evaluated unless m == K
         api.constrainednmf(V, labels, K, dict(cfg, alpha=0.5), handle=handle)
     assert e.value.code == 3

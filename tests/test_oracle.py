@@ -328,3 +328,21 @@ def test_constrainednmf_reference_defects_reproduced():
         O.constrainednmf(V, lab[:-1], 4, dict(maxiter=2))
     W, H, Z, A, c = O.constrainednmf(V, lab, 4, dict(divergence="ab", alpha=0, beta=1.0, maxiter=5, tolerance=1e-300))
     assert len(c) == 5  # the dual branch (alpha = 0) is well defined; its cost is Inf/NaN (-1/(alpha*beta))
+
+
+@pytest.mark.parametrize("shards,T,n", [(2, 4, 61), (3, 5, 50), (4, 2, 33), (8, 8, 120), (2, 1, 20)])
+def test_cnmf_column_shards_with_halos_match_literal(shards, T, n):
+    """The halo scheme of cnmf_driver.cu for several GPUs (T-1 columns of H on both sides, of V on the right;
+    own-column partial sums of A = V Hs' and Hs Hs') simulated rank by rank equals the literal cnmf.m loop."""
+    from oracle import restructured as R
+
+    rng = np.random.default_rng(shards * 10 + T)
+    m, K = 23, 3
+    V = rng.random((m, n)) + 0.01
+    cfg = dict(divergence="euclidean", W_init=rng.random((m, K, T)) + 0.1, H_init=rng.random((K, n)) + 0.1, maxiter=12,
+               tolerance=1e-300, W_sparsity=0.03, H_sparsity=0.07)
+    Wo, Ho, co = O.cnmf(V, K, T, cfg)
+    Ws, Hs, cs = R.cnmf_stacked_sharded(V, K, T, cfg, shards)
+    np.testing.assert_allclose(cs, co, rtol=1e-10)
+    np.testing.assert_allclose(Ws, Wo, rtol=1e-9)
+    np.testing.assert_allclose(Hs, Ho, rtol=1e-9)
