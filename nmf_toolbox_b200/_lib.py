@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnmfb200.so")
+# NMFB_LIB: path of an alternative build of the same library (kernel-tuning experiments only)
+LIB_PATH = os.environ.get("NMFB_LIB") or os.path.join(_HERE, "libnmfb200.so")
 
 _lib = None
 

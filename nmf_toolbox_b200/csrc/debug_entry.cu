@@ -1,6 +1,7 @@
 // Kernel-level test hooks (C ABI, device pointers in/out).  Used only by tests/ to check panel_gemm against a
 // plain matmul on the same GPU.  NOT part of libnmfb200.so: built into tests/libnmfb200_test.so together with
 // gemm_host.cu (csrc/testlib.cu), so the product library exports nothing but include/nmfb200.h.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -11,9 +12,17 @@
 
 using namespace nmfb;
 
-static int debug_cg() {  // NMFB_DEBUG_CG=2 runs the kernel-level tests on the CTA-pair kernel
+// NMFB_DEBUG_CG=2 runs the kernel-level tests on the CTA-pair kernel, 4 on clusters of two pairs sharing the Y
+// slab by TMA multicast (shapes that kernel cannot take - odd number of 256-row tiles, slabs that are not
+// 128 / 256 columns wide - fall back to plain pairs)
+static int debug_cg(int rows = 0, int ncols = 0) {
   const char* e = std::getenv("NMFB_DEBUG_CG");
-  return (e && e[0] == '2') ? 2 : 1;
+  int cg = (e && e[0] == '4') ? 4 : (e && e[0] == '2') ? 2 : 1;
+  if (cg == 4) {
+    const int tiles = (rows + 2 * kTileM - 1) / (2 * kTileM);
+    if (tiles % 2 != 0 || std::min(ncols, kMaxN) % 128 != 0) cg = 2;
+  }
+  return cg;
 }
 
 static int fail(char* err, int errlen, const std::string& msg) {
@@ -51,7 +60,7 @@ int nmfb_debug_gemm_store(const nmfb_debug_mat* X0, const nmfb_debug_mat* Y0, lo
     y1 = GemmOperand{{Y1->base, Y1->inner, Y1->outer, Y1->pitch}, Y1->mn_major != 0};
   }
   std::string e = plan_gemm(&L, x0, y0, kdim0, two ? &x1 : nullptr, two ? &y1 : nullptr, kdim1, rows,
-                            ncols, splits, sms, debug_cg());
+                            ncols, splits, sms, debug_cg(rows, ncols));
   if (!e.empty()) return fail(err, errlen, e);
   L.args.out0 = out0;
   L.args.out1 = out1;
@@ -78,7 +87,7 @@ int nmfb_debug_gemm_hupdate(const nmfb_debug_mat* X0, const nmfb_debug_mat* Y0, 
   GemmOperand y0{{Y0->base, Y0->inner, Y0->outer, Y0->pitch}, Y0->mn_major != 0};
   GemmOperand x1{{X1->base, X1->inner, X1->outer, X1->pitch}, X1->mn_major != 0};
   GemmOperand y1{{Y1->base, Y1->inner, Y1->outer, Y1->pitch}, Y1->mn_major != 0};
-  std::string e = plan_gemm(&L, x0, y0, kdim0, &x1, &y1, kdim1, rows, ncols, 1, sms, debug_cg());
+  std::string e = plan_gemm(&L, x0, y0, kdim0, &x1, &y1, kdim1, rows, ncols, 1, sms, debug_cg(rows, ncols));
   if (!e.empty()) return fail(err, errlen, e);
   L.args.Hm = Hm;
   L.args.Hr32 = Hr32;

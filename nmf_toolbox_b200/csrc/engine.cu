@@ -34,7 +34,7 @@ static int plan_common(nmfb_handle* h, GemmOp* op, const MatRef& X0, const MatRe
     x1 = operand(*X1);
     y1 = operand(*Y1);
   }
-  const int cg = pair_eligible(rows, ncols, Y0.mn, Y1 ? Y1->mn : false) ? 2 : 1;
+  const int cg = choose_cg(op->epi, rows, ncols, Y0.mn, Y1 ? Y1->mn : false, tile_n);
   std::string e = plan_gemm(&op->L, x0, y0, kdim0, X1 ? &x1 : nullptr, X1 ? &y1 : nullptr, kdim1,
                             rows, ncols, splits_hint, h->num_sms, cg, tile_n);
   if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "plan_gemm: %s", e.c_str());

@@ -74,11 +74,24 @@ bool pair_eligible(int rows, int ncols, bool y_mn_major0, bool y_mn_major1) {
   return true;
 }
 
+int choose_cg(int epi, int rows, int ncols, bool y_mn_major0, bool y_mn_major1, int tile_n) {
+  if (!pair_eligible(rows, ncols, y_mn_major0, y_mn_major1)) return 1;
+  // Two pairs sharing the Y slab by TMA multicast (cluster of four): the Euclidean iteration's two kernels only,
+  // an even number of 256-row tiles, slabs of 128 / 256 columns.  NMFB_CTA_GROUP=2 keeps plain pairs.
+  const char* env = std::getenv("NMFB_CTA_GROUP");
+  const bool want4 = env ? env[0] == '4' : false;
+  const int tiles = (rows + 2 * kTileM - 1) / (2 * kTileM);
+  const int box_n = std::min(ncols, tile_n > 0 ? tile_n : kMaxN);
+  if (want4 && (epi == EPI_STORE || epi == EPI_HUPDATE) && tiles % 2 == 0 && box_n % 128 == 0) return 4;
+  return 2;
+}
+
 std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const GemmOperand& Y0, long long kdim0,
                       const GemmOperand* X1, const GemmOperand* Y1, long long kdim1, int rows,
                       int ncols, int splits_hint, int num_sms, int cg, int tile_n) {
   if (ncols <= 0 || ncols % 32 != 0) return "plan_gemm: ncols must be a positive multiple of 32";
-  if (cg != 1 && cg != 2) return "plan_gemm: cta group must be 1 or 2";
+  if (cg != 1 && cg != 2 && cg != 4) return "plan_gemm: cta group must be 1, 2 or 4 (two pairs sharing the Y slab)";
+  const int pair = cg >= 2 ? 2 : 1;
   std::memset(L, 0, sizeof(*L));
   L->cg = cg;
   GemmArgs& a = L->args;
@@ -98,21 +111,23 @@ std::string plan_gemm(GemmLaunch* L, const GemmOperand& X0, const GemmOperand& Y
   a.ymn0 = Y0.mn_major ? 1 : 0;
   a.ymn1 = (Y1 && Y1->mn_major) ? 1 : 0;
   a.ncols_valid = ncols;
-  const int tile_rows = kTileM * cg;
+  const int tile_rows = kTileM * pair;
   const int tiles = (rows + tile_rows - 1) / tile_rows;
+  if (cg == 4 && (tiles % 2 != 0 || a.box_n % 128 != 0))
+    return "plan_gemm: the cluster-of-four kernel needs an even number of 256-row tiles and slabs of 128 or 256 columns";
   const int chunks = (ncols + tn - 1) / tn;
   int splits = 1;
   a.kb_per_split = std::max(a.nkb0, 1);
   if (splits_hint != 1) {
     if (splits_hint <= 0) {
-      splits = choose_splits(tiles * chunks * cg, a.nkb0, num_sms, &a.kb_per_split);
+      splits = choose_splits(tiles * chunks * pair, a.nkb0, num_sms, &a.kb_per_split);
     } else {
       int per = std::max(1, (a.nkb0 + splits_hint - 1) / splits_hint);
       splits = std::max(1, (a.nkb0 + per - 1) / per);
       a.kb_per_split = per;
     }
   }
-  L->grid = dim3(tiles * cg, chunks, splits);
+  L->grid = dim3(tiles * pair, chunks, splits);
 
   std::string e;
   auto xmap = [&](CUtensorMap* tm, const GemmOperand& X) {
@@ -191,7 +206,7 @@ static cudaError_t set_smem_attr() {
 
 template <int EPI>
 static cudaError_t launch_one(const GemmLaunch& L, cudaStream_t stream) {
-  if (L.cg == 2) {
+  if (L.cg >= 2) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = L.grid;
     cfg.blockDim = dim3(kGemmThreads);
@@ -199,11 +214,17 @@ static cudaError_t launch_one(const GemmLaunch& L, cudaStream_t stream) {
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = L.cg;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if constexpr (EPI == EPI_STORE || EPI == EPI_HUPDATE) {  // the two kernels of the Euclidean iteration
+      if (L.cg == 4)
+        return cudaLaunchKernelEx(&cfg, panel_gemm_kernel<EPI, 4>, L.tmX0, L.tmY0, L.tmX1, L.tmY1, L.tmXb, L.tmYb,
+                                  L.tmXc, L.tmYc, L.tmH, L.args);
+    }
+    if (L.cg == 4) return cudaErrorInvalidValue;
     return cudaLaunchKernelEx(&cfg, panel_gemm_kernel<EPI, 2>, L.tmX0, L.tmY0, L.tmX1, L.tmY1, L.tmXb, L.tmYb,
                               L.tmXc, L.tmYc, L.tmH, L.args);
   }
@@ -216,7 +237,8 @@ std::string launch_gemm(const GemmLaunch& L, int epi, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&]() {
-    cudaError_t e[12] = {set_smem_attr<EPI_ABQ, 1>(),   set_smem_attr<EPI_ABQ, 2>(),
+    cudaError_t e[14] = {set_smem_attr<EPI_STORE, 4>(), set_smem_attr<EPI_HUPDATE, 4>(),
+                         set_smem_attr<EPI_ABQ, 1>(),   set_smem_attr<EPI_ABQ, 2>(),
                          set_smem_attr<EPI_STORE, 1>(), set_smem_attr<EPI_HUPDATE, 1>(),
                          set_smem_attr<EPI_RECON, 1>(), set_smem_attr<EPI_RESID, 1>(),
                          set_smem_attr<EPI_KLQ, 1>(),   set_smem_attr<EPI_STORE, 2>(),

@@ -44,6 +44,8 @@ struct GemmLaunch {
 
 // Whether the CTA-pair kernel can run this problem (and is worth it).
 bool pair_eligible(int rows, int ncols, bool y_mn_major0, bool y_mn_major1);
+// 1 = single CTAs, 2 = CTA pairs, 4 = clusters of two pairs sharing the Y slab by TMA multicast
+int choose_cg(int epi, int rows, int ncols, bool y_mn_major0, bool y_mn_major1, int tile_n);
 
 // Builds tensor maps + args for out = X0*Y0^T (+ second accumulator X1*Y1^T).
 //   rows  : valid rows of X (output rows);  ncols: output columns (multiple of 32)

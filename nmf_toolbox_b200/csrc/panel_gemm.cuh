@@ -47,6 +47,9 @@ constexpr int kTileM = 128;   // output rows per CTA = TMEM lanes
 constexpr int kBlockK = 32;   // fp32 elements per 128-byte swizzle row
 constexpr int kUmmaK = 8;     // tf32 MMA K
 constexpr int kStages = 4;
+#ifndef NMFB_PAIR_STAGES
+#define NMFB_PAIR_STAGES 6  // operand ring of the CTA-pair kernels: 6 x 32 KB (7 fits the 227 KB limit as well)
+#endif
 constexpr int kMaxN = 256;    // widest accumulator (fp32 TMEM columns)
 constexpr int kChunkKb = 16;  // k-blocks accumulated in TMEM before promotion to registers (64 MMA steps:
                               // accumulate-truncation bias ~3e-6 relative, 2.5 % faster than 8)
@@ -61,10 +64,17 @@ constexpr int kGemmSmemBytes = kStages * kStageBytes + 1024;
 // compute one 256 x N tile.  Each CTA loads its own 128 rows of X but only HALF of the Y
 // slab (the tensor core reads the other half from the partner's shared memory), so a stage
 // is 32 KB instead of 48 KB - a third less L2->SM traffic per flop and room for 6 stages.
+// Cluster-of-four variant (CG = 4): two CTA pairs on neighbouring row tiles read the SAME Y slab, so each
+// CTA fetches only a QUARTER of it and TMA-multicasts that quarter to the CTA holding the same half in the
+// other pair.  Per CTA and stage the L2 -> SM traffic drops from 16 + 16 KB to 16 + 8 KB; the shared-memory
+// layout (and everything downstream of the full barriers) is the pair kernel's.  A stage is reusable only
+// when BOTH pairs have retired its MMAs (the multicast writes into the other pair's buffers too), so the
+// empty barriers collect one tcgen05.commit from each pair leader.
 template <int CG>
 struct TileCfg {
-  static constexpr int stages = CG == 2 ? 6 : kStages;
-  static constexpr int ybytes = kStageBytesY / CG;
+  static constexpr int pair = CG >= 2 ? 2 : 1;  // CTAs that share one MMA (cta_group)
+  static constexpr int stages = CG >= 2 ? NMFB_PAIR_STAGES : kStages;
+  static constexpr int ybytes = kStageBytesY / pair;
   static constexpr int stage_bytes = kStageBytesX + ybytes;
   static constexpr int smem_bytes = stages * stage_bytes + 1024;
 };
@@ -241,9 +251,12 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
   const int lane = threadIdx.x & 31;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
-  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
-  const int r0 = CG == 2 ? static_cast<int>(blockIdx.x >> 1) * (2 * kTileM) + static_cast<int>(rank) * kTileM
-                         : static_cast<int>(blockIdx.x) * kTileM;
+  constexpr bool kPair = CG >= 2;
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;  // rank in the cluster (CG = 4: 0..3, two pairs)
+  const uint32_t rank = crank & 1u;                        // position in the CTA pair; 0 = leader (issues the MMAs)
+  const uint32_t lead = crank & ~1u;                       // cluster rank of this pair's leader
+  const int r0 = kPair ? static_cast<int>(blockIdx.x >> 1) * (2 * kTileM) + static_cast<int>(rank) * kTileM
+                       : static_cast<int>(blockIdx.x) * kTileM;
   const int tile_n = a.tile_n > 0 ? a.tile_n : kMaxN;
   const int n0 = blockIdx.y * tile_n;
   const int bn = min(a.ncols - n0, tile_n);  // multiple of 32
@@ -258,11 +271,11 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < kNStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CG == 4 ? 2 : 1);  // CG = 4: both pairs must have retired the stage
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], kEpiWarps * CG);  // the leader's barrier collects both CTAs' epilogues
+      mbar_init(&tempty_bar[b], kEpiWarps * TC::pair);  // the leader's barrier collects both CTAs' epilogues
     }
     mbar_init(&h_bar, 1);
     fence_barrier_init();
@@ -274,7 +287,7 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     }
   }
   if (warp == 1) {
-    if constexpr (CG == 2) {
+    if constexpr (kPair) {
       tmem_alloc_pair(&tmem_slot, kTmemCols);
       tmem_relinquish_pair();
     } else {
@@ -283,25 +296,29 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     }
   }
   tc_fence_before();
-  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------ TMA producer
     // bytes that land per stage in BOTH CTAs of a pair are counted on the leader's barrier
-    const int ybox = a.box_n / CG;  // rows of Y this CTA loads
-    const uint32_t tx_bytes = CG * (kStageBytesX + ybox * 128);
-    const int yrow0 = n0 + static_cast<int>(rank) * (bn / CG);
+    const int ybox = a.box_n / TC::pair;  // rows of Y in this CTA's shared memory (its half of the slab)
+    const uint32_t tx_bytes = TC::pair * (kStageBytesX + ybox * 128);
+    const int yrow0 = n0 + static_cast<int>(rank) * (bn / TC::pair);
+    // CG = 4: this CTA fetches quarter `yq` of the slab (half of its half) and multicasts it to the CTA with the
+    // same position in the other pair
+    const int yq = CG == 4 ? static_cast<int>(crank >> 1) : 0;
+    const uint16_t ymask = static_cast<uint16_t>(0x5u << rank);
     const int total = n0kb + n1kb;
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0; it < total; ++it) {
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-      const uint32_t fb = CG == 2 ? map_to_cta(smem_u32(&full_bar[stage]), 0) : 0u;
+      const uint32_t fb = kPair ? map_to_cta(smem_u32(&full_bar[stage]), lead) : 0u;
       auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint64_t pol) {
-        if constexpr (CG == 2) tma_load_2d_pair(dst, tm, fb, c0, c1, pol);
+        if constexpr (kPair) tma_load_2d_pair(dst, tm, fb, c0, c1, pol);
         else tma_load_2d(dst, tm, &full_bar[stage], c0, c1, pol);
       };
       const bool ph1 = it >= n0kb;
@@ -325,7 +342,16 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       } else {
         load(xs, mx, kb * kBlockK, r0, kEvictFirst);
       }
-      if (ph1 ? a.ymn1 : a.ymn0) {
+      if constexpr (CG == 4) {
+        if (ph1 ? a.ymn1 : a.ymn0) {  // 32-row boxes: this CTA's half of the boxes of its half
+          const int nq = ybox >> 6;
+          for (int q = yq * nq; q < (yq + 1) * nq; ++q)
+            tma_load_2d_pair_mc(ys + q * 4096, my, &full_bar[stage], ymask, yrow0 + q * 32, kb * kBlockK, kEvictLast);
+        } else {  // one box of ybox / 2 rows (the tensor map was built with box_n / 4 rows)
+          tma_load_2d_pair_mc(ys + yq * (ybox >> 1) * 128, my, &full_bar[stage], ymask, kb * kBlockK,
+                              yrow0 + yq * (ybox >> 1), kEvictLast);
+        }
+      } else if (ph1 ? a.ymn1 : a.ymn0) {
         for (int q = 0; q < (ybox >> 5); ++q) load(ys + q * 4096, my, yrow0 + q * 32, kb * kBlockK, kEvictLast);
       } else {
         load(ys, my, kb * kBlockK, yrow0, kEvictLast);
@@ -360,7 +386,7 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       const int buf = ch & 1;
       const int use = ch >> 1;
       if (use > 0) {
-        if constexpr (CG == 2) mbar_wait_cluster(&tempty_bar[buf], (use - 1) & 1);
+        if constexpr (kPair) mbar_wait_cluster(&tempty_bar[buf], (use - 1) & 1);
         else mbar_wait(&tempty_bar[buf], (use - 1) & 1);
         tc_fence_after();
       }
@@ -368,7 +394,9 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       const int nkb = ph1 ? n1kb : min(chunk_kb, n0kb - ch * chunk_kb);
       const bool mn = ph1 ? (a.xmn1 != 0) : (a.xmn0 != 0);
       const bool ymn = ph1 ? (a.ymn1 != 0) : (a.ymn0 != 0);
-      const uint32_t idesc = make_idesc_tf32(kTileM * CG, bn, mn ? 1 : 0, ymn ? 1 : 0);
+      const uint32_t idesc = make_idesc_tf32(kTileM * TC::pair, bn, mn ? 1 : 0, ymn ? 1 : 0);
+      const uint16_t pair_mask = static_cast<uint16_t>(0x3u << lead);           // this pair's two CTAs
+      const uint16_t stage_mask = CG == 4 ? static_cast<uint16_t>(0xF) : pair_mask;  // everybody writing into the stage
       const uint32_t d = tmem_base + static_cast<uint32_t>(buf * kMaxN);
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(&full_bar[stage], phase);
@@ -381,11 +409,12 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
                                     : make_desc_kmajor_sw128(xs + s * (kUmmaK * 4));
           const uint64_t bdesc = ymn ? make_desc_mnmajor_sw128_32b(ys + s * 1024, 4096, 512)
                                      : make_desc_kmajor_sw128(ys + s * (kUmmaK * 4));
-          if constexpr (CG == 2) mma_tf32_ss_pair(d, adesc, bdesc, idesc, (i == 0 && s == 0) ? 0u : 1u);
+          if constexpr (kPair) mma_tf32_ss_pair(d, adesc, bdesc, idesc, (i == 0 && s == 0) ? 0u : 1u);
           else mma_tf32_ss(d, adesc, bdesc, idesc, (i == 0 && s == 0) ? 0u : 1u);
         }
-        // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-        if constexpr (CG == 2) tc_commit_pair(&empty_bar[stage], 0x3);
+        // frees the smem slot (in both CTAs of a pair; CG = 4: one of the two arrivals in all four CTAs) when
+        // these MMAs retire
+        if constexpr (kPair) tc_commit_pair(&empty_bar[stage], stage_mask);
         else tc_commit(&empty_bar[stage]);
         if (++stage == kNStages) {
           stage = 0;
@@ -393,7 +422,7 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         }
       }
       // chunk complete: wake the epilogue warps (of both CTAs)
-      if constexpr (CG == 2) tc_commit_pair(&tfull_bar[buf], 0x3);
+      if constexpr (kPair) tc_commit_pair(&tfull_bar[buf], pair_mask);
       else tc_commit(&tfull_bar[buf]);
     }
   } else if (warp >= 2) {
@@ -439,7 +468,7 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_remote(map_to_cta(smem_u32(&tempty_bar[buf]), 0));
+        if constexpr (kPair) mbar_arrive_remote(map_to_cta(smem_u32(&tempty_bar[buf]), lead));
         else mbar_arrive(&tempty_bar[buf]);
       }
     }
@@ -644,10 +673,10 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
   }
 
   tc_fence_before();
-  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();  // partner may still read our smem / TMEM
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();  // partner may still read our smem / TMEM
   if (warp == 1) {
     __syncwarp();
-    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+    if constexpr (kPair) tmem_dealloc_pair(tmem_base, kTmemCols);
     else tmem_dealloc(tmem_base, kTmemCols);
   }
 }

@@ -186,6 +186,21 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtens
       : "memory");
 }
 
+// Multicast variant for a cluster of TWO CTA pairs that share an operand slab: the bytes land at the same
+// shared-memory offset in every CTA of `mask`, and each destination's share of the completion is signalled
+// on the barrier at `bar`'s offset in the LEADER (even CTA) of that destination's pair - the barrier
+// operand is the issuing CTA's own address with the pair's peer bit cleared, as CUTLASS's
+// SM100_TMA_2SM_LOAD_MULTICAST does.
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t smem_dst, const CUtensorMap* tmap, uint64_t* bar,
+                                                    uint16_t mask, int c0, int c1, uint64_t policy) {
+  const uint32_t bar_addr = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      ".L2::cache_hint [%0], [%1, {%4, %5}], [%2], %3, %6;" ::"r"(smem_dst),
+      "l"(tmap), "r"(bar_addr), "h"(mask), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(

@@ -17,9 +17,10 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=[1, 2], ids=["cta1", "cta_pair"])
+@pytest.fixture(autouse=True, params=[1, 2, 4], ids=["cta1", "cta_pair", "two_pairs_multicast"])
 def cta_group(request):
-    """Every kernel-level test runs on the single-CTA kernel and on the CTA-pair (cta_group::2) kernel."""
+    """Every kernel-level test runs on the single-CTA kernel, on the CTA-pair (cta_group::2) kernel and on the
+    cluster of two pairs that share the Y slab by TMA multicast (shapes it cannot take fall back to pairs)."""
     os.environ["NMFB_DEBUG_CG"] = str(request.param)
     yield request.param
     os.environ.pop("NMFB_DEBUG_CG", None)
@@ -154,6 +155,27 @@ def test_mn_major_second_phase():
     e0 = relerr(o0, X0.double() @ Y0.double().T)
     e1 = relerr(o1, X1.double() @ Y1.double().T)
     assert e0 < TOL and e1 < TOL, (e0, e1)
+
+
+@pytest.mark.parametrize("rows,kdim,ncols,kdim1,x_mn", [(1024, 2048, 256, 256, True), (2048, 1000, 128, 128, False),
+                                                        (512, 4096 + 64, 512, 0, True)])
+def test_shapes_of_the_two_pair_multicast_kernel(rows, kdim, ncols, kdim1, x_mn):
+    """Even numbers of 256-row tiles and 128 / 256-column slabs: the shapes that run on clusters of two CTA pairs
+    sharing the Y slab by TMA multicast (A = V H' with column-major V, the H-step contraction, a second phase)."""
+    dev = torch.device("cuda:0")
+    X = rand((rows, kdim), dev, 1)
+    Y0 = rand((ncols, kdim), dev, 2)
+    if x_mn:
+        Xt = X.T.contiguous()
+        Xarg = Xt
+    else:
+        Xarg = X
+    X1 = rand((rows, kdim1), dev, 3) if kdim1 else None
+    Y1 = rand((ncols, kdim1), dev, 4) if kdim1 else None
+    o0, o1, _ = run_store(Xarg, Y0, kdim, rows, ncols, X1, Y1, kdim1, x0_mn=x_mn)
+    assert relerr(o0, X.double() @ Y0.double().T) < TOL
+    if kdim1:
+        assert relerr(o1, X1.double() @ Y1.double().T) < TOL
 
 
 @pytest.mark.parametrize("splits", [0, 3, 7])
