@@ -29,8 +29,14 @@
  * Multi-GPU (one process per GPU): each rank creates a handle, joins a
  * communicator (nmfb_comm_*), uploads its COLUMN SHARD of V and of H_init and
  * passes the full W_init; W is returned replicated, H as the rank's shard, the
- * cost trace is global.  One packed all-reduce per iteration carries the m x K
- * numerator partial, the K x K Gram matrix and the scalar sums.
+ * cost trace is global.  nmfb_nmf (all divergences, W_fixed and per-source fixed
+ * bases included): per iteration every rank fetches its ROW block of the ranks'
+ * m x K numerator partials over NVLink peer memory, takes the W step on those
+ * rows and delivers them to all ranks; a K x K Gram matrix and a few scalars are
+ * all-reduced (without peer access: one NCCL all-reduce of everything).
+ * nmfb_cnmf ('euclidean' / 'frobenius'): shards of CONSECUTIVE columns, each at
+ * least context_len - 1 wide; the halo columns are exchanged by the engine.
+ * nmfb_nmfsc, nmfb_cnmfsc, nmfb_lnmf, nmfb_constrainednmf: one GPU.
  */
 #ifndef NMFB200_H_
 #define NMFB200_H_
@@ -67,6 +73,12 @@ typedef enum nmfb_divergence {
                               (nmf.m:124-128); same availability as NMFB_DIV_IS       */
 } nmfb_divergence;
 
+/* Accuracy of the cost trace and of the stop test (nmf.m:221-224: stop when 0 < cost(i-1) - cost(i) < tolerance).
+ * The contractions multiply tf32-rounded operands with fp32 accumulation, so every cost entry agrees with the
+ * float64 reference to about 1e-5 relative (measured <= 1.3e-5; the trace form subtracts terms ~8x the cost, the
+ * direct form is ~3e-6).  A `tolerance` below ~1e-5 * cost therefore cannot be resolved: the loop may stop one or
+ * more iterations away from the reference's iteration, or run to maxiter.  For resolvable tolerances the default mode
+ * stops within one iteration of the reference, NMFB_COST_DIRECT at the same iteration (tests/test_gpu_parity.py). */
 typedef enum nmfb_cost_mode {
   NMFB_COST_AUTO = 0,   /* Euclidean: Gram/trace identity (no extra pass over V); KL: fused */
   NMFB_COST_DIRECT = 1  /* Euclidean: explicit 0.5*sum((V - W*H).^2) each iteration        */
