@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <vector>
 
@@ -222,10 +223,36 @@ int comm_allreduce(nmfb_handle* h, float* f, size_t nf, double* d1, size_t n1, d
 static void region_release(nmfb_handle* h, Comm* c, bool collective) {
   if (!c->region) return;
   cudaStreamSynchronize(h->stream);
+  bool peers_gone = true;
   if (c->p2p) {
+    // Freeing memory that a peer still has mapped is undefined.  Handles are destroyed at unrelated times, so the
+    // teardown cannot be a collective; instead every rank tells its peers "I am closing my mapping of your region"
+    // (a flag in THEIR region header, written just before the close) and frees its own region only once all
+    // peers have said so - or, if a peer never does (it may have died), after a bounded wait it leaves the region
+    // to the process teardown rather than freeing it under a live mapping.
+    const size_t off = 8 * kFlagBytes;
+    const int closing = 1;
+    for (int q = 0; q < c->nranks; ++q)
+      if (q != c->rank && c->table.base[q])
+        cudaMemcpy(c->table.base[q] + off + c->rank * sizeof(int), &closing, sizeof(int), cudaMemcpyHostToDevice);
     for (int q = 0; q < c->nranks; ++q)
       if (q != c->rank && c->table.base[q]) cudaIpcCloseMemHandle(c->table.base[q]);
     c->p2p = false;
+    if (!collective) {
+      int flags[kMaxRanks];
+      timespec t0, t1;
+      clock_gettime(CLOCK_MONOTONIC, &t0);
+      for (;;) {
+        peers_gone = cudaMemcpy(flags, c->region + off, sizeof(flags), cudaMemcpyDeviceToHost) == cudaSuccess;
+        for (int q = 0; peers_gone && q < c->nranks; ++q)
+          if (q != c->rank && flags[q] == 0) peers_gone = false;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        if (peers_gone || (t1.tv_sec - t0.tv_sec) + (t1.tv_nsec - t0.tv_nsec) * 1e-9 > 2.0) break;
+        timespec nap{0, 2000000};
+        nanosleep(&nap, nullptr);
+      }
+      cudaGetLastError();
+    }
     // nobody may free its region while a peer still has it mapped: meet once through NCCL
     float* one = nullptr;
     if (collective && cudaMalloc(&one, 4) == cudaSuccess) {
@@ -235,7 +262,7 @@ static void region_release(nmfb_handle* h, Comm* c, bool collective) {
       cudaFree(one);
     }
   }
-  cudaFree(c->region);
+  if (peers_gone) cudaFree(c->region);  // else: still mapped somewhere - left to the process teardown
   c->region = nullptr;
   c->region_bytes = 0;
 }

@@ -33,7 +33,7 @@ constexpr int kMaxBlocks = 256;                                      // grid cap
 constexpr size_t kFlagBytes = kMaxBlocks * kMaxRanks * sizeof(int);  // one barrier site: flags[block][rank]
 // Barrier sites (each with its own monotone epoch sequence): 0/1 all-reduce open/close, 2..4 sharded W step
 // (4 closing, 6 opening), 5 row gather of the fp32 W at the end of a run
-constexpr int kBarrierSites = 8;
+constexpr int kBarrierSites = 9;  // (site 7: cnmf halo exchange, site 8: teardown handshake)
 constexpr size_t kHeader = kBarrierSites * kFlagBytes;  // region = [flags | data]
 struct PeerTable {
   char* base[kMaxRanks];  // base[q] = rank q's registered region as seen from this process
