@@ -46,6 +46,8 @@ struct CnmfState {
   long long ldhm = 0;
   float *Hx = nullptr, *Vx = nullptr, *packed = nullptr;
   const float* Vmma = nullptr;
+  bool fold_stacks = false;   // single GPU: fold_update writes the next iteration's Hs itself
+  unsigned int* ticket = nullptr;
   size_t send_off = 0;  // byte offset of this rank's [2][K][halo] H columns (first / last own ones) in the region
   GemmOp gemmB;
   bool W_fixed = false, H_fixed = false, frobenius = false;
@@ -178,7 +180,7 @@ int enqueue_hstack(nmfb_handle* h, CnmfState* s, const int* stop) {
 // of cnmf.m:221-222 leaves V_pos unshifted.
 int enqueue_iteration_two_weight(nmfb_handle* h, CnmfState* s, int i) {
   const int* stop = s->stop;
-  if (!s->H_fixed || i == 0) NMFB_TRY(enqueue_hstack(h, s, stop));
+  if (i == 0 || (!s->H_fixed && !s->fold_stacks)) NMFB_TRY(enqueue_hstack(h, s, stop));
   s->gemmS.L.args.want_cost = i > 0 ? 1 : 0;
   NMFB_TRY(run_gemm(h, s->gemmS));
   if (i > 0) NMFB_TRY(enqueue_cost(h, s, i - 1));
@@ -210,7 +212,8 @@ int enqueue_iteration_two_weight(nmfb_handle* h, CnmfState* s, int i) {
   NMFB_TRY(run_gemm(h, s->gemmPd));
   fold_update_kernel<<<vec_grid(s->n, s->K), 256, 0, h->stream>>>(s->P, s->D, s->Hm, s->K, s->T, s->n, s->nx, s->ldh, s->ldhm,
                                                                   s->lambda_h, s->H_fixed ? 1 : 0, s->scal, stop,
-                                                                  s->expo, s->kl_quirk ? 1 : 0);
+                                                                  s->expo, s->kl_quirk ? 1 : 0,
+                                                                  s->fold_stacks ? s->Hs : nullptr, s->ldh);
   return check_launch(h, "fold_update");
 }
 
@@ -218,9 +221,31 @@ int enqueue_iteration(nmfb_handle* h, CnmfState* s, int i) {
   if (s->two_weight) return enqueue_iteration_two_weight(h, s, i);
   const int* stop = s->stop;
   const int m = s->m;
+  bool cost_done = false;
   if (!s->H_fixed || i == 0) {
-    NMFB_TRY(enqueue_hstack(h, s, stop));
-    NMFB_TRY(run_gram(h, s->gramH, stop));
+    if (i == 0 || !s->fold_stacks) NMFB_TRY(enqueue_hstack(h, s, stop));
+    if (!s->multi && !s->frobenius) {
+      // slab sum of Hs Hs' fused with <Wc'Wc, Hs Hs'>, the cost of the previous iteration and the stop test
+      CostArgs c{};
+      c.mode = 0;
+      c.iter = i - 1;
+      c.Kp = s->KTp;
+      c.GW = s->gramW.g32;
+      c.GH = s->gramH.g32;
+      c.vsq = s->vsq;
+      c.scal = s->scal;
+      c.wsum = s->wsum;
+      c.n_wsum = s->KTp;
+      c.lambda_w = s->lambda_w;
+      c.lambda_h = s->lambda_h;
+      c.tolerance = s->tolerance;
+      c.cost = s->cost;
+      c.stop = s->stop;
+      NMFB_TRY(run_gram_cost(h, s->gramH, s->ticket, c, i > 0));
+      cost_done = true;
+    } else {
+      NMFB_TRY(run_gram(h, s->gramH, stop));
+    }
   }
   if (s->multi) {  // partial sums over the column shards: [A | Hs Hs'] and the scalars in one all-reduce
     if (!s->W_fixed) NMFB_TRY(run_gemm(h, s->gemmA));
@@ -234,7 +259,7 @@ int enqueue_iteration(nmfb_handle* h, CnmfState* s, int i) {
       NMFB_TRY(check_launch(h, "round_copy(G_H)"));
     }
   }
-  if (i > 0) NMFB_TRY(enqueue_cost(h, s, i - 1));
+  if (i > 0 && !cost_done) NMFB_TRY(enqueue_cost(h, s, i - 1));
   if (!s->W_fixed) {
     NMFB_TRY(prof_mark(h, 0));
     if (s->multi) NMFB_TRY(run_gemm(h, s->gemmB));  // B = Wc (Hs Hs') with the summed Gram matrix
@@ -267,7 +292,7 @@ int enqueue_iteration(nmfb_handle* h, CnmfState* s, int i) {
   NMFB_TRY(prof_mark(h, 2));
   fold_update_kernel<<<vec_grid(s->n, s->K), 256, 0, h->stream>>>(s->P, s->D, s->Hm, s->K, s->T, s->n, s->nx, s->ldh, s->ldhm,
                                                                   s->lambda_h, s->H_fixed ? 1 : 0, s->scal,
-                                                                  stop);
+                                                                  stop, 0.f, 0, s->fold_stacks ? s->Hs : nullptr, s->ldh);
   NMFB_TRY(check_launch(h, "fold_update"));
   return prof_mark(h, 2);
 }
@@ -401,6 +426,8 @@ int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_
   if (!s->multi) NMFB_TRY(ar->alloc(h, &s->scal, 8));
   NMFB_TRY(ar->alloc(h, &s->cost, static_cast<size_t>(s->maxiter) + 1));
   NMFB_TRY(ar->alloc(h, &s->stop, 2));
+  NMFB_TRY(ar->alloc(h, &s->ticket, 2));
+  s->fold_stacks = !s->multi && std::getenv("NMFB_CNMF_HSTACK") == nullptr;
 
   {  // initial factors: defaults cnmf.m:311, 331-335 (rand; W normalised per basis)
     std::vector<float> tmp;

@@ -163,10 +163,12 @@ int run_gram_post_allreduce(nmfb_handle* h, const GramOp& op, unsigned int* tick
 }
 
 int launch_w_step(nmfb_handle* h, const WStepArgs& a) {
-  if (a.m <= kWThreads * kWCache)
-    w_step_kernel<true><<<a.K, kWThreads, 0, h->stream>>>(a);
+  if (a.m <= 256 * kWCache)
+    w_step_kernel<true, 256><<<a.K, 256, 0, h->stream>>>(a);
+  else if (a.m <= kWThreads * kWCache)
+    w_step_kernel<true, kWThreads><<<a.K, kWThreads, 0, h->stream>>>(a);
   else
-    w_step_kernel<false><<<a.K, kWThreads, 0, h->stream>>>(a);
+    w_step_kernel<false, kWThreads><<<a.K, kWThreads, 0, h->stream>>>(a);
   return check_launch(h, "w_step");
 }
 

@@ -270,8 +270,10 @@ struct WStepArgs {
   const float* lambda_k;  // optional per-basis lambda_W / fixed flags (multi-source runs, nmf.m:145,168)
   const int* fixed_k;
 };
-template <bool CACHED>
-__global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
+// THREADS: 1024 for long columns; 256 for columns of up to 4096 rows (cnmf: hundreds of short frame-columns -
+// four resident blocks per SM and four times cheaper block reductions)
+template <bool CACHED, int THREADS>
+__global__ void __launch_bounds__(THREADS) w_step_kernel(WStepArgs a) {
   NMFB_STOP_GUARD(a.stop);
   __shared__ double sh[32 * 2];
   __shared__ double bc[4];
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
     if (CACHED) {
 #pragma unroll
       for (int q = 0; q < kWCache; ++q) {
-        const int i = tid + q * kWThreads;
+        const int i = tid + q * THREADS;
         const bool ok = i < a.m;
         wv[q] = ok ? a.W[off + i] : 0.f;
         av[q] = ok ? a.A[off + i] : 0.f;
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
         s1 = fmaf(wv[q], bv[q], s1);
       }
     } else {
-      for (int i = tid; i < a.m; i += kWThreads) {
+      for (int i = tid; i < a.m; i += THREADS) {
         const float w = a.W[off + i];
         s0 = fmaf(w, a.A[off + i], s0);
         if (!kl) s1 = fmaf(w, a.B[off + i], s1);
@@ -344,12 +346,12 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
           neg = powf(neg, a.expo);
           pos = powf(pos, a.expo);
         }
-        const float wn = (tid + q * kWThreads < a.m) ? w * (neg / fmaxf(pos + lambda, NMFB_EPS)) : 0.f;
+        const float wn = (tid + q * THREADS < a.m) ? w * (neg / fmaxf(pos + lambda, NMFB_EPS)) : 0.f;
         wv[q] = wn;
         s2 = lnmf ? s2 + wn : fmaf(wn, wn, s2);
       }
     } else {
-      for (int i = tid; i < a.m; i += kWThreads) {
+      for (int i = tid; i < a.m; i += THREADS) {
         const float w = a.W[off + i];
         float neg = a.A[off + i] + w * pc;
         float pos = (kl ? bterm : a.B[off + i]) + w * qc;
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
       if (CACHED) {
 #pragma unroll
         for (int q = 0; q < kWCache; ++q) {
-          const int i = tid + q * kWThreads;
+          const int i = tid + q * THREADS;
           if (i < a.m) a.W[off + i] = wv[q];
         }
       }
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
       if (CACHED) {
 #pragma unroll
         for (int q = 0; q < kWCache; ++q) {
-          const int i = tid + q * kWThreads;
+          const int i = tid + q * THREADS;
           if (i < a.m) {
             const float w = wv[q] * mul;
             a.W[off + i] = w;
@@ -393,7 +395,7 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
           }
         }
       } else {
-        for (int i = tid; i < a.m; i += kWThreads) {
+        for (int i = tid; i < a.m; i += THREADS) {
           const float w = a.W[off + i] * mul;
           a.W[off + i] = w;
           a.Wt[off + i] = tf32_rn(w);
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
       // cnmf: the scale needs all T frames; park W' and come back
 #pragma unroll
       for (int q = 0; q < kWCache; ++q) {
-        const int i = tid + q * kWThreads;
+        const int i = tid + q * THREADS;
         if (i < a.m) a.W[off + i] = wv[q];
       }
     }
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(kWThreads) w_step_kernel(WStepArgs a) {
       const int c = k + a.K * t;
       const long long off = static_cast<long long>(c) * a.ld;
       float s3 = 0.f;
-      for (int i = tid; i < a.m; i += kWThreads) {
+      for (int i = tid; i < a.m; i += THREADS) {
         const float w = a.W[off + i] / div;
         a.W[off + i] = w;
         a.Wt[off + i] = tf32_rn(w);
@@ -761,7 +763,10 @@ __global__ void hstack_kernel(const float* __restrict__ H, float* __restrict__ H
 __global__ void fold_update_kernel(const float* __restrict__ P, const float* __restrict__ D,
                                    float* __restrict__ H, int K, int T, int n, int n_src, long long ldp, long long ld,
                                    float lambda, int freeze, double* scal, const int* stop,
-                                   float expo = 0.f, int pos_unshifted = 0) {
+                                   float expo = 0.f, int pos_unshifted = 0, float* __restrict__ Hs_out = nullptr,
+                                   long long lds = 0) {
+  // Hs_out (single GPU): the new H goes straight into the shifted stack of the next iteration,
+  // Hs[k + K*t][j + t] = tf32(H_new[k][j]) (cnmf.m:188), which saves the separate stacking pass
   // expo: outer exponent of both gradients (AB divergence, cnmf.m:229-232); pos_unshifted: the KL
   // branch of cnmf.m:221-222 does not shift V_pos
   NMFB_STOP_GUARD(stop);
@@ -790,7 +795,12 @@ __global__ void fold_update_kernel(const float* __restrict__ P, const float* __r
       h = h * (neg / fmaxf(pos + lambda, NMFB_EPS));
       H[k * ld + j] = h;
     }
-    acc[0] += static_cast<double>(neg) * tf32_rn(h);
+    const float ht = tf32_rn(h);
+    if (Hs_out != nullptr && !freeze) {
+      for (int t = 0; t < T; ++t)
+        if (j + t < n) Hs_out[static_cast<long long>(k + K * t) * lds + j + t] = ht;
+    }
+    acc[0] += static_cast<double>(neg) * ht;
     acc[1] += h;
   }
   block_sum<2>(acc, sh);
