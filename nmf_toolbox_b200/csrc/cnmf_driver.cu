@@ -550,8 +550,10 @@ int cnmf_run(nmfb_handle* h, CnmfState* s, int K, int T, const nmfb_config* cfg_
     MatRef Xh{s->Hs, nx, KTp, s->ldh, true};
     MatRef Ygw{s->gramW.gtf, KTp, KTp, KTp, false};
     const int tiles_h = (nx + kTileM - 1) / kTileM * ((KTp + kMaxN - 1) / kMaxN);
+    int p_tile_n = 0;  // experiment: narrower tiles against the 2.1-wave quantisation of the P, D contraction
+    if (const char* e = std::getenv("NMFB_CNMF_TILEN")) p_tile_n = std::atoi(e);
     NMFB_TRY(plan_store(h, ar, &s->gemmP, Xvt, Yw, m, &Xh, &Ygw, KTp, nx, KTp, s->P, s->D, s->ldh,
-                        tiles_h * 2 <= h->num_sms, stop));
+                        tiles_h * 2 <= h->num_sms, stop, nullptr, p_tile_n));
   }
   if (s->W_fixed) NMFB_TRY(run_gram(h, s->gramW, nullptr));
   // sum(H) for the sparsity term when H is never updated is accumulated by fold_update (freeze)

@@ -50,9 +50,9 @@ static int plan_common(nmfb_handle* h, GemmOp* op, const MatRef& X0, const MatRe
 int plan_store(nmfb_handle* h, Arena* ar, GemmOp* op, const MatRef& X0, const MatRef& Y0,
                long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1, int rows,
                int ncols, float* out0, float* out1, long long ldo, bool allow_split,
-               const int* stop, const ExtraSegs* segs) {
+               const int* stop, const ExtraSegs* segs, int tile_n) {
   op->epi = EPI_STORE;
-  NMFB_TRY(plan_common(h, op, X0, Y0, kdim0, X1, Y1, kdim1, rows, ncols, allow_split ? 0 : 1, segs));
+  NMFB_TRY(plan_common(h, op, X0, Y0, kdim0, X1, Y1, kdim1, rows, ncols, allow_split ? 0 : 1, segs, tile_n));
   GemmArgs& a = op->L.args;
   a.stop = stop;
   a.out1 = out1;

@@ -216,7 +216,7 @@ struct ExtraSegs {
 int plan_store(nmfb_handle* h, Arena* ar, GemmOp* op, const MatRef& X0, const MatRef& Y0,
                long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1, int rows,
                int ncols, float* out0, float* out1, long long ldo, bool allow_split,
-               const int* stop, const ExtraSegs* segs = nullptr);
+               const int* stop, const ExtraSegs* segs = nullptr, int tile_n = 0);
 int plan_fused(nmfb_handle* h, GemmOp* op, int epi, const MatRef& X0, const MatRef& Y0,
                long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1, int rows,
                int ncols, int ncols_valid, const int* stop, const ExtraSegs* segs = nullptr, int tile_n = 0);

@@ -190,16 +190,16 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
 
   const size_t cw = static_cast<size_t>(Kp) * ldw, ch = static_cast<size_t>(Kp) * ldh;
   NMFB_TRY(ar->alloc(h, &s->Wm, cw));
-  NMFB_TRY(ar->alloc(h, &s->Wt, cw));
-  NMFB_TRY(ar->alloc(h, &s->Wl, cw));
+  NMFB_TRY(ar->alloc(h, &s->Wt, 2 * cw));  // tf32 head and tail back to back: one stacked operand [W_hi; W_lo]
+  s->Wl = s->Wt + cw;
   NMFB_TRY(ar->alloc(h, &s->Wnew, cw));
   NMFB_TRY(ar->alloc(h, &s->Wnt, cw));
   NMFB_TRY(ar->alloc(h, &s->Wnl, cw));
   NMFB_TRY(ar->alloc(h, &s->A, cw));
   NMFB_TRY(ar->alloc(h, &s->B, cw));
   NMFB_TRY(ar->alloc(h, &s->Hm, ch));
-  NMFB_TRY(ar->alloc(h, &s->Ht, ch));
-  NMFB_TRY(ar->alloc(h, &s->Hl, ch));
+  NMFB_TRY(ar->alloc(h, &s->Ht, 2 * ch));  // [H_hi; H_lo]
+  s->Hl = s->Ht + ch;
   NMFB_TRY(ar->alloc(h, &s->Hnew, ch));
   NMFB_TRY(ar->alloc(h, &s->Hnt, ch));
   NMFB_TRY(ar->alloc(h, &s->Hnl, ch));
@@ -281,10 +281,40 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
     // N = W'V (nmfsc.m:144): rows = columns j of V (K-major), contraction over i
     MatRef Vk_hi{s->Vhi, m, n, h->ldv, false}, Vk_lo{s->Vlo, m, n, h->ldv, false};
     MatRef Wk_hi{s->Wt, m, Kp, ldw, false}, Wk_lo{s->Wl, m, Kp, ldw, false};
+    // The two contractions with V stream it as a tf32 head / tail pair (2 x m x n floats).  Written as three
+    // segments (V_hi W_hi + V_lo W_hi + V_hi W_lo) the head travels twice; with the small factor STACKED as
+    // [W_hi; W_lo] (twice the accumulator columns) two segments do, V_hi [W_hi; W_lo]' + V_lo [W_hi; W_lo]', and the
+    // two column halves are added when the split-K slabs are summed (the lo*lo term comes for free).
+    const bool folded = std::getenv("NMFB_SC_UNFOLDED") == nullptr;
+    auto plan_folded = [&](GemmOp* op, const MatRef& Xhi, const MatRef& Xlo, const MatRef& Y2, long long kdim, int rows,
+                           float* out, long long ldo, bool allow_split, const int* stop) -> int {
+      ExtraSegs e;
+      e.n = 1;
+      e.X[0] = Xlo;
+      e.Y[0] = Y2;
+      float* whole = nullptr;  // [2 Kp][ldo] when the contraction is not split
+      NMFB_TRY(ar->alloc(h, &whole, static_cast<size_t>(2 * Kp) * ldo));
+      NMFB_TRY(plan_store(h, ar, op, Xhi, Y2, kdim, nullptr, nullptr, 0, rows, 2 * Kp, whole, nullptr, ldo, allow_split,
+                          stop, &e));
+      if (op->splits == 1) {
+        op->parts = whole;
+        op->L.args.out0 = whole;
+        op->L.args.split_stride = 0;
+      }
+      op->splits *= 2;  // every slab is two half-slabs of Kp x ldo
+      op->count = static_cast<long long>(Kp) * ldo;
+      op->final0 = out;
+      return static_cast<int>(NMFB_OK);
+    };
     ExtraSegs eN = three(Vk_hi, Vk_lo, Wk_hi, Wk_lo);
     const int tiles_h = (n + kTileM - 1) / kTileM * ((Kp + kMaxN - 1) / kMaxN);
+    if (folded) {
+      MatRef Wk2{s->Wt, m, 2 * Kp, ldw, false};
+      NMFB_TRY(plan_folded(&s->gemmN, Vk_hi, Vk_lo, Wk2, m, n, s->N, ldh, tiles_h * 2 <= h->num_sms, sk0));
+    } else {
     NMFB_TRY(plan_store(h, ar, &s->gemmN, Vk_hi, Wk_hi, m, nullptr, nullptr, 0, n, Kp, s->N, nullptr, ldh,
                         tiles_h * 2 <= h->num_sms, sk0, &eN));
+    }
     // D = W'V_hat = (W'W) H (nmfsc.m:145): rows j (H is MN-major there), contraction over k
     MatRef Hm_hi{s->Ht, n, Kp, ldh, true}, Hm_lo{s->Hl, n, Kp, ldh, true};
     MatRef Gw_hi{s->gramW.gtf, Kp, Kp, Kp, false}, Gw_lo{s->gramW.glo, Kp, Kp, Kp, false};
@@ -296,8 +326,13 @@ int run(nmfb_handle* h, State* s, int K, const nmfb_config* cfg_in, float* W_out
     MatRef Hk_hi{s->Ht, n, Kp, ldh, false}, Hk_lo{s->Hl, n, Kp, ldh, false};
     ExtraSegs eA = three(Vm_hi, Vm_lo, Hk_hi, Hk_lo);
     const int tiles_w = (m + kTileM - 1) / kTileM * ((Kp + kMaxN - 1) / kMaxN);
+    if (folded) {
+      MatRef Hk2{s->Ht, n, 2 * Kp, ldh, false};
+      NMFB_TRY(plan_folded(&s->gemmA, Vm_hi, Vm_lo, Hk2, n, m, s->A, ldw, tiles_w * 2 <= h->num_sms, sk2));
+    } else {
     NMFB_TRY(plan_store(h, ar, &s->gemmA, Vm_hi, Hk_hi, n, nullptr, nullptr, 0, m, Kp, s->A, nullptr, ldw,
                         tiles_w * 2 <= h->num_sms, sk2, &eA));
+    }
     // B = V_hat H' = W (H H') (nmfsc.m:195)
     MatRef Wm_hi{s->Wt, m, Kp, ldw, true}, Wm_lo{s->Wl, m, Kp, ldw, true};
     MatRef Gh_hi{s->gramH.gtf, Kp, Kp, Kp, false}, Gh_lo{s->gramH.glo, Kp, Kp, Kp, false};
