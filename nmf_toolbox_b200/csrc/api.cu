@@ -71,6 +71,7 @@ extern "C" int nmfb_create(nmfb_handle** out, int device) {
     h->pool.cap = (np_env && np_env[0] == '1') ? 0 : prop.totalGlobalMem / 3;
   }
   // (stream priorities were tried for the side stream: no gain, slightly slower large GEMMs)
+  // (again with tail helpers on 144 SMs, main stream first: no difference)
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);

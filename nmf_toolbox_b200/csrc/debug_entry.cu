@@ -25,6 +25,38 @@ static int debug_cg(int rows = 0, int ncols = 0) {
   return cg;
 }
 
+// NMFB_DEBUG_TAIL=<helpers>: the pair kernel runs with that many tail-helper pairs (GemmArgs::sk_*) whenever the
+// launch has one column chunk, no split-K and at least two k-blocks; the scratch lives until `release`
+struct DebugTail {
+  float* part = nullptr;
+  unsigned int* flags = nullptr;
+  void release() {
+    cudaFree(part);
+    cudaFree(flags);
+    part = nullptr;
+    flags = nullptr;
+  }
+};
+static void debug_tail(GemmLaunch* L, DebugTail* t) {
+  const char* e = std::getenv("NMFB_DEBUG_TAIL");
+  if (!e) return;
+  const GemmArgs& a = L->args;
+  int helpers = std::atoi(e);
+  if (helpers <= 0 || L->cg != 2 || L->grid.y != 1 || L->grid.z != 1 || a.nkb0 < 2 || a.nkb_seg != a.nkb0) return;
+  const int tiles = static_cast<int>(L->grid.x) / 2;
+  helpers = std::min(helpers, tiles);
+  const int per = (tiles + helpers - 1) / helpers;
+  int kp = (a.nkb0 * per + per) / (per + 1);
+  kp = std::min(std::max(kp, 1), a.nkb0 - 1);
+  const size_t part_bytes = static_cast<size_t>(tiles) * a.ncols * 2 * kTileM * sizeof(float);
+  if (cudaMalloc(&t->part, part_bytes) != cudaSuccess) return;
+  if (cudaMalloc(&t->flags, 2 * tiles * sizeof(unsigned int)) != cudaSuccess) return;
+  cudaMemset(t->part, 0xff, part_bytes);  // NaN: a primary that does not wait for its helper is caught
+  cudaMemset(t->flags, 0, 2 * tiles * sizeof(unsigned int));
+  set_tail_helpers(L, helpers, kp, t->part, t->flags);
+  L->args.sk_epoch = 1;
+}
+
 static int fail(char* err, int errlen, const std::string& msg) {
   if (err && errlen > 0) {
     std::snprintf(err, errlen, "%s", msg.c_str());
@@ -67,9 +99,12 @@ int nmfb_debug_gemm_store(const nmfb_debug_mat* X0, const nmfb_debug_mat* Y0, lo
   L.args.ldo = ldo;
   L.args.split_stride = split_stride;
   if (splits_used) *splits_used = static_cast<int>(L.grid.z);
+  DebugTail tail;
+  debug_tail(&L, &tail);
   e = launch_gemm(L, EPI_STORE, 0);
   if (!e.empty()) return fail(err, errlen, e);
   cudaError_t ce = cudaDeviceSynchronize();
+  tail.release();
   if (ce != cudaSuccess) return fail(err, errlen, std::string("sync: ") + cudaGetErrorString(ce));
   return 0;
 }
@@ -96,9 +131,12 @@ int nmfb_debug_gemm_hupdate(const nmfb_debug_mat* X0, const nmfb_debug_mat* Y0, 
   L.args.ldc = ldc;
   L.args.lambda = lambda;
   L.args.scal = partials;
+  DebugTail tail;
+  debug_tail(&L, &tail);
   e = launch_gemm(L, EPI_HUPDATE, 0);
   if (!e.empty()) return fail(err, errlen, e);
   cudaError_t ce = cudaDeviceSynchronize();
+  tail.release();
   if (ce != cudaSuccess) return fail(err, errlen, std::string("sync: ") + cudaGetErrorString(ce));
   return 0;
 }

@@ -80,8 +80,24 @@ int plan_fused(nmfb_handle* h, GemmOp* op, int epi, const MatRef& X0, const MatR
   return NMFB_OK;
 }
 
+int enable_tail_helpers(nmfb_handle* h, Arena* ar, GemmOp* op, int reserve_sms) {
+  if (!op->planned || op->splits != 1) return NMFB_OK;
+  int kp = 0;
+  const int helpers = plan_tail_helpers(op->L, op->epi, h->num_sms, reserve_sms, &kp);
+  if (helpers <= 0) return NMFB_OK;
+  const size_t tiles = op->L.grid.x / 2;
+  float* part = nullptr;
+  unsigned int* flags = nullptr;
+  NMFB_TRY(ar->alloc(h, &part, tiles * static_cast<size_t>(op->L.args.ncols) * (2 * kTileM)));
+  NMFB_TRY(ar->alloc(h, &flags, 2 * tiles));
+  set_tail_helpers(&op->L, helpers, kp, part, flags);
+  op->sk_epoch = 0;
+  return NMFB_OK;
+}
+
 int run_gemm(nmfb_handle* h, const GemmOp& op) {
   if (!op.planned) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "internal: GEMM not planned");
+  if (op.L.args.sk_helpers > 0) const_cast<GemmArgs&>(op.L.args).sk_epoch = ++op.sk_epoch;  // flags count launches
   std::string e = launch_gemm(op.L, op.epi, h->stream);
   ++h->launches;
   if (!e.empty()) return h->fail(NMFB_ERR_CUDA, "%s", e.c_str());

@@ -193,6 +193,7 @@ struct GemmOp {
   float* final0 = nullptr;  // where the reduced phase-0 result goes
   long long count = 0;      // elements per slab
   bool planned = false;
+  mutable unsigned int sk_epoch = 0;  // launches so far of a plan with tail helpers (GemmArgs::sk_epoch)
 };
 
 struct MatRef {
@@ -221,6 +222,9 @@ int plan_fused(nmfb_handle* h, GemmOp* op, int epi, const MatRef& X0, const MatR
                long long kdim0, const MatRef* X1, const MatRef* Y1, long long kdim1, int rows,
                int ncols, int ncols_valid, const int* stop, const ExtraSegs* segs = nullptr, int tile_n = 0);
 int run_gemm(nmfb_handle* h, const GemmOp& op);
+// Lets a planned CTA-pair launch that leaves SMs idle use them for the tails of its contractions (GemmArgs::sk_*),
+// keeping `reserve_sms` SMs free for kernels meant to run beside it.  No effect when the plan is not eligible.
+int enable_tail_helpers(nmfb_handle* h, Arena* ar, GemmOp* op, int reserve_sms);
 
 // Gram matrix G = M M' of a factor stored as nvec contiguous vectors of length len
 // (nvec multiple of 32): fp32 result + tf32-rounded copy.

@@ -1,6 +1,7 @@
 #include "gemm_host.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -198,6 +199,66 @@ std::string add_segment(GemmLaunch* L, int seg, const GemmOperand& X, const Gemm
   return "";
 }
 
+static cudaError_t gemm_attrs_once();
+
+int plan_tail_helpers(const GemmLaunch& L, int epi, int num_sms, int reserve_sms, int* kp_out) {
+  if (const char* env = std::getenv("NMFB_TAIL_HELPERS"))
+    if (env[0] == '0') return 0;
+  const GemmArgs& a = L.args;
+  if (L.cg != 2 || L.grid.y != 1 || L.grid.z != 1 || a.nkb_seg != a.nkb0 || a.sk_helpers != 0) return 0;
+  if (epi != EPI_STORE && epi != EPI_HUPDATE) return 0;
+  const int tiles = static_cast<int>(L.grid.x) / 2;
+  if (tiles * 4 <= num_sms) return 0;  // at most half of the SMs busy: split-K territory
+  // co-resident clusters of this kernel (one CTA per SM: shared memory); the helpers must run beside the primaries
+  int max_clusters = 0;
+  if (gemm_attrs_once() != cudaSuccess) return 0;
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * 74, 1, 1);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = TileCfg<2>::smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = epi == EPI_STORE
+                        ? cudaOccupancyMaxActiveClusters(&max_clusters, panel_gemm_kernel<EPI_STORE, 2>, &cfg)
+                        : cudaOccupancyMaxActiveClusters(&max_clusters, panel_gemm_kernel<EPI_HUPDATE, 2>, &cfg);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+  }
+  const int pairs = std::min(num_sms / 2, max_clusters) - (reserve_sms + 1) / 2;
+  int helpers = pairs - tiles;
+  if (const char* env = std::getenv("NMFB_TAIL_HELPERS")) helpers = std::min(helpers, std::atoi(env));
+  if (helpers < 1 || a.nkb0 < 64) return 0;
+  helpers = std::min(helpers, tiles);
+  const int per_helper = (tiles + helpers - 1) / helpers;  // row tiles whose tail one helper pair takes
+  // the primary's kp k-blocks against per_helper tails of nkb0 - kp k-blocks.  A helper also stores one partial
+  // tile per row tile and restarts its accumulation, so the balance point sits ~1 % above nkb0 * per / (per + 1)
+  // (measured at 16384^2, K = 256: kp = 448 / 456 / 464 / 480 of 512 -> 540 / 497 / 493 / 504 us per iteration).
+  int kp = static_cast<int>(std::ceil(a.nkb0 * (per_helper + 0.12) / (per_helper + 1.0)));
+  if (const char* env = std::getenv("NMFB_TAIL_KP")) kp = std::atoi(env);  // tuning experiments
+  kp = std::min(std::max(kp, 1), a.nkb0 - 1);
+  *kp_out = kp;
+  return helpers;
+}
+
+void set_tail_helpers(GemmLaunch* L, int helpers, int kp, float* part, unsigned int* flags) {
+  GemmArgs& a = L->args;
+  a.sk_tiles = static_cast<int>(L->grid.x) / 2;
+  a.sk_helpers = helpers;
+  a.sk_kp = kp;
+  a.sk_part = part;
+  a.sk_flag = flags;
+  a.sk_epoch = 0;
+  L->grid.x = 2 * (a.sk_tiles + helpers);
+}
+
 template <int EPI, int CG>
 static cudaError_t set_smem_attr() {
   return cudaFuncSetAttribute(panel_gemm_kernel<EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -233,7 +294,7 @@ static cudaError_t launch_one(const GemmLaunch& L, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-std::string launch_gemm(const GemmLaunch& L, int epi, cudaStream_t stream) {
+static cudaError_t gemm_attrs_once() {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&]() {
@@ -247,6 +308,11 @@ std::string launch_gemm(const GemmLaunch& L, int epi, cudaStream_t stream) {
     for (cudaError_t x : e)
       if (x != cudaSuccess) attr_err = x;
   });
+  return attr_err;
+}
+
+std::string launch_gemm(const GemmLaunch& L, int epi, cudaStream_t stream) {
+  const cudaError_t attr_err = gemm_attrs_once();
   if (attr_err != cudaSuccess)
     return std::string("cudaFuncSetAttribute(panel_gemm): ") + cudaGetErrorString(attr_err);
   if (epi != EPI_STORE && L.grid.z != 1) return "launch_gemm: fused epilogues require splits == 1";

@@ -64,6 +64,14 @@ std::string set_h_prefetch(GemmLaunch* L, const float* Hm, long long n, long lon
 // EPI_RESID / EPI_KLQ: same staging for the tile of V (m x n column-major, leading dimension ldv).
 std::string set_v_prefetch(GemmLaunch* L, const float* V, long long m, long long n, long long ldv);
 
+// Tail helpers (GemmArgs::sk_*): how many helper CTA pairs a planned CTA-pair launch of `tiles` row tiles can
+// use when `reserve_sms` SMs are to stay free, and the k-block at which the primaries hand over to them.
+// Returns 0 when the launch is not eligible (single CTAs, several column chunks, split-K, segments, a grid
+// that already fills the GPU or one so small that split-K is the better tool).
+int plan_tail_helpers(const GemmLaunch& L, int epi, int num_sms, int reserve_sms, int* kp_out);
+// Adds the helpers to the grid.  part: tiles * ncols * 256 floats; flags: 2 * tiles words, zero-initialised.
+void set_tail_helpers(GemmLaunch* L, int helpers, int kp, float* part, unsigned int* flags);
+
 std::string launch_gemm(const GemmLaunch& L, int epi, cudaStream_t stream);
 
 }  // namespace nmfb

@@ -1,5 +1,6 @@
 // Host side of kl_fused_kernel: tensor maps, launch geometry, the two small finishing kernels.
 #include <algorithm>
+#include <cstdlib>
 
 #include "engine.cuh"
 #include "ew_kernels.cuh"
@@ -17,6 +18,45 @@ struct KlOp {
   bool planned = false;
 };
 
+// Column splits of a kl_fused launch.  One CTA pair is resident per two SMs (shared memory), so a launch of
+// pairs * splits clusters runs in ceil(pairs * splits / slots) waves of equal work items: 32 row blocks x 2 splits
+// keep 64 of the 74 pair slots busy, 32 x 9 fill 3.9 of 4 waves.  The estimate charges every work item a fixed
+// overhead (launch, TMEM allocation, the F tile, pipeline fill and drain: about four 64-column tiles) and every
+// extra split the traffic of one more partial slab (written by the kernel, read by the kernel that sums them).
+int choose_kl_splits(int pairs, int total_tiles, int rows, int Kp, int slots, int* per_out) {
+  int cap = 0;  // NMFB_KL_SPLITS=<n>: fixed number of splits (experiments); "0" = the round-1 rule (one wave)
+  const char* env = std::getenv("NMFB_KL_SPLITS");
+  if (env) cap = std::atoi(env);
+  const double tile_us = 1.2 * Kp / 128.0;                                  // measured: 0.62 ms for 512 tiles, Kp = 128
+  const double slab_us = static_cast<double>(rows) * Kp * 8.0 / 5.0e6;     // write + read of one slab at ~5 TB/s
+  auto shape = [&](int s, int* per) {
+    int p = (total_tiles + s - 1) / s;
+    p = (p + kKlOutChunk - 1) / kKlOutChunk * kKlOutChunk;  // whole accumulation chunks per split
+    *per = p;
+    return (total_tiles + p - 1) / p;
+  };
+  int best_s = 1, best_per = 0;
+  double best = 1e300;
+  const int s_max = std::max(1, std::min(total_tiles / kKlOutChunk, 64));
+  for (int s = 1; s <= s_max; ++s) {
+    int per = 0;
+    const int splits = shape(s, &per);
+    if (splits != s) continue;  // same shape as a smaller s
+    if (env && cap > 0 && s != std::min(cap, s_max)) continue;
+    if (env && cap == 0 && s != std::max(1, std::min(slots / pairs, total_tiles))) continue;
+    const long long waves = (static_cast<long long>(pairs) * splits + slots - 1) / slots;
+    const double t = waves * (per + 4.0) * tile_us + splits * slab_us;
+    if (t < best) {
+      best = t;
+      best_s = splits;
+      best_per = per;
+    }
+  }
+  if (best_per == 0) best_s = shape(1, &best_per);
+  *per_out = best_per;
+  return best_s;
+}
+
 // F: [Kp][ldf] rows contiguous (length rows); G: [Kp][ldg] (length cols); VT: [cols][ldvt] (rows contiguous)
 int plan_kl(nmfb_handle* h, Arena* ar, KlOp* op, const float* F, long long ldf, const float* G, long long ldg,
             const float* VT, long long ldvt, int rows, int cols, int Kp, const int* stop) {
@@ -29,11 +69,8 @@ int plan_kl(nmfb_handle* h, Arena* ar, KlOp* op, const float* F, long long ldf, 
     return h->fail(NMFB_ERR_CUDA, "kl V %s", e.c_str());
   const int pairs = (rows + 2 * kTileM - 1) / (2 * kTileM);
   const int total_tiles = (cols + kKlTileC - 1) / kKlTileC;
-  int splits = std::max(1, (h->num_sms / 2) / pairs);
-  splits = std::min(splits, total_tiles);
-  int per = (total_tiles + splits - 1) / splits;
-  per = (per + kKlOutChunk - 1) / kKlOutChunk * kKlOutChunk;  // whole accumulation chunks per split
-  splits = (total_tiles + per - 1) / per;
+  int per = 0;
+  const int splits = choose_kl_splits(pairs, total_tiles, rows, Kp, h->num_sms / 2, &per);
   op->splits = splits;
   op->grid = dim3(2 * pairs, splits, 1);
   KlArgs& a = op->args;

@@ -31,6 +31,9 @@
 
 using namespace nmfb;
 
+// SMs a contraction with tail helpers leaves to the Gram product running beside it (two CTA pairs)
+static constexpr int kTailReserveSms = 4;
+
 struct NmfSession {
   Arena ar;
   int K = 0, Kp = 0, m = 0, n = 0;
@@ -43,6 +46,7 @@ struct NmfSession {
   bool side_gh = false;  // several GPUs: gram(H) runs beside the A GEMM, joined before the all-reduce
   unsigned int* gates = nullptr;  // [0] G_H ready for iteration i (value i+1), [1] G_W ready
   bool h_split = false;  // too few sample tiles for the fused H update: split-K GEMM + h_finish
+  bool tail_a = false, tail_h = false;  // the A / H-step contraction runs with tail helpers on the idle SMs
   int h_tile_n = 0;      // fused H update with narrower tiles (more CTAs) instead of split-K
   float *Nbuf = nullptr, *Dbuf = nullptr;
   float lambda_w = 0.f, lambda_h = 0.f;
@@ -474,16 +478,32 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     const int ctasHf = h_tile_n > 0 ? ctasH * ((Kp + h_tile_n - 1) / h_tile_n) : ctasH;  // fused kernel's grid
     const bool h_grid_fits = s->h_split ? ctasH + 20 <= h->num_sms : ctasHf + 8 <= h->num_sms;
     s->gate_h = ((s->overlap && !s->h_split) || (can_side && s->h_split)) && h_grid_fits;
+    // Tail helpers (panel_gemm.cuh, GemmArgs::sk_*): at the north-star shape each of the two contractions has 64
+    // pair tiles - 128 of 148 SMs.  Helper pairs take the tails of the contractions so that 144 SMs work through
+    // the whole launch; the Gram product running beside it is then planned for the 4 SMs that stay free.
+    auto helpers_for = [&](int epi, int rows, long long kdim) {
+      if (multi || Kp > kMaxN) return 0;
+      GemmLaunch d;
+      std::memset(&d, 0, sizeof(d));
+      d.cg = choose_cg(epi, rows, Kp, false, false, 0);
+      d.grid = dim3(static_cast<unsigned>((rows + 2 * kTileM - 1) / (2 * kTileM)) * 2, 1, 1);
+      d.args.nkb0 = d.args.nkb_seg = static_cast<int>((kdim + kBlockK - 1) / kBlockK);
+      int kp = 0;
+      return plan_tail_helpers(d, epi, h->num_sms, kTailReserveSms, &kp);
+    };
+    s->tail_a = s->overlap && helpers_for(EPI_STORE, m, n) > 0;
+    s->tail_h = s->gate_h && !s->h_split && h_tile_n == 0 && helpers_for(EPI_HUPDATE, n, m) > 0;
     s->side_gh = multi && can_side;
     {
       const char* e4 = std::getenv("NMFB_WS_SIDE");
       s->ws_open_barrier = s->w_sharded && s->side_gh && !s->direct_cost && !(e4 && e4[0] == '0');
     }
   }
-  NMFB_TRY(plan_gram(h, ar, &s->gramW, s->Wt, Kp, m, s->ldw, stop, nullptr, 0, s->gate_h ? 20 : 0));
+  NMFB_TRY(plan_gram(h, ar, &s->gramW, s->Wt, Kp, m, s->ldw, stop, nullptr, 0,
+                     s->gate_h ? (s->tail_h ? kTailReserveSms : 20) : 0));
   if (!kl) {
     NMFB_TRY(plan_gram(h, ar, &s->gramH, s->Ht, Kp, n, s->ldh, stop, nullptr, 0,
-                       (s->overlap || s->side_gh) ? 20 : 0));
+                       (s->overlap || s->side_gh) ? (s->tail_a ? kTailReserveSms : 20) : 0));
     if (multi) {  // G_H must sit behind A in the packed buffer
       s->gramH.g32 = s->packed + static_cast<size_t>(Kp) * s->ldw;
     }
@@ -519,6 +539,7 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
       NMFB_TRY(plan_store(h, ar, &s->gemmA, Xv, Yh, n, &Xw, &Yg, Kp, m, Kp, s->A, s->B, s->ldw, false,
                           stop));
       if (s->overlap) s->gemmA.L.args.gate = s->gates + 0;
+      if (s->tail_a) NMFB_TRY(enable_tail_helpers(h, ar, &s->gemmA, kTailReserveSms));
     }
     // H update: N = W'V, D = G_W H (X = H, columns j contiguous -> MN-major).
     // Reading V with the contraction index contiguous (K-major) makes every TMA row a lone
@@ -560,10 +581,12 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
       NMFB_TRY(rc);
     } else {
     NMFB_TRY(plan_fused(h, &s->gemmH, EPI_HUPDATE, Xvt, Yw, m, &Xh, &Ygw, Kp, n, Kp, Kp, stop, nullptr, s->h_tile_n));
+    if (s->tail_h) NMFB_TRY(enable_tail_helpers(h, ar, &s->gemmH, kTailReserveSms));
     }
     if (s->gate_h) {
       const dim3 g = s->gemmH.L.grid;
-      if (static_cast<int>(g.x * g.y * g.z) + 8 > h->num_sms)  // cannot happen with the guard above
+      const int spare = s->gemmH.L.args.sk_helpers > 0 ? kTailReserveSms : 8;
+      if (static_cast<int>(g.x * g.y * g.z) + spare > h->num_sms)  // cannot happen with the guard above
         return h->fail(NMFB_ERR_CUDA, "internal: gated H-step grid of %u CTAs leaves no SM for gram(W)", g.x * g.y * g.z);
       s->gemmH.L.args.gate = s->gates + 1;
     }
@@ -667,6 +690,10 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     }
     }
   }
+  if (trace && !kl)
+    fprintf(stderr, "[nmfb] nmf setup: tail helpers A %d pairs (primaries stop at k-block %d of %d), H step %d pairs (%d of %d)\n",
+            s->gemmA.L.args.sk_helpers, s->gemmA.L.args.sk_kp, s->gemmA.L.args.nkb0, s->gemmH.L.args.sk_helpers,
+            s->gemmH.L.args.sk_kp, s->gemmH.L.args.nkb0);
   if (s->W_fixed) NMFB_TRY(run_gram(h, s->gramW, nullptr));
   D2FArgs da{s->wsum, s->wsf, Kp};
   d2f_kernel<<<(Kp + 127) / 128, 128, 0, h->stream>>>(da, nullptr);

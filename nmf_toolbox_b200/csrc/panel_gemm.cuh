@@ -139,6 +139,19 @@ struct GemmArgs {
   // its first phase-1 load.  Only valid when the grid leaves SMs free for that kernel.
   const unsigned int* gate;
   unsigned int gate_value;
+  // Tail helpers (CTA-pair kernels, one column chunk, no split-K): a grid of `sk_tiles` row tiles that
+  // leaves SMs idle (64 pair tiles on 148 SMs) is extended by `sk_helpers` CTA pairs.  The pair of row
+  // tile t (the "primary") contracts k-blocks [0, sk_kp) only; helper pair h contracts the tail
+  // [sk_kp, nkb0) of the tiles h, h + sk_helpers, ... one after the other, leaves each partial sum in
+  // sk_part ([tile][column][256 rows], L2-resident) and publishes sk_flag[2 * tile + cta] = sk_epoch.  The
+  // primary adds the partial to its own sum (registers) before its epilogue, so the fused epilogues are
+  // unchanged and every SM works through the whole launch (stream-K with a fixed split).
+  int sk_helpers;
+  int sk_tiles;
+  int sk_kp;
+  float* sk_part;
+  unsigned int* sk_flag;
+  unsigned int sk_epoch;
 };
 
 // EPI_ABQ: 16 columns of one row.  The mode is uniform over the launch, so the three variants are
@@ -255,15 +268,24 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
   const uint32_t crank = kPair ? cluster_ctarank() : 0u;  // rank in the cluster (CG = 4: 0..3, two pairs)
   const uint32_t rank = crank & 1u;                        // position in the CTA pair; 0 = leader (issues the MMAs)
   const uint32_t lead = crank & ~1u;                       // cluster rank of this pair's leader
-  const int r0 = kPair ? static_cast<int>(blockIdx.x >> 1) * (2 * kTileM) + static_cast<int>(rank) * kTileM
-                       : static_cast<int>(blockIdx.x) * kTileM;
+  // tail helpers (see GemmArgs): work items of this CTA pair
+  const bool sk = kPair && CG == 2 && a.sk_helpers > 0;
+  const int pair_idx = static_cast<int>(blockIdx.x >> 1);
+  const bool helper = sk && pair_idx >= a.sk_tiles;
+  const int first_tile = helper ? pair_idx - a.sk_tiles : pair_idx;
+  const int n_items = helper ? (a.sk_tiles - first_tile + a.sk_helpers - 1) / a.sk_helpers : 1;
+  const int item_rows = sk ? a.sk_helpers * 2 * kTileM : 0;  // row distance between a helper's tiles
+  const int r0_first = kPair ? first_tile * (2 * kTileM) + static_cast<int>(rank) * kTileM
+                             : static_cast<int>(blockIdx.x) * kTileM;
+  const int r0 = r0_first;  // primaries and every kernel without helpers: the one row tile of this CTA
   const int tile_n = a.tile_n > 0 ? a.tile_n : kMaxN;
   const int n0 = blockIdx.y * tile_n;
   const int bn = min(a.ncols - n0, tile_n);  // multiple of 32
   const int split = blockIdx.z;
-  const int kb_begin = split * a.kb_per_split;
-  const int n0kb = max(0, min(a.nkb0, kb_begin + a.kb_per_split) - kb_begin);
-  const int n1kb = (split == 0) ? a.nkb1 : 0;
+  const int kb_begin = sk ? (helper ? a.sk_kp : 0) : split * a.kb_per_split;
+  const int n0kb = sk ? (helper ? a.nkb0 - a.sk_kp : a.sk_kp)
+                      : max(0, min(a.nkb0, kb_begin + a.kb_per_split) - kb_begin);
+  const int n1kb = (split == 0 && !helper) ? a.nkb1 : 0;
   const int chunk_kb = a.chunk_kb > 0 ? a.chunk_kb : kChunkKb;
   const int nchunk0 = (n0kb + chunk_kb - 1) / chunk_kb;
   const int nchunks = nchunk0 + (n1kb > 0 ? 1 : 0);
@@ -313,6 +335,8 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     const int total = n0kb + n1kb;
     int stage = 0;
     uint32_t phase = 0;
+    for (int item = 0; item < n_items; ++item) {
+    const int r0 = r0_first + item * item_rows;  // a helper pair walks over its row tiles
     for (int it = 0; it < total; ++it) {
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -361,9 +385,10 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         phase ^= 1;
       }
     }
+    }
     if constexpr (EPI == EPI_HUPDATE || EPI == EPI_RESID || EPI == EPI_KLQ || EPI == EPI_ABQ) {
       // (EPI_RESID / EPI_KLQ / EPI_ABQ: the staged tile is the 128-row x bn-column tile of V)
-      if (a.h_prefetch) {
+      if (a.h_prefetch && !helper) {
         // the ring is not used again: wait until every stage has been consumed, then reuse the
         // buffers for this CTA's 128-sample tile of the H master, [k][128 samples] fp32
         for (int s2 = 0; s2 < kNStages; ++s2) {
@@ -382,9 +407,10 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     // ------------------------------------------------ MMA issuer (leader CTA of a pair)
     int stage = 0;
     uint32_t phase = 0;
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const int buf = ch & 1;
-      const int use = ch >> 1;
+    for (int gch = 0; gch < n_items * nchunks; ++gch) {  // chunks of all items alternate between the two buffers
+      const int ch = gch % nchunks;
+      const int buf = gch & 1;
+      const int use = gch >> 1;
       if (use > 0) {
         if constexpr (kPair) mbar_wait_cluster(&tempty_bar[buf], (use - 1) & 1);
         else mbar_wait(&tempty_bar[buf], (use - 1) & 1);
@@ -450,9 +476,11 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       tc_fence_after();
     }
     // promote finished phase-0 chunks from TMEM into registers
-    for (int ch = 0; ch < (direct ? 0 : nchunk0); ++ch) {
-      const int buf = ch & 1;
-      mbar_wait(&tfull_bar[buf], (ch >> 1) & 1);
+    int gch = 0;  // chunks seen so far (a helper pair runs through several row tiles)
+    for (int item = 0; item < n_items; ++item) {
+    for (int ch = 0; ch < (direct ? 0 : nchunk0); ++ch, ++gch) {
+      const int buf = gch & 1;
+      mbar_wait(&tfull_bar[buf], (gch >> 1) & 1);
       tc_fence_after();
       const uint32_t t0 = tlane + static_cast<uint32_t>(buf * kMaxN + g_begin * 16);
 #pragma unroll
@@ -470,6 +498,42 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       if (lane == 0) {
         if constexpr (kPair) mbar_arrive_remote(map_to_cta(smem_u32(&tempty_bar[buf]), lead));
         else mbar_arrive(&tempty_bar[buf]);
+      }
+    }
+    if (helper) {
+      // tail helper: the partial sum of this row tile goes to the scratch slab (coalesced along the rows, kept
+      // in L2), then the flag its primary CTA is waiting for
+      const int tile = first_tile + item * a.sk_helpers;
+      float* p = a.sk_part + (static_cast<long long>(tile) * a.ncols + g_begin * 16) * (2 * kTileM) +
+                 static_cast<int>(rank) * kTileM + q * 32 + lane;
+#pragma unroll
+      for (int g = 0; g < kMaxGroups; ++g) {
+        if (g < g_count) {
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            __stcg(p + (g * 16 + t) * (2 * kTileM), sum[g * 16 + t]);
+            sum[g * 16 + t] = 0.f;
+          }
+        }
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // epilogue warps only
+      if (warp == 2 && lane == 0) gate_publish(a.sk_flag + 2 * tile + static_cast<int>(rank), a.sk_epoch);
+    }
+    }
+    if (!helper) {
+    if (sk) {
+      // primary: add the tail of the contraction, formed by a helper pair meanwhile
+      if (lane == 0) gate_wait(a.sk_flag + 2 * pair_idx + static_cast<int>(rank), a.sk_epoch);
+      __syncwarp();
+      const float* p = a.sk_part + (static_cast<long long>(pair_idx) * a.ncols + g_begin * 16) * (2 * kTileM) +
+                       static_cast<int>(rank) * kTileM + q * 32 + lane;
+#pragma unroll
+      for (int g = 0; g < kMaxGroups; ++g) {
+        if (g < g_count) {
+#pragma unroll
+          for (int t = 0; t < 16; ++t) sum[g * 16 + t] += __ldcg(p + (g * 16 + t) * (2 * kTileM));
+        }
       }
     }
     // second accumulator (if any) sits in the next buffer of the alternation
@@ -670,6 +734,7 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         }
       }
     }
+    }  // !helper
   }
 
   tc_fence_before();

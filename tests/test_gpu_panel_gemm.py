@@ -17,13 +17,21 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=[1, 2, 4], ids=["cta1", "cta_pair", "two_pairs_multicast"])
+@pytest.fixture(autouse=True, params=[1, 2, 4, "2+tail"],
+                ids=["cta1", "cta_pair", "two_pairs_multicast", "cta_pair_tail_helpers"])
 def cta_group(request):
-    """Every kernel-level test runs on the single-CTA kernel, on the CTA-pair (cta_group::2) kernel and on the
-    cluster of two pairs that share the Y slab by TMA multicast (shapes it cannot take fall back to pairs)."""
-    os.environ["NMFB_DEBUG_CG"] = str(request.param)
+    """Every kernel-level test runs on the single-CTA kernel, on the CTA-pair (cta_group::2) kernel, on the
+    cluster of two pairs that share the Y slab by TMA multicast (shapes it cannot take fall back to pairs) and
+    on the pair kernel with tail helpers (two extra CTA pairs that contract the last third / half of every row
+    tile's k-blocks and hand the partial sums to the primaries; launches with several column chunks or split-K
+    run without them)."""
+    tail = request.param == "2+tail"
+    os.environ["NMFB_DEBUG_CG"] = "2" if tail else str(request.param)
+    if tail:
+        os.environ["NMFB_DEBUG_TAIL"] = "2"
     yield request.param
     os.environ.pop("NMFB_DEBUG_CG", None)
+    os.environ.pop("NMFB_DEBUG_TAIL", None)
 
 
 class DebugMat(ctypes.Structure):

@@ -120,6 +120,25 @@ def test_nmf_euclid_both_h_paths(api, handle, h_split, monkeypatch):
     assert cost_err(c, co) < COST_TOL and recon_err(W, H, Wo, Ho) < RECON_TOL
 
 
+def test_nmf_euclid_tail_helpers(api, handle, monkeypatch):
+    """38 / 39 pair tiles per contraction: too many for split-K, too few to fill 148 SMs.  Helper CTA pairs
+    contract the last third of every row tile's k-blocks and hand the partial sums to the primaries
+    (panel_gemm.cuh, GemmArgs::sk_*); same parity bar, and the run without helpers agrees to rounding."""
+    m, n, K, iters = 9600, 9750, 40, 10
+    rng = np.random.default_rng(5)
+    V = np.maximum(rng.random((m, n), dtype=np.float32), 2.0 ** -24).astype(np.float64)
+    cfg = dict(divergence="euclidean", W_init=np.maximum(rng.random((m, K)), O.EPS),
+               H_init=np.maximum(rng.random((K, n)), O.EPS), maxiter=iters, tolerance=1e-300)
+    W, H, c = api.nmf(V, K, cfg, handle=handle)
+    Wo, Ho, co = O.nmf(V, K, cfg)
+    assert cost_err(c, co) < COST_TOL
+    assert recon_err(W, H, Wo, Ho) < RECON_TOL
+    monkeypatch.setenv("NMFB_TAIL_HELPERS", "0")
+    W1, H1, c1 = api.nmf(V, K, cfg, handle=handle)
+    assert cost_err(c, c1) < 1e-5
+    assert recon_err(W, H, W1.astype(np.float64), H1.astype(np.float64)) < 1e-4
+
+
 @pytest.mark.parametrize("m,n,K,h_split", [(700, 900, 300, "1"), (700, 900, 300, "0"), (900, 700, 512, "1"), (64, 50, 70, "1")])
 def test_nmf_euclid_more_bases_than_one_column_chunk(api, handle, m, n, K, h_split, monkeypatch):
     """K > 256 spans several 256-wide accumulator chunks (grid.y > 1); K > m, n is legal too."""
