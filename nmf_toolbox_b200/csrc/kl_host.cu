@@ -1,10 +1,12 @@
 // Host side of kl_fused_kernel: tensor maps, launch geometry, the two small finishing kernels.
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "engine.cuh"
 #include "ew_kernels.cuh"
 #include "kl_fused.cuh"
+#include "ab_fused.cuh"
 #include "resid_fused.cuh"
 
 namespace nmfb {
@@ -18,43 +20,58 @@ struct KlOp {
   bool planned = false;
 };
 
-// Column splits of a kl_fused launch.  One CTA pair is resident per two SMs (shared memory), so a launch of
-// pairs * splits clusters runs in ceil(pairs * splits / slots) waves of equal work items: 32 row blocks x 2 splits
-// keep 64 of the 74 pair slots busy, 32 x 9 fill 3.9 of 4 waves.  The estimate charges every work item a fixed
-// overhead (launch, TMEM allocation, the F tile, pipeline fill and drain: about four 64-column tiles) and every
-// extra split the traffic of one more partial slab (written by the kernel, read by the kernel that sums them).
-int choose_kl_splits(int pairs, int total_tiles, int rows, int Kp, int slots, int* per_out) {
-  int cap = 0;  // NMFB_KL_SPLITS=<n>: fixed number of splits (experiments); "0" = the round-1 rule (one wave)
-  const char* env = std::getenv("NMFB_KL_SPLITS");
-  if (env) cap = std::atoi(env);
-  const double tile_us = 1.2 * Kp / 128.0;                                  // measured: 0.62 ms for 512 tiles, Kp = 128
-  const double slab_us = static_cast<double>(rows) * Kp * 8.0 / 5.0e6;     // write + read of one slab at ~5 TB/s
-  auto shape = [&](int s, int* per) {
-    int p = (total_tiles + s - 1) / s;
-    p = (p + kKlOutChunk - 1) / kKlOutChunk * kKlOutChunk;  // whole accumulation chunks per split
-    *per = p;
-    return (total_tiles + p - 1) / p;
-  };
-  int best_s = 1, best_per = 0;
+// Column splits of a kl_fused / ab_fused launch.  One CTA pair is resident per two SMs (shared memory), so the
+// pairs * splits clusters of a launch run as work items on `slots` pair slots, handed out in launch order (all
+// row blocks of split 0, then split 1, ...).  32 row blocks x 2 equal splits keep 64 of the 74 slots busy for
+// the whole launch; 32 x 3 with splits of 444 + 444 + 136 tiles put the 64 long items on 64 slots and the 32
+// short ones on the other 10 (three or four each): same work, every slot busy.  The planner tries every split
+// length (a multiple of the accumulation chunk; the last split takes the remainder), plays the launch through
+// a list scheduler and keeps the shortest.  Every work item is charged a fixed overhead (launch, TMEM
+// allocation, the F tile, pipeline fill, the partial slab, teardown: ~10 column tiles, fitted to measured launches
+// with 1, 2 and 9 equal splits) and every split the traffic of one more partial slab.
+int choose_kl_splits(int pairs, int total_tiles, int rows, int Kp, int slots, int* per_out, int max_per = 0) {
+  const char* env = std::getenv("NMFB_KL_SPLITS");  // "0": the round-1 rule (one wave of equal splits); n > 0: n equal splits
+  const int forced = env ? std::atoi(env) : -1;
+  const double tile_us = 1.2 * Kp / 128.0;                                // measured: 0.62 ms for 512 tiles, Kp = 128
+  const double slab_us = static_cast<double>(rows) * Kp * 8.0 / 5.0e6;   // write + read of one slab at ~5 TB/s
+  const double item_overhead = 10.0;                                      // in tiles
+  auto round_chunk = [](int p) { return (p + kKlOutChunk - 1) / kKlOutChunk * kKlOutChunk; };
+  if (max_per <= 0) max_per = total_tiles;
+  max_per = std::max(kKlOutChunk, max_per / kKlOutChunk * kKlOutChunk);
+  if (forced >= 0) {
+    const int s = forced > 0 ? forced : std::max(1, std::min(slots / std::max(1, pairs), total_tiles));
+    const int per = std::min(max_per, round_chunk((total_tiles + s - 1) / s));
+    *per_out = per;
+    return (total_tiles + per - 1) / per;
+  }
+  int best_per = std::min(max_per, round_chunk(total_tiles));
   double best = 1e300;
-  const int s_max = std::max(1, std::min(total_tiles / kKlOutChunk, 64));
-  for (int s = 1; s <= s_max; ++s) {
-    int per = 0;
-    const int splits = shape(s, &per);
-    if (splits != s) continue;  // same shape as a smaller s
-    if (env && cap > 0 && s != std::min(cap, s_max)) continue;
-    if (env && cap == 0 && s != std::max(1, std::min(slots / pairs, total_tiles))) continue;
-    const long long waves = (static_cast<long long>(pairs) * splits + slots - 1) / slots;
-    const double t = waves * (per + 4.0) * tile_us + splits * slab_us;
-    if (t < best) {
+  std::vector<double> slot_free(static_cast<size_t>(std::max(1, slots)));
+  for (int per = kKlOutChunk; per <= std::min(max_per, round_chunk(total_tiles)); per += kKlOutChunk) {
+    const int splits = (total_tiles + per - 1) / per;
+    if (static_cast<long long>(splits) * pairs > 65535 || splits > 256) continue;
+    std::fill(slot_free.begin(), slot_free.end(), 0.0);
+    // list scheduling in launch order; the slots form a heap keyed by the time they become free
+    auto cmp = [](double x, double y) { return x > y; };
+    double makespan = 0.0;
+    for (int y = 0; y < splits; ++y) {
+      const double len = std::min(per, total_tiles - y * per) + item_overhead;
+      for (int p = 0; p < pairs; ++p) {
+        std::pop_heap(slot_free.begin(), slot_free.end(), cmp);
+        const double done = slot_free.back() + len;
+        slot_free.back() = done;
+        std::push_heap(slot_free.begin(), slot_free.end(), cmp);
+        makespan = std::max(makespan, done);
+      }
+    }
+    const double t = makespan * tile_us + splits * slab_us;
+    if (t < best * (1.0 - 1e-9)) {
       best = t;
-      best_s = splits;
       best_per = per;
     }
   }
-  if (best_per == 0) best_s = shape(1, &best_per);
   *per_out = best_per;
-  return best_s;
+  return (total_tiles + best_per - 1) / best_per;
 }
 
 // F: [Kp][ldf] rows contiguous (length rows); G: [Kp][ldg] (length cols); VT: [cols][ldvt] (rows contiguous)
@@ -107,6 +124,89 @@ int run_kl(nmfb_handle* h, const KlOp& op) {
   cudaError_t e = cudaLaunchKernelEx(&cfg, kl_fused_kernel, op.tmF, op.tmG1, op.tmG2, op.tmV, op.args);
   ++h->launches;
   if (e != cudaSuccess) return h->fail(NMFB_ERR_CUDA, "launch of kl_fused failed: %s", cudaGetErrorString(e));
+  return NMFB_OK;
+}
+
+// ---------------------------------------------------------------- ab_fused (IS / AB divergences)
+struct AbOp {
+  CUtensorMap tmF, tmG1, tmG2, tmV;
+  AbArgs args;
+  dim3 grid;
+  int splits = 1;
+  int mode = ABQ_IS;
+  float* parts_n = nullptr;
+  float* parts_p = nullptr;
+  bool planned = false;
+};
+
+// Same operand conventions as plan_kl; mode = ABQ_IS / ABQ_AB / ABQ_AB_DUAL.
+int plan_ab(nmfb_handle* h, Arena* ar, AbOp* op, const float* F, long long ldf, const float* G, long long ldg,
+            const float* VT, long long ldvt, int rows, int cols, int Kp, int mode, float alpha, float beta,
+            const int* stop) {
+  if (Kp % 32 != 0 || Kp > kKlMaxKp) return h->fail(NMFB_ERR_INVALID_ARGUMENT, "plan_ab: Kp must be 32..128");
+  std::string e;
+  if (!(e = make_tmap(&op->tmF, Mat2D{F, rows, Kp, ldf}, 32, 32, true)).empty()) return h->fail(NMFB_ERR_CUDA, "ab F %s", e.c_str());
+  if (!(e = make_tmap(&op->tmG1, Mat2D{G, cols, Kp, ldg}, 32, 32, true)).empty()) return h->fail(NMFB_ERR_CUDA, "ab G1 %s", e.c_str());
+  if (!(e = make_tmap(&op->tmG2, Mat2D{G, cols, Kp, ldg}, 32, Kp / 2, false)).empty()) return h->fail(NMFB_ERR_CUDA, "ab G2 %s", e.c_str());
+  if (!(e = make_tmap(&op->tmV, Mat2D{VT, rows, cols, ldvt}, kTileM, kKlTileC, false, true)).empty())
+    return h->fail(NMFB_ERR_CUDA, "ab V %s", e.c_str());
+  const int pairs = (rows + 2 * kTileM - 1) / (2 * kTileM);
+  const int total_tiles = (cols + kKlTileC - 1) / kKlTileC;
+  int max_tiles = kAbMaxTiles;
+  if (const char* env = std::getenv("NMFB_AB_MAX_TILES")) max_tiles = std::max(kKlOutChunk, std::atoi(env));  // experiments
+  int per = 0;
+  const int splits = choose_kl_splits(pairs, total_tiles, rows, 2 * Kp, h->num_sms / 2, &per, max_tiles);
+  op->splits = splits;
+  op->mode = mode;
+  op->grid = dim3(2 * pairs, splits, 1);
+  AbArgs& a = op->args;
+  a.rows = rows;
+  a.cols = cols;
+  a.Kp = Kp;
+  a.tiles_per_split = per;
+  a.want_cost = 0;
+  a.alpha = alpha;
+  a.beta = beta;
+  a.ldo = (rows + 3) / 4 * 4;
+  a.slab = static_cast<long long>(Kp) * a.ldo;
+  a.scal = nullptr;
+  a.stop = stop;
+  NMFB_TRY(ar->alloc(h, &op->parts_n, static_cast<size_t>(splits) * a.slab));
+  NMFB_TRY(ar->alloc(h, &op->parts_p, static_cast<size_t>(splits) * a.slab));
+  a.out_n = op->parts_n;
+  a.out_p = op->parts_p;
+  op->planned = true;
+  return NMFB_OK;
+}
+
+int run_ab(nmfb_handle* h, const AbOp& op) {
+  static cudaError_t attr = []() {
+    cudaError_t e0 = cudaFuncSetAttribute(ab_fused_kernel<ABQ_IS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes);
+    cudaError_t e1 = cudaFuncSetAttribute(ab_fused_kernel<ABQ_AB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes);
+    cudaError_t e2 = cudaFuncSetAttribute(ab_fused_kernel<ABQ_AB_DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes);
+    return e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2);
+  }();
+  if (attr != cudaSuccess) return h->fail(NMFB_ERR_CUDA, "cudaFuncSetAttribute(ab_fused): %s", cudaGetErrorString(attr));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = op.grid;
+  cfg.blockDim = dim3(kKlThreads);
+  cfg.dynamicSmemBytes = kAbSmemBytes;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaSuccess;
+  switch (op.mode) {
+    case ABQ_IS: e = cudaLaunchKernelEx(&cfg, ab_fused_kernel<ABQ_IS>, op.tmF, op.tmG1, op.tmG2, op.tmV, op.args); break;
+    case ABQ_AB: e = cudaLaunchKernelEx(&cfg, ab_fused_kernel<ABQ_AB>, op.tmF, op.tmG1, op.tmG2, op.tmV, op.args); break;
+    default: e = cudaLaunchKernelEx(&cfg, ab_fused_kernel<ABQ_AB_DUAL>, op.tmF, op.tmG1, op.tmG2, op.tmV, op.args); break;
+  }
+  ++h->launches;
+  if (e != cudaSuccess) return h->fail(NMFB_ERR_CUDA, "launch of ab_fused failed: %s", cudaGetErrorString(e));
   return NMFB_OK;
 }
 

@@ -82,6 +82,8 @@ struct NmfSession {
   double ab_scale = 0.0; // -1/(alpha beta) of the AB cost (nmf.m:214)
   KlOp klW, klH;         // fused KL halves (kl_fused.cuh)
   bool kl_fused = false;
+  AbOp abW, abH;         // fused IS / AB halves (ab_fused.cuh)
+  bool ab_fused = false;
   bool kl_store_n = false;  // unfused KL whose H step needs N = W'Q as a matrix (lnmf, per-source settings, tied Z)
   // constrainednmf.m: H = Z*A, A the 0/1 label matrix (columns of H tied to columns of Z)
   bool tied = false;
@@ -152,10 +154,32 @@ static int plan_two_weight(nmfb_handle* h, NmfSession* s, const nmfb_config& cfg
     s->expo = static_cast<float>(1.0 / (dual ? cfg.beta : cfg.alpha));
     s->ab_scale = -1.0 / (cfg.alpha * cfg.beta);
   }
-  NMFB_TRY(ar->alloc(h, &s->Q, static_cast<size_t>(n) * h->ldv));
-  NMFB_TRY(ar->alloc(h, &s->Q2, static_cast<size_t>(n) * h->ldv));
   NMFB_TRY(ar->alloc(h, &s->Nbuf, static_cast<size_t>(Kp) * s->ldh));
   NMFB_TRY(ar->alloc(h, &s->Dbuf, static_cast<size_t>(Kp) * s->ldh));
+  {
+    // Fused path (ab_fused.cuh): V_hat and the two weight matrices stay on chip.  Needs K <= 128 and a row-major
+    // copy of V for the H half (one m x n buffer instead of the two the unfused path keeps for Qn and Qp).
+    size_t free_b = 0, total_b = 0;
+    const long long ldn = round_up(n, 4);
+    const size_t need = static_cast<size_t>(m) * ldn * sizeof(float);
+    const char* env = std::getenv("NMFB_AB_UNFUSED");
+    if (!(env && env[0] == '1') && Kp <= kKlMaxKp && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess &&
+        free_b + h->pool.held > need + (size_t(1) << 30)) {
+      float* Vrm = nullptr;
+      NMFB_TRY(ar->alloc(h, &Vrm, static_cast<size_t>(m) * ldn));
+      dim3 grid((n + 31) / 32, (m + 31) / 32);
+      transpose_kernel<<<grid, dim3(32, 8), 0, h->stream>>>(h->Vraw, h->ldv, Vrm, ldn, m, n);
+      NMFB_TRY(check_launch(h, "transpose(V)"));
+      const float al = static_cast<float>(cfg.alpha), be = static_cast<float>(cfg.beta);
+      NMFB_TRY(plan_ab(h, ar, &s->abW, s->Wt, s->ldw, s->Ht, s->ldh, h->Vraw, h->ldv, m, n, Kp, mode, al, be, stop));
+      NMFB_TRY(plan_ab(h, ar, &s->abH, s->Ht, s->ldh, s->Wt, s->ldw, Vrm, ldn, n, m, Kp, mode, al, be, stop));
+      s->abW.args.scal = s->scal + 2;
+      s->ab_fused = true;
+      return NMFB_OK;
+    }
+  }
+  NMFB_TRY(ar->alloc(h, &s->Q, static_cast<size_t>(n) * h->ldv));
+  NMFB_TRY(ar->alloc(h, &s->Q2, static_cast<size_t>(n) * h->ldv));
   MatRef Xs{s->Wt, m, Kp, s->ldw, true};
   MatRef Ys{s->Ht, n, Kp, s->ldh, true};
   NMFB_TRY(plan_fused(h, &s->gemmS, EPI_ABQ, Xs, Ys, Kp, nullptr, nullptr, 0, m, round_up(n, 64), n, stop));
@@ -922,11 +946,30 @@ static int enqueue_iteration_two_weight(nmfb_handle* h, NmfSession* s, int i) {
   const int K = s->K, n = s->n;
   const int cost_mode = s->divergence == NMFB_DIV_IS ? 4 : 5;
   const bool multi = comm_size(h->comm) > 1;
+  auto reduce_pair = [&](const AbOp& op, float* out_n, float* out_p) {
+    const long long cnt = op.args.slab;
+    const int blocks = static_cast<int>(std::min<long long>((cnt + 255) / 256, 2048));
+    split_reduce_kernel<<<blocks, 256, 0, h->stream>>>(op.parts_n, op.splits, cnt, out_n, cnt, s->stop);
+    NMFB_TRY(check_launch(h, "split_reduce(OUTn)"));
+    split_reduce_kernel<<<blocks, 256, 0, h->stream>>>(op.parts_p, op.splits, cnt, out_p, cnt, s->stop);
+    return check_launch(h, "split_reduce(OUTp)");
+  };
+  if (s->ab_fused) {
+    // A = Qn H', B = Qp H' (+ the divergence of iteration i-1) in one fused kernel
+    if (!s->W_fixed || i > 0) {
+      s->abW.args.want_cost = i > 0 ? 1 : 0;
+      NMFB_TRY(prof_mark(h, 0));
+      NMFB_TRY(run_ab(h, s->abW));
+      NMFB_TRY(prof_mark(h, 0));
+      if (!s->W_fixed) NMFB_TRY(reduce_pair(s->abW, s->A, s->B));
+    }
+  } else {
   s->gemmS.L.args.want_cost = i > 0 ? 1 : 0;
   NMFB_TRY(run_gemm(h, s->gemmS));  // weights from the current V_hat (+ divergence of iteration i-1)
   if (!s->W_fixed) {
     NMFB_TRY(run_gemm(h, s->gemmR));
     NMFB_TRY(run_gemm(h, s->gemmRb));
+  }
   }
   if (multi) {  // column shards: A, B and the cost sums are partial (one all-reduce, as for euclidean / KL)
     const bool small = s->w_sharded || s->W_fixed;  // the m x K partials are fetched row block by row block instead
@@ -936,8 +979,10 @@ static int enqueue_iteration_two_weight(nmfb_handle* h, NmfSession* s, int i) {
   if (i > 0) NMFB_TRY(enqueue_cost(h, s, i - 1, cost_mode));
   if (!s->W_fixed && s->w_sharded) {
     NMFB_TRY(enqueue_w_sharded(h, s, WSTEP_EUCLID, true));
-    s->gemmS.L.args.want_cost = 0;
-    NMFB_TRY(run_gemm(h, s->gemmS));  // refreshed V_hat (nmf.m:173)
+    if (!s->ab_fused) {
+      s->gemmS.L.args.want_cost = 0;
+      NMFB_TRY(run_gemm(h, s->gemmS));  // refreshed V_hat (nmf.m:173)
+    }
   } else if (!s->W_fixed) {
     WStepArgs w{};
     w.mode = WSTEP_EUCLID;  // same shape: neg = A + W diag(<W,B>), pos = B + W diag(<W,A>)
@@ -957,11 +1002,20 @@ static int enqueue_iteration_two_weight(nmfb_handle* h, NmfSession* s, int i) {
     w.lambda_k = s->lamW_k;
     w.fixed_k = s->fixW_k;
     NMFB_TRY(launch_w_step(h, w));
-    s->gemmS.L.args.want_cost = 0;
-    NMFB_TRY(run_gemm(h, s->gemmS));  // refreshed V_hat (nmf.m:173)
+    if (!s->ab_fused) {
+      s->gemmS.L.args.want_cost = 0;
+      NMFB_TRY(run_gemm(h, s->gemmS));  // refreshed V_hat (nmf.m:173)
+    }
   }
+  if (s->ab_fused) {  // N = W' Qn, D = W' Qp from the refreshed V_hat (nmf.m:173), again without leaving the chip
+    NMFB_TRY(prof_mark(h, 1));
+    NMFB_TRY(run_ab(h, s->abH));
+    NMFB_TRY(prof_mark(h, 1));
+    NMFB_TRY(reduce_pair(s->abH, s->Nbuf, s->Dbuf));
+  } else {
   NMFB_TRY(run_gemm(h, s->gemmHn));
   NMFB_TRY(run_gemm(h, s->gemmHd));
+  }
   if (s->tied) return enqueue_tied_update(h, s, s->Nbuf, 1, 0, s->ldh, s->Dbuf, nullptr, s->expo);
   h_finish_kernel<<<dim3(std::max(1, std::min(64, (n + 1023) / 1024)), K), 256, 0, h->stream>>>(
       s->Nbuf, s->Dbuf, s->Hm, s->Ht, s->ldh, n, s->lambda_h, s->H_fixed ? 1 : 0, s->scal, s->stop, s->expo, s->lamH_k,
@@ -1144,8 +1198,13 @@ static int enqueue_final_cost(nmfb_handle* h, NmfSession* s) {
   const int last = s->iters_enqueued - 1;
   const bool multi = comm_size(h->comm) > 1;
   if (s->two_weight) {
-    s->gemmS.L.args.want_cost = 1;
-    NMFB_TRY(run_gemm(h, s->gemmS));
+    if (s->ab_fused) {
+      s->abW.args.want_cost = 1;
+      NMFB_TRY(run_ab(h, s->abW));
+    } else {
+      s->gemmS.L.args.want_cost = 1;
+      NMFB_TRY(run_gemm(h, s->gemmS));
+    }
     if (multi) NMFB_TRY(comm_allreduce(h, nullptr, 0, nullptr, 0, s->scal, 4));
     return enqueue_cost(h, s, last, s->divergence == NMFB_DIV_IS ? 4 : 5);
   }

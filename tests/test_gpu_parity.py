@@ -302,6 +302,39 @@ def test_nmf_is_ab_vs_oracle(api, handle, div, alpha, beta, lw, lh, m, n, K, ite
     np.testing.assert_allclose((W.astype(np.float64) ** 2).sum(0), 1.0, rtol=1e-5)  # nmf.m:169
 
 
+@pytest.mark.parametrize("div,alpha,beta", [("is", 1, 1), ("ab", 0.5, 0.5), ("ab", 2, 1)])
+def test_nmf_is_ab_fused_kernel_shapes(api, handle, div, alpha, beta):
+    """ab_fused.cuh at a size with several row blocks, several column splits per half and ragged last tiles
+    (2100 x 4170, K = 100 -> 128 padded basis columns): V_hat and both weight matrices stay on chip."""
+    m, n, K, iters = 2100, 4170, 100, 12
+    rng = np.random.default_rng(m + n)
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    cfg = dict(divergence=div, alpha=alpha, beta=beta, W_init=np.maximum(rng.random((m, K)), O.EPS),
+               H_init=np.maximum(rng.random((K, n)), O.EPS), maxiter=iters, tolerance=1e-300, H_sparsity=0.05)
+    W, H, c = api.nmf(V, K, cfg, handle=handle)
+    Wo, Ho, co = O.nmf(V, K, cfg)
+    assert cost_err(c, co) < COST_TOL
+    assert recon_err(W, H, Wo, Ho) < RECON_TOL
+
+
+@pytest.mark.parametrize("K,env", [(24, "1"), (160, None)])
+def test_nmf_is_ab_unfused_path(api, handle, K, env, monkeypatch):
+    """Beyond 128 basis columns (or with NMFB_AB_UNFUSED=1) the two weight matrices are written by the EPI_ABQ
+    epilogue and contracted by four panel GEMMs, as in round 1."""
+    if env:
+        monkeypatch.setenv("NMFB_AB_UNFUSED", env)
+    m, n, iters = 700, 900, 20
+    rng = np.random.default_rng(K)
+    V = np.maximum(rng.random((m, n)), 2.0 ** -24)
+    for div, alpha, beta in [("is", 1, 1), ("ab", 0.5, 1.0)]:
+        cfg = dict(divergence=div, alpha=alpha, beta=beta, W_init=np.maximum(rng.random((m, K)), O.EPS),
+                   H_init=np.maximum(rng.random((K, n)), O.EPS), maxiter=iters, tolerance=1e-300)
+        W, H, c = api.nmf(V, K, cfg, handle=handle)
+        Wo, Ho, co = O.nmf(V, K, cfg)
+        assert cost_err(c, co) < COST_TOL
+        assert recon_err(W, H, Wo, Ho) < RECON_TOL
+
+
 def test_nmf_ab_nonfinite_cost(api, handle):
     """alpha + beta == 0 and alpha * beta == 0 divide by zero in the reference's cost (nmf.m:214): the
     cost entries are Inf / NaN there and here, the factors are still the reference's."""
