@@ -79,6 +79,10 @@ extern "C" int nmfb_create(nmfb_handle** out, int device) {
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
   if (e == cudaSuccess) e = cudaMallocHost(&h->pinned, 64 * sizeof(int));
+  h->stage_half = size_t(8) << 20;
+  if (e == cudaSuccess) e = cudaMallocHost(&h->stage, 2 * h->stage_half);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_stage[0], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_stage[1], cudaEventDisableTiming);
   if (e != cudaSuccess) {
     g_create_error = std::string("handle creation failed: ") + cudaGetErrorString(e);
     delete h;
@@ -99,6 +103,9 @@ extern "C" void nmfb_destroy(nmfb_handle* h) {
   if (h->Vwork) dev_free(h, h->Vwork, h->Vwork_bytes);
   h->pool.trim();
   if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->stage) cudaFreeHost(h->stage);
+  for (cudaEvent_t ev : h->ev_stage)
+    if (ev) cudaEventDestroy(ev);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);

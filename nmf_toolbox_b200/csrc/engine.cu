@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "ew_kernels.cuh"
@@ -242,12 +243,43 @@ int upload_colmajor(nmfb_handle* h, const float* host, int rows, int cols, float
                                  cudaMemcpyHostToDevice, h->stream));
   return NMFB_OK;
 }
-int download_colmajor(nmfb_handle* h, const float* dev, long long ld, int rows, int cols, float* host) {
-  NMFB_CUDA(h, cudaMemcpy2DAsync(host, static_cast<size_t>(rows) * sizeof(float), dev,
-                                 ld * sizeof(float), static_cast<size_t>(rows) * sizeof(float), cols,
-                                 cudaMemcpyDeviceToHost, h->stream));
-  NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+// Device -> host copy of `nrows` rows of `width` bytes (device pitch `pitch`, host rows packed).  Pinned or
+// registered destinations are written directly; pageable ones through the handle's two pinned bounce buffers, the
+// DMA of one chunk running while the host copies the previous one out.  Returns with the data in `host`.
+static int d2h_rows(nmfb_handle* h, char* host, const char* dev, size_t pitch, size_t width, size_t nrows) {
+  if (nrows == 0 || width == 0) return NMFB_OK;
+  cudaPointerAttributes attr{};
+  const bool pageable = cudaPointerGetAttributes(&attr, host) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+  cudaGetLastError();
+  const char* env = std::getenv("NMFB_NO_STAGING");
+  if (!pageable || h->stage == nullptr || width == 0 || width > h->stage_half || (env && env[0] == '1')) {
+    NMFB_CUDA(h, cudaMemcpy2DAsync(host, width, dev, pitch, width, nrows, cudaMemcpyDeviceToHost, h->stream));
+    NMFB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return NMFB_OK;
+  }
+  const size_t rpc = std::max<size_t>(1, h->stage_half / width);  // rows per chunk
+  const size_t nchunks = (nrows + rpc - 1) / rpc;
+  auto issue = [&](size_t c) -> cudaError_t {
+    const int b = static_cast<int>(c & 1);
+    const size_t r0 = c * rpc, r = std::min(rpc, nrows - r0);
+    cudaError_t e = cudaMemcpy2DAsync(h->stage + b * h->stage_half, width, dev + r0 * pitch, pitch, width, r,
+                                      cudaMemcpyDeviceToHost, h->stream);
+    return e != cudaSuccess ? e : cudaEventRecord(h->ev_stage[b], h->stream);
+  };
+  NMFB_CUDA(h, issue(0));
+  if (nchunks > 1) NMFB_CUDA(h, issue(1));
+  for (size_t c = 0; c < nchunks; ++c) {
+    const int b = static_cast<int>(c & 1);
+    NMFB_CUDA(h, cudaEventSynchronize(h->ev_stage[b]));
+    std::memcpy(host + c * rpc * width, h->stage + b * h->stage_half, std::min(rpc, nrows - c * rpc) * width);
+    if (c + 2 < nchunks) NMFB_CUDA(h, issue(c + 2));  // this buffer is free again
+  }
   return NMFB_OK;
+}
+
+int download_colmajor(nmfb_handle* h, const float* dev, long long ld, int rows, int cols, float* host) {
+  return d2h_rows(h, reinterpret_cast<char*>(host), reinterpret_cast<const char*>(dev), ld * sizeof(float),
+                  static_cast<size_t>(rows) * sizeof(float), static_cast<size_t>(cols));
 }
 
 int upload_H(nmfb_handle* h, Arena* ar, const float* host, int K, int n, float* Hm, long long ldh) {
@@ -271,11 +303,16 @@ int download_H(nmfb_handle* h, const float* Hm, long long ldh, int K, int n, flo
   // dst[r = j][c = k] = src[c = k][r = j]
   transpose_kernel<<<grid, dim3(32, 8), 0, h->stream>>>(Hm, ldh, tmp, K, n, K);
   int rc = check_launch(h, "transpose(H out)");
-  if (rc == NMFB_OK) {
-    cudaError_t e = cudaMemcpyAsync(host, tmp, static_cast<size_t>(n) * K * sizeof(float),
-                                    cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    if (e != cudaSuccess) rc = h->fail(NMFB_ERR_CUDA, "download H: %s", cudaGetErrorString(e));
+  if (rc == NMFB_OK) {  // [n][K] packed: rows of K floats
+    const size_t row = static_cast<size_t>(K) * sizeof(float);
+    const size_t group = std::max<size_t>(1, std::min<size_t>(static_cast<size_t>(n), (size_t(1) << 20) / row));
+    // copy in "rows" of `group` samples so that a chunk is a whole number of them (the tail separately)
+    const size_t whole = static_cast<size_t>(n) / group;
+    rc = d2h_rows(h, reinterpret_cast<char*>(host), reinterpret_cast<const char*>(tmp), group * row, group * row, whole);
+    const size_t rest = static_cast<size_t>(n) - whole * group;
+    if (rc == NMFB_OK && rest > 0)
+      rc = d2h_rows(h, reinterpret_cast<char*>(host) + whole * group * row,
+                    reinterpret_cast<const char*>(tmp) + whole * group * row, rest * row, rest * row, 1);
   }
   cudaStreamSynchronize(h->stream);  // (also on the error paths) nothing may still write the block
   dev_free(h, tmp, tmp_bytes);

@@ -84,6 +84,11 @@ struct nmfb_handle {
   // device and took up to 0.8 s when issued per call next to a large pinned user buffer):
   // (64 ints) [0..1] session stop flag / cost count, [2..3] run_chunked flags, [8..15] line-search state (nmfsc)
   int* pinned = nullptr;
+  // two pinned bounce buffers for results that go to pageable host memory (numpy / MATLAB arrays): a direct
+  // cudaMemcpy into pageable memory ran at ~3.7 GB/s (W and H of the north-star call: 9 ms of a 42 ms call)
+  char* stage = nullptr;
+  size_t stage_half = 0;
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
   int m = 0, n = 0;
   long long ldv = 0;
   // working copy (tf32-rounded / rescaled), allocated on demand, same shape as Vraw

@@ -209,29 +209,37 @@ int plan_tail_helpers(const GemmLaunch& L, int epi, int num_sms, int reserve_sms
   if (epi != EPI_STORE && epi != EPI_HUPDATE) return 0;
   const int tiles = static_cast<int>(L.grid.x) / 2;
   if (tiles * 4 <= num_sms) return 0;  // at most half of the SMs busy: split-K territory
-  // co-resident clusters of this kernel (one CTA per SM: shared memory); the helpers must run beside the primaries
+  // co-resident clusters of this kernel (one CTA per SM: shared memory); the helpers must run beside the primaries.
+  // Asked once per process: the occupancy query takes 1 - 100 ms (measured), far too long for every plan.
+  static int cached_clusters[2] = {-1, -1};
+  static std::mutex cache_mutex;
   int max_clusters = 0;
   if (gemm_attrs_once() != cudaSuccess) return 0;
   {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * 74, 1, 1);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = TileCfg<2>::smem_bytes;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = epi == EPI_STORE
-                        ? cudaOccupancyMaxActiveClusters(&max_clusters, panel_gemm_kernel<EPI_STORE, 2>, &cfg)
-                        : cudaOccupancyMaxActiveClusters(&max_clusters, panel_gemm_kernel<EPI_HUPDATE, 2>, &cfg);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      return 0;
+    std::lock_guard<std::mutex> lock(cache_mutex);
+    int& slot = cached_clusters[epi == EPI_STORE ? 0 : 1];
+    if (slot < 0) {
+      slot = 0;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * 74, 1, 1);
+      cfg.blockDim = dim3(kGemmThreads);
+      cfg.dynamicSmemBytes = TileCfg<2>::smem_bytes;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int q = 0;
+      cudaError_t e = epi == EPI_STORE ? cudaOccupancyMaxActiveClusters(&q, panel_gemm_kernel<EPI_STORE, 2>, &cfg)
+                                       : cudaOccupancyMaxActiveClusters(&q, panel_gemm_kernel<EPI_HUPDATE, 2>, &cfg);
+      if (e == cudaSuccess) slot = q;
+      else cudaGetLastError();
     }
+    max_clusters = slot;
   }
+  if (max_clusters <= 0) return 0;
   const int pairs = std::min(num_sms / 2, max_clusters) - (reserve_sms + 1) / 2;
   int helpers = pairs - tiles;
   if (const char* env = std::getenv("NMFB_TAIL_HELPERS")) helpers = std::min(helpers, std::atoi(env));
