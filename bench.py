@@ -68,6 +68,11 @@ CONFIGS = {
             workload="cnmf.m euclidean convolutive MU, V=1025x20000 dense uniform, K=64, T=8"),
     5: dict(alg="nmfsc", divergence=None, m=4096, n=4096, K=128, T=1, sharded=False, H_sparsity=0.7,
             workload="nmfsc.m projected-gradient H (H_sparsity=0.7) + multiplicative W, V=4096x4096 dense uniform, K=128"),
+    # not BASELINE configs: the widened divergences of SURVEY section 8(f), at the shape VERDICT r1 quotes for them
+    6: dict(alg="nmf", divergence="is", m=8192, n=8192, K=128, T=1, sharded=True,
+            workload="nmf.m Itakura-Saito MU (nmf.m:154-156,185-187), V=8192x8192 dense uniform, K=128"),
+    7: dict(alg="nmf", divergence="ab", alpha=0.5, beta=0.5, m=8192, n=8192, K=128, T=1, sharded=True,
+            workload="nmf.m alpha-beta MU (alpha=beta=0.5, nmf.m:161-163,192-194), V=8192x8192 dense uniform, K=128"),
 }
 V_SEED = 1234
 V_BLOCK = 256  # V is generated in blocks of 256 global columns, each with its own seed
@@ -81,6 +86,8 @@ def f_alg(c, m, n, K, T):
     """Algorithmic flops per iteration, SURVEY.md section 8(d)."""
     if c == 3:
         return 8.0 * m * n * K
+    if c in (6, 7):  # per half: V_hat and two weighted products
+        return 12.0 * m * n * K
     KT = K * T
     return 4.0 * m * n * KT + 4.0 * (m + n) * KT * KT
 
@@ -204,6 +211,9 @@ def cpu_reference(config_id, cfg, m, n, K, T, steps, warmup, budget_s):
             c = dict(W_init=W0.astype(np.float64), H_init=H0[:, :nn].astype(np.float64), tolerance=1e-300)
             if cfg["divergence"]:
                 c["divergence"] = cfg["divergence"]
+            for key in ("alpha", "beta"):
+                if key in cfg:
+                    c[key] = cfg[key]
             if cfg.get("H_sparsity"):
                 c["H_sparsity"] = cfg["H_sparsity"]
             return V, c
@@ -371,6 +381,9 @@ def main():
     base = dict(W_init=W0, H_init=H0, tolerance=1e-300)
     if cfg["divergence"]:
         base["divergence"] = cfg["divergence"]
+    for key in ("alpha", "beta"):
+        if key in cfg:
+            base[key] = cfg[key]
     if cfg.get("H_sparsity"):
         base["H_sparsity"] = cfg["H_sparsity"]
 
@@ -534,6 +547,14 @@ def main():
                         achieved=fl / (ms * 1e-3) / 1e12, peak=peak_tf, unit="TFLOP/s", ms_per_launch=ms,
                         ms_per_launch_w_half=ms_w, ms_per_launch_h_half=ms_h, algorithmic_flops_per_launch=fl,
                         algorithmic_bytes_per_launch=4.0 * m * nl, hbm_gbs_of_V_stream=4.0 * m * nl / (ms * 1e-3) / 1e9, traffic=None)
+        elif args.config in (6, 7):
+            ms_w, ms_h = breakdown["w_gemm"], breakdown["h_gemm"]
+            ms = max(ms_w, ms_h)
+            fl = 6.0 * m * nl * Kp
+            roof.update(bound="tensor", kernel="ab_fused_kernel (S = F G' -> Qn, Qp in TMEM -> OUTn += Qn G, OUTp += Qp G; W half and H half, nmf.m:154-164,185-195)",
+                        achieved=fl / (ms * 1e-3) / 1e12, peak=peak_tf, unit="TFLOP/s", ms_per_launch=ms,
+                        ms_per_launch_w_half=ms_w, ms_per_launch_h_half=ms_h, algorithmic_flops_per_launch=fl,
+                        algorithmic_bytes_per_launch=4.0 * m * nl, hbm_gbs_of_V_stream=4.0 * m * nl / (ms * 1e-3) / 1e9, traffic=None)
         elif args.config == 4:
             ms = breakdown["h_gemm"]
             fl = 2.0 * m * n * Kp + 2.0 * n * Kp * Kp
@@ -574,7 +595,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             try:
-                _, info, _ = cpu_reference(args.config, cfg, m, n, K, T, 5 if args.config in (2, 3) else 10, 1, 25.0)
+                _, info, _ = cpu_reference(args.config, cfg, m, n, K, T, 5 if args.config in (2, 3, 6, 7) else 10, 1, 25.0)
                 line["cpu_baseline"] = info
             except MemoryError as e:  # pragma: no cover
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": _usable_cores(), "kind": "port",

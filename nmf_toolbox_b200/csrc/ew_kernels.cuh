@@ -231,6 +231,23 @@ __global__ void split_reduce_kernel(const float* __restrict__ parts, int splits,
   }
 }
 
+// Two slab stacks in one launch (the two accumulators of ab_fused.cuh)
+__global__ void split_reduce2_kernel(const float* __restrict__ parts_a, const float* __restrict__ parts_b, int splits,
+                                     long long slab, float* __restrict__ out_a, float* __restrict__ out_b, long long count,
+                                     const int* stop) {
+  NMFB_STOP_GUARD(stop);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float sa = 0.f, sb = 0.f;
+    for (int z = 0; z < splits; ++z) {
+      sa += parts_a[z * slab + i];
+      sb += parts_b[z * slab + i];
+    }
+    out_a[i] = sa;
+    out_b[i] = sb;
+  }
+}
+
 // Per-column coefficients of the generic W step
 //   W' = W .* (A + W*p_c) ./ max(Bterm + W*q_c + lambda, eps)
 // Euclidean (nmf.m:149-150): p = <W_c,B_c>, q = <W_c,A_c>, Bterm = B
@@ -630,7 +647,8 @@ __global__ void gram_reduce_cost_kernel(const float* __restrict__ parts, int spl
 __global__ void h_finish_kernel(const float* __restrict__ N, const float* __restrict__ D, float* __restrict__ Hm,
                                 float* __restrict__ Ht, long long ld, int n, float lambda, int freeze,
                                 double* scal, const int* stop, float expo = 0.f,
-                                const float* lambda_k = nullptr, const int* fixed_k = nullptr) {
+                                const float* lambda_k = nullptr, const int* fixed_k = nullptr,
+                                int splits = 1, long long slab = 0 /* N, D given as `splits` partial slabs */) {
   NMFB_STOP_GUARD(stop);
   __shared__ double sh[64];
   const int k = blockIdx.y;
@@ -643,9 +661,11 @@ __global__ void h_finish_kernel(const float* __restrict__ N, const float* __rest
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const long long o = static_cast<long long>(k) * ld + j;
     float nv = N[o];
+    for (int z = 1; z < splits; ++z) nv += N[z * slab + o];
     float hv = Hm[o];
     if (!freeze) {
       float dv = D[o];
+      for (int z = 1; z < splits; ++z) dv += D[z * slab + o];
       if (powered) {
         nv = powf(nv, expo);
         dv = powf(dv, expo);

@@ -949,10 +949,8 @@ static int enqueue_iteration_two_weight(nmfb_handle* h, NmfSession* s, int i) {
   auto reduce_pair = [&](const AbOp& op, float* out_n, float* out_p) {
     const long long cnt = op.args.slab;
     const int blocks = static_cast<int>(std::min<long long>((cnt + 255) / 256, 2048));
-    split_reduce_kernel<<<blocks, 256, 0, h->stream>>>(op.parts_n, op.splits, cnt, out_n, cnt, s->stop);
-    NMFB_TRY(check_launch(h, "split_reduce(OUTn)"));
-    split_reduce_kernel<<<blocks, 256, 0, h->stream>>>(op.parts_p, op.splits, cnt, out_p, cnt, s->stop);
-    return check_launch(h, "split_reduce(OUTp)");
+    split_reduce2_kernel<<<blocks, 256, 0, h->stream>>>(op.parts_n, op.parts_p, op.splits, cnt, out_n, out_p, cnt, s->stop);
+    return check_launch(h, "split_reduce2(OUTn, OUTp)");
   };
   if (s->ab_fused) {
     // A = Qn H', B = Qp H' (+ the divergence of iteration i-1) in one fused kernel
@@ -1011,7 +1009,14 @@ static int enqueue_iteration_two_weight(nmfb_handle* h, NmfSession* s, int i) {
     NMFB_TRY(prof_mark(h, 1));
     NMFB_TRY(run_ab(h, s->abH));
     NMFB_TRY(prof_mark(h, 1));
-    NMFB_TRY(reduce_pair(s->abH, s->Nbuf, s->Dbuf));
+    if (s->tied) {
+      NMFB_TRY(reduce_pair(s->abH, s->Nbuf, s->Dbuf));
+    } else {  // the H update sums the partial slabs itself
+      h_finish_kernel<<<dim3(std::max(1, std::min(64, (n + 1023) / 1024)), K), 256, 0, h->stream>>>(
+          s->abH.parts_n, s->abH.parts_p, s->Hm, s->Ht, s->ldh, n, s->lambda_h, s->H_fixed ? 1 : 0, s->scal, s->stop,
+          s->expo, s->lamH_k, s->fixH_k, s->abH.splits, s->abH.args.slab);
+      return check_launch(h, "h_finish(slabs)");
+    }
   } else {
   NMFB_TRY(run_gemm(h, s->gemmHn));
   NMFB_TRY(run_gemm(h, s->gemmHd));
