@@ -246,10 +246,14 @@ int plan_tail_helpers(const GemmLaunch& L, int epi, int num_sms, int reserve_sms
   if (helpers < 1 || a.nkb0 < 64) return 0;
   helpers = std::min(helpers, tiles);
   const int per_helper = (tiles + helpers - 1) / helpers;  // row tiles whose tail one helper pair takes
-  // the primary's kp k-blocks against per_helper tails of nkb0 - kp k-blocks.  A helper also stores one partial
-  // tile per row tile and restarts its accumulation, so the balance point sits ~1 % above nkb0 * per / (per + 1)
-  // (measured at 16384^2, K = 256: kp = 448 / 456 / 464 / 480 of 512 -> 540 / 497 / 493 / 504 us per iteration).
-  int kp = static_cast<int>(std::ceil(a.nkb0 * (per_helper + 0.12) / (per_helper + 1.0)));
+  // Balance the primary's kp k-blocks against per_helper tails of nkb0 - kp k-blocks, each of which also costs the
+  // helper a pipeline restart, one stored partial tile and a flag: about 8 k-blocks' worth of time per row tile.
+  // Measured at 16384^2, K = 256 (nkb0 = 512, 8 tiles per helper): kp = 448 / 456 / 464 / 480 -> 540 / 497 / 493 /
+  // 504 us per iteration (the model gives 462); with short contractions (16384 x 2048: nkb0 = 64) the helpers were
+  // the slower side and the A GEMM took 69 us instead of 45 - no helpers unless they take at least 8 % off.
+  constexpr int kItemOverheadKb = 8;
+  int kp = static_cast<int>((static_cast<long long>(per_helper) * (a.nkb0 + kItemOverheadKb) + per_helper) / (per_helper + 1));
+  if (kp * 100LL > a.nkb0 * 92LL && !std::getenv("NMFB_TAIL_KP")) return 0;
   if (const char* env = std::getenv("NMFB_TAIL_KP")) kp = std::atoi(env);  // tuning experiments
   kp = std::min(std::max(kp, 1), a.nkb0 - 1);
   *kp_out = kp;
