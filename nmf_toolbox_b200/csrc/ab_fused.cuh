@@ -20,7 +20,7 @@
 // (as kl_fused does against the tensor core's truncating accumulation) does not fit the register file, so
 // the planner bounds a work item to kAbMaxTiles column tiles (512 accumulation steps: bias ~3e-5 relative,
 // common to OUTn and OUTp, so it cancels in the update's ratio - measured at 8192^2, K = 128, IS: cost error
-// against the oracle 1.6e-7 / 1.7e-7 / 1.8e-7 for chains of 16 / 32 / 64 tiles) and column splits do the rest.
+// against the float64 restatement 1.6e-7 / 1.7e-7 / 1.8e-7 for chains of 16 / 32 / 64 tiles); column splits do the rest.
 #pragma once
 #include "kl_fused.cuh"
 

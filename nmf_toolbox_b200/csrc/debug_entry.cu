@@ -141,4 +141,9 @@ int nmfb_debug_gemm_hupdate(const nmfb_debug_mat* X0, const nmfb_debug_mat* Y0, 
   return 0;
 }
 
+// Host-side planners (pure functions): exposed so that the CPU tests can check them without a GPU.
+int nmfb_debug_kl_splits(int pairs, int total_tiles, int rows, int Kp, int slots, int chunk, int max_per, int* per_out) {
+  return choose_kl_splits(pairs, total_tiles, rows, Kp, slots, chunk, per_out, max_per);
+}
+
 }  // extern "C"

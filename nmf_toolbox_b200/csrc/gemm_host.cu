@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace nmfb {
 
@@ -197,6 +198,60 @@ std::string add_segment(GemmLaunch* L, int seg, const GemmOperand& X, const Gemm
   }
   L->grid.z = splits;
   return "";
+}
+
+// Column splits of a kl_fused / ab_fused launch.  One CTA pair is resident per two SMs (shared memory), so the
+// pairs * splits clusters of a launch run as work items on `slots` pair slots, handed out in launch order (all
+// row blocks of split 0, then split 1, ...).  32 row blocks x 2 equal splits keep 64 of the 74 slots busy for
+// the whole launch; 32 x 3 with splits of 444 + 444 + 136 tiles put the 64 long items on 64 slots and the 32
+// short ones on the other 10 (three or four each): same work, every slot busy.  The planner tries every split
+// length (a multiple of the accumulation chunk; the last split takes the remainder), plays the launch through
+// a list scheduler and keeps the shortest.  Every work item is charged a fixed overhead (launch, TMEM
+// allocation, the F tile, pipeline fill, the partial slab, teardown: ~10 column tiles, fitted to measured launches
+// with 1, 2 and 9 equal splits) and every split the traffic of one more partial slab.
+int choose_kl_splits(int pairs, int total_tiles, int rows, int Kp, int slots, int chunk, int* per_out, int max_per) {
+  const char* env = std::getenv("NMFB_KL_SPLITS");  // "0": the round-1 rule (one wave of equal splits); n > 0: n equal splits
+  const int forced = env ? std::atoi(env) : -1;
+  const double tile_us = 1.2 * Kp / 128.0;                                // measured: 0.62 ms for 512 tiles, Kp = 128
+  const double slab_us = static_cast<double>(rows) * Kp * 8.0 / 5.0e6;   // write + read of one slab at ~5 TB/s
+  const double item_overhead = 10.0;                                      // in tiles
+  auto round_chunk = [chunk](int p) { return (p + chunk - 1) / chunk * chunk; };
+  if (max_per <= 0) max_per = total_tiles;
+  max_per = std::max(chunk, max_per / chunk * chunk);
+  if (forced >= 0) {
+    const int s = forced > 0 ? forced : std::max(1, std::min(slots / std::max(1, pairs), total_tiles));
+    const int per = std::min(max_per, round_chunk((total_tiles + s - 1) / s));
+    *per_out = per;
+    return (total_tiles + per - 1) / per;
+  }
+  int best_per = std::min(max_per, round_chunk(total_tiles));
+  double best = 1e300;
+  std::vector<double> slot_free(static_cast<size_t>(std::max(1, slots)));
+  for (int per = chunk; per <= std::min(max_per, round_chunk(total_tiles)); per += chunk) {
+    const int splits = (total_tiles + per - 1) / per;
+    if (static_cast<long long>(splits) * pairs > 65535 || splits > 256) continue;
+    std::fill(slot_free.begin(), slot_free.end(), 0.0);
+    // list scheduling in launch order; the slots form a heap keyed by the time they become free
+    auto cmp = [](double x, double y) { return x > y; };
+    double makespan = 0.0;
+    for (int y = 0; y < splits; ++y) {
+      const double len = std::min(per, total_tiles - y * per) + item_overhead;
+      for (int p = 0; p < pairs; ++p) {
+        std::pop_heap(slot_free.begin(), slot_free.end(), cmp);
+        const double done = slot_free.back() + len;
+        slot_free.back() = done;
+        std::push_heap(slot_free.begin(), slot_free.end(), cmp);
+        makespan = std::max(makespan, done);
+      }
+    }
+    const double t = makespan * tile_us + splits * slab_us;
+    if (t < best * (1.0 - 1e-9)) {
+      best = t;
+      best_per = per;
+    }
+  }
+  *per_out = best_per;
+  return (total_tiles + best_per - 1) / best_per;
 }
 
 static cudaError_t gemm_attrs_once();

@@ -64,6 +64,11 @@ std::string set_h_prefetch(GemmLaunch* L, const float* Hm, long long n, long lon
 // EPI_RESID / EPI_KLQ: same staging for the tile of V (m x n column-major, leading dimension ldv).
 std::string set_v_prefetch(GemmLaunch* L, const float* V, long long m, long long n, long long ldv);
 
+// Column splits of a kl_fused / ab_fused launch (work items of `per` column tiles, the last split takes the
+// remainder) chosen by playing the launch through a list scheduler of `slots` resident CTA pairs; see gemm_host.cu.
+// per is a multiple of `chunk` and at most max_per (0 = no bound).  Returns the number of splits.
+int choose_kl_splits(int pairs, int total_tiles, int rows, int Kp, int slots, int chunk, int* per_out, int max_per = 0);
+
 // Tail helpers (GemmArgs::sk_*): how many helper CTA pairs a planned CTA-pair launch of `tiles` row tiles can
 // use when `reserve_sms` SMs are to stay free, and the k-block at which the primaries hand over to them.
 // Returns 0 when the launch is not eligible (single CTAs, several column chunks, split-K, segments, a grid

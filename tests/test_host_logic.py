@@ -144,3 +144,35 @@ def test_header_is_valid_c99_and_matches_the_python_struct(tmp_path):
     C = api._Config
     assert [int(x) for x in out] == [ctypes.sizeof(C), C.W_init.offset, C.maxiter.offset, C.cost_mode.offset,
                                      C.W_sparsity_k.offset]
+
+
+def test_kl_split_planner():
+    """choose_kl_splits (gemm_host.cu): the column splits of a kl_fused / ab_fused launch are chosen by playing the
+    launch through a list scheduler of the 74 resident CTA-pair slots of a B200.  Pure host logic, called through
+    the test library's hook (no GPU needed)."""
+    import ctypes
+
+    path = os.path.join(ROOT, "tests", "libnmfb200_test.so")
+    if not os.path.exists(path):
+        pytest.skip("tests/libnmfb200_test.so not built")
+    lib = ctypes.CDLL(path)
+    per = ctypes.c_int(0)
+
+    def plan(rows, cols, Kp, max_per=0, slots=74, chunk=4):
+        pairs, tiles = -(-rows // 256), -(-cols // 64)
+        s = lib.nmfb_debug_kl_splits(pairs, tiles, rows, Kp, slots, chunk, max_per, ctypes.byref(per))
+        return pairs, tiles, s, per.value
+
+    # BASELINE config 3, W half: 32 row blocks x (460 + 460 + 104 tiles): 64 long items on 64 slots, the 32 short
+    # ones on the other ten - instead of 2 equal splits that leave ten slots idle for the whole launch
+    assert plan(8192, 65536, 128)[2:] == (3, 460)
+    # H half: 256 row blocks x 2 splits = 6.9 waves instead of 3.5 rounded up to 4
+    assert plan(65536, 8192, 128)[2:] == (2, 64)
+    for rows, cols, Kp, max_per in [(8192, 65536, 128, 0), (65536, 8192, 128, 0), (8192, 8192, 128, 64), (700, 900, 96, 0),
+                                    (300, 64, 32, 0), (100000, 130, 128, 0), (2100, 4170, 128, 64), (256, 64 * 1000, 128, 64)]:
+        pairs, tiles, s, p = plan(rows, cols, Kp, max_per)
+        assert s >= 1 and p >= 4 and p % 4 == 0, (rows, cols, s, p)
+        assert (s - 1) * p < tiles <= s * p, "splits must cover the column tiles exactly once"
+        if max_per:
+            assert p <= max_per
+        assert s <= 256 and s * pairs <= 65535  # gridDim.y and the cluster count stay launchable
