@@ -263,7 +263,7 @@ int plan_tail_helpers(const GemmLaunch& L, int epi, int num_sms, int reserve_sms
   if (L.cg != 2 || L.grid.y != 1 || L.grid.z != 1 || a.nkb_seg != a.nkb0 || a.sk_helpers != 0) return 0;
   if (epi != EPI_STORE && epi != EPI_HUPDATE) return 0;
   const int tiles = static_cast<int>(L.grid.x) / 2;
-  if (tiles * 4 <= num_sms) return 0;  // at most half of the SMs busy: split-K territory
+  if (tiles * 6 <= num_sms) return 0;  // a third of the SMs busy: split-K territory
   // co-resident clusters of this kernel (one CTA per SM: shared memory); the helpers must run beside the primaries.
   // Asked once per process: the occupancy query takes 1 - 100 ms (measured), far too long for every plan.
   static int cached_clusters[2] = {-1, -1};

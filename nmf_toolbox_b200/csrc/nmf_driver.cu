@@ -478,7 +478,22 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     const int ctasA = ((m + 2 * kTileM - 1) / (2 * kTileM)) * 2 * ((Kp + kMaxN - 1) / kMaxN);
     const int ctasH = ((n + 2 * kTileM - 1) / (2 * kTileM)) * 2 * ((Kp + kMaxN - 1) / kMaxN);
     const char* env = std::getenv("NMFB_OVERLAP");
+    auto helpers_for = [&](int epi, int rows, long long kdim) {
+      if (multi || Kp > kMaxN) return 0;
+      GemmLaunch d;
+      std::memset(&d, 0, sizeof(d));
+      d.cg = choose_cg(epi, rows, Kp, false, false, 0);
+      d.grid = dim3(static_cast<unsigned>((rows + 2 * kTileM - 1) / (2 * kTileM)) * 2, 1, 1);
+      d.args.nkb0 = d.args.nkb_seg = static_cast<int>((kdim + kBlockK - 1) / kBlockK);
+      int kp = 0;
+      return plan_tail_helpers(d, epi, h->num_sms, kTailReserveSms, &kp);
+    };
     s->h_split = ctasH * 2 <= h->num_sms && n > kTileM;
+    // Experiment (NMFB_H_TAIL=1): 25 - 37 sample tiles (a 2-GPU shard of the north-star problem has 32) with one
+    // helper pair per tile instead of split-K + h_finish: the fused H update is kept, N and D never exist in HBM.
+    // Measured at 16384 x 8192, K = 256: 153.6 us against 149.5 us for split-K + h_finish - no gain, off by default.
+    if (const char* e5 = std::getenv("NMFB_H_TAIL"))
+      if (e5[0] == '1' && s->h_split && helpers_for(EPI_HUPDATE, n, m) > 0) s->h_split = false;
     // Experiment (NMFB_H_TILEN=<width>): with few sample tiles, narrower tiles instead of split-K - twice the
     // CTAs, each still runs the whole contraction and keeps the fused H update.  Measured at 2 GPUs
     // (16384 x 8192 shard, K = 256): 222 us against 144 us for split-K + h_finish - every CTA streams the V
@@ -505,16 +520,6 @@ static int nmf_setup(nmfb_handle* h, NmfSession* s, int K, const nmfb_config* cf
     // Tail helpers (panel_gemm.cuh, GemmArgs::sk_*): at the north-star shape each of the two contractions has 64
     // pair tiles - 128 of 148 SMs.  Helper pairs take the tails of the contractions so that 144 SMs work through
     // the whole launch; the Gram product running beside it is then planned for the 4 SMs that stay free.
-    auto helpers_for = [&](int epi, int rows, long long kdim) {
-      if (multi || Kp > kMaxN) return 0;
-      GemmLaunch d;
-      std::memset(&d, 0, sizeof(d));
-      d.cg = choose_cg(epi, rows, Kp, false, false, 0);
-      d.grid = dim3(static_cast<unsigned>((rows + 2 * kTileM - 1) / (2 * kTileM)) * 2, 1, 1);
-      d.args.nkb0 = d.args.nkb_seg = static_cast<int>((kdim + kBlockK - 1) / kBlockK);
-      int kp = 0;
-      return plan_tail_helpers(d, epi, h->num_sms, kTailReserveSms, &kp);
-    };
     s->tail_a = s->overlap && helpers_for(EPI_STORE, m, n) > 0;
     s->tail_h = s->gate_h && !s->h_split && h_tile_n == 0 && helpers_for(EPI_HUPDATE, n, m) > 0;
     s->side_gh = multi && can_side;
