@@ -28,9 +28,13 @@ namespace nmfb {
 
 constexpr int kAbSlots = 2;        // S/Q slots in TMEM == ring of the MMA #1 view of G
 constexpr int kAbMaxTiles = 64;    // column tiles per work item (accumulation chain of OUT: 8 steps per tile)
+#ifndef NMFB_AB_VSLOTS
+#define NMFB_AB_VSLOTS 2
+#endif
+constexpr int kAbVSlots = NMFB_AB_VSLOTS;  // ring of V tiles (a third slot fits, 225 KB in all, and changes nothing: 257 vs 258 us)
 constexpr int kAbOffG2 = kKlOffG1 + kAbSlots * kKlG1Bytes;
 constexpr int kAbOffV = kAbOffG2 + kKlG2Slots * kKlG2Bytes;
-constexpr int kAbSmemBytes = kAbOffV + kKlVSlots * kKlVBytes + 1024;  // 193 KB
+constexpr int kAbSmemBytes = kAbOffV + kAbVSlots * kKlVBytes + 1024;
 
 struct AbArgs {
   int rows, cols, Kp;
@@ -80,8 +84,8 @@ ab_fused_kernel(const __grid_constant__ CUtensorMap tmF,    // F  [Kp][ld]  boxe
   __shared__ uint64_t g1_empty[kAbSlots];     // local : MMA #1 of the tile retired (commit, multicast)
   __shared__ uint64_t g2_full[kKlG2Slots];    // leader: MMA #2 view of G landed
   __shared__ uint64_t g2_empty[kKlG2Slots];   // local : both MMAs #2 of the tile retired (commit, multicast)
-  __shared__ uint64_t v_full[kKlVSlots];      // local : this CTA's V tile landed
-  __shared__ uint64_t v_empty[kKlVSlots];     // local : every epilogue warp has its V values in registers
+  __shared__ uint64_t v_full[kAbVSlots];      // local : this CTA's V tile landed
+  __shared__ uint64_t v_empty[kAbVSlots];     // local : every epilogue warp has its V values in registers
   __shared__ uint64_t s_full[kAbSlots];       // local : S tile complete (commit, multicast)
   __shared__ uint64_t q_full[kAbSlots];       // leader: both CTAs' weight tiles are in TMEM
   __shared__ uint64_t sq_free[kAbSlots];      // leader: MMAs #2 of the tile retired, S/Q slot reusable
@@ -115,7 +119,7 @@ ab_fused_kernel(const __grid_constant__ CUtensorMap tmF,    // F  [Kp][ld]  boxe
       mbar_init(&g2_full[i], 1);
       mbar_init(&g2_empty[i], 1);
     }
-    for (int i = 0; i < kKlVSlots; ++i) {
+    for (int i = 0; i < kAbVSlots; ++i) {
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], kKlEpiWarps);
     }
@@ -162,8 +166,8 @@ ab_fused_kernel(const __grid_constant__ CUtensorMap tmF,    // F  [Kp][ld]  boxe
         ++n1;
         progress = true;
       }
-      if (nv < ntiles && mbar_try_wait(&v_empty[nv % kKlVSlots], ((nv / kKlVSlots) & 1) ^ 1)) {
-        const int slot = nv % kKlVSlots;
+      if (nv < ntiles && mbar_try_wait(&v_empty[nv % kAbVSlots], ((nv / kAbVSlots) & 1) ^ 1)) {
+        const int slot = nv % kAbVSlots;
         mbar_arrive_expect_tx(&v_full[slot], kKlVBytes);
         tma_load_2d(sbase + kAbOffV + slot * kKlVBytes, &tmV, &v_full[slot], r0, (t_begin + nv) * kKlTileC,
                     kEvictFirst);
@@ -259,8 +263,8 @@ ab_fused_kernel(const __grid_constant__ CUtensorMap tmF,    // F  [Kp][ld]  boxe
       const int c0 = (t_begin + t) * kKlTileC + sub * 16;
       float va[16];
       {
-        const int vslot = t % kKlVSlots;
-        mbar_wait(&v_full[vslot], (t / kKlVSlots) & 1);
+        const int vslot = t % kAbVSlots;
+        mbar_wait(&v_full[vslot], (t / kAbVSlots) & 1);
         const float* vt = smem_f + (kAbOffV + vslot * kKlVBytes) / 4 + (sub * 16) * kTileM + q * 32 + lane;
 #pragma unroll
         for (int j = 0; j < 16; ++j) va[j] = vt[j * kTileM];

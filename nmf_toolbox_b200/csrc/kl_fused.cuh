@@ -26,7 +26,7 @@
 //             the two streams only meet at the S/Q buffers (mbarrier sq_free)
 //   warps 2-17 epilogue: S -> Q per tile (the MUFU-heavy part: one reciprocal, and for the cost
 //             one logarithm, per element); promotion of finished OUT chunks into registers
-// OUT is accumulated in chunks of kOutChunk tiles (32 MMA steps) that ping-pong between two
+// OUT is accumulated in chunks of kKlOutChunk tiles (64 MMA steps) that ping-pong between two
 // TMEM buffers and are promoted with round-to-nearest adds (the tensor core truncates when it
 // accumulates, see panel_gemm.cuh).  Columns are split over gridDim.y; each split writes a
 // partial slab that a small kernel sums (and, for the H half, turns into the H update).
@@ -39,7 +39,12 @@ constexpr int kKlTileC = 64;       // columns per tile
 constexpr int kKlG1Slots = 4;      // ring of the MMA #1 view of G == number of S/Q buffers in TMEM
 constexpr int kKlG2Slots = 2;      // ring of the MMA #2 view of G
 constexpr int kKlVSlots = 2;       // ring of V tiles
-constexpr int kKlOutChunk = 4;     // tiles per OUT accumulation chunk (4 * 8 = 32 MMA steps)
+#ifndef NMFB_KL_OUT_CHUNK
+#define NMFB_KL_OUT_CHUNK 8
+#endif
+// tiles per OUT accumulation chunk: 8 * 8 = 64 MMA steps, the chain length of the panel GEMM's chunks (bias ~3e-6);
+// 4 -> 8 is worth 2 % of config 3 (823 -> 840 it/s), the cost curve moves by 6e-9 relative
+constexpr int kKlOutChunk = NMFB_KL_OUT_CHUNK;
 constexpr int kKlMaxKp = 128;
 constexpr int kKlEpiWarps = 16;    // four warps per TMEM lane quarter, 16 tile columns each
 constexpr int kKlThreads = 64 + kKlEpiWarps * 32 + 32;  // + one more MMA-issuing warp
