@@ -30,6 +30,9 @@ LARGE = {
     "large_nmf_kl_8192_k128": ("nmf", 8192, 8192, 128, 1, 50, dict(divergence="kl")),
     "large_cnmf_1025x20000_k64_t8": ("cnmf", 1025, 20000, 64, 8, 30, dict(divergence="euclidean")),
     "large_nmfsc_4096_k128_h07": ("nmfsc", 4096, 4096, 128, 1, 30, dict(H_sparsity=0.7)),
+    # the widened divergences at the shape their fused kernel (ab_fused.cuh) is timed on
+    "large_nmf_is_8192_k128": ("nmf", 8192, 8192, 128, 1, 30, dict(divergence="is")),
+    "large_nmf_ab_8192_k128": ("nmf", 8192, 8192, 128, 1, 20, dict(divergence="ab", alpha=0.5, beta=0.5, H_sparsity=0.05)),
 }
 WIN_ROWS = 256
 WIN_COLS = 256

@@ -6,6 +6,8 @@ oracle's committed outputs (tests/golden/large_*.npz, generator tests/golden/mak
   large_nmf_kl_8192_k128         configs[2], one GPU's column shard: nmf.m KL, 8192 x 8192, K = 128, 50 iterations
   large_cnmf_1025x20000_k64_t8   configs[3]: cnmf.m euclidean, 1025 x 20000, K = 64, T = 8, 30 iterations
   large_nmfsc_4096_k128_h07      configs[4]: nmfsc.m, 4096 x 4096, K = 128, H_sparsity = 0.7, 30 iterations
+  large_nmf_is_8192_k128         nmf.m Itakura-Saito, 8192 x 8192, K = 128, 30 iterations (ab_fused.cuh)
+  large_nmf_ab_8192_k128         nmf.m alpha-beta (0.5, 0.5) with H sparsity, same shape, 20 iterations
 
 Stated tolerances (BASELINE.json north_star): cost within 1e-4 relative of the reference at EVERY
 iteration, W*H within 1e-3 relative (Frobenius norm, on a 256-row x 256-column window of V_hat whose
