@@ -25,6 +25,15 @@
  *     of the last failure is available from nmfb_last_error().  MATLAB error()
  *     sites of the reference map to NMFB_ERR_* codes (listed per function).
  *   - There is no CPU fallback: without a CUDA device nmfb_create fails.
+ *   - A call expects the device to itself while it runs.  Several kernels of an
+ *     iteration are planned to be resident together and wait for each other on
+ *     the device (a Gram product running beside the contraction that consumes it,
+ *     helper CTA pairs handing partial sums to the pairs that finish a tile, the
+ *     ranks of a multi-GPU run meeting in the sharded W step); the plans size
+ *     their grids from the SM count of the device.  Work of another handle or
+ *     process that occupies SMs for long can stall such a wait; a wait that lasts
+ *     ~2 s traps and the call returns NMFB_ERR_CUDA instead of hanging
+ *     (NMFB_TAIL_HELPERS=0 and NMFB_OVERLAP=0 plan without these waits).
  *
  * Multi-GPU (one process per GPU): each rank creates a handle, joins a
  * communicator (nmfb_comm_*), uploads its COLUMN SHARD of V and of H_init and
