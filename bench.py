@@ -568,6 +568,15 @@ def main():
             roof.update(bound="hbm", kernel="resid_fused_kernel (objective 0.5|V - WH|^2 of a line-search trial, split-tf32, nmfsc.m:160-161,237-238)",
                         achieved=by / (ms * 1e-3) / 1e9 if ms > 0 else None, peak=hbm_gbs, unit="GB/s", ms_per_launch=ms,
                         algorithmic_bytes_per_launch=by, algorithmic_flops_per_launch=2.0 * m * n * K, traffic=None)
+        if roof.get("traffic") is None and world == 1:  # static ncu figure of the same kernel at the same shape, if recorded
+            try:
+                with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                    tc = (json.load(f).get("configs") or {}).get(str(args.config))
+                if tc and (tc.get("m"), tc.get("n"), tc.get("K")) == (m, n, K):
+                    roof["traffic"] = tc.get("dram_bytes_per_launch")
+                    roof["traffic_source"] = "static: %s, %s (not re-measured in this run)" % (tc.get("kernel"), tc.get("source"))
+            except Exception:
+                pass
         roof["frac"] = (roof["achieved"] / roof["peak"]) if roof.get("achieved") else None
         if tf32_cublas and roof.get("unit") == "TFLOP/s" and "burst_tflops" in tf32_cublas:
             roof["frac_of_cublas_tf32_in_run"] = roof["achieved"] / tf32_cublas["burst_tflops" if burst else "sustained_tflops"]
