@@ -336,55 +336,55 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
     for (int item = 0; item < n_items; ++item) {
-    const int r0 = r0_first + item * item_rows;  // a helper pair walks over its row tiles
-    for (int it = 0; it < total; ++it) {
-      mbar_wait(&empty_bar[stage], phase ^ 1);
-      if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-      const uint32_t fb = kPair ? map_to_cta(smem_u32(&full_bar[stage]), lead) : 0u;
-      auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint64_t pol) {
-        if constexpr (kPair) tma_load_2d_pair(dst, tm, fb, c0, c1, pol);
-        else tma_load_2d(dst, tm, &full_bar[stage], c0, c1, pol);
-      };
-      const bool ph1 = it >= n0kb;
-      if (ph1 && it == n0kb && a.gate != nullptr) gate_wait(a.gate, a.gate_value);
-      int kb = ph1 ? (it - n0kb) : (kb_begin + it);
-      const CUtensorMap* mx = ph1 ? &tmX1 : &tmX0;
-      const CUtensorMap* my = ph1 ? &tmY1 : &tmY0;
-      if (!ph1 && kb >= a.nkb_seg) {  // second / third operand pair of a segmented phase 0
-        const int seg = kb / a.nkb_seg;
-        kb -= seg * a.nkb_seg;
-        mx = seg == 1 ? &tmXb : &tmXc;
-        my = seg == 1 ? &tmYb : &tmYc;
-      }
-      const uint32_t xs = sbase + stage * TC::stage_bytes;
-      const uint32_t ys = xs + kStageBytesX;
-      // X is streamed once (evict-first); Y is re-read by every CTA (evict-last).
-      if (ph1 ? a.xmn1 : a.xmn0) {
-        // rows are the contiguous dimension: four 32(rows) x 32(k) boxes
-#pragma unroll
-        for (int q = 0; q < 4; ++q) load(xs + q * 4096, mx, r0 + q * 32, kb * kBlockK, kEvictFirst);
-      } else {
-        load(xs, mx, kb * kBlockK, r0, kEvictFirst);
-      }
-      if constexpr (CG == 4) {
-        if (ph1 ? a.ymn1 : a.ymn0) {  // 32-row boxes: this CTA's half of the boxes of its half
-          const int nq = ybox >> 6;
-          for (int q = yq * nq; q < (yq + 1) * nq; ++q)
-            tma_load_2d_pair_mc(ys + q * 4096, my, &full_bar[stage], ymask, yrow0 + q * 32, kb * kBlockK, kEvictLast);
-        } else {  // one box of ybox / 2 rows (the tensor map was built with box_n / 4 rows)
-          tma_load_2d_pair_mc(ys + yq * (ybox >> 1) * 128, my, &full_bar[stage], ymask, kb * kBlockK,
-                              yrow0 + yq * (ybox >> 1), kEvictLast);
+      const int r0 = r0_first + item * item_rows;  // a helper pair walks over its row tiles
+      for (int it = 0; it < total; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+        const uint32_t fb = kPair ? map_to_cta(smem_u32(&full_bar[stage]), lead) : 0u;
+        auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint64_t pol) {
+          if constexpr (kPair) tma_load_2d_pair(dst, tm, fb, c0, c1, pol);
+          else tma_load_2d(dst, tm, &full_bar[stage], c0, c1, pol);
+        };
+        const bool ph1 = it >= n0kb;
+        if (ph1 && it == n0kb && a.gate != nullptr) gate_wait(a.gate, a.gate_value);
+        int kb = ph1 ? (it - n0kb) : (kb_begin + it);
+        const CUtensorMap* mx = ph1 ? &tmX1 : &tmX0;
+        const CUtensorMap* my = ph1 ? &tmY1 : &tmY0;
+        if (!ph1 && kb >= a.nkb_seg) {  // second / third operand pair of a segmented phase 0
+          const int seg = kb / a.nkb_seg;
+          kb -= seg * a.nkb_seg;
+          mx = seg == 1 ? &tmXb : &tmXc;
+          my = seg == 1 ? &tmYb : &tmYc;
         }
-      } else if (ph1 ? a.ymn1 : a.ymn0) {
-        for (int q = 0; q < (ybox >> 5); ++q) load(ys + q * 4096, my, yrow0 + q * 32, kb * kBlockK, kEvictLast);
-      } else {
-        load(ys, my, kb * kBlockK, yrow0, kEvictLast);
+        const uint32_t xs = sbase + stage * TC::stage_bytes;
+        const uint32_t ys = xs + kStageBytesX;
+        // X is streamed once (evict-first); Y is re-read by every CTA (evict-last).
+        if (ph1 ? a.xmn1 : a.xmn0) {
+          // rows are the contiguous dimension: four 32(rows) x 32(k) boxes
+  #pragma unroll
+          for (int q = 0; q < 4; ++q) load(xs + q * 4096, mx, r0 + q * 32, kb * kBlockK, kEvictFirst);
+        } else {
+          load(xs, mx, kb * kBlockK, r0, kEvictFirst);
+        }
+        if constexpr (CG == 4) {
+          if (ph1 ? a.ymn1 : a.ymn0) {  // 32-row boxes: this CTA's half of the boxes of its half
+            const int nq = ybox >> 6;
+            for (int q = yq * nq; q < (yq + 1) * nq; ++q)
+              tma_load_2d_pair_mc(ys + q * 4096, my, &full_bar[stage], ymask, yrow0 + q * 32, kb * kBlockK, kEvictLast);
+          } else {  // one box of ybox / 2 rows (the tensor map was built with box_n / 4 rows)
+            tma_load_2d_pair_mc(ys + yq * (ybox >> 1) * 128, my, &full_bar[stage], ymask, kb * kBlockK,
+                                yrow0 + yq * (ybox >> 1), kEvictLast);
+          }
+        } else if (ph1 ? a.ymn1 : a.ymn0) {
+          for (int q = 0; q < (ybox >> 5); ++q) load(ys + q * 4096, my, yrow0 + q * 32, kb * kBlockK, kEvictLast);
+        } else {
+          load(ys, my, kb * kBlockK, yrow0, kEvictLast);
+        }
+        if (++stage == kNStages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
-      if (++stage == kNStages) {
-        stage = 0;
-        phase ^= 1;
-      }
-    }
     }
     if constexpr (EPI == EPI_HUPDATE || EPI == EPI_RESID || EPI == EPI_KLQ || EPI == EPI_ABQ) {
       // (EPI_RESID / EPI_KLQ / EPI_ABQ: the staged tile is the 128-row x bn-column tile of V)
@@ -478,48 +478,48 @@ panel_gemm_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     // promote finished phase-0 chunks from TMEM into registers
     int gch = 0;  // chunks seen so far (a helper pair runs through several row tiles)
     for (int item = 0; item < n_items; ++item) {
-    for (int ch = 0; ch < (direct ? 0 : nchunk0); ++ch, ++gch) {
-      const int buf = gch & 1;
-      mbar_wait(&tfull_bar[buf], (gch >> 1) & 1);
-      tc_fence_after();
-      const uint32_t t0 = tlane + static_cast<uint32_t>(buf * kMaxN + g_begin * 16);
+      for (int ch = 0; ch < (direct ? 0 : nchunk0); ++ch, ++gch) {
+        const int buf = gch & 1;
+        mbar_wait(&tfull_bar[buf], (gch >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t0 = tlane + static_cast<uint32_t>(buf * kMaxN + g_begin * 16);
 #pragma unroll
-      for (int g = 0; g < kMaxGroups; ++g) {
-        if (g < g_count) {
-          float v[16];
-          tmem_ld16(t0 + g * 16, v);
-          tmem_ld_wait();
+        for (int g = 0; g < kMaxGroups; ++g) {
+          if (g < g_count) {
+            float v[16];
+            tmem_ld16(t0 + g * 16, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int t = 0; t < 16; ++t) sum[g * 16 + t] += v[t];
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (kPair) mbar_arrive_remote(map_to_cta(smem_u32(&tempty_bar[buf]), lead));
-        else mbar_arrive(&tempty_bar[buf]);
-      }
-    }
-    if (helper) {
-      // tail helper: the partial sum of this row tile goes to the scratch slab (coalesced along the rows, kept
-      // in L2), then the flag its primary CTA is waiting for
-      const int tile = first_tile + item * a.sk_helpers;
-      float* p = a.sk_part + (static_cast<long long>(tile) * a.ncols + g_begin * 16) * (2 * kTileM) +
-                 static_cast<int>(rank) * kTileM + q * 32 + lane;
-#pragma unroll
-      for (int g = 0; g < kMaxGroups; ++g) {
-        if (g < g_count) {
-#pragma unroll
-          for (int t = 0; t < 16; ++t) {
-            __stcg(p + (g * 16 + t) * (2 * kTileM), sum[g * 16 + t]);
-            sum[g * 16 + t] = 0.f;
+            for (int t = 0; t < 16; ++t) sum[g * 16 + t] += v[t];
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kPair) mbar_arrive_remote(map_to_cta(smem_u32(&tempty_bar[buf]), lead));
+          else mbar_arrive(&tempty_bar[buf]);
+        }
       }
-      __threadfence();
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // epilogue warps only
-      if (warp == 2 && lane == 0) gate_publish(a.sk_flag + 2 * tile + static_cast<int>(rank), a.sk_epoch);
-    }
+      if (helper) {
+        // tail helper: the partial sum of this row tile goes to the scratch slab (coalesced along the rows, kept
+        // in L2), then the flag its primary CTA is waiting for
+        const int tile = first_tile + item * a.sk_helpers;
+        float* p = a.sk_part + (static_cast<long long>(tile) * a.ncols + g_begin * 16) * (2 * kTileM) +
+                   static_cast<int>(rank) * kTileM + q * 32 + lane;
+#pragma unroll
+        for (int g = 0; g < kMaxGroups; ++g) {
+          if (g < g_count) {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              __stcg(p + (g * 16 + t) * (2 * kTileM), sum[g * 16 + t]);
+              sum[g * 16 + t] = 0.f;
+            }
+          }
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // epilogue warps only
+        if (warp == 2 && lane == 0) gate_publish(a.sk_flag + 2 * tile + static_cast<int>(rank), a.sk_epoch);
+      }
     }
     if (!helper) {
     if (sk) {
