@@ -146,4 +146,8 @@ int nmfb_debug_kl_splits(int pairs, int total_tiles, int rows, int Kp, int slots
   return choose_kl_splits(pairs, total_tiles, rows, Kp, slots, chunk, per_out, max_per);
 }
 
+int nmfb_debug_tail_balance(int tiles, int helpers, int nkb0, int* kp_out) {
+  return balance_tail_helpers(tiles, helpers, nkb0, kp_out);
+}
+
 }  // extern "C"

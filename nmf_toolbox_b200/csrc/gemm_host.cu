@@ -254,6 +254,27 @@ int choose_kl_splits(int pairs, int total_tiles, int rows, int Kp, int slots, in
   return (total_tiles + best_per - 1) / best_per;
 }
 
+// The arithmetic of plan_tail_helpers (pure: CPU-tested through the test library): `helpers` free CTA pairs for
+// `tiles` row tiles whose contractions are nkb0 k-blocks long.  Returns the helper pairs to launch (0 = none) and
+// the k-block at which the primaries hand over.
+int balance_tail_helpers(int tiles, int helpers, int nkb0, int* kp_out) {
+  if (helpers < 1 || nkb0 < 64) return 0;
+  helpers = std::min(helpers, tiles);
+  const int per_helper = (tiles + helpers - 1) / helpers;  // row tiles whose tail one helper pair takes
+  // Balance the primary's kp k-blocks against per_helper tails of nkb0 - kp k-blocks, each of which also costs the
+  // helper a pipeline restart, one stored partial tile and a flag: about 8 k-blocks' worth of time per row tile.
+  // Measured at 16384^2, K = 256 (nkb0 = 512, 8 tiles per helper): kp = 448 / 456 / 464 / 480 -> 540 / 497 / 493 /
+  // 504 us per iteration (the model gives 463); with short contractions (16384 x 2048: nkb0 = 64) the helpers were
+  // the slower side and the A GEMM took 69 us instead of 45 - no helpers unless they take at least 8 % off.
+  constexpr int kItemOverheadKb = 8;
+  int kp = static_cast<int>((static_cast<long long>(per_helper) * (nkb0 + kItemOverheadKb) + per_helper) / (per_helper + 1));
+  if (kp * 100LL > nkb0 * 92LL && !std::getenv("NMFB_TAIL_KP")) return 0;
+  if (const char* env = std::getenv("NMFB_TAIL_KP")) kp = std::atoi(env);  // tuning experiments
+  kp = std::min(std::max(kp, 1), nkb0 - 1);
+  *kp_out = kp;
+  return helpers;
+}
+
 static cudaError_t gemm_attrs_once();
 
 int plan_tail_helpers(const GemmLaunch& L, int epi, int num_sms, int reserve_sms, int* kp_out) {
@@ -298,21 +319,7 @@ int plan_tail_helpers(const GemmLaunch& L, int epi, int num_sms, int reserve_sms
   const int pairs = std::min(num_sms / 2, max_clusters) - (reserve_sms + 1) / 2;
   int helpers = pairs - tiles;
   if (const char* env = std::getenv("NMFB_TAIL_HELPERS")) helpers = std::min(helpers, std::atoi(env));
-  if (helpers < 1 || a.nkb0 < 64) return 0;
-  helpers = std::min(helpers, tiles);
-  const int per_helper = (tiles + helpers - 1) / helpers;  // row tiles whose tail one helper pair takes
-  // Balance the primary's kp k-blocks against per_helper tails of nkb0 - kp k-blocks, each of which also costs the
-  // helper a pipeline restart, one stored partial tile and a flag: about 8 k-blocks' worth of time per row tile.
-  // Measured at 16384^2, K = 256 (nkb0 = 512, 8 tiles per helper): kp = 448 / 456 / 464 / 480 -> 540 / 497 / 493 /
-  // 504 us per iteration (the model gives 462); with short contractions (16384 x 2048: nkb0 = 64) the helpers were
-  // the slower side and the A GEMM took 69 us instead of 45 - no helpers unless they take at least 8 % off.
-  constexpr int kItemOverheadKb = 8;
-  int kp = static_cast<int>((static_cast<long long>(per_helper) * (a.nkb0 + kItemOverheadKb) + per_helper) / (per_helper + 1));
-  if (kp * 100LL > a.nkb0 * 92LL && !std::getenv("NMFB_TAIL_KP")) return 0;
-  if (const char* env = std::getenv("NMFB_TAIL_KP")) kp = std::atoi(env);  // tuning experiments
-  kp = std::min(std::max(kp, 1), a.nkb0 - 1);
-  *kp_out = kp;
-  return helpers;
+  return balance_tail_helpers(tiles, helpers, a.nkb0, kp_out);
 }
 
 void set_tail_helpers(GemmLaunch* L, int helpers, int kp, float* part, unsigned int* flags) {

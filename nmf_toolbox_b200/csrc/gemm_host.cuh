@@ -74,6 +74,7 @@ int choose_kl_splits(int pairs, int total_tiles, int rows, int Kp, int slots, in
 // Returns 0 when the launch is not eligible (single CTAs, several column chunks, split-K, segments, a grid
 // that already fills the GPU or one so small that split-K is the better tool).
 int plan_tail_helpers(const GemmLaunch& L, int epi, int num_sms, int reserve_sms, int* kp_out);
+int balance_tail_helpers(int tiles, int helpers, int nkb0, int* kp_out);  // the pure part of the above
 // Adds the helpers to the grid.  part: tiles * ncols * 256 floats; flags: 2 * tiles words, zero-initialised.
 void set_tail_helpers(GemmLaunch* L, int helpers, int kp, float* part, unsigned int* flags);
 

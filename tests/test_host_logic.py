@@ -176,3 +176,36 @@ def test_kl_split_planner():
         if max_per:
             assert p <= max_per
         assert s <= 256 and s * pairs <= 65535  # gridDim.y and the cluster count stay launchable
+
+
+def test_tail_helper_balance():
+    """balance_tail_helpers (gemm_host.cu): where the primaries of a large contraction hand over to the helper CTA
+    pairs.  Pure host arithmetic behind plan_tail_helpers, called through the test library's hook."""
+    import ctypes
+
+    path = os.path.join(ROOT, "tests", "libnmfb200_test.so")
+    if not os.path.exists(path):
+        pytest.skip("tests/libnmfb200_test.so not built")
+    lib = ctypes.CDLL(path)
+    kp = ctypes.c_int(0)
+
+    def plan(tiles, helpers, nkb0):
+        h = lib.nmfb_debug_tail_balance(tiles, helpers, nkb0, ctypes.byref(kp))
+        return h, kp.value
+
+    # north star: 64 row tiles, 72 - 64 = 8 free pairs, 16384 / 32 = 512 k-blocks: each helper takes the tails of 8
+    # tiles, 8 * (512 - kp + 8) = kp  ->  kp = 463 (measured optimum between 456 and 464)
+    assert plan(64, 8, 512) == (8, 463)
+    assert plan(64, 8, 256) == (8, 235)          # a 2-GPU shard's A contraction: still worth 8 %
+    assert plan(64, 8, 128)[0] == 0              # shorter contractions: the per-tile cost of a helper eats the gain
+    assert plan(64, 8, 64)[0] == 0
+    assert plan(64, 0, 512)[0] == 0 and plan(64, -3, 512)[0] == 0
+    h, k = plan(38, 34, 300)                     # more free pairs than half the tiles: two tiles per helper
+    assert h == 34 and 0 < k < 300 and 2 * (300 - k + 8) <= k + 2
+    h, k = plan(32, 40, 512)                     # never more helpers than tiles
+    assert h == 32 and k == 260
+    for tiles, helpers, nkb0 in [(64, 8, 512), (50, 22, 1000), (70, 2, 4096), (40, 32, 100)]:
+        h, k = plan(tiles, helpers, nkb0)
+        if h:
+            per = -(-tiles // h)
+            assert 1 <= k < nkb0 and abs(per * (nkb0 - k + 8) - k) <= per + 1  # both sides finish together
